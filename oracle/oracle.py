@@ -1,0 +1,169 @@
+"""oracle/oracle.py — TEST INFRASTRUCTURE: ctypes front-end to libzkstd_oracle.so (Oracle A).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
+this.  Array conventions equal include/kgr_msm.h: points (n, 8) uint64 = x||y Montgomery limbs,
+optional (n,) uint8 infinity flags, scalars (n, 4) uint64 Montgomery, projective result (12,).
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libzkstd_oracle.so")
+
+BN254_G1, GRUMPKIN = 0, 1
+FIELD_FQ, FIELD_FR = 0, 1
+# base / scalar field ids per curve
+BASE_FIELD = {BN254_G1: FIELD_FQ, GRUMPKIN: FIELD_FR}
+SCALAR_FIELD = {BN254_G1: FIELD_FR, GRUMPKIN: FIELD_FQ}
+
+OPS = dict(add=0, sub=1, mul=2, square=3, double=4, neg=5, invert=6, mont_reduce=7, to_mont=8, from_u512=9)
+
+
+def build(force=False):
+    src = [os.path.join(_HERE, f) for f in ("zkstd_oracle.cpp", "zkstd_oracle.hpp")]
+    if force or not os.path.exists(_LIB_PATH) or any(
+            os.path.exists(s) and os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in src):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = ctypes.CDLL(_LIB_PATH)
+        u64p = ctypes.POINTER(ctypes.c_uint64)
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        L.zko_field_op.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, u64p]
+        L.zko_msm.argtypes = [ctypes.c_int, u64p, u8p, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.c_int, u64p]
+        L.zko_pedersen_commit.argtypes = [ctypes.c_int, u64p, u8p, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
+        L.zko_to_affine.argtypes = [ctypes.c_int, u64p, u64p]
+        L.zko_point_op.argtypes = [ctypes.c_int, ctypes.c_int, u64p, u64p, u64p]
+        L.zko_scalar_point.argtypes = [ctypes.c_int, u64p, u64p, u64p]
+        L.zko_generator.argtypes = [ctypes.c_int, u64p]
+        L.zko_random_field.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, u64p]
+        L.zko_random_points.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
+        L.zko_xorshift_u64.argtypes = [u8p, ctypes.c_size_t, u64p]
+        L.zko_window_bits.argtypes = [ctypes.c_size_t]
+        L.zko_window_bits.restype = ctypes.c_size_t
+        L.zko_get_at.argtypes = [ctypes.c_size_t, ctypes.c_size_t, u8p]
+        L.zko_get_at.restype = ctypes.c_size_t
+        _lib = L
+    return _lib
+
+
+def _u64(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64))
+
+
+def _u8(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8))
+
+
+def _c(a, dtype=np.uint64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+DEFAULT_SEED = bytes.fromhex("5962be5d763d318d17db37325406bce5")  # pallet/nova/src/tests.rs:69-74
+
+
+def _seed(seed):
+    s = np.frombuffer(bytes(seed), dtype=np.uint8).copy()
+    assert s.size == 16
+    return s
+
+
+def field_op(field_id, op, a, b=None):
+    a = _c(a)
+    out = np.zeros(4, dtype=np.uint64)
+    bb = _c(b) if b is not None else np.zeros(4, dtype=np.uint64)
+    rc = lib().zko_field_op(field_id, OPS[op], _u64(a), _u64(bb), _u64(out))
+    if rc == 1:
+        return None
+    assert rc == 0
+    return out
+
+
+def msm(curve, points, scalars, inf=None, threads=None):
+    points, scalars = _c(points).reshape(-1, 8), _c(scalars).reshape(-1, 4)
+    out = np.zeros(12, dtype=np.uint64)
+    infp = _u8(_c(inf, np.uint8)) if inf is not None else None
+    rc = lib().zko_msm(curve, _u64(points), infp, points.shape[0], _u64(scalars), scalars.shape[0],
+                       threads or os.cpu_count() or 1, _u64(out))
+    assert rc == 0
+    return out
+
+
+def pedersen_commit(curve, points, scalars, inf=None):
+    points, scalars = _c(points).reshape(-1, 8), _c(scalars).reshape(-1, 4)
+    out = np.zeros(9, dtype=np.uint64)
+    infp = _u8(_c(inf, np.uint8)) if inf is not None else None
+    assert lib().zko_pedersen_commit(curve, _u64(points), infp, points.shape[0], _u64(scalars), scalars.shape[0], _u64(out)) == 0
+    return out
+
+
+def to_affine(curve, proj):
+    """-> (9,) uint64: x(4) y(4) is_infinity."""
+    proj = _c(proj)
+    out = np.zeros(9, dtype=np.uint64)
+    assert lib().zko_to_affine(curve, _u64(proj), _u64(out)) == 0
+    return out
+
+
+def point_op(curve, op, a, b=None, out_len=12):
+    a = _c(a)
+    bb = _c(b) if b is not None else np.zeros(12, dtype=np.uint64)
+    out = np.zeros(out_len, dtype=np.uint64)
+    assert lib().zko_point_op(curve, op, _u64(a), _u64(bb), _u64(out)) == 0
+    return out
+
+
+def scalar_point(curve, proj, scalar):
+    proj, scalar = _c(proj), _c(scalar)
+    out = np.zeros(12, dtype=np.uint64)
+    assert lib().zko_scalar_point(curve, _u64(proj), _u64(scalar), _u64(out)) == 0
+    return out
+
+
+def generator(curve):
+    out = np.zeros(8, dtype=np.uint64)
+    assert lib().zko_generator(curve, _u64(out)) == 0
+    return out
+
+
+def random_field(field_id, n, seed=DEFAULT_SEED):
+    out = np.zeros((n, 4), dtype=np.uint64)
+    s = _seed(seed)
+    assert lib().zko_random_field(field_id, _u8(s), n, _u64(out)) == 0
+    return out
+
+
+def random_points(curve, n, seed=DEFAULT_SEED, threads=None, return_scalars=False):
+    xy = np.zeros((n, 8), dtype=np.uint64)
+    ks = np.zeros((n, 4), dtype=np.uint64)
+    s = _seed(seed)
+    assert lib().zko_random_points(curve, _u8(s), n, threads or os.cpu_count() or 1, _u64(xy), _u64(ks)) == 0
+    return (xy, ks) if return_scalars else xy
+
+
+def xorshift_u64(n, seed=DEFAULT_SEED):
+    out = np.zeros(n, dtype=np.uint64)
+    s = _seed(seed)
+    assert lib().zko_xorshift_u64(_u8(s), n, _u64(out)) == 0
+    return out
+
+
+def window_bits(n):
+    return int(lib().zko_window_bits(n))
+
+
+def get_at(segment, c, bytes32):
+    b = np.frombuffer(bytes(bytes32), dtype=np.uint8).copy()
+    return int(lib().zko_get_at(segment, c, _u8(b)))
