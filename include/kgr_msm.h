@@ -1,0 +1,120 @@
+/* kgr_msm.h — C ABI of the B200-native MSM engine for Kogarashi's BN254 G1 and Grumpkin curves.
+ *
+ * The reference has no FFI for this path: the boundary is two Rust functions,
+ *   groth16/src/msm.rs:6        fn msm_curve_addition<C: BNAffine>(bases: &[C], coeffs: &[C::Scalar]) -> C::Extended
+ *   nova/src/pedersen.rs:15     fn PedersenCommitment::<C>::commit(&self, m: &DenseVectors<C::Scalar>) -> C
+ * and the zkstd trait surface they are generic over (zkstd/src/traits/curve/weierstrass.rs:7-97,
+ * zkstd/src/traits/field.rs:13-40).  This header is what a Rust `extern "C"` block (see
+ * INTEGRATION.md and rust/kogarashi-msm-b200) or any other FFI binds instead.
+ *
+ * Data formats (all little endian, plain pointers, caller-owned for the duration of the call):
+ *   points   n x 8 uint64   x[4] || y[4], Montgomery limbs exactly as stored in bn_254::Fq /
+ *                           bn_254::Fr (`inner()`, bn254/src/fq.rs:102, fr.rs:118)
+ *   inf      n x uint8      is_infinity flags (bn254/src/g1.rs:21); NULL = no identity points
+ *   scalars  n x 4 uint64   KGR_SCALARS_MONTGOMERY: the in-memory form (`Fr.0`, fr.rs:71);
+ *                           KGR_SCALARS_CANONICAL:  `to_raw_bytes()` output read as 4 LE words
+ *                           (zkstd/src/macros/field.rs:102-104), must be < the scalar modulus
+ *   result   12 uint64      homogeneous projective X[4] Y[4] Z[4] in Montgomery form, i.e. the
+ *                           fields of G1Projective / grumpkin::Projective (g1.rs:119); identity =
+ *                           (0, R, 0) as in zkstd/src/macros/curve/weierstrass/group.rs:106-110.
+ *                           Any representative of the correct group element may be returned;
+ *                           compare after to_affine (macros/curve/weierstrass.rs:57-66).
+ *
+ * Every function returns 0 on success or a negative KGR_E_* code; kgr_last_error() gives the
+ * text for the calling thread.  No C++ exception crosses this boundary.  There is no CPU
+ * fallback: without a usable CUDA device kgr_init fails with KGR_E_NO_DEVICE.
+ */
+#ifndef KGR_MSM_H
+#define KGR_MSM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { KGR_CURVE_BN254_G1 = 0, KGR_CURVE_GRUMPKIN = 1 };
+enum { KGR_SCALARS_MONTGOMERY = 0, KGR_SCALARS_CANONICAL = 1 };
+enum {
+    KGR_OK = 0,
+    KGR_E_NO_DEVICE = -1,   /* no CUDA device / driver */
+    KGR_E_CUDA = -2,        /* a CUDA runtime call failed (see kgr_last_error) */
+    KGR_E_ARG = -3,         /* bad argument */
+    KGR_E_NOT_INIT = -4,    /* kgr_init has not been called */
+    KGR_E_TOO_LARGE = -5    /* exceeds the engine's limits */
+};
+
+typedef struct kgr_bases kgr_bases_t; /* opaque handle: a point vector resident on the GPUs */
+
+/* Select the GPUs of this process.  devices == NULL or n_devices == 0: the current device only.
+ * Large MSMs are sharded evenly over the listed devices, each returns one partial point
+ * (one D2H copy per GPU) and the host adds them; no NCCL is involved. */
+int kgr_init(const int *devices, int n_devices);
+int kgr_shutdown(void);
+const char *kgr_last_error(void);
+int kgr_device_count(void); /* devices selected by kgr_init (0 before) */
+
+/* Upload a base vector once (Groth16 CRS queries `params.{h,l,a,b_g1}`, groth16/src/prover.rs:51-62;
+ * Pedersen `ck.g`, nova/src/pedersen.rs:6-13).  The vector is split into contiguous shards, one per device. */
+int kgr_bases_register(int curve, const uint64_t *xy, const uint8_t *inf, size_t n, kgr_bases_t **out);
+int kgr_bases_free(kgr_bases_t *bases);
+size_t kgr_bases_len(const kgr_bases_t *bases);
+
+/* sum_{i<n} scalars[i] * bases[base_off + i]   (replaces msm_curve_addition, groth16/src/msm.rs:6-48).
+ * Host scalars; the H2D copy of the scalars and the 96-byte D2H of the result are part of the call. */
+int kgr_msm(kgr_bases_t *bases, size_t base_off, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t out[12]);
+
+/* Same with everything passed from host memory each call; pairs = min(n_bases, n_scalars) exactly
+ * like coeffs.iter().zip(bases.iter()) (msm.rs:25). */
+int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, int scalar_fmt,
+                    size_t n_scalars, uint64_t out[12]);
+
+/* Scalars already resident on the device that holds the bases (single-device contexts only):
+ * d_scalars is a device pointer to n x 4 uint64.  Used for kernel-only timing and by callers
+ * that produce scalars on the GPU. */
+int kgr_msm_device(kgr_bases_t *bases, size_t base_off, const void *d_scalars, int scalar_fmt, size_t n, uint64_t out[12]);
+
+/* PedersenCommitment::commit (nova/src/pedersen.rs:15-20): MSM followed by to_affine.
+ * out = x[4] y[4] is_infinity (identity -> (0, R, 1) as in group.rs:22-26). */
+int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t out[9]);
+
+/* Projective -> affine normalisation on the host (zkstd/src/macros/curve/weierstrass.rs:57-66);
+ * out = x[4] y[4] is_infinity. */
+int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]);
+/* a + b on the host for two projective points (used to combine per-GPU / per-rank partial sums). */
+int kgr_proj_add(int curve, const uint64_t a[12], const uint64_t b[12], uint64_t out[12]);
+
+/* Tuning knobs: "window_bits" (0 = auto), "chunk" (entries per accumulate thread, 0 = auto),
+ * "reduce_fanin" (power of two). */
+int kgr_set_param(const char *name, long value);
+
+/* Per-phase device time (ms, CUDA events on the engine's stream) of the last MSM on device slot
+ * `dev`: [0] total, [1] count, [2] scan, [3] fill, [4] accumulate, [5] fixup, [6] reduce+final,
+ * [7] H2D scalars.  Also the shape used: shape = {c, W, B, L, K, n}. */
+int kgr_last_timing(int dev, float ms[8], uint32_t shape[6]);
+
+/* ---- test / bench utilities (exercise the same device code the MSM uses) ------------------- */
+/* Elementwise field ops on the device: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 neg
+ * 5 from_mont 6 to_mont 7 inv 8 dbl.  a, b, out: host arrays of n x 4 uint64. */
+int kgr_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
+/* Elementwise point ops: op 0: proj(a_xyzz-from-affine madd b_affine), i.e. a + b for affine inputs with flags
+ * (inf bytes may be NULL); out n x 12 projective. op 1: a + a.  op 2: a + b computed through xyzz_add. */
+int kgr_test_point_op(int curve, int op, const uint64_t *a_xy, const uint8_t *a_inf, const uint64_t *b_xy, const uint8_t *b_inf, size_t n,
+                      uint64_t *out);
+/* out[i] = k[i] * G as affine (x||y Montgomery), computed on the device (fixed-base double-and-add +
+ * batched normalisation).  k: host n x 4 uint64, Montgomery form of the curve's scalar field. */
+int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy);
+/* Same but leaves the points on the device as a registered base vector (for large benchmarks).
+ * Scalars are derived on the device from a 64-bit seed (splitmix64 -> 8 words -> from_u512 like
+ * zkstd/src/arithmetic/limbs/bits_256/represent.rs:18-28,80-103).  If k_out != NULL it receives the n scalars (Montgomery). */
+int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, uint64_t *k_out);
+/* Integer-pipe microbenchmark on device slot 0: fills results[0..7] with giga-ops/s of
+ * [0] IMAD (mad.lo.u32), [1] IMAD.HI, [2] IMAD.WIDE.U32, [3] IMAD.WIDE.U32.X carry chains,
+ * [4] IADD3, [5] field multiplications (Fq), [6] XYZZ mixed adds, [7] SM clock MHz seen. */
+int kgr_microbench(double results[8]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KGR_MSM_H */

@@ -1,0 +1,94 @@
+"""ctypes binding of libkgr_msm.so (the C ABI in include/kgr_msm.h).
+
+The library is built in tree by `make -C kogarashi_b200/csrc` (or __graft_entry__.build()).  There
+is deliberately no fallback: if the shared object is missing or no CUDA device is usable, every
+entry point raises.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkgr_msm.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+EXPORTS = [
+    "kgr_init", "kgr_shutdown", "kgr_last_error", "kgr_device_count", "kgr_bases_register", "kgr_bases_free",
+    "kgr_bases_len", "kgr_msm", "kgr_msm_oneshot", "kgr_msm_device", "kgr_pedersen_commit", "kgr_to_affine",
+    "kgr_proj_add", "kgr_set_param", "kgr_last_timing", "kgr_test_field_op", "kgr_test_point_op",
+    "kgr_fixed_base_mul", "kgr_bases_generate", "kgr_microbench",
+]
+
+
+class KgrError(RuntimeError):
+    pass
+
+
+def build(force=False):
+    """Compile the CUDA engine for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "kgr_msm.h"))
+    stale = (not os.path.exists(LIB_PATH)) or any(os.path.getmtime(s) > os.path.getmtime(LIB_PATH) for s in srcs)
+    if force or stale:
+        subprocess.check_call(["make", "-C", CSRC, "-s"])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KgrError(f"{LIB_PATH} is missing: build it with `make -C {CSRC}` (no CPU fallback exists)")
+    L = ctypes.CDLL(LIB_PATH)
+    u64p, u8p, vp = ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint8), ctypes.c_void_p
+    sz, ci = ctypes.c_size_t, ctypes.c_int
+    L.kgr_init.argtypes = [ctypes.POINTER(ci), ci]
+    L.kgr_last_error.restype = ctypes.c_char_p
+    L.kgr_bases_register.argtypes = [ci, u64p, u8p, sz, ctypes.POINTER(vp)]
+    L.kgr_bases_free.argtypes = [vp]
+    L.kgr_bases_len.argtypes = [vp]
+    L.kgr_bases_len.restype = sz
+    L.kgr_msm.argtypes = [vp, sz, u64p, ci, sz, u64p]
+    L.kgr_msm_oneshot.argtypes = [ci, u64p, u8p, sz, u64p, ci, sz, u64p]
+    L.kgr_msm_device.argtypes = [vp, sz, vp, ci, sz, u64p]
+    L.kgr_pedersen_commit.argtypes = [vp, u64p, ci, sz, u64p]
+    L.kgr_to_affine.argtypes = [ci, u64p, u64p]
+    L.kgr_proj_add.argtypes = [ci, u64p, u64p, u64p]
+    L.kgr_set_param.argtypes = [ctypes.c_char_p, ctypes.c_long]
+    L.kgr_last_timing.argtypes = [ci, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_uint32)]
+    L.kgr_test_field_op.argtypes = [ci, ci, u64p, u64p, sz, u64p]
+    L.kgr_test_point_op.argtypes = [ci, ci, u64p, u8p, u64p, u8p, sz, u64p]
+    L.kgr_fixed_base_mul.argtypes = [ci, u64p, sz, u64p]
+    L.kgr_bases_generate.argtypes = [ci, ctypes.c_uint64, sz, ctypes.POINTER(vp), u64p]
+    L.kgr_microbench.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != 0:
+        raise KgrError(f"kgr error {rc}: {lib().kgr_last_error().decode(errors='replace')}")
+
+
+_initialised = False
+
+
+def init(devices=None):
+    """kgr_init: devices=None -> the current CUDA device of this process."""
+    global _initialised
+    L = lib()
+    if devices is None:
+        check(L.kgr_init(None, 0))
+    else:
+        arr = (ctypes.c_int * len(devices))(*devices)
+        check(L.kgr_init(arr, len(devices)))
+    _initialised = True
+
+
+def ensure_init():
+    if not _initialised:
+        init()

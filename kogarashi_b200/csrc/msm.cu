@@ -1,0 +1,960 @@
+// msm.cu — kernels, per-GPU engine and the C ABI (include/kgr_msm.h) of the MSM engine.
+//
+// One Engine per selected GPU: its own stream, grow-only workspace in HBM, pinned staging for the
+// scalar upload and the 128-byte result.  A registered base vector is split into contiguous
+// shards, one per GPU; kgr_msm enqueues the whole pipeline on every GPU from one host
+// thread per device, each GPU returns one XYZZ point, and the host adds them with the same
+// field/curve code compiled for the CPU (field.cuh host bodies).  No NCCL, no CPU fallback for
+// the MSM itself.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/kgr_msm.h"
+#include "msm_kernels.cuh"
+#include "scan.cuh"
+
+namespace kgr {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+struct CudaError {
+    cudaError_t e;
+    const char *what;
+    int line;
+};
+#define CK(expr)                                                      \
+    do {                                                              \
+        cudaError_t _e = (expr);                                      \
+        if (_e != cudaSuccess) throw CudaError{_e, #expr, __LINE__};  \
+    } while (0)
+
+// ---- kernels ----------------------------------------------------------------------------------
+constexpr int TPB_SCALAR = 256;
+constexpr int TPB_ACC = 128;
+constexpr int TPB_RED = 64;
+
+template <class C> __global__ void __launch_bounds__(TPB_SCALAR) k_count(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
+    body_count<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_SCALAR) k_fill(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets,
+                                                     uint32_t *entries) {
+    body_fill<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts, offsets, entries);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_ACC) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+                                                        XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail) {
+    body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
+                                                   const XyzzPt<C> *tail) {
+    body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_reduce(uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
+                                                    const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a) {
+    body_reduce<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a);
+}
+// Horner over windows; writes the XYZZ result (32 words) for the host-side cross-GPU sum.
+template <class C> __global__ void k_final(MsmShape sh, const XyzzPt<C> *win_a, XyzzPt<C> *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XyzzPt<C> r = win_a[sh.W - 1];
+    for (uint32_t w = sh.W - 1; w-- > 0;) {
+        for (uint32_t d = 0; d < sh.c; d++) r = xyzz_dbl(r);
+        xyzz_add(r, win_a[w]);
+    }
+    store_xyzz(out, r);
+}
+template <class C> __global__ void k_fold_inf(AffinePt<C> *pts, const uint8_t *inf, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !inf[i]) return;
+    pts[i].x = fp_zero<typename C::Base>();
+    pts[i].y = fp_zero<typename C::Base>();
+}
+
+// ---- test / utility kernels -------------------------------------------------------------------
+template <class P> __global__ void k_field_op(int op, const Fp<P> *a, const Fp<P> *b, Fp<P> *out, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<P> x = a[i], y = b ? b[i] : fp_zero<P>(), r;
+    switch (op) {
+        case 0: r = fp_add(x, y); break;
+        case 1: r = fp_sub(x, y); break;
+        case 2: r = fp_mul(x, y); break;
+        case 3: r = fp_sqr(x); break;
+        case 4: r = fp_neg(x); break;
+        case 5: r = fp_from_mont(x); break;
+        case 6: r = fp_to_mont(x); break;
+        case 7: r = fp_inv(x); break;
+        default: r = fp_dbl(x); break;
+    }
+    out[i] = r;
+}
+template <class C> __global__ void k_point_op(int op, const AffinePt<C> *a, const AffinePt<C> *b, uint32_t *out24, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XyzzPt<C> acc = xyzz_from_affine(a[i]);
+    if (op == 0) xyzz_madd(acc, b[i]);
+    else if (op == 1) acc = xyzz_dbl(acc);
+    else {
+        // go through a non-trivial representative of b: (b + a) - a would need neg; use b doubled path instead
+        XyzzPt<C> q = xyzz_from_affine(b[i]);
+        XyzzPt<C> t = xyzz_dbl(q);      // 2b
+        xyzz_madd(t, b[i]);             // 3b  (non-unit zz)
+        xyzz_add(acc, t);               // a + 3b
+    }
+    Fp<typename C::Base> o[3];
+    xyzz_to_projective(acc, o);
+    for (int k = 0; k < 3; k++)
+        for (int j = 0; j < 8; j++) out24[24 * (size_t)i + 8 * k + j] = o[k].v[j];
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+// k_i = from_u512(8 words of splitmix64(seed, i)) in the curve's scalar field (Montgomery form)
+template <class C> __global__ void k_gen_scalars(uint64_t seed, uint64_t first, uint32_t n, Fp<typename C::Scalar> *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[16];
+    for (int j = 0; j < 8; j++) {
+        uint64_t v = splitmix64(seed ^ splitmix64((first + i) * 8 + j));
+        w[2 * j] = (uint32_t)v;
+        w[2 * j + 1] = (uint32_t)(v >> 32);
+    }
+    out[i] = fp_from_u512<typename C::Scalar>(w);
+}
+// out[i] = k[i] * G, affine.  MSB-first double-and-add on the canonical scalar, then one inversion.
+template <class C> __global__ void __launch_bounds__(128) k_fixed_base(const Fp<typename C::Scalar> *k, AffinePt<C> g, uint32_t n, AffinePt<C> *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<typename C::Scalar> s = fp_from_mont(k[i]);
+    XyzzPt<C> acc = xyzz_identity<C>();
+    for (int bit = 255; bit >= 0; bit--) {
+        acc = xyzz_dbl(acc);
+        if ((s.v[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, g);
+    }
+    out[i] = xyzz_to_affine(acc);
+}
+
+// ---- integer-pipe microbenchmarks -------------------------------------------------------------
+template <int MODE> __global__ void __launch_bounds__(256) k_ubench(uint32_t *sink, uint32_t a, uint32_t b, int iters) {
+    uint32_t x[8];
+    uint64_t y[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        x[j] = threadIdx.x * 7 + j;
+        y[j] = x[j];
+    }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 8; rep++) {
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
+            } else if (MODE == 1) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
+            } else if (MODE == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y[j]) : "r"(a), "r"(x[j]));
+            } else if (MODE == 3) {
+                uint32_t top = 0;
+                chain_cmad(x, a, b, a ^ 0x55u, b ^ 0x33u, x[0] | 1u, top);
+                x[1] ^= top;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(a));
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc ^= x[j] ^ (uint32_t)y[j] ^ (uint32_t)(y[j] >> 32);
+    if (acc == 0x12345u) sink[0] = acc;
+}
+__global__ void __launch_bounds__(256) k_ubench_fmul(Fp<FqP> *sink, Fp<FqP> a, Fp<FqP> b, int iters) {
+    a.v[0] ^= threadIdx.x;
+    for (int it = 0; it < iters; it++) {
+        a = fp_mul(a, b);
+        b = fp_mul(b, a);
+    }
+    if (a.v[0] == 0x12345u && b.v[1] == 7u) sink[0] = a;
+}
+__global__ void __launch_bounds__(128) k_ubench_madd(XyzzPt<Bn254G1> *sink, AffinePt<Bn254G1> p, AffinePt<Bn254G1> q, int iters) {
+    XyzzPt<Bn254G1> acc = xyzz_from_affine(p);
+    acc.x.v[0] ^= (threadIdx.x & 1);  // not a curve point any more; the formulas do not care
+    for (int it = 0; it < iters; it++) xyzz_madd(acc, q);
+    if (acc.x.v[0] == 0x12345u && acc.y.v[1] == 7u) sink[0] = acc;
+}
+__global__ void k_clock(uint64_t *out) {
+    uint64_t t0, c0, t1, c1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    c0 = clock64();
+    do {
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    } while (t1 - t0 < 2000000ULL);
+    c1 = clock64();
+    out[0] = t1 - t0;
+    out[1] = c1 - c0;
+}
+
+// ---- engine -----------------------------------------------------------------------------------
+struct Params {
+    long window_bits = 0, chunk = 0, reduce_fanin = 16;
+};
+static Params g_params;
+
+template <class T> struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    void ensure(size_t n) {
+        if (n <= cap) return;
+        if (p) CK(cudaFree(p));
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8;
+        CK(cudaMalloc(&p, want * sizeof(T)));
+        cap = want;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+enum { EV_START, EV_H2D, EV_COUNT, EV_SCAN, EV_FILL, EV_ACC, EV_FIXUP, EV_END, EV_N };
+
+struct Engine {
+    int dev = -1;
+    int sm_count = 0;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[EV_N] = {};
+    DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars;
+    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result;  // raw bytes, cast per curve
+    uint32_t *h_result = nullptr;                                         // pinned, 32 words
+    uint64_t *h_stage = nullptr;                                          // pinned staging for scalars
+    size_t h_stage_cap = 0;
+    size_t counts_zeroed = 0;  // counts[0..counts_zeroed) are known to be zero
+    float last_ms[8] = {};
+    uint32_t last_shape[6] = {};
+    int acc_blocks_per_sm[2] = {0, 0};
+
+    void init(int device) {
+        dev = device;
+        CK(cudaSetDevice(dev));
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, dev));
+        sm_count = prop.multiProcessorCount;
+        CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        for (auto &e : ev) CK(cudaEventCreate(&e));
+        CK(cudaMallocHost(&h_result, 32 * sizeof(uint32_t)));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_per_sm[0], k_accumulate<Bn254G1>, TPB_ACC, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_per_sm[1], k_accumulate<GrumpkinC>, TPB_ACC, 0));
+    }
+    void destroy() {
+        if (dev < 0) return;
+        cudaSetDevice(dev);
+        cudaStreamSynchronize(st);
+        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release();
+        bucket_acc.release(); head.release(); tail.release(); result.release();
+        for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
+        if (h_result) cudaFreeHost(h_result);
+        if (h_stage) cudaFreeHost(h_stage);
+        for (auto &e : ev) if (e) cudaEventDestroy(e);
+        if (st) cudaStreamDestroy(st);
+        dev = -1;
+    }
+    uint64_t *stage(size_t words) {
+        if (words > h_stage_cap) {
+            if (h_stage) CK(cudaFreeHost(h_stage));
+            h_stage = nullptr;
+            CK(cudaMallocHost(&h_stage, words * sizeof(uint64_t)));
+            h_stage_cap = words;
+        }
+        return h_stage;
+    }
+};
+
+static std::mutex g_mu;
+static std::vector<Engine> g_engines;
+
+// cost model for the window size: accumulate adds + reduce adds (general adds ~1.4x a mixed add)
+// + a latency term for the serial depth of the reduce tree.
+static uint32_t choose_window_bits(uint32_t n) {
+    if (g_params.window_bits > 0) return (uint32_t)std::min<long>(std::max<long>(g_params.window_bits, 1), 24);
+    double best = 1e300;
+    uint32_t best_c = 1;
+    for (uint32_t c = 1; c <= 22; c++) {
+        double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1);
+        double cost = (double)n * W + 3.0 * 1.4 * W * B + 2000.0 * c;
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+static MsmShape make_shape(uint32_t n, int blocks_per_sm, int sm_count) {
+    MsmShape sh;
+    sh.n = n;
+    sh.c = choose_window_bits(n);
+    sh.W = (255 + sh.c - 1) / sh.c;
+    sh.B = 1u << (sh.c - 1);
+    sh.G = sh.W * sh.B;
+    sh.K = (uint32_t)g_params.reduce_fanin;
+    uint64_t M = (uint64_t)n * sh.W;
+    if (g_params.chunk > 0) {
+        sh.L = (uint32_t)g_params.chunk;
+    } else {
+        // pick the chunk length that minimises (waves x (L + per-chunk overhead)) for this GPU
+        uint64_t concurrent = (uint64_t)std::max(1, blocks_per_sm) * TPB_ACC * std::max(1, sm_count);
+        double best = 1e300;
+        uint32_t bestL = 32;
+        for (uint32_t L = 16; L <= 256; L += 4) {
+            uint64_t chunks = (M + L - 1) / L;
+            uint64_t waves = (chunks + concurrent - 1) / concurrent;
+            double cost = (double)waves * (L + 2.0);
+            if (cost < best - 1e-9) { best = cost; bestL = L; }
+        }
+        sh.L = bestL;
+    }
+    return sh;
+}
+
+// Enqueue one MSM over n pairs on engine e.  d_scalars: device pointer (n x 8 words).
+template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d_scalars, int is_mont, uint32_t n) {
+    typedef XyzzPt<C> X;
+    MsmShape sh = make_shape(n, e.acc_blocks_per_sm[C::ID], e.sm_count);
+    uint64_t M64 = (uint64_t)n * sh.W;
+    if (M64 >= (1ull << 32) - 1) throw CudaError{cudaErrorInvalidValue, "n * windows exceeds 2^32 entries", __LINE__};
+    uint32_t Mmax = (uint32_t)M64;
+    uint32_t chunks = (Mmax + sh.L - 1) / sh.L;
+    uint32_t cnt1 = (sh.B + sh.K - 1) / sh.K;
+
+    size_t G1 = (size_t)sh.G + 1;
+    if (e.counts.cap < G1) e.counts_zeroed = 0;
+    e.counts.ensure(G1);
+    e.offsets.ensure(G1 + 4);
+    e.tile_sums.ensure(scan_num_tiles((uint32_t)G1) + 1);
+    e.entries.ensure((size_t)Mmax + 1);
+    e.bucket_acc.ensure((size_t)sh.G * sizeof(X));
+    e.head.ensure((size_t)chunks * sizeof(X));
+    e.tail.ensure((size_t)chunks * sizeof(X));
+    for (int i = 0; i < 2; i++) {
+        e.lvl_s[i].ensure((size_t)sh.W * cnt1 * sizeof(X));
+        e.lvl_a[i].ensure((size_t)sh.W * cnt1 * sizeof(X));
+    }
+    e.result.ensure(sizeof(X));
+    if (e.counts_zeroed < G1) {
+        CK(cudaMemsetAsync(e.counts.p, 0, e.counts.cap * sizeof(uint32_t), e.st));
+        e.counts_zeroed = e.counts.cap;
+    }
+
+    CK(cudaEventRecord(e.ev[EV_H2D], e.st));
+    uint32_t sblocks = (n + TPB_SCALAR - 1) / TPB_SCALAR;
+    k_count<C><<<sblocks, TPB_SCALAR, 0, e.st>>>(sh, d_scalars, is_mont, e.counts.p);
+    CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
+    exclusive_scan_u32(e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p, e.st);
+    CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
+    k_fill<C><<<sblocks, TPB_SCALAR, 0, e.st>>>(sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
+    CK(cudaEventRecord(e.ev[EV_FILL], e.st));
+    k_accumulate<C><<<(chunks + TPB_ACC - 1) / TPB_ACC, TPB_ACC, 0, e.st>>>(sh, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
+                                                                            (X *)e.tail.p);
+    CK(cudaEventRecord(e.ev[EV_ACC], e.st));
+    k_fixup<C><<<(sh.G + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p);
+    CK(cudaEventRecord(e.ev[EV_FIXUP], e.st));
+    // hierarchical reduce: level 0 reads the buckets, later levels ping-pong
+    uint32_t cnt = sh.B, m_log2 = 0, klog = 0;
+    while ((1u << klog) < sh.K) klog++;
+    const X *in_s = (const X *)e.bucket_acc.p, *in_a = nullptr;
+    int pp = 0;
+    for (;;) {
+        uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
+        uint32_t threads = sh.W * cnt_out;
+        X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
+        k_reduce<C><<<(threads + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh.W, cnt, sh.K, m_log2, in_s, in_a, os, oa);
+        in_s = os;
+        in_a = oa;
+        cnt = cnt_out;
+        m_log2 += klog;
+        pp ^= 1;
+        if (cnt == 1) break;
+    }
+    k_final<C><<<1, 32, 0, e.st>>>(sh, in_a, (X *)e.result.p);
+    CK(cudaMemcpyAsync(e.h_result, e.result.p, sizeof(X), cudaMemcpyDeviceToHost, e.st));
+    CK(cudaEventRecord(e.ev[EV_END], e.st));
+    CK(cudaGetLastError());
+    e.last_shape[0] = sh.c; e.last_shape[1] = sh.W; e.last_shape[2] = sh.B; e.last_shape[3] = sh.L; e.last_shape[4] = sh.K; e.last_shape[5] = n;
+}
+
+static void collect_timing(Engine &e) {
+    auto el = [&](int a, int b) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e.ev[a], e.ev[b]);
+        return ms;
+    };
+    e.last_ms[0] = el(EV_START, EV_END);
+    e.last_ms[7] = el(EV_START, EV_H2D);
+    e.last_ms[1] = el(EV_H2D, EV_COUNT);
+    e.last_ms[2] = el(EV_COUNT, EV_SCAN);
+    e.last_ms[3] = el(EV_SCAN, EV_FILL);
+    e.last_ms[4] = el(EV_FILL, EV_ACC);
+    e.last_ms[5] = el(EV_ACC, EV_FIXUP);
+    e.last_ms[6] = el(EV_FIXUP, EV_END);
+}
+
+struct Shard {
+    int eng = 0;
+    size_t first = 0, count = 0;
+    void *d_pts = nullptr;
+};
+}  // namespace kgr
+
+struct kgr_bases {
+    int curve = 0;
+    size_t n = 0;
+    std::vector<kgr::Shard> shards;
+};
+
+namespace kgr {
+
+template <class C> static void upload_shard(Engine &e, Shard &s, const uint64_t *xy, const uint8_t *inf) {
+    CK(cudaSetDevice(e.dev));
+    CK(cudaMalloc(&s.d_pts, std::max<size_t>(s.count, 1) * sizeof(AffinePt<C>)));
+    if (s.count == 0) return;
+    CK(cudaMemcpyAsync(s.d_pts, xy + 8 * s.first, s.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st));
+    if (inf) {
+        uint8_t *d_inf = nullptr;
+        CK(cudaMalloc(&d_inf, s.count));
+        CK(cudaMemcpyAsync(d_inf, inf + s.first, s.count, cudaMemcpyHostToDevice, e.st));
+        k_fold_inf<C><<<(unsigned)((s.count + 255) / 256), 256, 0, e.st>>>((AffinePt<C> *)s.d_pts, d_inf, (uint32_t)s.count);
+        CK(cudaStreamSynchronize(e.st));
+        CK(cudaFree(d_inf));
+    }
+    CK(cudaStreamSynchronize(e.st));
+}
+
+static void make_shards(kgr_bases *b, size_t n) {
+    size_t ne = g_engines.size();
+    size_t per = (n + ne - 1) / ne;
+    for (size_t i = 0; i < ne; i++) {
+        Shard s;
+        s.eng = (int)i;
+        s.first = std::min(n, i * per);
+        s.count = std::min(n, (i + 1) * per) - s.first;
+        b->shards.push_back(s);
+    }
+}
+
+// Host-side sum of the per-GPU XYZZ partials and conversion to the reference's projective form.
+template <class C> static void combine_partials(const std::vector<const uint32_t *> &parts, uint64_t out[12]) {
+    XyzzPt<C> acc = xyzz_identity<C>();
+    for (const uint32_t *p : parts) {
+        XyzzPt<C> q;
+        std::memcpy(&q, p, sizeof q);
+        xyzz_add(acc, q);
+    }
+    Fp<typename C::Base> o[3];
+    xyzz_to_projective(acc, o);
+    std::memcpy(out, o, 96);
+}
+
+// Run an MSM over [off, off+n) of a registered vector.  scalars: host pointer unless on_device.
+template <class C> static void run_msm(kgr_bases *b, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t out[12]) {
+    struct Job {
+        Engine *e;
+        const AffinePt<C> *pts;
+        size_t sc_first, count;
+    };
+    std::vector<Job> jobs;
+    for (auto &s : b->shards) {
+        size_t lo = std::max(off, s.first), hi = std::min(off + n, s.first + s.count);
+        if (lo >= hi) continue;
+        jobs.push_back(Job{&g_engines[s.eng], (const AffinePt<C> *)s.d_pts + (lo - s.first), lo - off, hi - lo});
+    }
+    if (on_device && jobs.size() > 1) throw CudaError{cudaErrorInvalidValue, "device-resident scalars need a single-device range", __LINE__};
+    int is_mont = (fmt == KGR_SCALARS_MONTGOMERY);
+    std::vector<CudaError> errs(jobs.size(), CudaError{cudaSuccess, "", 0});
+    auto launch = [&](size_t j) {
+        try {
+            Job &jb = jobs[j];
+            Engine &e = *jb.e;
+            CK(cudaSetDevice(e.dev));
+            CK(cudaEventRecord(e.ev[EV_START], e.st));
+            const uint32_t *d_sc;
+            if (on_device) {
+                d_sc = reinterpret_cast<const uint32_t *>(scalars) + 8 * jb.sc_first;
+            } else {
+                e.scalars.ensure(jb.count * 8);
+                CK(cudaMemcpyAsync(e.scalars.p, scalars + 4 * jb.sc_first, jb.count * 32, cudaMemcpyHostToDevice, e.st));
+                d_sc = e.scalars.p;
+            }
+            enqueue_msm<C>(e, jb.pts, d_sc, is_mont, (uint32_t)jb.count);
+            CK(cudaStreamSynchronize(e.st));
+            collect_timing(e);
+        } catch (CudaError &ce) {
+            errs[j] = ce;
+        }
+    };
+    if (jobs.size() <= 1) {
+        for (size_t j = 0; j < jobs.size(); j++) launch(j);
+    } else {
+        std::vector<std::thread> th;
+        for (size_t j = 0; j < jobs.size(); j++) th.emplace_back(launch, j);
+        for (auto &t : th) t.join();
+    }
+    for (auto &ce : errs)
+        if (ce.e != cudaSuccess) throw ce;
+    std::vector<const uint32_t *> parts;
+    for (auto &jb : jobs) parts.push_back(jb.e->h_result);
+    combine_partials<C>(parts, out);
+}
+
+template <class C> static void proj_to_affine_host(const uint64_t in[12], uint64_t out[9]) {
+    typedef typename C::Base F;
+    Fp<F> x, y, z;
+    std::memcpy(&x, in, 32);
+    std::memcpy(&y, in + 4, 32);
+    std::memcpy(&z, in + 8, 32);
+    if (fp_is_zero(z)) {
+        Fp<F> zero = fp_zero<F>(), one = fp_one<F>();
+        std::memcpy(out, &zero, 32);
+        std::memcpy(out + 4, &one, 32);
+        out[8] = 1;
+        return;
+    }
+    Fp<F> zi = fp_inv(z);
+    Fp<F> ax = fp_mul(x, zi), ay = fp_mul(y, zi);
+    std::memcpy(out, &ax, 32);
+    std::memcpy(out + 4, &ay, 32);
+    out[8] = 0;
+}
+
+// (X : Y : Z) homogeneous -> XYZZ with zz = Z^2, zzz = Z^3, X' = X*Z, Y' = Y*Z^2
+template <class C> static XyzzPt<C> proj_to_xyzz_host(const uint64_t in[12]) {
+    typedef typename C::Base F;
+    Fp<F> x, y, z;
+    std::memcpy(&x, in, 32);
+    std::memcpy(&y, in + 4, 32);
+    std::memcpy(&z, in + 8, 32);
+    if (fp_is_zero(z)) return xyzz_identity<C>();
+    XyzzPt<C> r;
+    r.zz = fp_sqr(z);
+    r.zzz = fp_mul(r.zz, z);
+    r.x = fp_mul(x, z);
+    r.y = fp_mul(y, r.zz);
+    return r;
+}
+
+template <class F> static int test_field_op(Engine &e, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
+    CK(cudaSetDevice(e.dev));
+    Fp<F> *da = nullptr, *db = nullptr, *dout = nullptr;
+    CK(cudaMalloc(&da, n * 32));
+    CK(cudaMalloc(&dout, n * 32));
+    CK(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
+    if (b) {
+        CK(cudaMalloc(&db, n * 32));
+        CK(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
+    }
+    k_field_op<F><<<(unsigned)((n + 127) / 128), 128, 0, e.st>>>(op, da, db, dout, (uint32_t)n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e.st));
+    CK(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
+    cudaFree(da);
+    cudaFree(dout);
+    if (db) cudaFree(db);
+    return 0;
+}
+
+template <class C>
+static int test_point_op(Engine &e, int op, const uint64_t *a, const uint8_t *ainf, const uint64_t *b, const uint8_t *binf, size_t n, uint64_t *out) {
+    CK(cudaSetDevice(e.dev));
+    Shard sa, sb;
+    sa.count = sb.count = n;
+    upload_shard<C>(e, sa, a, ainf);
+    upload_shard<C>(e, sb, b, binf);
+    uint32_t *dout = nullptr;
+    CK(cudaMalloc(&dout, n * 96));
+    k_point_op<C><<<(unsigned)((n + 63) / 64), 64, 0, e.st>>>(op, (AffinePt<C> *)sa.d_pts, (AffinePt<C> *)sb.d_pts, dout, (uint32_t)n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e.st));
+    CK(cudaMemcpy(out, dout, n * 96, cudaMemcpyDeviceToHost));
+    cudaFree(dout);
+    cudaFree(sa.d_pts);
+    cudaFree(sb.d_pts);
+    return 0;
+}
+
+template <class C> static AffinePt<C> generator_affine();
+template <> AffinePt<Bn254G1> generator_affine<Bn254G1>() {  // bn254/src/params.rs:8-9: (1, 2)
+    AffinePt<Bn254G1> g;
+    g.x = fp_one<FqP>();
+    Fp<FqP> two = fp_zero<FqP>();
+    two.v[0] = 2;
+    g.y = fp_to_mont(two);
+    return g;
+}
+template <> AffinePt<GrumpkinC> generator_affine<GrumpkinC>() {  // grumpkin/src/params.rs:4-11 (Montgomery limbs as stored)
+    AffinePt<GrumpkinC> g;
+    g.x = fp_one<FrP>();
+    const uint64_t gy[4] = {0x11b2dff1448c41d8ULL, 0x23d3446f21c77dc3ULL, 0xaa7b8cf435dfafbbULL, 0x14b34cf69dc25d68ULL};
+    std::memcpy(&g.y, gy, 32);
+    return g;
+}
+
+template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed, uint64_t *k_out) {
+    typedef Fp<typename C::Scalar> S;
+    CK(cudaSetDevice(e.dev));
+    CK(cudaMalloc(&s.d_pts, std::max<size_t>(s.count, 1) * sizeof(AffinePt<C>)));
+    if (!s.count) return;
+    S *dk = nullptr;
+    CK(cudaMalloc(&dk, s.count * sizeof(S)));
+    uint32_t n = (uint32_t)s.count;
+    k_gen_scalars<C><<<(n + 255) / 256, 256, 0, e.st>>>(seed, (uint64_t)s.first, n, dk);
+    k_fixed_base<C><<<(n + 127) / 128, 128, 0, e.st>>>(dk, generator_affine<C>(), n, (AffinePt<C> *)s.d_pts);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e.st));
+    if (k_out) CK(cudaMemcpy(k_out + 4 * s.first, dk, s.count * sizeof(S), cudaMemcpyDeviceToHost));
+    CK(cudaFree(dk));
+}
+
+template <int MODE> static double ubench_mode(Engine &e, uint32_t *sink, double ops_per_thread_iter) {
+    const int iters = 2000, blocks = e.sm_count * 8, tpb = 256;
+    k_ubench<MODE><<<blocks, tpb, 0, e.st>>>(sink, 3, 5, 10);
+    cudaEvent_t a, b;
+    CK(cudaEventCreate(&a));
+    CK(cudaEventCreate(&b));
+    CK(cudaEventRecord(a, e.st));
+    k_ubench<MODE><<<blocks, tpb, 0, e.st>>>(sink, 3, 5, iters);
+    CK(cudaEventRecord(b, e.st));
+    CK(cudaStreamSynchronize(e.st));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, a, b));
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    return (double)blocks * tpb * iters * ops_per_thread_iter / (ms * 1e-3) / 1e9;
+}
+
+static int guarded(const std::function<int()> &f) {
+    try {
+        return f();
+    } catch (CudaError &ce) {
+        char buf[512];
+        std::snprintf(buf, sizeof buf, "CUDA error %d (%s) at msm.cu:%d: %s", (int)ce.e, cudaGetErrorString(ce.e), ce.line, ce.what);
+        cudaGetLastError();
+        return fail(ce.e == cudaErrorInvalidValue ? KGR_E_ARG : KGR_E_CUDA, buf);
+    } catch (std::exception &ex) {
+        return fail(KGR_E_CUDA, std::string("exception: ") + ex.what());
+    } catch (...) {
+        return fail(KGR_E_CUDA, "unknown exception");
+    }
+}
+
+#define DISPATCH(curve, CALL)                                              \
+    do {                                                                   \
+        if ((curve) == KGR_CURVE_BN254_G1) { CALL(Bn254G1); }              \
+        else if ((curve) == KGR_CURVE_GRUMPKIN) { CALL(GrumpkinC); }       \
+        else return fail(KGR_E_ARG, "unknown curve id");                   \
+    } while (0)
+
+}  // namespace kgr
+
+using namespace kgr;
+
+extern "C" {
+
+const char *kgr_last_error(void) { return g_err.c_str(); }
+
+int kgr_init(const int *devices, int n_devices) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return guarded([&]() -> int {
+        int count = 0;
+        cudaError_t ce = cudaGetDeviceCount(&count);
+        if (ce != cudaSuccess || count == 0) {
+            cudaGetLastError();
+            return fail(KGR_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(ce));
+        }
+        for (auto &e : g_engines) e.destroy();
+        g_engines.clear();
+        std::vector<int> devs;
+        if (!devices || n_devices <= 0) {
+            int cur = 0;
+            CK(cudaGetDevice(&cur));
+            devs.push_back(cur);
+        } else {
+            for (int i = 0; i < n_devices; i++) {
+                if (devices[i] < 0 || devices[i] >= count) return fail(KGR_E_ARG, "device index out of range");
+                devs.push_back(devices[i]);
+            }
+        }
+        g_engines.resize(devs.size());
+        for (size_t i = 0; i < devs.size(); i++) g_engines[i].init(devs[i]);
+        return KGR_OK;
+    });
+}
+
+int kgr_shutdown(void) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto &e : g_engines) e.destroy();
+    g_engines.clear();
+    return KGR_OK;
+}
+
+int kgr_device_count(void) { return (int)g_engines.size(); }
+
+int kgr_set_param(const char *name, long value) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    std::string s(name ? name : "");
+    if (s == "window_bits") g_params.window_bits = value;
+    else if (s == "chunk") g_params.chunk = value;
+    else if (s == "reduce_fanin") {
+        if (value < 2 || (value & (value - 1))) return fail(KGR_E_ARG, "reduce_fanin must be a power of two >= 2");
+        g_params.reduce_fanin = value;
+    } else return fail(KGR_E_ARG, "unknown parameter");
+    return KGR_OK;
+}
+
+int kgr_bases_register(int curve, const uint64_t *xy, const uint8_t *inf, size_t n, kgr_bases_t **out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (!out || (!xy && n)) return fail(KGR_E_ARG, "null pointer");
+    if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 bases per vector");
+    return guarded([&]() -> int {
+        kgr_bases *b = new kgr_bases;
+        b->curve = curve;
+        b->n = n;
+        make_shards(b, n);
+#define CALL(C) for (auto &s : b->shards) upload_shard<C>(g_engines[s.eng], s, xy, inf)
+        DISPATCH(curve, CALL);
+#undef CALL
+        *out = b;
+        return KGR_OK;
+    });
+}
+
+int kgr_bases_free(kgr_bases_t *b) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!b) return KGR_OK;
+    for (auto &s : b->shards)
+        if (s.d_pts && s.eng < (int)g_engines.size()) {
+            cudaSetDevice(g_engines[s.eng].dev);
+            cudaFree(s.d_pts);
+        }
+    delete b;
+    return KGR_OK;
+}
+
+size_t kgr_bases_len(const kgr_bases_t *b) { return b ? b->n : 0; }
+
+static int msm_common(kgr_bases_t *b, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t out[12]) {
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (!b || !out || (!scalars && n)) return fail(KGR_E_ARG, "null pointer");
+    if (off > b->n || n > b->n - off) return fail(KGR_E_ARG, "range exceeds the registered vector");
+    if (fmt != KGR_SCALARS_MONTGOMERY && fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
+    return guarded([&]() -> int {
+#define CALL(C) run_msm<C>(b, off, scalars, on_device, fmt, n, out)
+        DISPATCH(b->curve, CALL);
+#undef CALL
+        return KGR_OK;
+    });
+}
+
+int kgr_msm(kgr_bases_t *b, size_t off, const uint64_t *scalars, int fmt, size_t n, uint64_t out[12]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_common(b, off, scalars, false, fmt, n, out);
+}
+
+int kgr_msm_device(kgr_bases_t *b, size_t off, const void *d_scalars, int fmt, size_t n, uint64_t out[12]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    return msm_common(b, off, (const uint64_t *)d_scalars, true, fmt, n, out);
+}
+
+int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, int fmt, size_t n_scalars,
+                    uint64_t out[12]) {
+    size_t n = std::min(n_bases, n_scalars);  // zip semantics, groth16/src/msm.rs:25
+    kgr_bases_t *b = nullptr;
+    int rc = kgr_bases_register(curve, xy, inf, n, &b);
+    if (rc) return rc;
+    rc = kgr_msm(b, 0, scalars, fmt, n, out);
+    kgr_bases_free(b);
+    return rc;
+}
+
+int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]) {
+    if (!in || !out) return fail(KGR_E_ARG, "null pointer");
+#define CALL(C) proj_to_affine_host<C>(in, out)
+    DISPATCH(curve, CALL);
+#undef CALL
+    return KGR_OK;
+}
+
+int kgr_proj_add(int curve, const uint64_t a[12], const uint64_t b[12], uint64_t out[12]) {
+    if (!a || !b || !out) return fail(KGR_E_ARG, "null pointer");
+#define CALL(C)                                                   \
+    {                                                             \
+        XyzzPt<C> x = proj_to_xyzz_host<C>(a), y = proj_to_xyzz_host<C>(b); \
+        xyzz_add(x, y);                                           \
+        Fp<typename C::Base> o[3];                                \
+        xyzz_to_projective(x, o);                                 \
+        std::memcpy(out, o, 96);                                  \
+    }
+    DISPATCH(curve, CALL);
+#undef CALL
+    return KGR_OK;
+}
+
+int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int fmt, size_t n, uint64_t out[9]) {
+    if (!ck) return fail(KGR_E_ARG, "null pointer");
+    uint64_t proj[12];
+    size_t pairs = std::min(n, ck->n);  // m.iter().zip(self.g.iter()), nova/src/pedersen.rs:16-17
+    int rc = kgr_msm(ck, 0, scalars, fmt, pairs, proj);
+    if (rc) return rc;
+    return kgr_to_affine(ck->curve, proj, out);
+}
+
+int kgr_last_timing(int dev, float ms[8], uint32_t shape[6]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dev < 0 || dev >= (int)g_engines.size()) return fail(KGR_E_ARG, "device slot out of range");
+    if (ms) std::memcpy(ms, g_engines[dev].last_ms, sizeof(float) * 8);
+    if (shape) std::memcpy(shape, g_engines[dev].last_shape, sizeof(uint32_t) * 6);
+    return KGR_OK;
+}
+
+int kgr_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    return guarded([&]() -> int {
+        if (field == 0) return test_field_op<FqP>(g_engines[0], op, a, b, n, out);
+        if (field == 1) return test_field_op<FrP>(g_engines[0], op, a, b, n, out);
+        return fail(KGR_E_ARG, "unknown field id");
+    });
+}
+
+int kgr_test_point_op(int curve, int op, const uint64_t *a_xy, const uint8_t *a_inf, const uint64_t *b_xy, const uint8_t *b_inf, size_t n,
+                      uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    return guarded([&]() -> int {
+#define CALL(C) return test_point_op<C>(g_engines[0], op, a_xy, a_inf, b_xy, b_inf, n, out)
+        DISPATCH(curve, CALL);
+#undef CALL
+    });
+}
+
+int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        void *dk = nullptr, *dp = nullptr;
+        CK(cudaMalloc(&dk, n * 32 + 32));
+        CK(cudaMalloc(&dp, n * 64 + 64));
+        CK(cudaMemcpy(dk, k, n * 32, cudaMemcpyHostToDevice));
+#define CALL(C) k_fixed_base<C><<<(unsigned)((n + 127) / 128), 128, 0, e.st>>>((const Fp<C::Scalar> *)dk, generator_affine<C>(), (uint32_t)n, (AffinePt<C> *)dp)
+        DISPATCH(curve, CALL);
+#undef CALL
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e.st));
+        CK(cudaMemcpy(out_xy, dp, n * 64, cudaMemcpyDeviceToHost));
+        cudaFree(dk);
+        cudaFree(dp);
+        return KGR_OK;
+    });
+}
+
+int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, uint64_t *k_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (!out) return fail(KGR_E_ARG, "null pointer");
+    if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 bases per vector");
+    return guarded([&]() -> int {
+        kgr_bases *b = new kgr_bases;
+        b->curve = curve;
+        b->n = n;
+        make_shards(b, n);
+#define CALL(C) for (auto &s : b->shards) generate_shard<C>(g_engines[s.eng], s, seed, k_out)
+        DISPATCH(curve, CALL);
+#undef CALL
+        *out = b;
+        return KGR_OK;
+    });
+}
+
+int kgr_microbench(double r[8]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        uint32_t *sink = nullptr;
+        CK(cudaMalloc(&sink, 4096));
+        r[0] = ubench_mode<0>(e, sink, 64);
+        r[1] = ubench_mode<1>(e, sink, 64);
+        r[2] = ubench_mode<2>(e, sink, 64);
+        r[3] = ubench_mode<3>(e, sink, 8 * 4);  // 4 wide mads per chain, 8 chains per iteration
+        r[4] = ubench_mode<4>(e, sink, 64);
+        cudaEvent_t a, b;
+        CK(cudaEventCreate(&a));
+        CK(cudaEventCreate(&b));
+        float ms = 0;
+        {
+            Fp<FqP> x = fp_one<FqP>(), y = fp_one<FqP>();
+            y.v[0] ^= 0x1234;
+            const int iters = 500, blocks = e.sm_count * 8;
+            k_ubench_fmul<<<blocks, 256, 0, e.st>>>((Fp<FqP> *)sink, x, y, 4);
+            CK(cudaEventRecord(a, e.st));
+            k_ubench_fmul<<<blocks, 256, 0, e.st>>>((Fp<FqP> *)sink, x, y, iters);
+            CK(cudaEventRecord(b, e.st));
+            CK(cudaStreamSynchronize(e.st));
+            CK(cudaEventElapsedTime(&ms, a, b));
+            r[5] = (double)blocks * 256 * iters * 2 / (ms * 1e-3) / 1e9;
+        }
+        {
+            AffinePt<Bn254G1> g = generator_affine<Bn254G1>();
+            XyzzPt<Bn254G1> d = xyzz_dbl_affine(g);
+            AffinePt<Bn254G1> g2 = xyzz_to_affine(d);
+            const int iters = 200, blocks = e.sm_count * 16;
+            k_ubench_madd<<<blocks, 128, 0, e.st>>>((XyzzPt<Bn254G1> *)sink, g, g2, 4);
+            CK(cudaEventRecord(a, e.st));
+            k_ubench_madd<<<blocks, 128, 0, e.st>>>((XyzzPt<Bn254G1> *)sink, g, g2, iters);
+            CK(cudaEventRecord(b, e.st));
+            CK(cudaStreamSynchronize(e.st));
+            CK(cudaEventElapsedTime(&ms, a, b));
+            r[6] = (double)blocks * 128 * iters / (ms * 1e-3) / 1e9;
+        }
+        {
+            uint64_t *d = nullptr, h[2];
+            CK(cudaMalloc(&d, 16));
+            k_clock<<<1, 1, 0, e.st>>>(d);
+            CK(cudaStreamSynchronize(e.st));
+            CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
+            cudaFree(d);
+            r[7] = (double)h[1] / (double)h[0] * 1e3;  // cycles per ns -> MHz
+        }
+        cudaEventDestroy(a);
+        cudaEventDestroy(b);
+        cudaFree(sink);
+        CK(cudaGetLastError());
+        return KGR_OK;
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,275 @@
+// msm_kernels.cuh — per-thread bodies of the MSM pipeline.
+//
+// Replaces the hot loops of groth16/src/msm.rs:6-48 (bucket fill :25-30, running sum :35-40,
+// window shift :41, fold :45-47) with a bucket-sorted pipeline:
+//
+//   recode   canonical scalar -> W signed c-bit digits (|d| <= 2^(c-1)), one bucket id per digit
+//   count    histogram of bucket ids            (global bucket g = window * B + |d| - 1)
+//   scan     exclusive prefix sum -> offsets[g]  (scan.cuh)
+//   fill     counting-sort scatter of (point index | sign << 31) into entries[]
+//   accumulate  thread t owns entries [t*L, (t+1)*L): XYZZ mixed adds into a register accumulator,
+//            flushing at bucket boundaries; buckets cut by a chunk boundary go to head/tail slots
+//   fixup    stitches the head/tail partial sums of buckets that span chunks
+//   reduce   hierarchical running sums: groups of K, (S, A) = (sum, weighted sum), log_K(B) levels
+//   final    Horner over windows with c doublings per step, XYZZ -> projective
+//
+// The reference cuts unsigned digits from the canonical scalar (msm.rs:26,75-91) and uses
+// c = f(len) (:7-14); signed digits / a different c change only the representative, never the
+// group element.  Every body takes an explicit thread id so tests/host_emu.cpp can execute the
+// identical logic on the CPU.
+#pragma once
+#include "curve.cuh"
+
+namespace kgr {
+
+struct MsmShape {
+    uint32_t n;  // scalar-point pairs (min(len) zip semantics are applied by the host layer)
+    uint32_t c;  // window bits
+    uint32_t W;  // windows = ceil(255 / c)  (scalars < 2^254, one spare bit for the signed carry)
+    uint32_t B;  // buckets per window = 2^(c-1)
+    uint32_t G;  // W * B
+    uint32_t L;  // entries per accumulate thread
+    uint32_t K;  // reduce fan-in
+};
+
+KGR_HD uint32_t window_raw(const uint32_t s[8], uint32_t bit, uint32_t c) {
+    uint32_t limb = bit >> 5, sh = bit & 31;
+    if (limb >= 8) return 0;
+    uint64_t v = s[limb];
+    if (limb + 1 < 8) v |= (uint64_t)s[limb + 1] << 32;
+    return (uint32_t)(v >> sh) & ((1u << c) - 1u);
+}
+
+// Load scalar i as canonical limbs.  Montgomery inputs (the reference's in-memory form, fr.rs:71)
+// are reduced exactly like to_raw_bytes does (zkstd/src/macros/field.rs:102-104 -> fr.rs:74-84).
+template <class C> KGR_HD void load_scalar(const uint32_t *scalars, uint32_t i, int is_mont, uint32_t out[8]) {
+    Fp<typename C::Scalar> s;
+#if defined(__CUDA_ARCH__)
+    const uint4 *p = reinterpret_cast<const uint4 *>(scalars) + 2 * (size_t)i;
+    uint4 lo = p[0], hi = p[1];
+    s.v[0] = lo.x; s.v[1] = lo.y; s.v[2] = lo.z; s.v[3] = lo.w;
+    s.v[4] = hi.x; s.v[5] = hi.y; s.v[6] = hi.z; s.v[7] = hi.w;
+#else
+    for (int k = 0; k < 8; k++) s.v[k] = scalars[8 * (size_t)i + k];
+#endif
+    if (is_mont) s = fp_from_mont(s);
+    for (int k = 0; k < 8; k++) out[k] = s.v[k];
+}
+
+// Signed recoding.  Calls f(window, bucket_in_window, sign) for each non-zero digit.
+template <class Fn> KGR_HD void for_each_digit(const uint32_t s[8], const MsmShape &sh, Fn f) {
+    uint32_t carry = 0;
+    for (uint32_t w = 0; w < sh.W; w++) {
+        uint32_t d = window_raw(s, w * sh.c, sh.c) + carry;
+        carry = 0;
+        uint32_t sign = 0;
+        if (d > sh.B) {
+            d = (1u << sh.c) - d;
+            sign = 1;
+            carry = 1;
+        }
+        if (d != 0) f(w, d - 1, sign);
+    }
+}
+
+KGR_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicAdd(p, v);
+#else
+    uint32_t o = *p;
+    *p = o + v;
+    return o;
+#endif
+}
+KGR_HD uint32_t atomic_sub_u32(uint32_t *p, uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return atomicSub(p, v);
+#else
+    uint32_t o = *p;
+    *p = o - v;
+    return o;
+#endif
+}
+
+// ---- count / fill ---------------------------------------------------------------------------
+template <class C> KGR_HD void body_count(uint32_t i, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
+    if (i >= sh.n) return;
+    uint32_t s[8];
+    load_scalar<C>(scalars, i, is_mont, s);
+    for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t) { atomic_add_u32(&counts[w * sh.B + b], 1u); });
+}
+
+// counts[] is consumed back to zero (positions are handed out from the end of each bucket), so
+// the histogram buffer is clean for the next MSM without a memset.
+template <class C>
+KGR_HD void body_fill(uint32_t i, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets,
+                      uint32_t *entries) {
+    if (i >= sh.n) return;
+    uint32_t s[8];
+    load_scalar<C>(scalars, i, is_mont, s);
+    for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t sign) {
+        uint32_t g = w * sh.B + b;
+        uint32_t k = atomic_sub_u32(&counts[g], 1u) - 1u;
+        entries[offsets[g] + k] = i | (sign << 31);
+    });
+}
+
+// ---- accumulate -----------------------------------------------------------------------------
+template <class C> KGR_HD AffinePt<C> load_affine(const AffinePt<C> *bases, uint32_t idx) {
+    AffinePt<C> p;
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(bases + idx);
+    uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
+    p.x.v[0] = a.x; p.x.v[1] = a.y; p.x.v[2] = a.z; p.x.v[3] = a.w;
+    p.x.v[4] = b.x; p.x.v[5] = b.y; p.x.v[6] = b.z; p.x.v[7] = b.w;
+    p.y.v[0] = c.x; p.y.v[1] = c.y; p.y.v[2] = c.z; p.y.v[3] = c.w;
+    p.y.v[4] = d.x; p.y.v[5] = d.y; p.y.v[6] = d.z; p.y.v[7] = d.w;
+#else
+    p = bases[idx];
+#endif
+    return p;
+}
+
+template <class C> KGR_HD void store_xyzz(XyzzPt<C> *dst, const XyzzPt<C> &p) {
+#if defined(__CUDA_ARCH__)
+    uint4 *q = reinterpret_cast<uint4 *>(dst);
+    const uint32_t *s = p.x.v;
+    q[0] = make_uint4(s[0], s[1], s[2], s[3]);
+    q[1] = make_uint4(s[4], s[5], s[6], s[7]);
+    s = p.y.v;
+    q[2] = make_uint4(s[0], s[1], s[2], s[3]);
+    q[3] = make_uint4(s[4], s[5], s[6], s[7]);
+    s = p.zz.v;
+    q[4] = make_uint4(s[0], s[1], s[2], s[3]);
+    q[5] = make_uint4(s[4], s[5], s[6], s[7]);
+    s = p.zzz.v;
+    q[6] = make_uint4(s[0], s[1], s[2], s[3]);
+    q[7] = make_uint4(s[4], s[5], s[6], s[7]);
+#else
+    *dst = p;
+#endif
+}
+
+// first g with offsets[g+1] > pos  (offsets is non-decreasing, offsets[G] = M > pos)
+KGR_HD uint32_t bucket_of_position(const uint32_t *offsets, uint32_t G, uint32_t pos) {
+    uint32_t lo = 0, hi = G;  // answer in [lo, hi)
+    while (hi - lo > 1) {
+        uint32_t mid = lo + ((hi - lo) >> 1);
+        if (offsets[mid] <= pos) lo = mid;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <class C>
+KGR_HD void flush_segment(uint32_t t, uint32_t g, uint32_t s, uint32_t e, const uint32_t *offsets, const XyzzPt<C> &acc, XyzzPt<C> *bucket_acc,
+                          XyzzPt<C> *head, XyzzPt<C> *tail) {
+    uint32_t lo = offsets[g], hi = offsets[g + 1];
+    if (lo < s) store_xyzz(&head[t], acc);
+    else if (hi > e) store_xyzz(&tail[t], acc);
+    else store_xyzz(&bucket_acc[g], acc);
+}
+
+template <class C>
+KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+                            XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail) {
+    uint32_t M = offsets[sh.G];
+    uint64_t s64 = (uint64_t)t * sh.L;
+    if (s64 >= M) return;
+    uint32_t s = (uint32_t)s64;
+    uint32_t e = (M - s > sh.L) ? s + sh.L : M;
+    uint32_t g = bucket_of_position(offsets, sh.G, s);
+    uint32_t g_end = offsets[g + 1];
+    XyzzPt<C> acc = xyzz_identity<C>();
+    uint32_t ent = entries[s];
+    AffinePt<C> pt = load_affine(bases, ent & 0x7fffffffu);
+    for (uint32_t pos = s; pos < e; pos++) {
+        // prefetch the next entry's point while this one is being added
+        uint32_t ent_next = 0;
+        AffinePt<C> pt_next = pt;
+        if (pos + 1 < e) {
+            ent_next = entries[pos + 1];
+            pt_next = load_affine(bases, ent_next & 0x7fffffffu);
+        }
+        if (pos >= g_end) {
+            flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);
+            acc = xyzz_identity<C>();
+            do {
+                g++;
+                g_end = offsets[g + 1];
+            } while (pos >= g_end);
+        }
+        pt.y = fp_cneg(pt.y, (ent >> 31) != 0);
+        xyzz_madd(acc, pt);
+        ent = ent_next;
+        pt = pt_next;
+    }
+    flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);
+}
+
+// One thread per bucket: empty buckets become the identity, buckets cut by chunk boundaries get
+// their pieces summed (tail of the first chunk, heads of the following ones).
+template <class C>
+KGR_HD void body_fixup(uint32_t g, const MsmShape &sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
+                       const XyzzPt<C> *tail) {
+    if (g >= sh.G) return;
+    uint32_t lo = offsets[g], hi = offsets[g + 1];
+    if (lo == hi) {
+        store_xyzz(&bucket_acc[g], xyzz_identity<C>());
+        return;
+    }
+    uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L;
+    if (t0 == t1) return;
+    XyzzPt<C> acc = tail[t0];
+    for (uint32_t t = t0 + 1; t <= t1; t++) xyzz_add(acc, head[t]);
+    store_xyzz(&bucket_acc[g], acc);
+}
+
+// ---- reduce ---------------------------------------------------------------------------------
+// Level l combines K consecutive elements of a window, each standing for m = 2^m_log2 buckets
+// with (s_i, a_i) = (plain sum, sum weighted 1..m):
+//   S = sum s_i ;  A = sum a_i + m * sum_i i*s_i          (i = 0..K-1)
+// Level 0 has a_i == s_i == bucket i (in_a == nullptr).
+template <class C>
+KGR_HD void body_reduce(uint32_t tid, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
+                        const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a) {
+    uint32_t cnt_out = (cnt_in + K - 1) / K;
+    if (tid >= n_windows * cnt_out) return;
+    uint32_t w = tid / cnt_out, gi = tid % cnt_out;
+    uint32_t base = gi * K;
+    uint32_t k = (cnt_in - base < K) ? cnt_in - base : K;
+    const XyzzPt<C> *s_in = in_s + (size_t)w * cnt_in + base;
+    XyzzPt<C> run = xyzz_identity<C>(), T = xyzz_identity<C>();
+    for (uint32_t i = k; i-- > 1;) {
+        xyzz_add(run, s_in[i]);
+        xyzz_add(T, run);
+    }
+    xyzz_add(run, s_in[0]);  // run = S
+    XyzzPt<C> A;
+    if (in_a) {
+        const XyzzPt<C> *a_in = in_a + (size_t)w * cnt_in + base;
+        A = a_in[0];
+        for (uint32_t i = 1; i < k; i++) xyzz_add(A, a_in[i]);
+    } else {
+        A = run;
+    }
+    for (uint32_t d = 0; d < m_log2; d++) T = xyzz_dbl(T);
+    xyzz_add(A, T);
+    store_xyzz(&out_s[(size_t)w * cnt_out + gi], run);
+    store_xyzz(&out_a[(size_t)w * cnt_out + gi], A);
+}
+
+// Horner over the per-window sums (msm.rs:41,45-47 in one pass), then XYZZ -> (X : Y : Z).
+template <class C> KGR_HD void body_final(const MsmShape &sh, const XyzzPt<C> *win_a, uint32_t *out24) {
+    XyzzPt<C> r = win_a[sh.W - 1];
+    for (uint32_t w = sh.W - 1; w-- > 0;) {
+        for (uint32_t d = 0; d < sh.c; d++) r = xyzz_dbl(r);
+        xyzz_add(r, win_a[w]);
+    }
+    Fp<typename C::Base> o[3];
+    xyzz_to_projective(r, o);
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < 8; i++) out24[8 * k + i] = o[k].v[i];
+}
+
+}  // namespace kgr

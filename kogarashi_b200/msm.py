@@ -1,0 +1,169 @@
+"""Host-side mirror of the reference's MSM entry point over the C ABI.
+
+Reference interface mirrored here (paths relative to the Kogarashi repo):
+  groth16/src/msm.rs:6   pub fn msm_curve_addition<C: BNAffine>(bases: &[C], coeffs: &[C::Scalar]) -> C::Extended
+Semantics kept: pairs = zip(coeffs, bases) (msm.rs:25), identity bases allowed, the result is a
+projective representative (compare after to_affine).  Arrays are numpy uint64 views of the
+reference's own limbs: points (n, 8) = x||y Montgomery, scalars (n, 4) Montgomery (`Fr.0`).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+BN254_G1 = 0   # bn_254::G1Affine, scalars bn_254::Fr
+GRUMPKIN = 1   # grumpkin::Affine, scalars bn_254::Fq
+SCALARS_MONTGOMERY = 0
+SCALARS_CANONICAL = 1
+
+_u64p = ctypes.POINTER(ctypes.c_uint64)
+_u8p = ctypes.POINTER(ctypes.c_uint8)
+
+
+def _u64(a):
+    return a.ctypes.data_as(_u64p)
+
+
+def _c(a, dtype=np.uint64):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class Bases:
+    """A base vector resident on the GPU(s) (kgr_bases_register): a Groth16 CRS query or a Pedersen ck."""
+
+    def __init__(self, curve, points=None, inf=None, _handle=None, _n=None):
+        _lib.ensure_init()
+        self.curve = curve
+        if _handle is not None:
+            self._h, self.n = _handle, _n
+            return
+        pts = _c(points).reshape(-1, 8)
+        self.n = pts.shape[0]
+        h = ctypes.c_void_p()
+        infp = None
+        if inf is not None:
+            inf = _c(inf, np.uint8)
+            assert inf.shape[0] == self.n
+            infp = inf.ctypes.data_as(_u8p)
+        _lib.check(_lib.lib().kgr_bases_register(curve, _u64(pts), infp, self.n, ctypes.byref(h)))
+        self._h = h
+
+    @classmethod
+    def generate(cls, curve, n, seed=1, return_scalars=False):
+        """n points k_i*G computed on the device from a seed (large synthetic benchmarks/tests)."""
+        _lib.ensure_init()
+        h = ctypes.c_void_p()
+        ks = np.zeros((n, 4), dtype=np.uint64) if return_scalars else None
+        _lib.check(_lib.lib().kgr_bases_generate(curve, seed, n, ctypes.byref(h), _u64(ks) if ks is not None else None))
+        b = cls(curve, _handle=h, _n=n)
+        return (b, ks) if return_scalars else b
+
+    def __len__(self):
+        return self.n
+
+    def free(self):
+        if getattr(self, "_h", None):
+            _lib.lib().kgr_bases_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def msm_curve_addition(bases, coeffs, curve=BN254_G1, inf=None, scalar_fmt=SCALARS_MONTGOMERY, base_off=0):
+    """sum_i coeffs[i] * bases[i] over the first min(len) pairs -> (12,) uint64 projective (X, Y, Z).
+
+    `bases` is either a registered `Bases` (device-resident, only the scalars are uploaded) or an
+    (n, 8) uint64 array (uploaded for this call, like the reference's by-slice signature)."""
+    _lib.ensure_init()
+    sc = _c(coeffs).reshape(-1, 4)
+    out = np.zeros(12, dtype=np.uint64)
+    L = _lib.lib()
+    if isinstance(bases, Bases):
+        n = min(sc.shape[0], bases.n - base_off)
+        _lib.check(L.kgr_msm(bases._h, base_off, _u64(sc), scalar_fmt, n, _u64(out)))
+    else:
+        pts = _c(bases).reshape(-1, 8)
+        infp = None
+        if inf is not None:
+            inf = _c(inf, np.uint8)
+            infp = inf.ctypes.data_as(_u8p)
+        _lib.check(L.kgr_msm_oneshot(curve, _u64(pts), infp, pts.shape[0], _u64(sc), scalar_fmt, sc.shape[0], _u64(out)))
+    return out
+
+
+def msm_device(bases, d_scalars_ptr, n, scalar_fmt=SCALARS_MONTGOMERY, base_off=0):
+    """MSM with the scalars already in device memory (raw pointer, n x 4 uint64)."""
+    out = np.zeros(12, dtype=np.uint64)
+    _lib.check(_lib.lib().kgr_msm_device(bases._h, base_off, ctypes.c_void_p(d_scalars_ptr), scalar_fmt, n, _u64(out)))
+    return out
+
+
+def to_affine(curve, proj):
+    """BNProjective::to_affine (zkstd/src/macros/curve/weierstrass.rs:57-66) -> (9,) x, y, is_infinity."""
+    proj = _c(proj)
+    out = np.zeros(9, dtype=np.uint64)
+    _lib.check(_lib.lib().kgr_to_affine(curve, _u64(proj), _u64(out)))
+    return out
+
+
+def proj_add(curve, a, b):
+    a, b = _c(a), _c(b)
+    out = np.zeros(12, dtype=np.uint64)
+    _lib.check(_lib.lib().kgr_proj_add(curve, _u64(a), _u64(b), _u64(out)))
+    return out
+
+
+def last_timing(dev=0):
+    ms = (ctypes.c_float * 8)()
+    shape = (ctypes.c_uint32 * 6)()
+    _lib.check(_lib.lib().kgr_last_timing(dev, ms, shape))
+    keys = ["total", "count", "scan", "fill", "accumulate", "fixup", "reduce_final", "h2d"]
+    return dict(zip(keys, [float(x) for x in ms])), dict(zip(["c", "W", "B", "L", "K", "n"], [int(x) for x in shape]))
+
+
+def set_param(name, value):
+    _lib.check(_lib.lib().kgr_set_param(name.encode(), int(value)))
+
+
+def microbench():
+    _lib.ensure_init()
+    r = (ctypes.c_double * 8)()
+    _lib.check(_lib.lib().kgr_microbench(r))
+    keys = ["imad_gops", "imad_hi_gops", "imad_wide_gops", "imad_wide_x_gops", "iadd3_gops", "fq_mul_gops", "xyzz_madd_gops", "sm_mhz"]
+    return dict(zip(keys, [float(x) for x in r]))
+
+
+def test_field_op(field, op, a, b=None):
+    _lib.ensure_init()
+    a = _c(a).reshape(-1, 4)
+    out = np.zeros_like(a)
+    bp = None
+    if b is not None:
+        b = _c(b).reshape(-1, 4)
+        bp = _u64(b)
+    _lib.check(_lib.lib().kgr_test_field_op(field, op, _u64(a), bp, a.shape[0], _u64(out)))
+    return out
+
+
+def test_point_op(curve, op, a, b, a_inf=None, b_inf=None):
+    _lib.ensure_init()
+    a, b = _c(a).reshape(-1, 8), _c(b).reshape(-1, 8)
+    out = np.zeros((a.shape[0], 12), dtype=np.uint64)
+    ai = _c(a_inf, np.uint8) if a_inf is not None else None
+    bi = _c(b_inf, np.uint8) if b_inf is not None else None
+    _lib.check(_lib.lib().kgr_test_point_op(curve, op, _u64(a), ai.ctypes.data_as(_u8p) if ai is not None else None, _u64(b),
+                                            bi.ctypes.data_as(_u8p) if bi is not None else None, a.shape[0], _u64(out)))
+    return out
+
+
+def fixed_base_mul(curve, k):
+    _lib.ensure_init()
+    k = _c(k).reshape(-1, 4)
+    out = np.zeros((k.shape[0], 8), dtype=np.uint64)
+    _lib.check(_lib.lib().kgr_fixed_base_mul(curve, _u64(k), k.shape[0], _u64(out)))
+    return out

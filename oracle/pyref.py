@@ -90,12 +90,17 @@ def int_to_limbs(v, n=4):
     return [(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(n)]
 
 
+_RINV = {}
+
+
 def to_mont(v, p):
     return v * R256 % p
 
 
 def from_mont(v, p):
-    return v * pow(R256, -1, p) % p
+    if p not in _RINV:
+        _RINV[p] = pow(R256, -1, p)
+    return v * _RINV[p] % p
 
 
 def from_u512(words, p):

@@ -1,0 +1,32 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(ROOT, "tests", "golden", "msm_vectors.npz"))
+
+
+def golden_case_names(prefix=None):
+    z = np.load(os.path.join(ROOT, "tests", "golden", "msm_vectors.npz"))
+    names = sorted({k[: -len("_aff")] for k in z.files if k.endswith("_aff")})
+    return [n for n in names if prefix is None or n.startswith(prefix)]
+
+
+def same_affine(a, b):
+    """zkstd affine equality (macros/curve/weierstrass/group.rs:5-13): identities compare equal regardless of coordinates."""
+    a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)
+    if int(a[8]) or int(b[8]):
+        return bool(int(a[8]) and int(b[8]))
+    return bool((a[:8] == b[:8]).all())

@@ -1,0 +1,166 @@
+"""CPU tests: pin the oracle (the restated reference algorithm) against every fixed value the reference
+states for this path, against the reference's own property tests, and against the committed goldens."""
+import numpy as np
+import pytest
+from conftest import golden_case_names, same_affine
+
+from oracle import oracle as A
+from oracle import pyref as B
+
+
+def L(limbs):
+    return np.array(limbs, dtype=np.uint64)
+
+
+# bn254/src/fq.rs:10-44, bn254/src/fr.rs:11-51 — constants as written in the reference
+FQ = dict(P=[0x3c208c16d87cfd47, 0x97816a916871ca8d, 0xb85045b68181585d, 0x30644e72e131a029],
+          R=[0xd35d438dc58f0d9d, 0x0a78eb28f5c70b3d, 0x666ea36f7879462c, 0x0e0a77c19a07df2f],
+          R2=[0xf32cfc5b538afa89, 0xb5e71911d44501fb, 0x47ab1eff0a417ff6, 0x06d89f71cab8351f],
+          R3=[0xb1cd6dafda1530df, 0x62f210e6a7283db6, 0xef7f0b0c0ada0afb, 0x20fd6e902d592544], INV=0x87d20782e4866389)
+FR = dict(P=[0x43e1f593f0000001, 0x2833e84879b97091, 0xb85045b68181585d, 0x30644e72e131a029],
+          R=[0xac96341c4ffffffb, 0x36fc76959f60cd29, 0x666ea36f7879462e, 0x0e0a77c19a07df2f],
+          R2=[0x1bb8e645ae216da7, 0x53fe3ab1e35c59e3, 0x8c49833d53bb8085, 0x0216d0b17f4e44a5],
+          R3=[0x5e94d8e1b4bf0040, 0x2a489cbe1cfbb6b8, 0x893cc664a19fcfed, 0x0cf8594b7fcc657c], INV=0xc2e1f593efffffff)
+
+
+@pytest.mark.parametrize("fid,K,p", [(A.FIELD_FQ, FQ, B.FQ), (A.FIELD_FR, FR, B.FR)])
+def test_reference_constants(fid, K, p):
+    assert B.limbs_to_int(K["P"]) == p
+    assert B.limbs_to_int(K["R"]) == (1 << 256) % p
+    assert B.limbs_to_int(K["R2"]) == (1 << 512) % p
+    assert B.limbs_to_int(K["R3"]) == (1 << 768) % p
+    assert K["INV"] == (-pow(p, -1, 1 << 64)) % (1 << 64)
+    # the oracle's one()/to_mont agree with those constants
+    one = A.field_op(fid, "to_mont", L([1, 0, 0, 0]))
+    assert list(one) == K["R"]
+    assert list(A.field_op(fid, "mont_reduce", one)) == [1, 0, 0, 0]
+
+
+@pytest.mark.parametrize("fid,p", [(A.FIELD_FQ, B.FQ), (A.FIELD_FR, B.FR)])
+def test_field_ops_vs_bigint(fid, p):
+    rng = np.random.default_rng(7)
+    vals = [0, 1, 2, p - 1, p - 2, (1 << 253) % p] + [int.from_bytes(rng.bytes(40), "little") % p for _ in range(300)]
+    for i in range(len(vals) - 1):
+        a, b = vals[i], vals[i + 1]
+        am, bm = L(B.int_to_limbs(B.to_mont(a, p))), L(B.int_to_limbs(B.to_mont(b, p)))
+        dec = lambda x: B.from_mont(B.limbs_to_int(x), p)
+        assert dec(A.field_op(fid, "add", am, bm)) == (a + b) % p
+        assert dec(A.field_op(fid, "sub", am, bm)) == (a - b) % p
+        assert dec(A.field_op(fid, "mul", am, bm)) == (a * b) % p
+        assert dec(A.field_op(fid, "square", am)) == (a * a) % p
+        assert dec(A.field_op(fid, "double", am)) == (2 * a) % p
+        assert dec(A.field_op(fid, "neg", am)) == (-a) % p
+        assert B.limbs_to_int(A.field_op(fid, "mont_reduce", am)) == a
+        inv = A.field_op(fid, "invert", am)
+        if a == 0:
+            assert inv is None  # normal.rs:263-265
+        elif i < 40:
+            assert dec(inv) == pow(a, -1, p)
+
+
+def test_from_u512_sampler_matches_bigint():
+    # represent.rs:18-28 / 80-103 on the restated xorshift128 stream
+    words = A.xorshift_u64(16)
+    rng = B.XorShift128(A.DEFAULT_SEED)
+    assert [int(w) for w in words] == [rng.next_u64() for _ in range(16)]
+    for fid, p in ((A.FIELD_FQ, B.FQ), (A.FIELD_FR, B.FR)):
+        got = A.random_field(fid, 2)
+        for k in range(2):
+            assert B.from_mont(B.limbs_to_int(got[k]), p) == B.from_u512([int(w) for w in words[8 * k:8 * k + 8]], p)
+
+
+@pytest.mark.parametrize("curve", [A.BN254_G1, A.GRUMPKIN])
+def test_generators_and_curve_params(curve):
+    cm = B.CURVES[curve]
+    g = A.generator(curve)
+    gx, gy = B.from_mont(B.limbs_to_int(g[:4]), cm.p), B.from_mont(B.limbs_to_int(g[4:]), cm.p)
+    assert (gx, gy) == cm.g and cm.on_curve((gx, gy))
+    assert int(A.point_op(curve, 6, np.concatenate([g, L([0])]), out_len=1)[0]) == 1
+    if curve == A.BN254_G1:
+        assert (gx, gy) == (1, 2)  # bn254/src/params.rs:8-9
+
+
+@pytest.mark.parametrize("curve", [A.BN254_G1, A.GRUMPKIN])
+def test_curve_properties(curve):
+    """zkstd/src/macros/curve/weierstrass/test.rs:2-224 restated: identities, associativity, doubling, 7g+16g=23g."""
+    cm = B.CURVES[curve]
+    g = A.generator(curve)
+    gp = np.concatenate([g, L(B.int_to_limbs(B.to_mont(1, cm.p)))])
+    ident = np.concatenate([L([0, 0, 0, 0]), L(B.int_to_limbs(B.to_mont(1, cm.p))), L([0, 0, 0, 0])])
+    eq = lambda a, b: int(A.point_op(curve, 5, a, b, out_len=1)[0]) == 1
+    add = lambda a, b: A.point_op(curve, 0, a, b)
+    dbl = lambda a: A.point_op(curve, 1, a)
+    sm = lambda a, k: A.scalar_point(curve, a, L(B.int_to_limbs(B.to_mont(k % cm.r, cm.r))))
+    assert eq(add(gp, ident), gp) and eq(add(ident, gp), gp)
+    a, b, c = sm(gp, 1234567), sm(gp, 987654321987654321), sm(gp, 5)
+    assert eq(add(add(a, b), c), add(add(c, a), b))
+    assert eq(dbl(add(a, b)), add(dbl(a), dbl(b)))
+    assert eq(sm(a, 8), dbl(dbl(dbl(a))))
+    assert eq(add(sm(gp, 7), sm(gp, 16)), sm(gp, 23))
+    assert eq(add(a, a), dbl(a))                     # equal operands take the doubling branch (weierstrass.rs:112-114)
+    neg_a = a.copy()
+    neg_a[4:8] = A.field_op(A.BASE_FIELD[curve], "neg", a[4:8])
+    assert eq(add(a, neg_a), ident)                  # opposite operands (weierstrass.rs:115-117)
+    assert eq(sm(gp, cm.r), ident) and eq(sm(gp, 0), ident)
+    # mixed add agrees with projective add, including the doubling / identity branches
+    a_aff = A.to_affine(curve, a)
+    assert eq(A.point_op(curve, 2, b, a_aff), add(b, a))
+    assert eq(A.point_op(curve, 2, a, a_aff), dbl(a))
+    assert eq(A.point_op(curve, 2, neg_a, a_aff), ident)
+    # affine + affine (second hit of a bucket, msm.rs:62)
+    b_aff = A.to_affine(curve, b)
+    assert eq(A.point_op(curve, 3, a_aff, b_aff), add(a, b))
+    assert eq(A.point_op(curve, 3, a_aff, a_aff), dbl(a))
+    # scalar_point against the independent big-int model
+    k = 0x1234567890ABCDEF1234567890ABCDEF1234567890ABCDEF
+    aff = A.to_affine(curve, sm(gp, k))
+    assert (B.from_mont(B.limbs_to_int(aff[:4]), cm.p), B.from_mont(B.limbs_to_int(aff[4:8]), cm.p)) == cm.mul(cm.g, k)
+
+
+def test_window_bits_and_get_at():
+    # groth16/src/msm.rs:7-14 — values quoted in SURVEY.md §3.1
+    assert [A.window_bits(n) for n in (1, 3, 4, 31, 32, 1 << 16, 1 << 20, 1 << 24, 1 << 26)] == [1, 1, 3, 3, 6, 13, 16, 19, 20]
+    raw = bytes(range(1, 33))
+    v = int.from_bytes(raw, "little")
+    for c in (1, 3, 13, 16, 19, 20):
+        for seg in range(256 // c + 1):
+            # msm.rs:75-91 reads at most 8 bytes from byte floor(seg*c/8); windows past byte 32 are 0
+            skip = seg * c
+            exp = 0 if skip // 8 >= 32 else (v >> skip) & ((1 << c) - 1)
+            assert A.get_at(seg, c, raw) == exp
+
+
+def test_msm_equals_naive_sum_reference_unit_test():
+    """groth16/src/msm.rs:118-135: n = 32 random G1 points/scalars, msm == sum of scalar multiplications."""
+    n = 32
+    pts = A.random_points(A.BN254_G1, n, seed=bytes(range(16)))
+    sc = A.random_field(A.FIELD_FR, n, seed=bytes(range(16, 32)))
+    msm_aff = A.to_affine(A.BN254_G1, A.msm(A.BN254_G1, pts, sc))
+    naive = A.pedersen_commit(A.BN254_G1, pts, sc)  # fold of sum + p_i * k_i, then to_affine
+    assert same_affine(msm_aff, naive)
+    # linearity: msm(P, a) + msm(P, b) == msm(P, a + b)
+    sc2 = A.random_field(A.FIELD_FR, n, seed=bytes(range(32, 48)))
+    ssum = np.stack([A.field_op(A.FIELD_FR, "add", sc[i], sc2[i]) for i in range(n)])
+    lhs = A.point_op(A.BN254_G1, 0, A.msm(A.BN254_G1, pts, sc), A.msm(A.BN254_G1, pts, sc2))
+    assert same_affine(A.to_affine(A.BN254_G1, lhs), A.to_affine(A.BN254_G1, A.msm(A.BN254_G1, pts, ssum)))
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_oracle_reproduces_golden(golden, name):
+    curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
+    proj = A.msm(curve, golden[name + "_pts"], golden[name + "_sc"], inf=golden[name + "_inf"], threads=2)
+    assert same_affine(A.to_affine(curve, proj), golden[name + "_aff"])
+
+
+@pytest.mark.parametrize("name", ["g1_uniform_33", "gr_uniform_33", "g1_identity_bases_40", "gr_dup_neg_96", "g1_cancel_32"])
+def test_golden_matches_bigint_model(golden, name):
+    curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
+    cm = B.CURVES[curve]
+    pts, sc, inf, aff = (golden[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
+    P = [None if f else (B.from_mont(B.limbs_to_int(p[:4]), cm.p), B.from_mont(B.limbs_to_int(p[4:]), cm.p)) for p, f in zip(pts, inf)]
+    S = [B.from_mont(B.limbs_to_int(s), cm.r) for s in sc]
+    exp = cm.msm(P, S)
+    if exp is None:
+        assert int(aff[8]) == 1
+    else:
+        assert (B.from_mont(B.limbs_to_int(aff[:4]), cm.p), B.from_mont(B.limbs_to_int(aff[4:8]), cm.p)) == exp
