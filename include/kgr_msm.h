@@ -75,6 +75,10 @@ int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_
  * that produce scalars on the GPU. */
 int kgr_msm_device(kgr_bases_t *bases, size_t base_off, const void *d_scalars, int scalar_fmt, size_t n, uint64_t out[12]);
 
+/* Copy n registered points starting at `off` back to the host (x||y Montgomery; identity entries
+ * come back as (0, 0), the device encoding). */
+int kgr_bases_download(const kgr_bases_t *bases, size_t off, size_t n, uint64_t *xy_out);
+
 /* PedersenCommitment::commit (nova/src/pedersen.rs:15-20): MSM followed by to_affine.
  * out = x[4] y[4] is_infinity (identity -> (0, R, 1) as in group.rs:22-26). */
 int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t out[9]);
@@ -86,13 +90,24 @@ int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]);
 int kgr_proj_add(int curve, const uint64_t a[12], const uint64_t b[12], uint64_t out[12]);
 
 /* Tuning knobs: "window_bits" (0 = auto), "chunk" (entries per accumulate thread, 0 = auto),
- * "reduce_fanin" (power of two). */
+ * "reduce_fanin" (power of two), "running_sum_stop" (elements per window below which the reduce
+ * switches from running sums to the parallel weighting pass), "final_on_device" (1: Horner over
+ * windows in a one-thread kernel and one point per GPU in the D2H copy; 0 (default): the W window
+ * sums come back in one D2H copy and the host applies the doublings). */
 int kgr_set_param(const char *name, long value);
 
-/* Per-phase device time (ms, CUDA events on the engine's stream) of the last MSM on device slot
- * `dev`: [0] total, [1] count, [2] scan, [3] fill, [4] accumulate, [5] fixup, [6] reduce+final,
- * [7] H2D scalars.  Also the shape used: shape = {c, W, B, L, K, n}. */
-int kgr_last_timing(int dev, float ms[8], uint32_t shape[6]);
+/* Per-phase time (ms) of the last MSM on device slot `dev`, CUDA events on the engine's stream:
+ * [1] count, [2] scan, [3] fill, [4] accumulate, [5] fixup, [6] reduce (+ D2H of the window sums),
+ * [7] H2D of scalars (and bases for oneshot); [8] host finish (Horner over windows + sum over GPUs,
+ * host clock); [0] total = device events start..end + [8].  shape = {c, W, B, L, K, n}. */
+int kgr_last_timing(int dev, float ms[9], uint32_t shape[6]);
+
+/* CUDA events on the engine's own stream (the stream every kernel of this library is launched
+ * on), for timing a region of calls from outside: 4 event slots per device slot. */
+int kgr_event_record(int dev, int idx);
+int kgr_event_elapsed_ms(int dev, int idx_a, int idx_b, float *ms);
+/* Number of kernels this library has launched on device slot `dev` since kgr_init. */
+int kgr_launch_count(int dev, uint64_t *count);
 
 /* ---- test / bench utilities (exercise the same device code the MSM uses) ------------------- */
 /* Elementwise field ops on the device: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 neg

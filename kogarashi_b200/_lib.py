@@ -16,7 +16,8 @@ EXPORTS = [
     "kgr_init", "kgr_shutdown", "kgr_last_error", "kgr_device_count", "kgr_bases_register", "kgr_bases_free",
     "kgr_bases_len", "kgr_msm", "kgr_msm_oneshot", "kgr_msm_device", "kgr_pedersen_commit", "kgr_to_affine",
     "kgr_proj_add", "kgr_set_param", "kgr_last_timing", "kgr_test_field_op", "kgr_test_point_op",
-    "kgr_fixed_base_mul", "kgr_bases_generate", "kgr_microbench",
+    "kgr_fixed_base_mul", "kgr_bases_generate", "kgr_microbench", "kgr_bases_download", "kgr_event_record",
+    "kgr_event_elapsed_ms", "kgr_launch_count",
 ]
 
 
@@ -65,6 +66,10 @@ def lib():
     L.kgr_fixed_base_mul.argtypes = [ci, u64p, sz, u64p]
     L.kgr_bases_generate.argtypes = [ci, ctypes.c_uint64, sz, ctypes.POINTER(vp), u64p]
     L.kgr_microbench.argtypes = [ctypes.POINTER(ctypes.c_double)]
+    L.kgr_bases_download.argtypes = [vp, sz, sz, u64p]
+    L.kgr_event_record.argtypes = [ci, ci]
+    L.kgr_event_elapsed_ms.argtypes = [ci, ci, ci, ctypes.POINTER(ctypes.c_float)]
+    L.kgr_launch_count.argtypes = [ci, ctypes.POINTER(ctypes.c_uint64)]
     _lib = L
     return L
 

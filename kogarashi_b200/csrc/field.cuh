@@ -295,6 +295,56 @@ template <class P> KGR_HD Fp<P> fp_cneg(const Fp<P> &a, bool sign) {
 // before each division, hence OD < 2^256 (no carry out of the odd chain) and the carry out of the
 // even chain fits in od[7].  Final value < 2p, one conditional subtraction.
 template <class P> KGR_HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
+#if !defined(__CUDA_ARCH__) && defined(__SIZEOF_INT128__) && !defined(KGR_HOST_EMULATE_CHAINS)
+    // Host side of the product (combining per-GPU partial sums, window Horner): word-serial CIOS
+    // on 4 x u64 with unsigned __int128.  tests/host_emu.cpp defines KGR_HOST_EMULATE_CHAINS to
+    // exercise the even/odd chain algorithm below instead.
+    typedef unsigned __int128 u128;
+    uint64_t x[4], y[4], m[4], t[6] = {0, 0, 0, 0, 0, 0};
+    for (int i = 0; i < 4; i++) {
+        x[i] = (uint64_t)a.v[2 * i] | ((uint64_t)a.v[2 * i + 1] << 32);
+        y[i] = (uint64_t)b.v[2 * i] | ((uint64_t)b.v[2 * i + 1] << 32);
+        m[i] = (uint64_t)P::mod(2 * i) | ((uint64_t)P::mod(2 * i + 1) << 32);
+    }
+    // -p^-1 mod 2^64 from the 32-bit constant by one Newton step: inv64 = inv32 * (2 + p0 * inv32)
+    uint64_t inv = (uint64_t)P::INV;
+    inv *= 2 + m[0] * inv;
+    for (int i = 0; i < 4; i++) {
+        u128 c = 0;
+        for (int j = 0; j < 4; j++) {
+            c += (u128)x[j] * y[i] + t[j];
+            t[j] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[4] = (uint64_t)c;
+        t[5] = (uint64_t)(c >> 64);
+        uint64_t k = t[0] * inv;
+        c = ((u128)k * m[0] + t[0]) >> 64;
+        for (int j = 1; j < 4; j++) {
+            c += (u128)k * m[j] + t[j];
+            t[j - 1] = (uint64_t)c;
+            c >>= 64;
+        }
+        c += t[4];
+        t[3] = (uint64_t)c;
+        t[4] = t[5] + (uint64_t)(c >> 64);
+    }
+    uint64_t d[4], brw = 0;
+    for (int i = 0; i < 4; i++) {
+        u128 s = (u128)t[i] - m[i] - brw;
+        d[i] = (uint64_t)s;
+        brw = (uint64_t)(s >> 64) & 1;
+    }
+    bool ge = t[4] != 0 || brw == 0;
+    Fp<P> r;
+    for (int i = 0; i < 4; i++) {
+        uint64_t v = ge ? d[i] : t[i];
+        r.v[2 * i] = (uint32_t)v;
+        r.v[2 * i + 1] = (uint32_t)(v >> 32);
+    }
+    return r;
+#else
     uint32_t ev[8], od[8];
     const uint32_t *x = a.v;
     // round 0: plain products
@@ -330,6 +380,7 @@ template <class P> KGR_HD Fp<P> fp_mul(const Fp<P> &a, const Fp<P> &b) {
     chain_add8(r.v, ev, sh);
     fp_final_sub<P>(r.v);
     return r;
+#endif
 }
 
 template <class P> KGR_HD Fp<P> fp_sqr(const Fp<P> &a) { return fp_mul(a, a); }

@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -61,15 +62,72 @@ __global__ void __launch_bounds__(TPB_ACC) k_accumulate(MsmShape sh, const Affin
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
-                                                   const XyzzPt<C> *tail) {
-    body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail);
+                                                   const XyzzPt<C> *tail, uint32_t *worklist, uint32_t *worklist_len) {
+    body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+}
+
+// XYZZ points in shared memory, word-major (word k of thread t at sm[k * TPB + t]): conflict-free.
+constexpr int TPB_TREE = 128;
+template <class C> __device__ __forceinline__ void sm_put(uint32_t *sm, int t, const XyzzPt<C> &p) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&p);
+#pragma unroll
+    for (int k = 0; k < 32; k++) sm[k * TPB_TREE + t] = w[k];
+}
+template <class C> __device__ __forceinline__ XyzzPt<C> sm_get(const uint32_t *sm, int t) {
+    XyzzPt<C> p;
+    uint32_t *w = reinterpret_cast<uint32_t *>(&p);
+#pragma unroll
+    for (int k = 0; k < 32; k++) w[k] = sm[k * TPB_TREE + t];
+    return p;
+}
+// Sum of the TPB_TREE per-thread points of a CTA, returned in thread 0 (log2(TPB_TREE) add latencies).
+template <class C> __device__ __forceinline__ XyzzPt<C> block_tree_sum(XyzzPt<C> v, uint32_t *sm) {
+    const int t = threadIdx.x;
+    sm_put<C>(sm, t, v);
+    __syncthreads();
+    for (int s = TPB_TREE / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            XyzzPt<C> o = sm_get<C>(sm, t + s);
+            xyzz_add(v, o);
+            sm_put<C>(sm, t, v);
+        }
+        __syncthreads();
+    }
+    return v;
+}
+// One CTA per queued hot bucket (grid-stride over the worklist).
+template <class C>
+__global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
+                                                         const XyzzPt<C> *tail, const uint32_t *worklist, const uint32_t *worklist_len) {
+    __shared__ uint32_t sm[32 * TPB_TREE];
+    uint32_t n = *worklist_len;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        uint32_t g = worklist[i];
+        XyzzPt<C> v = fixup_long_partial<C>(g, threadIdx.x, TPB_TREE, sh, offsets, head, tail);
+        v = block_tree_sum<C>(v, sm);
+        if (threadIdx.x == 0) store_xyzz(&bucket_acc[g], v);
+        __syncthreads();
+    }
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_reduce(uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
                                                     const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a) {
     body_reduce<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a);
 }
-// Horner over windows; writes the XYZZ result (32 words) for the host-side cross-GPU sum.
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_weight(uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const XyzzPt<C> *in_s, const XyzzPt<C> *in_a,
+                                                    XyzzPt<C> *out) {
+    body_weight<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt, m_log2, in_s, in_a, out);
+}
+// grid (ceil(cnt_in / TPB_TREE), windows): out[w][block] = sum of in[w][block * TPB_TREE ...]
+template <class C> __global__ void __launch_bounds__(TPB_TREE) k_tree_sum(const XyzzPt<C> *in, uint32_t cnt_in, XyzzPt<C> *out) {
+    __shared__ uint32_t sm[32 * TPB_TREE];
+    uint32_t i = blockIdx.x * TPB_TREE + threadIdx.x, w = blockIdx.y;
+    XyzzPt<C> v = (i < cnt_in) ? in[(size_t)w * cnt_in + i] : xyzz_identity<C>();
+    v = block_tree_sum<C>(v, sm);
+    if (threadIdx.x == 0) store_xyzz(&out[(size_t)w * gridDim.x + blockIdx.x], v);
+}
+// Horner over windows on the device (kept for kgr_set_param("final_on_device", 1)); one thread.
 template <class C> __global__ void k_final(MsmShape sh, const XyzzPt<C> *win_a, XyzzPt<C> *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     XyzzPt<C> r = win_a[sh.W - 1];
@@ -218,7 +276,7 @@ __global__ void k_clock(uint64_t *out) {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096;
 };
 static Params g_params;
 
@@ -248,15 +306,20 @@ struct Engine {
     int sm_count = 0;
     cudaStream_t st = nullptr;
     cudaEvent_t ev[EV_N] = {};
-    DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars;
+    DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist;
     DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result;  // raw bytes, cast per curve
-    uint32_t *h_result = nullptr;                                         // pinned, 32 words
+    uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
+    uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
+    uint32_t result_c = 0;                                                // window bits to apply between them (0: already combined)
     uint64_t *h_stage = nullptr;                                          // pinned staging for scalars
     size_t h_stage_cap = 0;
     size_t counts_zeroed = 0;  // counts[0..counts_zeroed) are known to be zero
-    float last_ms[8] = {};
+    float last_ms[9] = {};
     uint32_t last_shape[6] = {};
     int acc_blocks_per_sm[2] = {0, 0};
+    uint64_t launches = 0;            // kernels of this library launched on this engine since init
+    cudaEvent_t user_ev[4] = {};      // kgr_event_record / kgr_event_elapsed_ms
+    DevBuf<uint8_t> oneshot_pts, oneshot_inf;  // device copy of the bases of kgr_msm_oneshot
 
     void init(int device) {
         dev = device;
@@ -266,7 +329,8 @@ struct Engine {
         sm_count = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         for (auto &e : ev) CK(cudaEventCreate(&e));
-        CK(cudaMallocHost(&h_result, 32 * sizeof(uint32_t)));
+        for (auto &e : user_ev) CK(cudaEventCreate(&e));
+        CK(cudaMallocHost(&h_result, 256 * 32 * sizeof(uint32_t)));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_per_sm[0], k_accumulate<Bn254G1>, TPB_ACC, 0));
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_per_sm[1], k_accumulate<GrumpkinC>, TPB_ACC, 0));
     }
@@ -274,12 +338,14 @@ struct Engine {
         if (dev < 0) return;
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
-        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release();
+        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release();
         bucket_acc.release(); head.release(); tail.release(); result.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
         if (h_stage) cudaFreeHost(h_stage);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (auto &e : user_ev) if (e) cudaEventDestroy(e);
+        oneshot_pts.release(); oneshot_inf.release();
         if (st) cudaStreamDestroy(st);
         dev = -1;
     }
@@ -362,6 +428,7 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
         e.lvl_a[i].ensure((size_t)sh.W * cnt1 * sizeof(X));
     }
     e.result.ensure(sizeof(X));
+    e.worklist.ensure((size_t)sh.G + 2);
     if (e.counts_zeroed < G1) {
         CK(cudaMemsetAsync(e.counts.p, 0, e.counts.cap * sizeof(uint32_t), e.st));
         e.counts_zeroed = e.counts.cap;
@@ -372,33 +439,70 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     k_count<C><<<sblocks, TPB_SCALAR, 0, e.st>>>(sh, d_scalars, is_mont, e.counts.p);
     CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
     exclusive_scan_u32(e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p, e.st);
+    e.launches += (scan_num_tiles((uint32_t)G1) > 1) ? 3 : 1;
     CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
     k_fill<C><<<sblocks, TPB_SCALAR, 0, e.st>>>(sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
     CK(cudaEventRecord(e.ev[EV_FILL], e.st));
     k_accumulate<C><<<(chunks + TPB_ACC - 1) / TPB_ACC, TPB_ACC, 0, e.st>>>(sh, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
                                                                             (X *)e.tail.p);
     CK(cudaEventRecord(e.ev[EV_ACC], e.st));
-    k_fixup<C><<<(sh.G + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p);
+    CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
+    k_fixup<C><<<(sh.G + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p,
+                                                                     e.worklist.p + 1, e.worklist.p);
+    k_fixup_long<C><<<std::min<uint32_t>(sh.G, 4 * (uint32_t)e.sm_count), TPB_TREE, 0, e.st>>>(sh, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p,
+                                                                                               (const X *)e.tail.p, e.worklist.p + 1, e.worklist.p);
     CK(cudaEventRecord(e.ev[EV_FIXUP], e.st));
-    // hierarchical reduce: level 0 reads the buckets, later levels ping-pong
+    // Reduce.  Running-sum levels (fan-in K) while many elements per window remain (throughput regime),
+    // then one fully parallel weighting pass and block-level tree sums (latency regime).
     uint32_t cnt = sh.B, m_log2 = 0, klog = 0;
     while ((1u << klog) < sh.K) klog++;
     const X *in_s = (const X *)e.bucket_acc.p, *in_a = nullptr;
     int pp = 0;
-    for (;;) {
+    do {
         uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
         uint32_t threads = sh.W * cnt_out;
         X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
         k_reduce<C><<<(threads + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh.W, cnt, sh.K, m_log2, in_s, in_a, os, oa);
+        e.launches++;
         in_s = os;
         in_a = oa;
         cnt = cnt_out;
         m_log2 += klog;
         pp ^= 1;
-        if (cnt == 1) break;
+    } while (cnt > (uint32_t)g_params.running_sum_stop);
+    const X *win = in_a;  // [W] once cnt == 1
+    if (cnt > 1) {
+        X *v = (X *)e.lvl_s[pp].p;
+        uint32_t threads = sh.W * cnt;
+        k_weight<C><<<(threads + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh.W, cnt, m_log2, in_s, in_a, v);
+        e.launches++;
+        const X *tin = v;
+        X *tout = (X *)e.lvl_a[pp].p;
+        while (cnt > 1) {
+            uint32_t blocks = (cnt + TPB_TREE - 1) / TPB_TREE;
+            k_tree_sum<C><<<dim3(blocks, sh.W), TPB_TREE, 0, e.st>>>(tin, cnt, tout);
+            e.launches++;
+            cnt = blocks;
+            X *nxt = (X *)tin;
+            tin = tout;
+            tout = nxt;
+        }
+        win = tin;
     }
-    k_final<C><<<1, 32, 0, e.st>>>(sh, in_a, (X *)e.result.p);
-    CK(cudaMemcpyAsync(e.h_result, e.result.p, sizeof(X), cudaMemcpyDeviceToHost, e.st));
+    if (g_params.final_on_device) {
+        k_final<C><<<1, 32, 0, e.st>>>(sh, win, (X *)e.result.p);
+        e.launches++;
+        CK(cudaMemcpyAsync(e.h_result, e.result.p, sizeof(X), cudaMemcpyDeviceToHost, e.st));
+        e.n_result = 1;
+        e.result_c = 0;
+    } else {
+        // one D2H copy of the W window sums; the host applies the c doublings between windows
+        // (254 sequential doublings: ~1 ms on one GPU thread, ~0.1 ms on a host core)
+        CK(cudaMemcpyAsync(e.h_result, win, (size_t)sh.W * sizeof(X), cudaMemcpyDeviceToHost, e.st));
+        e.n_result = sh.W;
+        e.result_c = sh.c;
+    }
+    e.launches += 6;  // count, fill, accumulate, fixup, fixup_long (+ memset)
     CK(cudaEventRecord(e.ev[EV_END], e.st));
     CK(cudaGetLastError());
     e.last_shape[0] = sh.c; e.last_shape[1] = sh.W; e.last_shape[2] = sh.B; e.last_shape[3] = sh.L; e.last_shape[4] = sh.K; e.last_shape[5] = n;
@@ -451,7 +555,7 @@ template <class C> static void upload_shard(Engine &e, Shard &s, const uint64_t 
     CK(cudaStreamSynchronize(e.st));
 }
 
-static void make_shards(kgr_bases *b, size_t n) {
+static void make_shards(std::vector<Shard> &shards, size_t n) {
     size_t ne = g_engines.size();
     size_t per = (n + ne - 1) / ne;
     for (size_t i = 0; i < ne; i++) {
@@ -459,35 +563,57 @@ static void make_shards(kgr_bases *b, size_t n) {
         s.eng = (int)i;
         s.first = std::min(n, i * per);
         s.count = std::min(n, (i + 1) * per) - s.first;
-        b->shards.push_back(s);
+        shards.push_back(s);
     }
 }
 
-// Host-side sum of the per-GPU XYZZ partials and conversion to the reference's projective form.
-template <class C> static void combine_partials(const std::vector<const uint32_t *> &parts, uint64_t out[12]) {
+// Host side of the result: per GPU, Horner over its W window sums (c doublings between windows —
+// what msm.rs:41 does with c*i doublings per window), then the sum over GPUs and the conversion to
+// the reference's projective form.  Runs on the CPU build of field.cuh / curve.cuh.
+struct Partial {
+    const uint32_t *pts;
+    uint32_t count, c;
+};
+template <class C> static void combine_partials(const std::vector<Partial> &parts, uint64_t out[12]) {
     XyzzPt<C> acc = xyzz_identity<C>();
-    for (const uint32_t *p : parts) {
-        XyzzPt<C> q;
-        std::memcpy(&q, p, sizeof q);
-        xyzz_add(acc, q);
+    for (const Partial &p : parts) {
+        if (!p.count) continue;
+        XyzzPt<C> r;
+        std::memcpy(&r, p.pts + 32 * (size_t)(p.count - 1), sizeof r);
+        for (uint32_t w = p.count - 1; w-- > 0;) {
+            for (uint32_t d = 0; d < p.c; d++) r = xyzz_dbl(r);
+            XyzzPt<C> q;
+            std::memcpy(&q, p.pts + 32 * (size_t)w, sizeof q);
+            xyzz_add(r, q);
+        }
+        xyzz_add(acc, r);
     }
     Fp<typename C::Base> o[3];
     xyzz_to_projective(acc, o);
     std::memcpy(out, o, 96);
 }
 
-// Run an MSM over [off, off+n) of a registered vector.  scalars: host pointer unless on_device.
-template <class C> static void run_msm(kgr_bases *b, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t out[12]) {
+struct HostPts {
+    const uint64_t *xy;
+    const uint8_t *inf;
+};
+
+// Run an MSM over [off, off+n) of a sharded base vector.  scalars: host pointer unless on_device.
+// hp != nullptr: the bases themselves come from host memory for this call only (kgr_msm_oneshot);
+// each GPU uploads its shard into a cached buffer on its own stream before the pipeline.
+template <class C>
+static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t out[12],
+                    const HostPts *hp) {
     struct Job {
         Engine *e;
         const AffinePt<C> *pts;
-        size_t sc_first, count;
+        size_t pt_first, sc_first, count;
     };
     std::vector<Job> jobs;
-    for (auto &s : b->shards) {
+    for (auto &s : shards) {
         size_t lo = std::max(off, s.first), hi = std::min(off + n, s.first + s.count);
         if (lo >= hi) continue;
-        jobs.push_back(Job{&g_engines[s.eng], (const AffinePt<C> *)s.d_pts + (lo - s.first), lo - off, hi - lo});
+        jobs.push_back(Job{&g_engines[s.eng], hp ? nullptr : (const AffinePt<C> *)s.d_pts + (lo - s.first), lo, lo - off, hi - lo});
     }
     if (on_device && jobs.size() > 1) throw CudaError{cudaErrorInvalidValue, "device-resident scalars need a single-device range", __LINE__};
     int is_mont = (fmt == KGR_SCALARS_MONTGOMERY);
@@ -506,6 +632,17 @@ template <class C> static void run_msm(kgr_bases *b, size_t off, const uint64_t 
                 CK(cudaMemcpyAsync(e.scalars.p, scalars + 4 * jb.sc_first, jb.count * 32, cudaMemcpyHostToDevice, e.st));
                 d_sc = e.scalars.p;
             }
+            if (hp) {
+                e.oneshot_pts.ensure(jb.count * sizeof(AffinePt<C>));
+                CK(cudaMemcpyAsync(e.oneshot_pts.p, hp->xy + 8 * jb.pt_first, jb.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st));
+                if (hp->inf) {
+                    e.oneshot_inf.ensure(jb.count);
+                    CK(cudaMemcpyAsync(e.oneshot_inf.p, hp->inf + jb.pt_first, jb.count, cudaMemcpyHostToDevice, e.st));
+                    k_fold_inf<C><<<(unsigned)((jb.count + 255) / 256), 256, 0, e.st>>>((AffinePt<C> *)e.oneshot_pts.p, e.oneshot_inf.p, (uint32_t)jb.count);
+                    e.launches++;
+                }
+                jb.pts = (const AffinePt<C> *)e.oneshot_pts.p;
+            }
             enqueue_msm<C>(e, jb.pts, d_sc, is_mont, (uint32_t)jb.count);
             CK(cudaStreamSynchronize(e.st));
             collect_timing(e);
@@ -522,9 +659,15 @@ template <class C> static void run_msm(kgr_bases *b, size_t off, const uint64_t 
     }
     for (auto &ce : errs)
         if (ce.e != cudaSuccess) throw ce;
-    std::vector<const uint32_t *> parts;
-    for (auto &jb : jobs) parts.push_back(jb.e->h_result);
+    std::vector<Partial> parts;
+    for (auto &jb : jobs) parts.push_back(Partial{jb.e->h_result, jb.e->n_result, jb.e->result_c});
+    auto t0 = std::chrono::steady_clock::now();
     combine_partials<C>(parts, out);
+    float host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    for (auto &jb : jobs) {
+        jb.e->last_ms[8] = host_ms;
+        jb.e->last_ms[0] += host_ms;  // total = device events + host finish
+    }
 }
 
 template <class C> static void proj_to_affine_host(const uint64_t in[12], uint64_t out[9]) {
@@ -727,7 +870,9 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "reduce_fanin") {
         if (value < 2 || (value & (value - 1))) return fail(KGR_E_ARG, "reduce_fanin must be a power of two >= 2");
         g_params.reduce_fanin = value;
-    } else return fail(KGR_E_ARG, "unknown parameter");
+    } else if (s == "final_on_device") g_params.final_on_device = value;
+    else if (s == "running_sum_stop") g_params.running_sum_stop = std::max<long>(1, value);
+    else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
 }
 
@@ -740,7 +885,7 @@ int kgr_bases_register(int curve, const uint64_t *xy, const uint8_t *inf, size_t
         kgr_bases *b = new kgr_bases;
         b->curve = curve;
         b->n = n;
-        make_shards(b, n);
+        make_shards(b->shards, n);
 #define CALL(C) for (auto &s : b->shards) upload_shard<C>(g_engines[s.eng], s, xy, inf)
         DISPATCH(curve, CALL);
 #undef CALL
@@ -769,7 +914,7 @@ static int msm_common(kgr_bases_t *b, size_t off, const uint64_t *scalars, bool 
     if (off > b->n || n > b->n - off) return fail(KGR_E_ARG, "range exceeds the registered vector");
     if (fmt != KGR_SCALARS_MONTGOMERY && fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
     return guarded([&]() -> int {
-#define CALL(C) run_msm<C>(b, off, scalars, on_device, fmt, n, out)
+#define CALL(C) run_msm<C>(b->shards, off, scalars, on_device, fmt, n, out, nullptr)
         DISPATCH(b->curve, CALL);
 #undef CALL
         return KGR_OK;
@@ -788,13 +933,67 @@ int kgr_msm_device(kgr_bases_t *b, size_t off, const void *d_scalars, int fmt, s
 
 int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, int fmt, size_t n_scalars,
                     uint64_t out[12]) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     size_t n = std::min(n_bases, n_scalars);  // zip semantics, groth16/src/msm.rs:25
-    kgr_bases_t *b = nullptr;
-    int rc = kgr_bases_register(curve, xy, inf, n, &b);
-    if (rc) return rc;
-    rc = kgr_msm(b, 0, scalars, fmt, n, out);
-    kgr_bases_free(b);
-    return rc;
+    if (!out || (n && (!xy || !scalars))) return fail(KGR_E_ARG, "null pointer");
+    if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 pairs per call");
+    if (fmt != KGR_SCALARS_MONTGOMERY && fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
+    return guarded([&]() -> int {
+        std::vector<Shard> shards;
+        make_shards(shards, n);
+        HostPts hp{xy, inf};
+#define CALL(C) run_msm<C>(shards, 0, scalars, false, fmt, n, out, &hp)
+        DISPATCH(curve, CALL);
+#undef CALL
+        return KGR_OK;
+    });
+}
+
+int kgr_bases_download(const kgr_bases_t *b, size_t off, size_t n, uint64_t *xy_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!b || (!xy_out && n)) return fail(KGR_E_ARG, "null pointer");
+    if (off > b->n || n > b->n - off) return fail(KGR_E_ARG, "range exceeds the registered vector");
+    return guarded([&]() -> int {
+        for (auto &s : b->shards) {
+            size_t lo = std::max(off, s.first), hi = std::min(off + n, s.first + s.count);
+            if (lo >= hi) continue;
+            CK(cudaSetDevice(g_engines[s.eng].dev));
+            CK(cudaMemcpy(xy_out + 8 * (lo - off), (const uint8_t *)s.d_pts + 64 * (lo - s.first), 64 * (hi - lo), cudaMemcpyDeviceToHost));
+        }
+        return KGR_OK;
+    });
+}
+
+int kgr_event_record(int dev, int idx) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dev < 0 || dev >= (int)g_engines.size() || idx < 0 || idx >= 4) return fail(KGR_E_ARG, "bad device slot / event index");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[dev];
+        CK(cudaSetDevice(e.dev));
+        CK(cudaEventRecord(e.user_ev[idx], e.st));
+        return KGR_OK;
+    });
+}
+
+int kgr_event_elapsed_ms(int dev, int idx_a, int idx_b, float *ms) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dev < 0 || dev >= (int)g_engines.size() || idx_a < 0 || idx_a >= 4 || idx_b < 0 || idx_b >= 4 || !ms)
+        return fail(KGR_E_ARG, "bad device slot / event index");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[dev];
+        CK(cudaSetDevice(e.dev));
+        CK(cudaEventSynchronize(e.user_ev[idx_b]));
+        CK(cudaEventElapsedTime(ms, e.user_ev[idx_a], e.user_ev[idx_b]));
+        return KGR_OK;
+    });
+}
+
+int kgr_launch_count(int dev, uint64_t *count) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (dev < 0 || dev >= (int)g_engines.size() || !count) return fail(KGR_E_ARG, "bad device slot");
+    *count = g_engines[dev].launches;
+    return KGR_OK;
 }
 
 int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]) {
@@ -832,7 +1031,7 @@ int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int fmt, size_
 int kgr_last_timing(int dev, float ms[8], uint32_t shape[6]) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (dev < 0 || dev >= (int)g_engines.size()) return fail(KGR_E_ARG, "device slot out of range");
-    if (ms) std::memcpy(ms, g_engines[dev].last_ms, sizeof(float) * 8);
+    if (ms) std::memcpy(ms, g_engines[dev].last_ms, sizeof(float) * 9);
     if (shape) std::memcpy(shape, g_engines[dev].last_shape, sizeof(uint32_t) * 6);
     return KGR_OK;
 }
@@ -889,7 +1088,7 @@ int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, ui
         kgr_bases *b = new kgr_bases;
         b->curve = curve;
         b->n = n;
-        make_shards(b, n);
+        make_shards(b->shards, n);
 #define CALL(C) for (auto &s : b->shards) generate_shard<C>(g_engines[s.eng], s, seed, k_out)
         DISPATCH(curve, CALL);
 #undef CALL

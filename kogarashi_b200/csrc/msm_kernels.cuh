@@ -208,10 +208,13 @@ KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *b
 }
 
 // One thread per bucket: empty buckets become the identity, buckets cut by chunk boundaries get
-// their pieces summed (tail of the first chunk, heads of the following ones).
+// their pieces summed (tail of the first chunk, heads of the following ones).  Buckets cut into
+// more than FIXUP_INLINE_MAX pieces (a hot bucket: skewed scalars, or the thin top window) are
+// queued for the block-cooperative kernel instead of being walked by one thread.
+constexpr uint32_t FIXUP_INLINE_MAX = 6;
 template <class C>
 KGR_HD void body_fixup(uint32_t g, const MsmShape &sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
-                       const XyzzPt<C> *tail) {
+                       const XyzzPt<C> *tail, uint32_t *worklist, uint32_t *worklist_len) {
     if (g >= sh.G) return;
     uint32_t lo = offsets[g], hi = offsets[g + 1];
     if (lo == hi) {
@@ -220,9 +223,25 @@ KGR_HD void body_fixup(uint32_t g, const MsmShape &sh, const uint32_t *offsets, 
     }
     uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L;
     if (t0 == t1) return;
+    if (t1 - t0 > FIXUP_INLINE_MAX && worklist) {
+        worklist[atomic_add_u32(worklist_len, 1u)] = g;
+        return;
+    }
     XyzzPt<C> acc = tail[t0];
     for (uint32_t t = t0 + 1; t <= t1; t++) xyzz_add(acc, head[t]);
     store_xyzz(&bucket_acc[g], acc);
+}
+
+// Partial sum of the pieces of hot bucket g owned by lane `lane` of `lanes` cooperating threads
+// (piece 0 is tail[t0], piece k >= 1 is head[t0 + k]); the caller tree-adds the lane results.
+template <class C>
+KGR_HD XyzzPt<C> fixup_long_partial(uint32_t g, uint32_t lane, uint32_t lanes, const MsmShape &sh, const uint32_t *offsets, const XyzzPt<C> *head,
+                                    const XyzzPt<C> *tail) {
+    uint32_t lo = offsets[g], hi = offsets[g + 1];
+    uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L;
+    XyzzPt<C> acc = xyzz_identity<C>();
+    for (uint32_t t = t0 + lane; t <= t1; t += lanes) xyzz_add(acc, t == t0 ? tail[t0] : head[t]);
+    return acc;
 }
 
 // ---- reduce ---------------------------------------------------------------------------------
@@ -257,6 +276,30 @@ KGR_HD void body_reduce(uint32_t tid, uint32_t n_windows, uint32_t cnt_in, uint3
     xyzz_add(A, T);
     store_xyzz(&out_s[(size_t)w * cnt_out + gi], run);
     store_xyzz(&out_a[(size_t)w * cnt_out + gi], A);
+}
+
+// Closes the reduction once few elements per window are left: element g of a window stands for
+// m = 2^m_log2 buckets starting at bucket g*m, with (s_g, a_g) = (plain sum, sum weighted 1..m), so
+// its contribution to the window sum is a_g + m*g*s_g; g*s_g by MSB-first double-and-add.  All
+// elements are independent, the results are then tree-summed per window (k_tree_sum).
+template <class C>
+KGR_HD void body_weight(uint32_t tid, uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const XyzzPt<C> *in_s, const XyzzPt<C> *in_a,
+                        XyzzPt<C> *out) {
+    if (tid >= n_windows * cnt) return;
+    uint32_t g = tid % cnt;
+    XyzzPt<C> s = in_s[tid];
+    XyzzPt<C> acc = xyzz_identity<C>();
+    if (g != 0) {
+        int top = 31;
+        while (!((g >> top) & 1)) top--;
+        for (int bit = top; bit >= 0; bit--) {
+            acc = xyzz_dbl(acc);
+            if ((g >> bit) & 1) xyzz_add(acc, s);
+        }
+        for (uint32_t d = 0; d < m_log2; d++) acc = xyzz_dbl(acc);
+    }
+    xyzz_add(acc, in_a ? in_a[tid] : s);
+    store_xyzz(&out[tid], acc);
 }
 
 // Horner over the per-window sums (msm.rs:41,45-47 in one pass), then XYZZ -> (X : Y : Z).

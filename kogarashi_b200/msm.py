@@ -62,6 +62,13 @@ class Bases:
     def __len__(self):
         return self.n
 
+    def download(self, off=0, n=None):
+        """Copy registered points back to the host as (n, 8) uint64 (identity entries read (0, 0))."""
+        n = self.n - off if n is None else n
+        out = np.zeros((n, 8), dtype=np.uint64)
+        _lib.check(_lib.lib().kgr_bases_download(self._h, off, n, _u64(out)))
+        return out
+
     def free(self):
         if getattr(self, "_h", None):
             _lib.lib().kgr_bases_free(self._h)
@@ -119,11 +126,42 @@ def proj_add(curve, a, b):
 
 
 def last_timing(dev=0):
-    ms = (ctypes.c_float * 8)()
+    ms = (ctypes.c_float * 9)()
     shape = (ctypes.c_uint32 * 6)()
     _lib.check(_lib.lib().kgr_last_timing(dev, ms, shape))
-    keys = ["total", "count", "scan", "fill", "accumulate", "fixup", "reduce_final", "h2d"]
+    keys = ["total", "count", "scan", "fill", "accumulate", "fixup", "reduce", "h2d", "host_finish"]
     return dict(zip(keys, [float(x) for x in ms])), dict(zip(["c", "W", "B", "L", "K", "n"], [int(x) for x in shape]))
+
+
+def event_record(idx, dev=0):
+    _lib.check(_lib.lib().kgr_event_record(dev, idx))
+
+
+def event_elapsed_ms(a, b, dev=0):
+    ms = ctypes.c_float()
+    _lib.check(_lib.lib().kgr_event_elapsed_ms(dev, a, b, ctypes.byref(ms)))
+    return float(ms.value)
+
+
+def launch_count(dev=0):
+    c = ctypes.c_uint64()
+    _lib.check(_lib.lib().kgr_launch_count(dev, ctypes.byref(c)))
+    return int(c.value)
+
+
+def msm_oneshot_ptr(curve, xy_ptr, n_bases, sc_ptr, n_scalars, scalar_fmt=SCALARS_MONTGOMERY):
+    """kgr_msm_oneshot on raw host pointers (e.g. pinned torch tensors): bases and scalars are uploaded inside the call."""
+    out = np.zeros(12, dtype=np.uint64)
+    L = _lib.lib()
+    _lib.check(L.kgr_msm_oneshot(curve, ctypes.cast(xy_ptr, _u64p), None, n_bases, ctypes.cast(sc_ptr, _u64p), scalar_fmt, n_scalars, _u64(out)))
+    return out
+
+
+def msm_host_ptr(bases, sc_ptr, n, scalar_fmt=SCALARS_MONTGOMERY, base_off=0):
+    """kgr_msm on a raw host pointer to the scalars (registered bases)."""
+    out = np.zeros(12, dtype=np.uint64)
+    _lib.check(_lib.lib().kgr_msm(bases._h, base_off, ctypes.cast(sc_ptr, _u64p), scalar_fmt, n, _u64(out)))
+    return out
 
 
 def set_param(name, value):

@@ -4,7 +4,7 @@
 // the pipeline LOGIC (recoding, counting sort, chunked accumulation, fix-up, hierarchical
 // reduction, Horner) without a GPU; the PTX bodies themselves are covered by the -m gpu tests.
 //
-// usage: host_emu <curve 0|1> <n> <c> <L> <K> <mode> <seed>
+// usage: host_emu <curve 0|1> <n> <c> <L> <K> <mode> <seed> [running_sum_stop]
 //   mode 0 uniform scalars, 1 skewed (zeros/ones/r-1), 2 duplicate + opposite points + identity bases,
 //        3 canonical-format scalars
 #include <cstdio>
@@ -12,12 +12,13 @@
 #include <random>
 #include <vector>
 
+#define KGR_HOST_EMULATE_CHAINS 1  // run the even/odd carry-chain algorithm, not the u128 host shortcut
 #include "../kogarashi_b200/csrc/msm_kernels.cuh"
 #include "../oracle/zkstd_oracle.hpp"
 
 using namespace kgr;
 
-template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, uint32_t K, int mode, uint64_t seed) {
+template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, uint32_t K, int mode, uint64_t seed, uint32_t rs_stop) {
     typedef zko::Curve<OC> Cv;
     typedef zko::Field<typename OC::Scalar> Fs;
     typedef zko::Field<typename OC::Base> Fb;
@@ -99,7 +100,18 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memset(head.data(), 0xCD, head.size() * sizeof(XyzzPt<C>));
     memset(tail.data(), 0xEF, tail.size() * sizeof(XyzzPt<C>));
     for (uint32_t t = 0; t < chunks; t++) body_accumulate<C>(t, sh, bases.data(), offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data());
-    for (uint32_t g = 0; g < sh.G; g++) body_fixup<C>(g, sh, offsets.data(), bucket_acc.data(), head.data(), tail.data());
+    std::vector<uint32_t> worklist(sh.G + 1);
+    uint32_t wl_len = 0;
+    for (uint32_t g = 0; g < sh.G; g++) body_fixup<C>(g, sh, offsets.data(), bucket_acc.data(), head.data(), tail.data(), worklist.data(), &wl_len);
+    for (uint32_t i = 0; i < wl_len; i++) {  // k_fixup_long: lanes cooperate, then a tree sum
+        const uint32_t lanes = 5;
+        XyzzPt<C> tot = xyzz_identity<C>();
+        for (uint32_t lane = 0; lane < lanes; lane++) {
+            XyzzPt<C> part = fixup_long_partial<C>(worklist[i], lane, lanes, sh, offsets.data(), head.data(), tail.data());
+            xyzz_add(tot, part);
+        }
+        bucket_acc[worklist[i]] = tot;
+    }
     uint32_t cnt = sh.B, m_log2 = 0, klog = 0;
     while ((1u << klog) < K) klog++;
     uint32_t cnt1 = (sh.B + K - 1) / K;
@@ -112,10 +124,21 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         for (uint32_t t = 0; t < sh.W * cnt_out; t++) body_reduce<C>(t, sh.W, cnt, K, m_log2, in_s, in_a, ls[pp].data(), la[pp].data());
         in_s = ls[pp].data(); in_a = la[pp].data();
         cnt = cnt_out; m_log2 += klog; pp ^= 1;
-        if (cnt == 1) break;
+        if (cnt <= rs_stop) break;
+    }
+    std::vector<XyzzPt<C>> win(sh.W);
+    if (cnt > 1) {  // k_weight + k_tree_sum
+        std::vector<XyzzPt<C>> v((size_t)sh.W * cnt);
+        for (uint32_t t = 0; t < sh.W * cnt; t++) body_weight<C>(t, sh.W, cnt, m_log2, in_s, in_a, v.data());
+        for (uint32_t w = 0; w < sh.W; w++) {
+            win[w] = xyzz_identity<C>();
+            for (uint32_t i = 0; i < cnt; i++) xyzz_add(win[w], v[(size_t)w * cnt + i]);
+        }
+    } else {
+        for (uint32_t w = 0; w < sh.W; w++) win[w] = in_a[w];
     }
     uint32_t out24[24];
-    body_final<C>(sh, in_a, out24);
+    body_final<C>(sh, win.data(), out24);
     zko::Proj got;
     memcpy(got.x.data(), out24, 32); memcpy(got.y.data(), out24 + 8, 32); memcpy(got.z.data(), out24 + 16, 32);
     zko::Affine got_aff = Cv::to_affine(got);
@@ -131,6 +154,7 @@ int main(int argc, char **argv) {
     uint32_t n = (uint32_t)atol(argv[2]), c = (uint32_t)atol(argv[3]), L = (uint32_t)atol(argv[4]), K = (uint32_t)atol(argv[5]);
     int mode = atoi(argv[6]);
     uint64_t seed = strtoull(argv[7], nullptr, 10);
-    if (curve == 0) return run<Bn254G1, zko::Bn254G1>(n, c, L, K, mode, seed);
-    return run<GrumpkinC, zko::Grumpkin>(n, c, L, K, mode, seed);
+    uint32_t rs_stop = argc > 8 ? (uint32_t)atol(argv[8]) : 1;
+    if (curve == 0) return run<Bn254G1, zko::Bn254G1>(n, c, L, K, mode, seed, rs_stop);
+    return run<GrumpkinC, zko::Grumpkin>(n, c, L, K, mode, seed, rs_stop);
 }

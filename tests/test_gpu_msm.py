@@ -108,6 +108,20 @@ def test_msm_golden_under_forced_shapes(k, golden, c, chunk):
         k.set_param("chunk", 0)
 
 
+@pytest.mark.parametrize("param,value", [("final_on_device", 1), ("running_sum_stop", 1), ("running_sum_stop", 1 << 20), ("reduce_fanin", 4)])
+def test_msm_golden_under_reduce_variants(k, golden, param, value):
+    """Device-side Horner, pure running-sum reduction, pure weighting-pass reduction, small fan-in: same element."""
+    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16}
+    k.set_param(param, value)
+    try:
+        for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96", "gr_cancel_32", "gr_uniform_100"):
+            curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
+            pts, sc, inf, aff = (golden[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve, inf=inf)), aff), (name, param, value)
+    finally:
+        k.set_param(param, defaults[param])
+
+
 @pytest.mark.parametrize("curve,logn", [(A.BN254_G1, 10), (A.GRUMPKIN, 12), (A.BN254_G1, 16)])
 def test_msm_vs_oracle_seeded(k, curve, logn):
     """Same seeded inputs through the CUDA path and through the restated reference algorithm (config #1 is 2^16)."""

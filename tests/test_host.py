@@ -29,6 +29,8 @@ EMU_CASES = [
     (0, 1, 4, 16, 16, 0, 1), (0, 2, 1, 16, 2, 0, 2), (0, 3, 3, 16, 4, 0, 3), (0, 37, 5, 8, 4, 0, 4), (0, 300, 8, 16, 16, 0, 5),
     (0, 300, 8, 16, 16, 1, 6), (0, 300, 7, 5, 8, 2, 7), (1, 257, 9, 32, 16, 0, 8), (1, 200, 6, 16, 2, 2, 9), (0, 129, 1, 16, 16, 0, 10),
     (0, 500, 11, 64, 16, 3, 11), (1, 64, 13, 16, 16, 1, 12), (0, 700, 10, 256, 4, 1, 13), (1, 333, 12, 1, 16, 2, 14),
+    # running_sum_stop > 1: the weighting pass + tree sum close the reduction; small chunks + skew: hot-bucket worklist
+    (0, 300, 8, 16, 4, 0, 15, 16), (1, 300, 9, 2, 2, 1, 16, 64), (0, 400, 6, 3, 4, 2, 17, 4096), (0, 600, 10, 2, 16, 1, 18, 8),
 ]
 
 
