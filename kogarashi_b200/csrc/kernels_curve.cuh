@@ -1,0 +1,159 @@
+// kernels_curve.cuh — __global__ wrappers of the per-thread bodies (msm_kernels.cuh), templated on the curve.
+// Included only by launch_impl.cuh, which is compiled once per curve (kernels_g1.cu, kernels_grumpkin.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "launch.cuh"
+#include "msm_kernels.cuh"
+
+namespace kgr {
+
+
+template <class C> __global__ void __launch_bounds__(TPB_SCALAR) k_count(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
+    body_count<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_SCALAR) k_fill(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets,
+                                                     uint32_t *entries) {
+    body_fill<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts, offsets, entries);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_ACC) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+                                                        XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail) {
+    body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
+                                                   const XyzzPt<C> *tail, uint32_t *worklist, uint32_t *worklist_len) {
+    body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+}
+
+// XYZZ points in shared memory, word-major (word k of thread t at sm[k * TPB + t]): conflict-free.
+template <class C> __device__ __forceinline__ void sm_put(uint32_t *sm, int t, const XyzzPt<C> &p) {
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(&p);
+#pragma unroll
+    for (int k = 0; k < 32; k++) sm[k * TPB_TREE + t] = w[k];
+}
+template <class C> __device__ __forceinline__ XyzzPt<C> sm_get(const uint32_t *sm, int t) {
+    XyzzPt<C> p;
+    uint32_t *w = reinterpret_cast<uint32_t *>(&p);
+#pragma unroll
+    for (int k = 0; k < 32; k++) w[k] = sm[k * TPB_TREE + t];
+    return p;
+}
+// Sum of the TPB_TREE per-thread points of a CTA, returned in thread 0 (log2(TPB_TREE) add latencies).
+template <class C> __device__ __forceinline__ XyzzPt<C> block_tree_sum(XyzzPt<C> v, uint32_t *sm) {
+    const int t = threadIdx.x;
+    sm_put<C>(sm, t, v);
+    __syncthreads();
+    for (int s = TPB_TREE / 2; s > 0; s >>= 1) {
+        if (t < s) {
+            XyzzPt<C> o = sm_get<C>(sm, t + s);
+            xyzz_add(v, o);
+            sm_put<C>(sm, t, v);
+        }
+        __syncthreads();
+    }
+    return v;
+}
+// One CTA per queued hot bucket (grid-stride over the worklist).
+template <class C>
+__global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
+                                                         const XyzzPt<C> *tail, const uint32_t *worklist, const uint32_t *worklist_len) {
+    __shared__ uint32_t sm[32 * TPB_TREE];
+    uint32_t n = *worklist_len;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        uint32_t g = worklist[i];
+        XyzzPt<C> v = fixup_long_partial<C>(g, threadIdx.x, TPB_TREE, sh, offsets, head, tail);
+        v = block_tree_sum<C>(v, sm);
+        if (threadIdx.x == 0) store_xyzz(&bucket_acc[g], v);
+        __syncthreads();
+    }
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_reduce(uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
+                                                    const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a) {
+    body_reduce<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_weight(uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const XyzzPt<C> *in_s, const XyzzPt<C> *in_a,
+                                                    XyzzPt<C> *out) {
+    body_weight<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt, m_log2, in_s, in_a, out);
+}
+// grid (ceil(cnt_in / TPB_TREE), windows): out[w][block] = sum of in[w][block * TPB_TREE ...]
+template <class C> __global__ void __launch_bounds__(TPB_TREE) k_tree_sum(const XyzzPt<C> *in, uint32_t cnt_in, XyzzPt<C> *out) {
+    __shared__ uint32_t sm[32 * TPB_TREE];
+    uint32_t i = blockIdx.x * TPB_TREE + threadIdx.x, w = blockIdx.y;
+    XyzzPt<C> v = (i < cnt_in) ? in[(size_t)w * cnt_in + i] : xyzz_identity<C>();
+    v = block_tree_sum<C>(v, sm);
+    if (threadIdx.x == 0) store_xyzz(&out[(size_t)w * gridDim.x + blockIdx.x], v);
+}
+// Horner over windows on the device (kept for kgr_set_param("final_on_device", 1)); one thread.
+template <class C> __global__ void k_final(MsmShape sh, const XyzzPt<C> *win_a, XyzzPt<C> *out) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    XyzzPt<C> r = win_a[sh.W - 1];
+    for (uint32_t w = sh.W - 1; w-- > 0;) {
+        for (uint32_t d = 0; d < sh.c; d++) r = xyzz_dbl(r);
+        xyzz_add(r, win_a[w]);
+    }
+    store_xyzz(out, r);
+}
+template <class C> __global__ void k_fold_inf(AffinePt<C> *pts, const uint8_t *inf, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !inf[i]) return;
+    pts[i].x = fp_zero<typename C::Base>();
+    pts[i].y = fp_zero<typename C::Base>();
+}
+
+template <class C> __global__ void k_point_op(int op, const AffinePt<C> *a, const AffinePt<C> *b, uint32_t *out24, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    XyzzPt<C> acc = xyzz_from_affine(a[i]);
+    if (op == 0) xyzz_madd(acc, b[i]);
+    else if (op == 1) acc = xyzz_dbl(acc);
+    else {
+        // go through a non-trivial representative of b: (b + a) - a would need neg; use b doubled path instead
+        XyzzPt<C> q = xyzz_from_affine(b[i]);
+        XyzzPt<C> t = xyzz_dbl(q);      // 2b
+        xyzz_madd(t, b[i]);             // 3b  (non-unit zz)
+        xyzz_add(acc, t);               // a + 3b
+    }
+    Fp<typename C::Base> o[3];
+    xyzz_to_projective(acc, o);
+    for (int k = 0; k < 3; k++)
+        for (int j = 0; j < 8; j++) out24[24 * (size_t)i + 8 * k + j] = o[k].v[j];
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+// k_i = from_u512(8 words of splitmix64(seed, i)) in the curve's scalar field (Montgomery form)
+template <class C> __global__ void k_gen_scalars(uint64_t seed, uint64_t first, uint32_t n, Fp<typename C::Scalar> *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t w[16];
+    for (int j = 0; j < 8; j++) {
+        uint64_t v = splitmix64(seed ^ splitmix64((first + i) * 8 + j));
+        w[2 * j] = (uint32_t)v;
+        w[2 * j + 1] = (uint32_t)(v >> 32);
+    }
+    out[i] = fp_from_u512<typename C::Scalar>(w);
+}
+// out[i] = k[i] * G, affine.  MSB-first double-and-add on the canonical scalar, then one inversion.
+template <class C> __global__ void __launch_bounds__(128) k_fixed_base(const Fp<typename C::Scalar> *k, AffinePt<C> g, uint32_t n, AffinePt<C> *out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Fp<typename C::Scalar> s = fp_from_mont(k[i]);
+    XyzzPt<C> acc = xyzz_identity<C>();
+    for (int bit = 255; bit >= 0; bit--) {
+        acc = xyzz_dbl(acc);
+        if ((s.v[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, g);
+    }
+    out[i] = xyzz_to_affine(acc);
+}
+
+
+}  // namespace kgr

@@ -1,0 +1,49 @@
+// launch.cuh — host-callable launchers, one set per curve.  The engine (msm.cu) sees only these
+// declarations; the kernels are compiled in kernels_g1.cu / kernels_grumpkin.cu / kernels_util.cu so the
+// three translation units build in parallel.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "msm_kernels.cuh"
+
+namespace kgr {
+
+constexpr int TPB_SCALAR = 256;
+constexpr int TPB_ACC = 128;
+constexpr int TPB_RED = 64;
+constexpr int TPB_TREE = 128;
+
+template <class C> struct Launch {
+    typedef XyzzPt<C> X;
+    typedef AffinePt<C> A;
+    typedef Fp<typename C::Scalar> S;
+    static int accumulate_blocks_per_sm();
+    static void count(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts);
+    static void fill(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets, uint32_t *entries);
+    static void accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks, const A *bases, const uint32_t *offsets, const uint32_t *entries, X *bucket_acc,
+                           X *head, X *tail);
+    static void fixup(cudaStream_t st, const MsmShape &sh, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail, uint32_t *worklist,
+                      uint32_t *worklist_len);
+    static void reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a);
+    static void weight(cudaStream_t st, uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const X *in_s, const X *in_a, X *out);
+    static void tree_sum(cudaStream_t st, uint32_t n_windows, const X *in, uint32_t cnt_in, X *out);
+    static void final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out);
+    static void fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n);
+    static void point_op(cudaStream_t st, int op, const A *a, const A *b, uint32_t *out24, uint32_t n);
+    static void gen_scalars(cudaStream_t st, uint64_t seed, uint64_t first, uint32_t n, S *out);
+    static void fixed_base(cudaStream_t st, const S *k, const A &g, uint32_t n, A *out);
+};
+
+struct LaunchUtil {
+    // field: 0 Fq, 1 Fr (test hook for the PTX carry chains)
+    static void field_op(cudaStream_t st, int field, int op, const void *a, const void *b, void *out, uint32_t n);
+    static void exclusive_scan(cudaStream_t st, const uint32_t *in, uint32_t *out, uint32_t len, uint32_t *tile_sums);
+    static uint32_t scan_tiles(uint32_t len);
+    static int scan_launches(uint32_t len);
+    static void ubench(cudaStream_t st, int mode, int blocks, uint32_t *sink, int iters);          // modes 0..4
+    static void ubench_fmul(cudaStream_t st, int blocks, void *sink, int iters);
+    static void ubench_madd(cudaStream_t st, int blocks, void *sink, const AffinePt<Bn254G1> &p, const AffinePt<Bn254G1> &q, int iters);
+    static void clock_probe(cudaStream_t st, uint64_t *out2);
+};
+
+}  // namespace kgr

@@ -1,0 +1,55 @@
+// launch_impl.cuh — definitions of Launch<C>; include once per curve and instantiate explicitly.
+#pragma once
+#include "kernels_curve.cuh"
+#include "launch.cuh"
+
+namespace kgr {
+
+static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
+
+template <class C> int Launch<C>::accumulate_blocks_per_sm() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accumulate<C>, TPB_ACC, 0);
+    return nb;
+}
+template <class C> void Launch<C>::count(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
+    k_count<C><<<cdiv(sh.n, TPB_SCALAR), TPB_SCALAR, 0, st>>>(sh, scalars, is_mont, counts);
+}
+template <class C>
+void Launch<C>::fill(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets, uint32_t *entries) {
+    k_fill<C><<<cdiv(sh.n, TPB_SCALAR), TPB_SCALAR, 0, st>>>(sh, scalars, is_mont, counts, offsets, entries);
+}
+template <class C>
+void Launch<C>::accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks, const A *bases, const uint32_t *offsets, const uint32_t *entries, X *bucket_acc,
+                           X *head, X *tail) {
+    k_accumulate<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, bases, offsets, entries, bucket_acc, head, tail);
+}
+template <class C>
+void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail, uint32_t *worklist,
+                      uint32_t *worklist_len) {
+    k_fixup<C><<<cdiv(sh.G, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+    unsigned blocks = sh.G < 4u * (unsigned)sm_count ? sh.G : 4u * (unsigned)sm_count;
+    k_fixup_long<C><<<blocks, TPB_TREE, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+}
+template <class C>
+void Launch<C>::reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a) {
+    uint32_t threads = n_windows * ((cnt_in + K - 1) / K);
+    k_reduce<C><<<cdiv(threads, TPB_RED), TPB_RED, 0, st>>>(n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a);
+}
+template <class C> void Launch<C>::weight(cudaStream_t st, uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const X *in_s, const X *in_a, X *out) {
+    k_weight<C><<<cdiv((size_t)n_windows * cnt, TPB_RED), TPB_RED, 0, st>>>(n_windows, cnt, m_log2, in_s, in_a, out);
+}
+template <class C> void Launch<C>::tree_sum(cudaStream_t st, uint32_t n_windows, const X *in, uint32_t cnt_in, X *out) {
+    k_tree_sum<C><<<dim3(cdiv(cnt_in, TPB_TREE), n_windows), TPB_TREE, 0, st>>>(in, cnt_in, out);
+}
+template <class C> void Launch<C>::final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out) { k_final<C><<<1, 32, 0, st>>>(sh, win_a, out); }
+template <class C> void Launch<C>::fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n) { k_fold_inf<C><<<cdiv(n, 256), 256, 0, st>>>(pts, inf, n); }
+template <class C> void Launch<C>::point_op(cudaStream_t st, int op, const A *a, const A *b, uint32_t *out24, uint32_t n) {
+    k_point_op<C><<<cdiv(n, 64), 64, 0, st>>>(op, a, b, out24, n);
+}
+template <class C> void Launch<C>::gen_scalars(cudaStream_t st, uint64_t seed, uint64_t first, uint32_t n, S *out) {
+    k_gen_scalars<C><<<cdiv(n, 256), 256, 0, st>>>(seed, first, n, out);
+}
+template <class C> void Launch<C>::fixed_base(cudaStream_t st, const S *k, const A &g, uint32_t n, A *out) { k_fixed_base<C><<<cdiv(n, 128), 128, 0, st>>>(k, g, n, out); }
+
+}  // namespace kgr

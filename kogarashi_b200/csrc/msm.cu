@@ -20,8 +20,7 @@
 #include <vector>
 
 #include "../../include/kgr_msm.h"
-#include "msm_kernels.cuh"
-#include "scan.cuh"
+#include "launch.cuh"
 
 namespace kgr {
 
@@ -41,238 +40,6 @@ struct CudaError {
         cudaError_t _e = (expr);                                      \
         if (_e != cudaSuccess) throw CudaError{_e, #expr, __LINE__};  \
     } while (0)
-
-// ---- kernels ----------------------------------------------------------------------------------
-constexpr int TPB_SCALAR = 256;
-constexpr int TPB_ACC = 128;
-constexpr int TPB_RED = 64;
-
-template <class C> __global__ void __launch_bounds__(TPB_SCALAR) k_count(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
-    body_count<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts);
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_SCALAR) k_fill(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets,
-                                                     uint32_t *entries) {
-    body_fill<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts, offsets, entries);
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_ACC) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                                                        XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail) {
-    body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail);
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
-                                                   const XyzzPt<C> *tail, uint32_t *worklist, uint32_t *worklist_len) {
-    body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
-}
-
-// XYZZ points in shared memory, word-major (word k of thread t at sm[k * TPB + t]): conflict-free.
-constexpr int TPB_TREE = 128;
-template <class C> __device__ __forceinline__ void sm_put(uint32_t *sm, int t, const XyzzPt<C> &p) {
-    const uint32_t *w = reinterpret_cast<const uint32_t *>(&p);
-#pragma unroll
-    for (int k = 0; k < 32; k++) sm[k * TPB_TREE + t] = w[k];
-}
-template <class C> __device__ __forceinline__ XyzzPt<C> sm_get(const uint32_t *sm, int t) {
-    XyzzPt<C> p;
-    uint32_t *w = reinterpret_cast<uint32_t *>(&p);
-#pragma unroll
-    for (int k = 0; k < 32; k++) w[k] = sm[k * TPB_TREE + t];
-    return p;
-}
-// Sum of the TPB_TREE per-thread points of a CTA, returned in thread 0 (log2(TPB_TREE) add latencies).
-template <class C> __device__ __forceinline__ XyzzPt<C> block_tree_sum(XyzzPt<C> v, uint32_t *sm) {
-    const int t = threadIdx.x;
-    sm_put<C>(sm, t, v);
-    __syncthreads();
-    for (int s = TPB_TREE / 2; s > 0; s >>= 1) {
-        if (t < s) {
-            XyzzPt<C> o = sm_get<C>(sm, t + s);
-            xyzz_add(v, o);
-            sm_put<C>(sm, t, v);
-        }
-        __syncthreads();
-    }
-    return v;
-}
-// One CTA per queued hot bucket (grid-stride over the worklist).
-template <class C>
-__global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
-                                                         const XyzzPt<C> *tail, const uint32_t *worklist, const uint32_t *worklist_len) {
-    __shared__ uint32_t sm[32 * TPB_TREE];
-    uint32_t n = *worklist_len;
-    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        uint32_t g = worklist[i];
-        XyzzPt<C> v = fixup_long_partial<C>(g, threadIdx.x, TPB_TREE, sh, offsets, head, tail);
-        v = block_tree_sum<C>(v, sm);
-        if (threadIdx.x == 0) store_xyzz(&bucket_acc[g], v);
-        __syncthreads();
-    }
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_RED) k_reduce(uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
-                                                    const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a) {
-    body_reduce<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a);
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_RED) k_weight(uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const XyzzPt<C> *in_s, const XyzzPt<C> *in_a,
-                                                    XyzzPt<C> *out) {
-    body_weight<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt, m_log2, in_s, in_a, out);
-}
-// grid (ceil(cnt_in / TPB_TREE), windows): out[w][block] = sum of in[w][block * TPB_TREE ...]
-template <class C> __global__ void __launch_bounds__(TPB_TREE) k_tree_sum(const XyzzPt<C> *in, uint32_t cnt_in, XyzzPt<C> *out) {
-    __shared__ uint32_t sm[32 * TPB_TREE];
-    uint32_t i = blockIdx.x * TPB_TREE + threadIdx.x, w = blockIdx.y;
-    XyzzPt<C> v = (i < cnt_in) ? in[(size_t)w * cnt_in + i] : xyzz_identity<C>();
-    v = block_tree_sum<C>(v, sm);
-    if (threadIdx.x == 0) store_xyzz(&out[(size_t)w * gridDim.x + blockIdx.x], v);
-}
-// Horner over windows on the device (kept for kgr_set_param("final_on_device", 1)); one thread.
-template <class C> __global__ void k_final(MsmShape sh, const XyzzPt<C> *win_a, XyzzPt<C> *out) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    XyzzPt<C> r = win_a[sh.W - 1];
-    for (uint32_t w = sh.W - 1; w-- > 0;) {
-        for (uint32_t d = 0; d < sh.c; d++) r = xyzz_dbl(r);
-        xyzz_add(r, win_a[w]);
-    }
-    store_xyzz(out, r);
-}
-template <class C> __global__ void k_fold_inf(AffinePt<C> *pts, const uint8_t *inf, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n || !inf[i]) return;
-    pts[i].x = fp_zero<typename C::Base>();
-    pts[i].y = fp_zero<typename C::Base>();
-}
-
-// ---- test / utility kernels -------------------------------------------------------------------
-template <class P> __global__ void k_field_op(int op, const Fp<P> *a, const Fp<P> *b, Fp<P> *out, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fp<P> x = a[i], y = b ? b[i] : fp_zero<P>(), r;
-    switch (op) {
-        case 0: r = fp_add(x, y); break;
-        case 1: r = fp_sub(x, y); break;
-        case 2: r = fp_mul(x, y); break;
-        case 3: r = fp_sqr(x); break;
-        case 4: r = fp_neg(x); break;
-        case 5: r = fp_from_mont(x); break;
-        case 6: r = fp_to_mont(x); break;
-        case 7: r = fp_inv(x); break;
-        default: r = fp_dbl(x); break;
-    }
-    out[i] = r;
-}
-template <class C> __global__ void k_point_op(int op, const AffinePt<C> *a, const AffinePt<C> *b, uint32_t *out24, uint32_t n) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    XyzzPt<C> acc = xyzz_from_affine(a[i]);
-    if (op == 0) xyzz_madd(acc, b[i]);
-    else if (op == 1) acc = xyzz_dbl(acc);
-    else {
-        // go through a non-trivial representative of b: (b + a) - a would need neg; use b doubled path instead
-        XyzzPt<C> q = xyzz_from_affine(b[i]);
-        XyzzPt<C> t = xyzz_dbl(q);      // 2b
-        xyzz_madd(t, b[i]);             // 3b  (non-unit zz)
-        xyzz_add(acc, t);               // a + 3b
-    }
-    Fp<typename C::Base> o[3];
-    xyzz_to_projective(acc, o);
-    for (int k = 0; k < 3; k++)
-        for (int j = 0; j < 8; j++) out24[24 * (size_t)i + 8 * k + j] = o[k].v[j];
-}
-
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ULL;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-    return x ^ (x >> 31);
-}
-// k_i = from_u512(8 words of splitmix64(seed, i)) in the curve's scalar field (Montgomery form)
-template <class C> __global__ void k_gen_scalars(uint64_t seed, uint64_t first, uint32_t n, Fp<typename C::Scalar> *out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t w[16];
-    for (int j = 0; j < 8; j++) {
-        uint64_t v = splitmix64(seed ^ splitmix64((first + i) * 8 + j));
-        w[2 * j] = (uint32_t)v;
-        w[2 * j + 1] = (uint32_t)(v >> 32);
-    }
-    out[i] = fp_from_u512<typename C::Scalar>(w);
-}
-// out[i] = k[i] * G, affine.  MSB-first double-and-add on the canonical scalar, then one inversion.
-template <class C> __global__ void __launch_bounds__(128) k_fixed_base(const Fp<typename C::Scalar> *k, AffinePt<C> g, uint32_t n, AffinePt<C> *out) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    Fp<typename C::Scalar> s = fp_from_mont(k[i]);
-    XyzzPt<C> acc = xyzz_identity<C>();
-    for (int bit = 255; bit >= 0; bit--) {
-        acc = xyzz_dbl(acc);
-        if ((s.v[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, g);
-    }
-    out[i] = xyzz_to_affine(acc);
-}
-
-// ---- integer-pipe microbenchmarks -------------------------------------------------------------
-template <int MODE> __global__ void __launch_bounds__(256) k_ubench(uint32_t *sink, uint32_t a, uint32_t b, int iters) {
-    uint32_t x[8];
-    uint64_t y[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        x[j] = threadIdx.x * 7 + j;
-        y[j] = x[j];
-    }
-    for (int it = 0; it < iters; it++) {
-#pragma unroll
-        for (int rep = 0; rep < 8; rep++) {
-            if (MODE == 0) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) asm volatile("mad.lo.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
-            } else if (MODE == 1) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) asm volatile("mad.hi.u32 %0, %0, %1, %2;" : "+r"(x[j]) : "r"(a), "r"(b));
-            } else if (MODE == 2) {
-#pragma unroll
-                for (int j = 0; j < 8; j++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(y[j]) : "r"(a), "r"(x[j]));
-            } else if (MODE == 3) {
-                uint32_t top = 0;
-                chain_cmad(x, a, b, a ^ 0x55u, b ^ 0x33u, x[0] | 1u, top);
-                x[1] ^= top;
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; j++) asm volatile("add.u32 %0, %0, %1;" : "+r"(x[j]) : "r"(a));
-            }
-        }
-    }
-    uint32_t acc = 0;
-#pragma unroll
-    for (int j = 0; j < 8; j++) acc ^= x[j] ^ (uint32_t)y[j] ^ (uint32_t)(y[j] >> 32);
-    if (acc == 0x12345u) sink[0] = acc;
-}
-__global__ void __launch_bounds__(256) k_ubench_fmul(Fp<FqP> *sink, Fp<FqP> a, Fp<FqP> b, int iters) {
-    a.v[0] ^= threadIdx.x;
-    for (int it = 0; it < iters; it++) {
-        a = fp_mul(a, b);
-        b = fp_mul(b, a);
-    }
-    if (a.v[0] == 0x12345u && b.v[1] == 7u) sink[0] = a;
-}
-__global__ void __launch_bounds__(128) k_ubench_madd(XyzzPt<Bn254G1> *sink, AffinePt<Bn254G1> p, AffinePt<Bn254G1> q, int iters) {
-    XyzzPt<Bn254G1> acc = xyzz_from_affine(p);
-    acc.x.v[0] ^= (threadIdx.x & 1);  // not a curve point any more; the formulas do not care
-    for (int it = 0; it < iters; it++) xyzz_madd(acc, q);
-    if (acc.x.v[0] == 0x12345u && acc.y.v[1] == 7u) sink[0] = acc;
-}
-__global__ void k_clock(uint64_t *out) {
-    uint64_t t0, c0, t1, c1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    c0 = clock64();
-    do {
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    } while (t1 - t0 < 2000000ULL);
-    c1 = clock64();
-    out[0] = t1 - t0;
-    out[1] = c1 - c0;
-}
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
@@ -331,8 +98,8 @@ struct Engine {
         for (auto &e : ev) CK(cudaEventCreate(&e));
         for (auto &e : user_ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&h_result, 256 * 32 * sizeof(uint32_t)));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_per_sm[0], k_accumulate<Bn254G1>, TPB_ACC, 0));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_blocks_per_sm[1], k_accumulate<GrumpkinC>, TPB_ACC, 0));
+        acc_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_blocks_per_sm();
+        acc_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_blocks_per_sm();
     }
     void destroy() {
         if (dev < 0) return;
@@ -363,15 +130,21 @@ struct Engine {
 static std::mutex g_mu;
 static std::vector<Engine> g_engines;
 
-// cost model for the window size: accumulate adds + reduce adds (general adds ~1.4x a mixed add)
-// + a latency term for the serial depth of the reduce tree.
+// Cost model for the window size, fitted to the per-phase timings in profiles/r01_phase_sweep.md (ns):
+//   accumulate 0.174 per entry; counting sort 0.0155 per entry growing with the histogram size G
+//   (random L2 atomics + sector-granular scatter); reduce 0.4 ms fixed + 0.7 per bucket;
+//   a thin top window (few leading scalar bits) concentrates n / 2^t entries in 2^t buckets.
 static uint32_t choose_window_bits(uint32_t n) {
     if (g_params.window_bits > 0) return (uint32_t)std::min<long>(std::max<long>(g_params.window_bits, 1), 24);
     double best = 1e300;
     uint32_t best_c = 1;
     for (uint32_t c = 1; c <= 22; c++) {
-        double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1);
-        double cost = (double)n * W + 3.0 * 1.4 * W * B + 2000.0 * c;
+        double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1), G = W * B;
+        double lg = std::log2(G);
+        double sort_ns = 0.0155 + (lg > 19 ? 0.008 * (lg - 19) : 0.0);
+        double cost = (double)n * W * (0.174 + sort_ns) + 0.7 * G + (G > 64 ? 0.4e6 : 0.1e6);
+        int top_bits = 255 - (int)c * ((int)W - 1);  // bits of the top window incl. the carry bit
+        if (top_bits < 8 && top_bits < (int)c) cost += 0.08 * n * (8 - top_bits);
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -418,7 +191,7 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     if (e.counts.cap < G1) e.counts_zeroed = 0;
     e.counts.ensure(G1);
     e.offsets.ensure(G1 + 4);
-    e.tile_sums.ensure(scan_num_tiles((uint32_t)G1) + 1);
+    e.tile_sums.ensure(LaunchUtil::scan_tiles((uint32_t)G1) + 1);
     e.entries.ensure((size_t)Mmax + 1);
     e.bucket_acc.ensure((size_t)sh.G * sizeof(X));
     e.head.ensure((size_t)chunks * sizeof(X));
@@ -435,22 +208,18 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     }
 
     CK(cudaEventRecord(e.ev[EV_H2D], e.st));
-    uint32_t sblocks = (n + TPB_SCALAR - 1) / TPB_SCALAR;
-    k_count<C><<<sblocks, TPB_SCALAR, 0, e.st>>>(sh, d_scalars, is_mont, e.counts.p);
+    typedef Launch<C> K;
+    K::count(e.st, sh, d_scalars, is_mont, e.counts.p);
     CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
-    exclusive_scan_u32(e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p, e.st);
-    e.launches += (scan_num_tiles((uint32_t)G1) > 1) ? 3 : 1;
+    LaunchUtil::exclusive_scan(e.st, e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p);
+    e.launches += LaunchUtil::scan_launches((uint32_t)G1);
     CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
-    k_fill<C><<<sblocks, TPB_SCALAR, 0, e.st>>>(sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
+    K::fill(e.st, sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
     CK(cudaEventRecord(e.ev[EV_FILL], e.st));
-    k_accumulate<C><<<(chunks + TPB_ACC - 1) / TPB_ACC, TPB_ACC, 0, e.st>>>(sh, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
-                                                                            (X *)e.tail.p);
+    K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p);
     CK(cudaEventRecord(e.ev[EV_ACC], e.st));
     CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
-    k_fixup<C><<<(sh.G + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p,
-                                                                     e.worklist.p + 1, e.worklist.p);
-    k_fixup_long<C><<<std::min<uint32_t>(sh.G, 4 * (uint32_t)e.sm_count), TPB_TREE, 0, e.st>>>(sh, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p,
-                                                                                               (const X *)e.tail.p, e.worklist.p + 1, e.worklist.p);
+    K::fixup(e.st, sh, e.sm_count, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.worklist.p + 1, e.worklist.p);
     CK(cudaEventRecord(e.ev[EV_FIXUP], e.st));
     // Reduce.  Running-sum levels (fan-in K) while many elements per window remain (throughput regime),
     // then one fully parallel weighting pass and block-level tree sums (latency regime).
@@ -460,9 +229,8 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     int pp = 0;
     do {
         uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
-        uint32_t threads = sh.W * cnt_out;
         X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
-        k_reduce<C><<<(threads + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh.W, cnt, sh.K, m_log2, in_s, in_a, os, oa);
+        K::reduce(e.st, sh.W, cnt, sh.K, m_log2, in_s, in_a, os, oa);
         e.launches++;
         in_s = os;
         in_a = oa;
@@ -473,14 +241,13 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     const X *win = in_a;  // [W] once cnt == 1
     if (cnt > 1) {
         X *v = (X *)e.lvl_s[pp].p;
-        uint32_t threads = sh.W * cnt;
-        k_weight<C><<<(threads + TPB_RED - 1) / TPB_RED, TPB_RED, 0, e.st>>>(sh.W, cnt, m_log2, in_s, in_a, v);
+        K::weight(e.st, sh.W, cnt, m_log2, in_s, in_a, v);
         e.launches++;
         const X *tin = v;
         X *tout = (X *)e.lvl_a[pp].p;
         while (cnt > 1) {
             uint32_t blocks = (cnt + TPB_TREE - 1) / TPB_TREE;
-            k_tree_sum<C><<<dim3(blocks, sh.W), TPB_TREE, 0, e.st>>>(tin, cnt, tout);
+            K::tree_sum(e.st, sh.W, tin, cnt, tout);
             e.launches++;
             cnt = blocks;
             X *nxt = (X *)tin;
@@ -490,7 +257,7 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
         win = tin;
     }
     if (g_params.final_on_device) {
-        k_final<C><<<1, 32, 0, e.st>>>(sh, win, (X *)e.result.p);
+        K::final_horner(e.st, sh, win, (X *)e.result.p);
         e.launches++;
         CK(cudaMemcpyAsync(e.h_result, e.result.p, sizeof(X), cudaMemcpyDeviceToHost, e.st));
         e.n_result = 1;
@@ -548,7 +315,7 @@ template <class C> static void upload_shard(Engine &e, Shard &s, const uint64_t 
         uint8_t *d_inf = nullptr;
         CK(cudaMalloc(&d_inf, s.count));
         CK(cudaMemcpyAsync(d_inf, inf + s.first, s.count, cudaMemcpyHostToDevice, e.st));
-        k_fold_inf<C><<<(unsigned)((s.count + 255) / 256), 256, 0, e.st>>>((AffinePt<C> *)s.d_pts, d_inf, (uint32_t)s.count);
+        Launch<C>::fold_inf(e.st, (AffinePt<C> *)s.d_pts, d_inf, (uint32_t)s.count);
         CK(cudaStreamSynchronize(e.st));
         CK(cudaFree(d_inf));
     }
@@ -638,7 +405,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 if (hp->inf) {
                     e.oneshot_inf.ensure(jb.count);
                     CK(cudaMemcpyAsync(e.oneshot_inf.p, hp->inf + jb.pt_first, jb.count, cudaMemcpyHostToDevice, e.st));
-                    k_fold_inf<C><<<(unsigned)((jb.count + 255) / 256), 256, 0, e.st>>>((AffinePt<C> *)e.oneshot_pts.p, e.oneshot_inf.p, (uint32_t)jb.count);
+                    Launch<C>::fold_inf(e.st, (AffinePt<C> *)e.oneshot_pts.p, e.oneshot_inf.p, (uint32_t)jb.count);
                     e.launches++;
                 }
                 jb.pts = (const AffinePt<C> *)e.oneshot_pts.p;
@@ -706,7 +473,7 @@ template <class C> static XyzzPt<C> proj_to_xyzz_host(const uint64_t in[12]) {
     return r;
 }
 
-template <class F> static int test_field_op(Engine &e, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
+template <class F, int FIELD_ID> static int test_field_op(Engine &e, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out) {
     CK(cudaSetDevice(e.dev));
     Fp<F> *da = nullptr, *db = nullptr, *dout = nullptr;
     CK(cudaMalloc(&da, n * 32));
@@ -716,7 +483,7 @@ template <class F> static int test_field_op(Engine &e, int op, const uint64_t *a
         CK(cudaMalloc(&db, n * 32));
         CK(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
     }
-    k_field_op<F><<<(unsigned)((n + 127) / 128), 128, 0, e.st>>>(op, da, db, dout, (uint32_t)n);
+    LaunchUtil::field_op(e.st, FIELD_ID, op, da, db, dout, (uint32_t)n);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e.st));
     CK(cudaMemcpy(out, dout, n * 32, cudaMemcpyDeviceToHost));
@@ -735,7 +502,7 @@ static int test_point_op(Engine &e, int op, const uint64_t *a, const uint8_t *ai
     upload_shard<C>(e, sb, b, binf);
     uint32_t *dout = nullptr;
     CK(cudaMalloc(&dout, n * 96));
-    k_point_op<C><<<(unsigned)((n + 63) / 64), 64, 0, e.st>>>(op, (AffinePt<C> *)sa.d_pts, (AffinePt<C> *)sb.d_pts, dout, (uint32_t)n);
+    Launch<C>::point_op(e.st, op, (AffinePt<C> *)sa.d_pts, (AffinePt<C> *)sb.d_pts, dout, (uint32_t)n);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e.st));
     CK(cudaMemcpy(out, dout, n * 96, cudaMemcpyDeviceToHost));
@@ -770,22 +537,22 @@ template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed
     S *dk = nullptr;
     CK(cudaMalloc(&dk, s.count * sizeof(S)));
     uint32_t n = (uint32_t)s.count;
-    k_gen_scalars<C><<<(n + 255) / 256, 256, 0, e.st>>>(seed, (uint64_t)s.first, n, dk);
-    k_fixed_base<C><<<(n + 127) / 128, 128, 0, e.st>>>(dk, generator_affine<C>(), n, (AffinePt<C> *)s.d_pts);
+    Launch<C>::gen_scalars(e.st, seed, (uint64_t)s.first, n, dk);
+    Launch<C>::fixed_base(e.st, dk, generator_affine<C>(), n, (AffinePt<C> *)s.d_pts);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e.st));
     if (k_out) CK(cudaMemcpy(k_out + 4 * s.first, dk, s.count * sizeof(S), cudaMemcpyDeviceToHost));
     CK(cudaFree(dk));
 }
 
-template <int MODE> static double ubench_mode(Engine &e, uint32_t *sink, double ops_per_thread_iter) {
+static double ubench_mode(Engine &e, int mode, uint32_t *sink, double ops_per_thread_iter) {
     const int iters = 2000, blocks = e.sm_count * 8, tpb = 256;
-    k_ubench<MODE><<<blocks, tpb, 0, e.st>>>(sink, 3, 5, 10);
+    LaunchUtil::ubench(e.st, mode, blocks, sink, 10);
     cudaEvent_t a, b;
     CK(cudaEventCreate(&a));
     CK(cudaEventCreate(&b));
     CK(cudaEventRecord(a, e.st));
-    k_ubench<MODE><<<blocks, tpb, 0, e.st>>>(sink, 3, 5, iters);
+    LaunchUtil::ubench(e.st, mode, blocks, sink, iters);
     CK(cudaEventRecord(b, e.st));
     CK(cudaStreamSynchronize(e.st));
     float ms = 0;
@@ -1040,8 +807,8 @@ int kgr_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, s
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     return guarded([&]() -> int {
-        if (field == 0) return test_field_op<FqP>(g_engines[0], op, a, b, n, out);
-        if (field == 1) return test_field_op<FrP>(g_engines[0], op, a, b, n, out);
+        if (field == 0) return test_field_op<FqP, 0>(g_engines[0], op, a, b, n, out);
+        if (field == 1) return test_field_op<FrP, 1>(g_engines[0], op, a, b, n, out);
         return fail(KGR_E_ARG, "unknown field id");
     });
 }
@@ -1067,7 +834,7 @@ int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy)
         CK(cudaMalloc(&dk, n * 32 + 32));
         CK(cudaMalloc(&dp, n * 64 + 64));
         CK(cudaMemcpy(dk, k, n * 32, cudaMemcpyHostToDevice));
-#define CALL(C) k_fixed_base<C><<<(unsigned)((n + 127) / 128), 128, 0, e.st>>>((const Fp<C::Scalar> *)dk, generator_affine<C>(), (uint32_t)n, (AffinePt<C> *)dp)
+#define CALL(C) Launch<C>::fixed_base(e.st, (const Fp<C::Scalar> *)dk, generator_affine<C>(), (uint32_t)n, (AffinePt<C> *)dp)
         DISPATCH(curve, CALL);
 #undef CALL
         CK(cudaGetLastError());
@@ -1105,22 +872,20 @@ int kgr_microbench(double r[8]) {
         CK(cudaSetDevice(e.dev));
         uint32_t *sink = nullptr;
         CK(cudaMalloc(&sink, 4096));
-        r[0] = ubench_mode<0>(e, sink, 64);
-        r[1] = ubench_mode<1>(e, sink, 64);
-        r[2] = ubench_mode<2>(e, sink, 64);
-        r[3] = ubench_mode<3>(e, sink, 8 * 4);  // 4 wide mads per chain, 8 chains per iteration
-        r[4] = ubench_mode<4>(e, sink, 64);
+        r[0] = ubench_mode(e, 0, sink, 64);
+        r[1] = ubench_mode(e, 1, sink, 64);
+        r[2] = ubench_mode(e, 2, sink, 64);
+        r[3] = ubench_mode(e, 3, sink, 8 * 4);  // 4 wide mads per chain, 8 chains per iteration
+        r[4] = ubench_mode(e, 4, sink, 64);
         cudaEvent_t a, b;
         CK(cudaEventCreate(&a));
         CK(cudaEventCreate(&b));
         float ms = 0;
         {
-            Fp<FqP> x = fp_one<FqP>(), y = fp_one<FqP>();
-            y.v[0] ^= 0x1234;
             const int iters = 500, blocks = e.sm_count * 8;
-            k_ubench_fmul<<<blocks, 256, 0, e.st>>>((Fp<FqP> *)sink, x, y, 4);
+            LaunchUtil::ubench_fmul(e.st, blocks, sink, 4);
             CK(cudaEventRecord(a, e.st));
-            k_ubench_fmul<<<blocks, 256, 0, e.st>>>((Fp<FqP> *)sink, x, y, iters);
+            LaunchUtil::ubench_fmul(e.st, blocks, sink, iters);
             CK(cudaEventRecord(b, e.st));
             CK(cudaStreamSynchronize(e.st));
             CK(cudaEventElapsedTime(&ms, a, b));
@@ -1131,9 +896,9 @@ int kgr_microbench(double r[8]) {
             XyzzPt<Bn254G1> d = xyzz_dbl_affine(g);
             AffinePt<Bn254G1> g2 = xyzz_to_affine(d);
             const int iters = 200, blocks = e.sm_count * 16;
-            k_ubench_madd<<<blocks, 128, 0, e.st>>>((XyzzPt<Bn254G1> *)sink, g, g2, 4);
+            LaunchUtil::ubench_madd(e.st, blocks, sink, g, g2, 4);
             CK(cudaEventRecord(a, e.st));
-            k_ubench_madd<<<blocks, 128, 0, e.st>>>((XyzzPt<Bn254G1> *)sink, g, g2, iters);
+            LaunchUtil::ubench_madd(e.st, blocks, sink, g, g2, iters);
             CK(cudaEventRecord(b, e.st));
             CK(cudaStreamSynchronize(e.st));
             CK(cudaEventElapsedTime(&ms, a, b));
@@ -1142,7 +907,7 @@ int kgr_microbench(double r[8]) {
         {
             uint64_t *d = nullptr, h[2];
             CK(cudaMalloc(&d, 16));
-            k_clock<<<1, 1, 0, e.st>>>(d);
+            LaunchUtil::clock_probe(e.st, d);
             CK(cudaStreamSynchronize(e.st));
             CK(cudaMemcpy(h, d, 16, cudaMemcpyDeviceToHost));
             cudaFree(d);

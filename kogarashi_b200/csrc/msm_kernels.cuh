@@ -56,9 +56,13 @@ template <class C> KGR_HD void load_scalar(const uint32_t *scalars, uint32_t i, 
     for (int k = 0; k < 8; k++) out[k] = s.v[k];
 }
 
-// Signed recoding.  Calls f(window, bucket_in_window, sign) for each non-zero digit.
-template <class Fn> KGR_HD void for_each_digit(const uint32_t s[8], const MsmShape &sh, Fn f) {
-    uint32_t carry = 0;
+// Signed recoding.  Calls f(window, bucket_in_window, sign) for each non-zero digit of the windows
+// below the top one and returns the top window's digit as (bucket | sign << 31), NO_DIGIT if zero.
+// The top window is returned separately because it is structurally hot: it only holds the
+// 254 - c*(W-1) leading scalar bits, so a handful of buckets receive n / 2^t entries each.
+constexpr uint32_t NO_DIGIT = 0xffffffffu;
+template <class Fn> KGR_HD uint32_t for_each_digit(const uint32_t s[8], const MsmShape &sh, Fn f) {
+    uint32_t carry = 0, top = NO_DIGIT;
     for (uint32_t w = 0; w < sh.W; w++) {
         uint32_t d = window_raw(s, w * sh.c, sh.c) + carry;
         carry = 0;
@@ -68,8 +72,12 @@ template <class Fn> KGR_HD void for_each_digit(const uint32_t s[8], const MsmSha
             sign = 1;
             carry = 1;
         }
-        if (d != 0) f(w, d - 1, sign);
+        if (d != 0) {
+            if (w + 1 == sh.W) top = (d - 1) | (sign << 31);
+            else f(w, d - 1, sign);
+        }
     }
+    return top;
 }
 
 KGR_HD uint32_t atomic_add_u32(uint32_t *p, uint32_t v) {
@@ -91,12 +99,40 @@ KGR_HD uint32_t atomic_sub_u32(uint32_t *p, uint32_t v) {
 #endif
 }
 
+// Warp-aggregated "take `1` from counter[key]" for keys that collide inside a warp: lanes with the
+// same key elect a leader (match.any), the leader does one atomic for the whole group and every
+// lane derives its own slot from its rank in the group.  `sub`: counts are consumed (fill) instead of
+// incremented (count).  Returns the value the counter had for this lane's unit (fill uses it).
+// Must be called by all 32 lanes of the warp; lanes without work pass key = NO_DIGIT.
+KGR_HD uint32_t warp_aggregated_take(uint32_t *counters, uint32_t key, bool sub) {
+#if defined(__CUDA_ARCH__)
+    unsigned group = __match_any_sync(0xffffffffu, key);
+    if (key == NO_DIGIT) return 0;
+    unsigned lane = threadIdx.x & 31;
+    unsigned leader = __ffs(group) - 1;
+    unsigned rank = __popc(group & ((1u << lane) - 1u));
+    unsigned cnt = __popc(group);
+    uint32_t base = 0;
+    if (lane == leader) base = sub ? atomicSub(&counters[key], cnt) - cnt : atomicAdd(&counters[key], cnt);
+    base = __shfl_sync(group, base, leader);
+    return base + rank;
+#else
+    if (key == NO_DIGIT) return 0;
+    return sub ? atomic_sub_u32(&counters[key], 1u) - 1u : atomic_add_u32(&counters[key], 1u);
+#endif
+}
+
 // ---- count / fill ---------------------------------------------------------------------------
+// i may be >= n (whole warps run so that the warp-aggregated top window sees all 32 lanes).
 template <class C> KGR_HD void body_count(uint32_t i, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
-    if (i >= sh.n) return;
-    uint32_t s[8];
-    load_scalar<C>(scalars, i, is_mont, s);
-    for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t) { atomic_add_u32(&counts[w * sh.B + b], 1u); });
+    uint32_t top = NO_DIGIT;
+    if (i < sh.n) {
+        uint32_t s[8];
+        load_scalar<C>(scalars, i, is_mont, s);
+        top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t) { atomic_add_u32(&counts[w * sh.B + b], 1u); });
+    }
+    uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.B + (top & 0x7fffffffu);
+    (void)warp_aggregated_take(counts, key, false);
 }
 
 // counts[] is consumed back to zero (positions are handed out from the end of each bucket), so
@@ -104,14 +140,19 @@ template <class C> KGR_HD void body_count(uint32_t i, const MsmShape &sh, const 
 template <class C>
 KGR_HD void body_fill(uint32_t i, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets,
                       uint32_t *entries) {
-    if (i >= sh.n) return;
-    uint32_t s[8];
-    load_scalar<C>(scalars, i, is_mont, s);
-    for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t sign) {
-        uint32_t g = w * sh.B + b;
-        uint32_t k = atomic_sub_u32(&counts[g], 1u) - 1u;
-        entries[offsets[g] + k] = i | (sign << 31);
-    });
+    uint32_t top = NO_DIGIT;
+    if (i < sh.n) {
+        uint32_t s[8];
+        load_scalar<C>(scalars, i, is_mont, s);
+        top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t sign) {
+            uint32_t g = w * sh.B + b;
+            uint32_t k = atomic_sub_u32(&counts[g], 1u) - 1u;
+            entries[offsets[g] + k] = i | (sign << 31);
+        });
+    }
+    uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.B + (top & 0x7fffffffu);
+    uint32_t k = warp_aggregated_take(counts, key, true);
+    if (key != NO_DIGIT) entries[offsets[key] + k] = i | (top & 0x80000000u);
 }
 
 // ---- accumulate -----------------------------------------------------------------------------
