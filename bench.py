@@ -253,25 +253,18 @@ def main():
     assert (k.to_affine(curve, out_e2e) == k.to_affine(curve, out)).all() and (k.to_affine(curve, out_reg) == k.to_affine(curve, out)).all()
 
     # ---- max over ranks, partial sums to rank 0 -----------------------------------------------------
+    from kogarashi_b200 import sharding
     stats = torch.tensor([dev_ms, e2e_ms, e2e_reg_ms, wall_ms], dtype=torch.float64, device="cuda")
-    partial = torch.from_numpy(out.view(np.int64)).cuda()
     if world > 1:
         dist.all_reduce(stats, op=dist.ReduceOp.MAX)
-        parts = [torch.empty_like(partial) for _ in range(world)]
-        dist.all_gather(parts, partial)
-    else:
-        parts = [partial]
+    parts = sharding.gather_partials(out, device="cuda")  # one 96-byte point per rank, after the timed region
     dev_ms, e2e_ms, e2e_reg_ms, wall_ms = [float(x) for x in stats.cpu()]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    total = np.zeros(12, dtype=np.uint64)
-    total[4:8] = k.to_affine(curve, np.zeros(12, dtype=np.uint64))[4:8]  # identity (0, R, 0)
-    for p in parts:
-        total = k.proj_add(curve, total, p.cpu().numpy().view(np.uint64))
-    total_aff = k.to_affine(curve, total)
+    total_aff = k.to_affine(curve, sharding.combine_partials(curve, parts))
 
     ms_per_step = dev_ms / args.steps
     value = world * n / ms_per_step / 1e3

@@ -18,7 +18,7 @@ __global__ void __launch_bounds__(TPB_SCALAR) k_fill(MsmShape sh, const uint32_t
     body_fill<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts, offsets, entries);
 }
 template <class C>
-__global__ void __launch_bounds__(TPB_ACC) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+__global__ void __launch_bounds__(TPB_ACC, 4) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
                                                         XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail) {
     body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail);
 }

@@ -1,0 +1,40 @@
+"""GPU tests of the in-process multi-GPU path (kgr_init with several devices): contiguous shards, one partial
+result per GPU, host-side combination.  Skipped on a single-GPU box."""
+import numpy as np
+import pytest
+from conftest import same_affine
+
+from oracle import oracle as A
+
+pytestmark = pytest.mark.gpu
+
+
+def _ngpu():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("curve", [A.BN254_G1, A.GRUMPKIN])
+def test_sharded_msm_matches_oracle(curve):
+    ng = _ngpu()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import kogarashi_b200 as k
+    k.init(list(range(min(ng, 8))))
+    try:
+        n = 5001  # ragged shards
+        pool = A.random_points(curve, 512, seed=bytes(range(3, 19)))
+        pts = np.tile(pool, (10, 1))[:n]
+        sc = A.random_field(A.SCALAR_FIELD[curve], n, seed=bytes(range(4, 20)))
+        exp = A.to_affine(curve, A.msm(curve, pts, sc))
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp)          # oneshot, sharded
+        bases = k.Bases(curve, pts)
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc)), exp)                      # registered, sharded
+        off = 1234                                                                                        # window crossing shard borders
+        exp2 = A.to_affine(curve, A.msm(curve, pts[off:], sc[: n - off]))
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc[: n - off], base_off=off)), exp2)
+        tiny = k.msm_curve_addition(pts[:3], sc[:3], curve=curve)                                         # fewer pairs than GPUs
+        assert same_affine(k.to_affine(curve, tiny), A.to_affine(curve, A.msm(curve, pts[:3], sc[:3])))
+        bases.free()
+    finally:
+        k.init()

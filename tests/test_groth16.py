@@ -1,0 +1,92 @@
+"""BASELINE config #4: Groth16 proof of the reference's example circuit (groth16/examples/simple.rs, x^3 + x + 5 = 35)
+under fixed randomness.  CPU part: the big-int restatement of setup + create_proof yields a proof that satisfies the
+Groth16 equation (checked in the exponent).  GPU part: the G1 commitments A and C computed by the CUDA MSM engine from the
+device-resident CRS are byte-identical to the all-CPU computation (B is a G2 element and stays on the CPU path)."""
+import numpy as np
+import pytest
+
+from oracle import groth16_ref as G
+from oracle import pyref as B
+
+SETUP_SEED = bytes.fromhex("5962be5d763d318d17db37325406bce5")   # pallet/nova/src/tests.rs:69-74
+PROVE_SEED = bytes(range(1, 17))
+
+
+@pytest.fixture(scope="module")
+def fixture():
+    P, trap, uvw = G.setup(B.XorShift128(SETUP_SEED))
+    proof, internals = G.create_proof(P, B.XorShift128(PROVE_SEED), 3, 35)
+    return P, trap, uvw, proof, internals
+
+
+def test_example_circuit_shape():
+    cs = G.example_circuit(3, 35)
+    assert (cs.m, cs.l, cs.m_l_1) == (4, 3, 3)
+    assert cs.x == [1, 3, 35] and cs.w == [9, 27, 30]
+    a, b, c = cs.evaluate()
+    assert all((ai * bi - ci) % G.R == 0 for ai, bi, ci in zip(a, b, c))
+
+
+def test_fft_roundtrip_and_coset():
+    f = G.Fft(2)
+    c = [5, 7, 11, 13]
+    assert f.idft(f.dft(c)) == c and f.coset_idft(f.coset_dft(c)) == c
+    # dft evaluates the polynomial on the domain
+    assert f.dft(c)[1] == sum(cj * pow(f.omega, j, G.R) for j, cj in enumerate(c)) % G.R
+
+
+def test_reference_prover_restatement_verifies(fixture):
+    P, trap, uvw, proof, internals = fixture
+    assert len(P["h"]) == 3 and len(P["a"]) == 6 and len(P["l"]) == 3 and len(P["ic"]) == 3
+    assert len(internals["q"]) <= 3
+    ok_points, ok_pairing = G.exponent_check(trap, uvw, internals, proof)
+    assert ok_points and ok_pairing
+    assert len(G.proof_bytes(proof)) == 65 + 129 + 65
+    # a wrong public output must not verify
+    bad, bad_int = G.create_proof(P, B.XorShift128(PROVE_SEED), 3, 36)
+    assert not G.exponent_check(trap, uvw, bad_int, bad)[1]
+
+
+def _pts(points):
+    xy = np.zeros((len(points), 8), dtype=np.uint64)
+    inf = np.zeros(len(points), dtype=np.uint8)
+    for i, p in enumerate(points):
+        if p is None:
+            inf[i] = 1
+            xy[i, 4:] = B.int_to_limbs(B.to_mont(1, B.FQ))   # (0, R, inf) as the reference stores the identity
+        else:
+            xy[i, :4] = B.int_to_limbs(B.to_mont(p[0], B.FQ))
+            xy[i, 4:] = B.int_to_limbs(B.to_mont(p[1], B.FQ))
+    return xy, inf
+
+
+@pytest.mark.gpu
+def test_proof_bytes_identical_with_g1_msms_on_gpu(fixture):
+    import kogarashi_b200 as k
+    from kogarashi_b200.groth16 import Groth16G1Prover
+    k.init()
+    P, trap, uvw, proof, internals = fixture
+    vk = P["vk"]
+    one = lambda p: _pts([p])[0][0]
+    prover = Groth16G1Prover(one(vk["delta_g1"]), one(vk["alpha_g1"]), one(vk["beta_g1"]), *_pts(P["a"]), *_pts(P["b_g1"]), *_pts(P["h"]), *_pts(P["l"]))
+    A, C = prover.commitments(internals["q"], internals["inputs"], internals["aux"], internals["r"], internals["s"])
+
+    def enc(aff):
+        return np.asarray(aff[:8], dtype="<u8").tobytes() + bytes([int(aff[8])])
+
+    assert enc(A) == G.encode_g1(proof["a"])
+    assert enc(C) == G.encode_g1(proof["c"])
+    gpu_proof = enc(A) + G.encode_g2(proof["b"]) + enc(C)
+    assert gpu_proof == G.proof_bytes(proof)
+    # the six MSMs of prover.rs:51-62 one by one through the reference-shaped entry point (3-point MSMs, c = 1 / 3 windows,
+    # identity CRS entries, len(bases) > len(coeffs), the `[l..]` slice)
+    from oracle import oracle as A_
+    l = internals["l"]
+    sc = lambda v: np.array([B.int_to_limbs(B.to_mont(x, B.FR)) for x in v], dtype=np.uint64).reshape(-1, 4)
+    for pts, coeffs in ((P["h"], internals["q"]), (P["l"], internals["aux"]), (P["a"], internals["inputs"]), (P["a"][l:], internals["aux"]),
+                        (P["b_g1"], internals["inputs"]), (P["b_g1"][l:], internals["aux"])):
+        xy, inf = _pts(pts)
+        got = k.to_affine(k.BN254_G1, k.msm_curve_addition(xy, sc(coeffs), curve=k.BN254_G1, inf=inf))
+        exp = G.G1.msm(pts, coeffs)
+        assert enc(got) == G.encode_g1(exp)
+    prover.free()
