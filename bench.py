@@ -116,14 +116,14 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": smax, "reasons": sorted(seen), "samples": len(sm)}
 
 
-def cpu_msm_rate(pts, sc, threads, repeats=1):
+def cpu_msm_rate(pts, sc, threads, repeats=1, curve=0):
     """Mpoints/s of the restated reference algorithm (oracle) on `threads` host threads."""
     from oracle import oracle as A
     best = None
     out = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        out = A.msm(A.BN254_G1, pts, sc, threads=threads)
+        out = A.msm(curve, pts, sc, threads=threads)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return pts.shape[0] / best / 1e6, best, out
@@ -138,9 +138,10 @@ def run_reference(args, rank, world):
     n_full = 1 << args.logn
     # calibrate, then bound the per-step sample so that the whole run stays within a few minutes
     cal_n = 1 << 13
-    pool = A.random_points(A.BN254_G1, cal_n, seed=bytes(range(16)))
+    cid = 0 if args.curve == "bn254_g1" else 1
+    pool = A.random_points(cid, cal_n, seed=bytes(range(16)))
     sc_cal = random_scalars(cal_n, 1)
-    rate, _, _ = cpu_msm_rate(pool, sc_cal, cores)
+    rate, _, _ = cpu_msm_rate(pool, sc_cal, cores, curve=cid)
     budget_s = 150.0
     n_s = n_full
     while n_s > cal_n and (args.steps + args.warmup) * n_s / (rate * 1e6) > budget_s:
@@ -148,16 +149,16 @@ def run_reference(args, rank, world):
     pts = np.tile(pool, (n_s // cal_n, 1))
     sc = random_scalars(n_s, 2)
     for _ in range(args.warmup):
-        cpu_msm_rate(pts, sc, cores)
+        cpu_msm_rate(pts, sc, cores, curve=cid)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_msm_rate(pts, sc, cores)
+        cpu_msm_rate(pts, sc, cores, curve=cid)
     dt = time.perf_counter() - t0
     value = n_s * args.steps / dt / 1e6
-    sample = f"{args.steps} x MSM of 2^{int(math.log2(n_s))} BN254 G1 points (workload 2^{args.logn}); {cal_n} distinct points tiled, uniform Fr scalars"
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    sample = f"{args.steps} x MSM of 2^{int(math.log2(n_s))} {args.curve} points (workload 2^{args.logn}); {cal_n} distinct points tiled, uniform scalars"
+    line = {"impl": "reference", "metric": METRIC if cid == 0 else "grumpkin_msm_throughput", "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Montgomery Fq/Fr)",
-            "data": "synthetic", "config": {"workload": f"BN254 G1 MSM, 2^{args.logn} points per GPU", "sample_points_per_step": n_s},
+            "data": "synthetic", "config": {"workload": f"{args.curve} MSM, 2^{args.logn} points per GPU", "sample_points_per_step": n_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "note": "C++ restatement of groth16::msm::msm_curve_addition + zkstd arithmetic (oracle/), std::thread over windows like rayon; the Rust reference cannot be compiled in this image"}
@@ -171,6 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--logn", type=int, default=20, help="log2 of the points per GPU (BASELINE configs[1]: 2^20 on 1 B200)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--curve", default="bn254_g1", choices=["bn254_g1", "grumpkin"], help="grumpkin = BASELINE configs[2] (Nova secondary-curve commitment shape)")
     ap.add_argument("--cpu-sample-logn", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -197,7 +199,8 @@ def main():
     k.init([local_rank])
 
     n = 1 << args.logn
-    curve = k.BN254_G1
+    curve = k.BN254_G1 if args.curve == "bn254_g1" else k.GRUMPKIN
+    metric = METRIC if curve == k.BN254_G1 else "grumpkin_msm_throughput"
     # this rank's shard of the (world * n)-point vector: bases k_i*G for global indices [rank*n, (rank+1)*n)
     bases, ks = k.Bases.generate(curve, n, seed=1000 + rank, return_scalars=True)
     sc = random_scalars(n, 77 + rank)
@@ -282,9 +285,9 @@ def main():
                 "kernel": "whole pipeline; k_accumulate is the dominant kernel (see phases_ms)",
                 "algorithmic_imads_per_launch": alg,
                 "hbm": {"achieved_gbs": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "note": "96 B/point algorithmic traffic; the path is multiply-bound, not HBM-bound"}}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+    line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq/Fr, 8x32-bit)", "data": "synthetic",
-            "config": {"workload": f"BN254 G1 MSM, 2^{args.logn} points per GPU ({world * n} total), uniform Fr scalars, bases k_i*G", "l2": "flushed between steps (512 MiB write)",
+            "config": {"workload": f"{args.curve} MSM, 2^{args.logn} points per GPU ({world * n} total), uniform scalars, bases k_i*G", "l2": "flushed between steps (512 MiB write)",
                        "shape": shape, "timing": "sum of per-step CUDA-event durations on the engine stream; wall_ms_per_step includes the flush and host gaps"},
             "wall_ms_per_step": wall_ms / args.steps, "phases_ms": phases, "clocks": clocks, "gpu_launches": launches,
             "e2e": {"value": world * n / e2e_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": 96 * n, "d2h_bytes_per_step": 128, "ms_per_step": e2e_ms,
@@ -297,13 +300,13 @@ def main():
     if world == 1:
         from oracle import oracle as A  # checker only
         from oracle import pyref as B
-        r = B.FR
+        r = B.CURVES[curve].r
         acc = 0
         for a, b in zip(ks, sc):
             acc += B.from_mont(B.limbs_to_int(a), r) * B.from_mont(B.limbs_to_int(b), r)
-        g = A.generator(A.BN254_G1)
-        one = A.field_op(A.FIELD_FQ, "to_mont", np.array([1, 0, 0, 0], dtype=np.uint64))
-        exp = A.to_affine(A.BN254_G1, A.scalar_point(A.BN254_G1, np.concatenate([g, one]), np.array(B.int_to_limbs(B.to_mont(acc % r, r)), dtype=np.uint64)))
+        g = A.generator(curve)
+        one = A.field_op(A.BASE_FIELD[curve], "to_mont", np.array([1, 0, 0, 0], dtype=np.uint64))
+        exp = A.to_affine(curve, A.scalar_point(curve, np.concatenate([g, one]), np.array(B.int_to_limbs(B.to_mont(acc % r, r)), dtype=np.uint64)))
         line["checksum_ok"] = bool((exp == total_aff).all())
 
     # ---- cpu_baseline: the restated reference algorithm on the host cores, bounded sample ------------
@@ -311,12 +314,12 @@ def main():
         cores = os.cpu_count() or 1
         s_logn = args.cpu_sample_logn or min(args.logn, 20)
         ns = 1 << s_logn
-        rate, secs, cpu_out = cpu_msm_rate(pts_host[:ns], sc[:ns], cores)
+        rate, secs, cpu_out = cpu_msm_rate(pts_host[:ns], sc[:ns], cores, curve=curve)
         from oracle import oracle as A
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"one MSM over the first 2^{s_logn} pairs of the same inputs, {secs:.2f} s, C++ restatement of the reference algorithm (c={ref_window_bits(ns)})"}
         if ns == n:
-            line["cpu_baseline"]["bit_exact_with_gpu"] = bool((A.to_affine(A.BN254_G1, cpu_out) == total_aff).all())
+            line["cpu_baseline"]["bit_exact_with_gpu"] = bool((A.to_affine(curve, cpu_out) == total_aff).all())
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

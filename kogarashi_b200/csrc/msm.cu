@@ -72,6 +72,10 @@ struct Engine {
     int dev = -1;
     int sm_count = 0;
     cudaStream_t st = nullptr;
+    cudaStream_t st_copy = nullptr;   // second stream: oneshot base upload overlaps count/scan/fill
+    cudaEvent_t ev_pts = nullptr;     // bases of the current oneshot call are on the device
+    cudaEvent_t ev_sc = nullptr;      // scalars of the current call are on the device (orders the two uploads)
+    bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist;
     DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result;  // raw bytes, cast per curve
@@ -95,6 +99,9 @@ struct Engine {
         CK(cudaGetDeviceProperties(&prop, dev));
         sm_count = prop.multiProcessorCount;
         CK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ev_pts, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_sc, cudaEventDisableTiming));
         for (auto &e : ev) CK(cudaEventCreate(&e));
         for (auto &e : user_ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&h_result, 256 * 32 * sizeof(uint32_t)));
@@ -114,6 +121,9 @@ struct Engine {
         for (auto &e : user_ev) if (e) cudaEventDestroy(e);
         oneshot_pts.release(); oneshot_inf.release();
         if (st) cudaStreamDestroy(st);
+        if (st_copy) cudaStreamDestroy(st_copy);
+        if (ev_pts) cudaEventDestroy(ev_pts);
+        if (ev_sc) cudaEventDestroy(ev_sc);
         dev = -1;
     }
     uint64_t *stage(size_t words) {
@@ -216,6 +226,10 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
     K::fill(e.st, sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
     CK(cudaEventRecord(e.ev[EV_FILL], e.st));
+    if (e.wait_pts) {
+        CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
+        e.wait_pts = false;
+    }
     K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p);
     CK(cudaEventRecord(e.ev[EV_ACC], e.st));
     CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
@@ -391,6 +405,10 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             Engine &e = *jb.e;
             CK(cudaSetDevice(e.dev));
             CK(cudaEventRecord(e.ev[EV_START], e.st));
+            auto dbg_t0 = std::chrono::steady_clock::now();
+            auto dbg = [&](const char *what) {
+                if (getenv("KGR_DEBUG")) fprintf(stderr, "[kgr] %s at %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dbg_t0).count());
+            };
             const uint32_t *d_sc;
             if (on_device) {
                 d_sc = reinterpret_cast<const uint32_t *>(scalars) + 8 * jb.sc_first;
@@ -398,20 +416,32 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 e.scalars.ensure(jb.count * 8);
                 CK(cudaMemcpyAsync(e.scalars.p, scalars + 4 * jb.sc_first, jb.count * 32, cudaMemcpyHostToDevice, e.st));
                 d_sc = e.scalars.p;
+                dbg("scalars memcpyAsync returned");
             }
             if (hp) {
+                // bases of this call: uploaded on the copy stream while count/scan/fill (which only need the
+                // scalars) run on the main stream; the accumulate kernel waits for ev_pts
+                // (the scalars go first on the link: the copy stream waits for them, otherwise the two uploads
+                // share the PCIe bandwidth and the scalar-only kernels start late)
                 e.oneshot_pts.ensure(jb.count * sizeof(AffinePt<C>));
-                CK(cudaMemcpyAsync(e.oneshot_pts.p, hp->xy + 8 * jb.pt_first, jb.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st));
+                CK(cudaEventRecord(e.ev_sc, e.st));
+                CK(cudaStreamWaitEvent(e.st_copy, e.ev_sc, 0));
+                CK(cudaMemcpyAsync(e.oneshot_pts.p, hp->xy + 8 * jb.pt_first, jb.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st_copy));
                 if (hp->inf) {
                     e.oneshot_inf.ensure(jb.count);
-                    CK(cudaMemcpyAsync(e.oneshot_inf.p, hp->inf + jb.pt_first, jb.count, cudaMemcpyHostToDevice, e.st));
-                    Launch<C>::fold_inf(e.st, (AffinePt<C> *)e.oneshot_pts.p, e.oneshot_inf.p, (uint32_t)jb.count);
+                    CK(cudaMemcpyAsync(e.oneshot_inf.p, hp->inf + jb.pt_first, jb.count, cudaMemcpyHostToDevice, e.st_copy));
+                    Launch<C>::fold_inf(e.st_copy, (AffinePt<C> *)e.oneshot_pts.p, e.oneshot_inf.p, (uint32_t)jb.count);
                     e.launches++;
                 }
+                CK(cudaEventRecord(e.ev_pts, e.st_copy));
+                dbg("points memcpyAsync returned");
+                e.wait_pts = true;
                 jb.pts = (const AffinePt<C> *)e.oneshot_pts.p;
             }
             enqueue_msm<C>(e, jb.pts, d_sc, is_mont, (uint32_t)jb.count);
+            dbg("pipeline enqueued");
             CK(cudaStreamSynchronize(e.st));
+            dbg("stream synchronized");
             collect_timing(e);
         } catch (CudaError &ce) {
             errs[j] = ce;
