@@ -61,6 +61,14 @@ int kgr_bases_register(int curve, const uint64_t *xy, const uint8_t *inf, size_t
 int kgr_bases_free(kgr_bases_t *bases);
 size_t kgr_bases_len(const kgr_bases_t *bases);
 
+/* Optional, for vectors that are reused many times (a CRS, a Pedersen key): build the table
+ * 2^(c*w) * P_i for every window w on the device (W x the memory of the vector; one-time cost of about
+ * 254 doublings + W inversions per point).  Afterwards every kgr_msm* call on this handle runs in
+ * window-collapsed mode: all windows share one bucket set, so the bucket reduction shrinks W-fold and
+ * the 254 final doublings disappear.  window_bits = 0 picks c from the cost model.  The result is the
+ * same group element. */
+int kgr_bases_precompute(kgr_bases_t *bases, int window_bits);
+
 /* sum_{i<n} scalars[i] * bases[base_off + i]   (replaces msm_curve_addition, groth16/src/msm.rs:6-48).
  * Host scalars; the H2D copy of the scalars and the 96-byte D2H of the result are part of the call. */
 int kgr_msm(kgr_bases_t *bases, size_t base_off, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t out[12]);

@@ -98,6 +98,10 @@ template <class C> __global__ void k_final(MsmShape sh, const XyzzPt<C> *win_a, 
     }
     store_xyzz(out, r);
 }
+template <class C>
+__global__ void __launch_bounds__(128) k_precompute(uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const AffinePt<C> *pts, AffinePt<C> *table) {
+    body_precompute<C>(blockIdx.x * blockDim.x + threadIdx.x, n, c, W, stride, pts, table);
+}
 template <class C> __global__ void k_fold_inf(AffinePt<C> *pts, const uint8_t *inf, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !inf[i]) return;

@@ -29,6 +29,7 @@ template <class C> struct Launch {
     static void tree_sum(cudaStream_t st, uint32_t n_windows, const X *in, uint32_t cnt_in, X *out);
     static void final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out);
     static void fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n);
+    static void precompute(cudaStream_t st, uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const A *pts, A *table);
     static void point_op(cudaStream_t st, int op, const A *a, const A *b, uint32_t *out24, uint32_t n);
     static void gen_scalars(cudaStream_t st, uint64_t seed, uint64_t first, uint32_t n, S *out);
     static void fixed_base(cudaStream_t st, const S *k, const A &g, uint32_t n, A *out);

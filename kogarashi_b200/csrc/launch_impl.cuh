@@ -44,6 +44,9 @@ template <class C> void Launch<C>::tree_sum(cudaStream_t st, uint32_t n_windows,
 }
 template <class C> void Launch<C>::final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out) { k_final<C><<<1, 32, 0, st>>>(sh, win_a, out); }
 template <class C> void Launch<C>::fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n) { k_fold_inf<C><<<cdiv(n, 256), 256, 0, st>>>(pts, inf, n); }
+template <class C> void Launch<C>::precompute(cudaStream_t st, uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const A *pts, A *table) {
+    k_precompute<C><<<cdiv(n, 128), 128, 0, st>>>(n, c, W, stride, pts, table);
+}
 template <class C> void Launch<C>::point_op(cudaStream_t st, int op, const A *a, const A *b, uint32_t *out24, uint32_t n) {
     k_point_op<C><<<cdiv(n, 64), 64, 0, st>>>(op, a, b, out24, n);
 }

@@ -160,13 +160,34 @@ static uint32_t choose_window_bits(uint32_t n) {
     return best_c;
 }
 
-static MsmShape make_shape(uint32_t n, int blocks_per_sm, int sm_count) {
+// Window size for the collapsed mode: one bucket set shared by all windows, so the reduce term is B, not W * B
+// (constants fitted to profiles/r01_precompute.md: 0.16 ns per entry, single-window reduce 0.45 ms + 0.9 ns per bucket).
+static uint32_t choose_window_bits_collapsed(uint32_t n) {
+    double best = 1e300;
+    uint32_t best_c = 1;
+    for (uint32_t c = 1; c <= 23; c++) {
+        double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1);
+        double lg = std::log2(B);
+        double sort_ns = 0.02 + (lg > 19 ? 0.008 * (lg - 19) : 0.0);
+        double cost = (double)n * W * (0.16 + sort_ns) + 0.9 * B + (B > 64 ? 0.45e6 : 0.1e6);
+        int top_bits = 255 - (int)c * ((int)W - 1);
+        if (top_bits < 10 && top_bits < (int)c) cost += 0.03 * n * (10 - top_bits);
+        if (cost < best) { best = cost; best_c = c; }
+    }
+    return best_c;
+}
+
+// table_c == 0: normal mode.  Otherwise the bases pointer is a precomputed table built for window size table_c.
+static MsmShape make_shape(uint32_t n, int blocks_per_sm, int sm_count, uint32_t table_c = 0, uint32_t table_stride = 0, uint32_t table_off = 0) {
     MsmShape sh;
     sh.n = n;
-    sh.c = choose_window_bits(n);
+    sh.c = table_c ? table_c : choose_window_bits(n);
     sh.W = (255 + sh.c - 1) / sh.c;
     sh.B = 1u << (sh.c - 1);
-    sh.G = sh.W * sh.B;
+    sh.G = table_c ? sh.B : sh.W * sh.B;
+    sh.gstride = table_c ? 0 : sh.B;
+    sh.pstride = table_c ? table_stride : 0;
+    sh.poff = table_c ? table_off : 0;
     sh.K = (uint32_t)g_params.reduce_fanin;
     uint64_t M = (uint64_t)n * sh.W;
     if (g_params.chunk > 0) {
@@ -188,9 +209,12 @@ static MsmShape make_shape(uint32_t n, int blocks_per_sm, int sm_count) {
 }
 
 // Enqueue one MSM over n pairs on engine e.  d_scalars: device pointer (n x 8 words).
-template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d_scalars, int is_mont, uint32_t n) {
+template <class C>
+static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d_scalars, int is_mont, uint32_t n, uint32_t table_c = 0,
+                        uint32_t table_stride = 0, uint32_t table_off = 0) {
     typedef XyzzPt<C> X;
-    MsmShape sh = make_shape(n, e.acc_blocks_per_sm[C::ID], e.sm_count);
+    MsmShape sh = make_shape(n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
+    const uint32_t nwin = table_c ? 1u : sh.W;  // independent bucket sets to reduce
     uint64_t M64 = (uint64_t)n * sh.W;
     if (M64 >= (1ull << 32) - 1) throw CudaError{cudaErrorInvalidValue, "n * windows exceeds 2^32 entries", __LINE__};
     uint32_t Mmax = (uint32_t)M64;
@@ -207,8 +231,8 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     e.head.ensure((size_t)chunks * sizeof(X));
     e.tail.ensure((size_t)chunks * sizeof(X));
     for (int i = 0; i < 2; i++) {
-        e.lvl_s[i].ensure((size_t)sh.W * cnt1 * sizeof(X));
-        e.lvl_a[i].ensure((size_t)sh.W * cnt1 * sizeof(X));
+        e.lvl_s[i].ensure((size_t)nwin * cnt1 * sizeof(X));
+        e.lvl_a[i].ensure((size_t)nwin * cnt1 * sizeof(X));
     }
     e.result.ensure(sizeof(X));
     e.worklist.ensure((size_t)sh.G + 2);
@@ -244,7 +268,7 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     do {
         uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
         X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
-        K::reduce(e.st, sh.W, cnt, sh.K, m_log2, in_s, in_a, os, oa);
+        K::reduce(e.st, nwin, cnt, sh.K, m_log2, in_s, in_a, os, oa);
         e.launches++;
         in_s = os;
         in_a = oa;
@@ -255,13 +279,13 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     const X *win = in_a;  // [W] once cnt == 1
     if (cnt > 1) {
         X *v = (X *)e.lvl_s[pp].p;
-        K::weight(e.st, sh.W, cnt, m_log2, in_s, in_a, v);
+        K::weight(e.st, nwin, cnt, m_log2, in_s, in_a, v);
         e.launches++;
         const X *tin = v;
         X *tout = (X *)e.lvl_a[pp].p;
         while (cnt > 1) {
             uint32_t blocks = (cnt + TPB_TREE - 1) / TPB_TREE;
-            K::tree_sum(e.st, sh.W, tin, cnt, tout);
+            K::tree_sum(e.st, nwin, tin, cnt, tout);
             e.launches++;
             cnt = blocks;
             X *nxt = (X *)tin;
@@ -270,7 +294,7 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
         }
         win = tin;
     }
-    if (g_params.final_on_device) {
+    if (g_params.final_on_device && !table_c) {
         K::final_horner(e.st, sh, win, (X *)e.result.p);
         e.launches++;
         CK(cudaMemcpyAsync(e.h_result, e.result.p, sizeof(X), cudaMemcpyDeviceToHost, e.st));
@@ -279,8 +303,8 @@ template <class C> static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases
     } else {
         // one D2H copy of the W window sums; the host applies the c doublings between windows
         // (254 sequential doublings: ~1 ms on one GPU thread, ~0.1 ms on a host core)
-        CK(cudaMemcpyAsync(e.h_result, win, (size_t)sh.W * sizeof(X), cudaMemcpyDeviceToHost, e.st));
-        e.n_result = sh.W;
+        CK(cudaMemcpyAsync(e.h_result, win, (size_t)nwin * sizeof(X), cudaMemcpyDeviceToHost, e.st));
+        e.n_result = nwin;
         e.result_c = sh.c;
     }
     e.launches += 6;  // count, fill, accumulate, fixup, fixup_long (+ memset)
@@ -309,6 +333,8 @@ struct Shard {
     int eng = 0;
     size_t first = 0, count = 0;
     void *d_pts = nullptr;
+    void *d_table = nullptr;  // kgr_bases_precompute: W * count affine points, table[w * count + i] = 2^(c*w) * P_i
+    uint32_t table_c = 0;
 };
 }  // namespace kgr
 
@@ -389,12 +415,16 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         Engine *e;
         const AffinePt<C> *pts;
         size_t pt_first, sc_first, count;
+        uint32_t table_c, table_stride, table_off;
     };
     std::vector<Job> jobs;
     for (auto &s : shards) {
         size_t lo = std::max(off, s.first), hi = std::min(off + n, s.first + s.count);
         if (lo >= hi) continue;
-        jobs.push_back(Job{&g_engines[s.eng], hp ? nullptr : (const AffinePt<C> *)s.d_pts + (lo - s.first), lo, lo - off, hi - lo});
+        if (!hp && s.d_table)
+            jobs.push_back(Job{&g_engines[s.eng], (const AffinePt<C> *)s.d_table, lo, lo - off, hi - lo, s.table_c, (uint32_t)s.count, (uint32_t)(lo - s.first)});
+        else
+            jobs.push_back(Job{&g_engines[s.eng], hp ? nullptr : (const AffinePt<C> *)s.d_pts + (lo - s.first), lo, lo - off, hi - lo, 0, 0, 0});
     }
     if (on_device && jobs.size() > 1) throw CudaError{cudaErrorInvalidValue, "device-resident scalars need a single-device range", __LINE__};
     int is_mont = (fmt == KGR_SCALARS_MONTGOMERY);
@@ -438,7 +468,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 e.wait_pts = true;
                 jb.pts = (const AffinePt<C> *)e.oneshot_pts.p;
             }
-            enqueue_msm<C>(e, jb.pts, d_sc, is_mont, (uint32_t)jb.count);
+            enqueue_msm<C>(e, jb.pts, d_sc, is_mont, (uint32_t)jb.count, jb.table_c, jb.table_stride, jb.table_off);
             dbg("pipeline enqueued");
             CK(cudaStreamSynchronize(e.st));
             dbg("stream synchronized");
@@ -698,12 +728,41 @@ int kgr_bases_free(kgr_bases_t *b) {
         if (s.d_pts && s.eng < (int)g_engines.size()) {
             cudaSetDevice(g_engines[s.eng].dev);
             cudaFree(s.d_pts);
+            if (s.d_table) cudaFree(s.d_table);
         }
     delete b;
     return KGR_OK;
 }
 
 size_t kgr_bases_len(const kgr_bases_t *b) { return b ? b->n : 0; }
+
+int kgr_bases_precompute(kgr_bases_t *b, int window_bits) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (!b) return fail(KGR_E_ARG, "null pointer");
+    if (window_bits < 0 || window_bits > 24) return fail(KGR_E_ARG, "window_bits out of range");
+    return guarded([&]() -> int {
+        for (auto &s : b->shards) {
+            if (!s.count) continue;
+            Engine &e = g_engines[s.eng];
+            CK(cudaSetDevice(e.dev));
+            uint32_t c = window_bits ? (uint32_t)window_bits : choose_window_bits_collapsed((uint32_t)s.count);
+            uint32_t W = (255 + c - 1) / c;
+            if ((uint64_t)W * s.count >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "precomputed table would exceed 2^31 points");
+            if (s.d_table) CK(cudaFree(s.d_table));
+            s.d_table = nullptr;
+            s.table_c = 0;
+            CK(cudaMalloc(&s.d_table, (size_t)W * s.count * 64));
+#define CALL(C) Launch<C>::precompute(e.st, (uint32_t)s.count, c, W, (uint32_t)s.count, (const AffinePt<C> *)s.d_pts, (AffinePt<C> *)s.d_table)
+            DISPATCH(b->curve, CALL);
+#undef CALL
+            CK(cudaGetLastError());
+            CK(cudaStreamSynchronize(e.st));
+            s.table_c = c;
+        }
+        return KGR_OK;
+    });
+}
 
 static int msm_common(kgr_bases_t *b, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t out[12]) {
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");

@@ -30,6 +30,12 @@ struct MsmShape {
     uint32_t G;  // W * B
     uint32_t L;  // entries per accumulate thread
     uint32_t K;  // reduce fan-in
+    // Window-collapsed mode (bases registered with kgr_bases_precompute): the table holds 2^(c*w) * P_i for
+    // every window w at index w * pstride + i, so all windows share ONE set of B buckets (gstride = 0,
+    // G = B) and no doublings remain after the bucket reduction.  Normal mode: gstride = B, pstride = 0.
+    uint32_t gstride;  // global bucket id = w * gstride + bucket
+    uint32_t pstride;  // entry payload  = w * pstride + poff + i
+    uint32_t poff;
 };
 
 KGR_HD uint32_t window_raw(const uint32_t s[8], uint32_t bit, uint32_t c) {
@@ -129,9 +135,9 @@ template <class C> KGR_HD void body_count(uint32_t i, const MsmShape &sh, const 
     if (i < sh.n) {
         uint32_t s[8];
         load_scalar<C>(scalars, i, is_mont, s);
-        top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t) { atomic_add_u32(&counts[w * sh.B + b], 1u); });
+        top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t) { atomic_add_u32(&counts[w * sh.gstride + b], 1u); });
     }
-    uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.B + (top & 0x7fffffffu);
+    uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.gstride + (top & 0x7fffffffu);
     (void)warp_aggregated_take(counts, key, false);
 }
 
@@ -145,14 +151,14 @@ KGR_HD void body_fill(uint32_t i, const MsmShape &sh, const uint32_t *scalars, i
         uint32_t s[8];
         load_scalar<C>(scalars, i, is_mont, s);
         top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t sign) {
-            uint32_t g = w * sh.B + b;
+            uint32_t g = w * sh.gstride + b;
             uint32_t k = atomic_sub_u32(&counts[g], 1u) - 1u;
-            entries[offsets[g] + k] = i | (sign << 31);
+            entries[offsets[g] + k] = (w * sh.pstride + sh.poff + i) | (sign << 31);
         });
     }
-    uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.B + (top & 0x7fffffffu);
+    uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.gstride + (top & 0x7fffffffu);
     uint32_t k = warp_aggregated_take(counts, key, true);
-    if (key != NO_DIGIT) entries[offsets[key] + k] = i | (top & 0x80000000u);
+    if (key != NO_DIGIT) entries[offsets[key] + k] = ((sh.W - 1) * sh.pstride + sh.poff + i) | (top & 0x80000000u);
 }
 
 // ---- accumulate -----------------------------------------------------------------------------
@@ -283,6 +289,17 @@ KGR_HD XyzzPt<C> fixup_long_partial(uint32_t g, uint32_t lane, uint32_t lanes, c
     XyzzPt<C> acc = xyzz_identity<C>();
     for (uint32_t t = t0 + lane; t <= t1; t += lanes) xyzz_add(acc, t == t0 ? tail[t0] : head[t]);
     return acc;
+}
+
+// Table for the window-collapsed mode: table[w * stride + i] = 2^(c*w) * P_i as an affine point.
+template <class C> KGR_HD void body_precompute(uint32_t i, uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const AffinePt<C> *pts, AffinePt<C> *table) {
+    if (i >= n) return;
+    XyzzPt<C> acc = xyzz_from_affine(pts[i]);
+    for (uint32_t w = 0; w < W; w++) {
+        table[(size_t)w * stride + i] = xyzz_to_affine(acc);
+        if (w + 1 < W)
+            for (uint32_t d = 0; d < c; d++) acc = xyzz_dbl(acc);
+    }
 }
 
 // ---- reduce ---------------------------------------------------------------------------------

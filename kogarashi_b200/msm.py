@@ -62,6 +62,11 @@ class Bases:
     def __len__(self):
         return self.n
 
+    def precompute(self, window_bits=0):
+        """kgr_bases_precompute: build the 2^(c*w) * P_i table so that MSMs on this vector run window-collapsed."""
+        _lib.check(_lib.lib().kgr_bases_precompute(self._h, window_bits))
+        return self
+
     def download(self, off=0, n=None):
         """Copy registered points back to the host as (n, 8) uint64 (identity entries read (0, 0))."""
         n = self.n - off if n is None else n

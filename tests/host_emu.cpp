@@ -6,7 +6,7 @@
 //
 // usage: host_emu <curve 0|1> <n> <c> <L> <K> <mode> <seed> [running_sum_stop]
 //   mode 0 uniform scalars, 1 skewed (zeros/ones/r-1), 2 duplicate + opposite points + identity bases,
-//        3 canonical-format scalars
+//        3 canonical-format scalars; add 10 for the window-collapsed (precomputed table) mode
 #include <cstdio>
 #include <cstdlib>
 #include <random>
@@ -19,6 +19,8 @@
 using namespace kgr;
 
 template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, uint32_t K, int mode, uint64_t seed, uint32_t rs_stop) {
+    const bool collapsed = (mode >= 10);  // window-collapsed mode on a precomputed table
+    if (collapsed) mode -= 10;
     typedef zko::Curve<OC> Cv;
     typedef zko::Field<typename OC::Scalar> Fs;
     typedef zko::Field<typename OC::Base> Fb;
@@ -84,7 +86,18 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         memcpy(&scalars[8 * (size_t)i], v.data(), 32);
     }
     MsmShape sh;
-    sh.n = n; sh.c = c; sh.W = (255 + c - 1) / c; sh.B = 1u << (c - 1); sh.G = sh.W * sh.B; sh.L = L; sh.K = K;
+    sh.n = n; sh.c = c; sh.W = (255 + c - 1) / c; sh.B = 1u << (c - 1); sh.G = collapsed ? sh.B : sh.W * sh.B; sh.L = L; sh.K = K;
+    sh.gstride = collapsed ? 0 : sh.B; sh.pstride = collapsed ? n + 5 : 0; sh.poff = collapsed ? 5 : 0;
+    const uint32_t nwin = collapsed ? 1 : sh.W;
+    std::vector<AffinePt<C>> table;
+    if (collapsed) {  // table built over a longer vector (5 dummy leading points) to exercise pstride / poff
+        std::vector<AffinePt<C>> ext(n + 5);
+        for (uint32_t i = 0; i < 5; i++) ext[i] = bases[0];
+        for (uint32_t i = 0; i < n; i++) ext[5 + i] = bases[i];
+        table.resize((size_t)sh.W * (n + 5));
+        for (uint32_t i = 0; i < n + 5; i++) body_precompute<C>(i, n + 5, sh.c, sh.W, n + 5, ext.data(), table.data());
+    }
+    const AffinePt<C> *acc_bases = collapsed ? table.data() : bases.data();
     std::vector<uint32_t> counts(sh.G + 1, 0), offsets(sh.G + 2, 0);
     for (uint32_t i = 0; i < n; i++) body_count<C>(i, sh, scalars.data(), is_mont, counts.data());
     uint32_t run_sum = 0;
@@ -99,7 +112,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memset(bucket_acc.data(), 0xAB, bucket_acc.size() * sizeof(XyzzPt<C>));
     memset(head.data(), 0xCD, head.size() * sizeof(XyzzPt<C>));
     memset(tail.data(), 0xEF, tail.size() * sizeof(XyzzPt<C>));
-    for (uint32_t t = 0; t < chunks; t++) body_accumulate<C>(t, sh, bases.data(), offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data());
+    for (uint32_t t = 0; t < chunks; t++) body_accumulate<C>(t, sh, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data());
     std::vector<uint32_t> worklist(sh.G + 1);
     uint32_t wl_len = 0;
     for (uint32_t g = 0; g < sh.G; g++) body_fixup<C>(g, sh, offsets.data(), bucket_acc.data(), head.data(), tail.data(), worklist.data(), &wl_len);
@@ -116,29 +129,31 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     while ((1u << klog) < K) klog++;
     uint32_t cnt1 = (sh.B + K - 1) / K;
     std::vector<XyzzPt<C>> ls[2], la[2];
-    for (int i = 0; i < 2; i++) { ls[i].resize((size_t)sh.W * cnt1); la[i].resize((size_t)sh.W * cnt1); }
+    for (int i = 0; i < 2; i++) { ls[i].resize((size_t)nwin * cnt1); la[i].resize((size_t)nwin * cnt1); }
     const XyzzPt<C> *in_s = bucket_acc.data(), *in_a = nullptr;
     int pp = 0;
     for (;;) {
         uint32_t cnt_out = (cnt + K - 1) / K;
-        for (uint32_t t = 0; t < sh.W * cnt_out; t++) body_reduce<C>(t, sh.W, cnt, K, m_log2, in_s, in_a, ls[pp].data(), la[pp].data());
+        for (uint32_t t = 0; t < nwin * cnt_out; t++) body_reduce<C>(t, nwin, cnt, K, m_log2, in_s, in_a, ls[pp].data(), la[pp].data());
         in_s = ls[pp].data(); in_a = la[pp].data();
         cnt = cnt_out; m_log2 += klog; pp ^= 1;
         if (cnt <= rs_stop) break;
     }
-    std::vector<XyzzPt<C>> win(sh.W);
+    std::vector<XyzzPt<C>> win(nwin);
     if (cnt > 1) {  // k_weight + k_tree_sum
-        std::vector<XyzzPt<C>> v((size_t)sh.W * cnt);
-        for (uint32_t t = 0; t < sh.W * cnt; t++) body_weight<C>(t, sh.W, cnt, m_log2, in_s, in_a, v.data());
-        for (uint32_t w = 0; w < sh.W; w++) {
+        std::vector<XyzzPt<C>> v((size_t)nwin * cnt);
+        for (uint32_t t = 0; t < nwin * cnt; t++) body_weight<C>(t, nwin, cnt, m_log2, in_s, in_a, v.data());
+        for (uint32_t w = 0; w < nwin; w++) {
             win[w] = xyzz_identity<C>();
             for (uint32_t i = 0; i < cnt; i++) xyzz_add(win[w], v[(size_t)w * cnt + i]);
         }
     } else {
-        for (uint32_t w = 0; w < sh.W; w++) win[w] = in_a[w];
+        for (uint32_t w = 0; w < nwin; w++) win[w] = in_a[w];
     }
     uint32_t out24[24];
-    body_final<C>(sh, win.data(), out24);
+    MsmShape shf = sh;
+    shf.W = nwin;  // collapsed: a single window sum, no doublings left
+    body_final<C>(shf, win.data(), out24);
     zko::Proj got;
     memcpy(got.x.data(), out24, 32); memcpy(got.y.data(), out24 + 8, 32); memcpy(got.z.data(), out24 + 16, 32);
     zko::Affine got_aff = Cv::to_affine(got);

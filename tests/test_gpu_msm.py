@@ -141,6 +141,38 @@ def test_msm_vs_oracle_seeded(k, curve, logn):
     bases.free()
 
 
+@pytest.mark.parametrize("window_bits", [0, 3, 7, 12])
+def test_precomputed_bases_same_element(k, golden, window_bits):
+    """kgr_bases_precompute (window-collapsed mode on the 2^(c*w) * P_i table): same group element for every golden case,
+    for sub-ranges (base_off) and for both scalar formats."""
+    for name in ("g1_uniform_1024", "gr_uniform_100", "gr_skewed_128", "g1_dup_neg_96", "gr_identity_bases_40", "g1_cancel_32", "g1_rm1_scalars",
+                 "g1_zero_scalars", "gr_uniform_1", "g1_uniform_3"):
+        curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
+        pts, sc, inf, aff = (golden[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
+        bases = k.Bases(curve, pts, inf).precompute(window_bits)
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc)), aff), (name, window_bits)
+        if len(sc) > 8:
+            off = 5
+            exp = A.to_affine(curve, A.msm(curve, pts[off:], sc[: len(sc) - off], inf=inf[off:]))
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc[: len(sc) - off], base_off=off)), exp), (name, "off")
+        bases.free()
+
+
+def test_precomputed_bases_checksum_2p18(k):
+    curve, n = A.BN254_G1, 1 << 18
+    cm = B.CURVES[curve]
+    bases, ks = k.Bases.generate(curve, n, seed=21, return_scalars=True)
+    bases.precompute()
+    sc = A.random_field(A.SCALAR_FIELD[curve], n, seed=bytes(range(40, 56)))
+    got = k.msm_curve_addition(bases, sc)
+    g = A.generator(curve)
+    one = A.field_op(A.BASE_FIELD[curve], "to_mont", np.array([1, 0, 0, 0], dtype=np.uint64))
+    s = _dot_mod(ks, sc, cm.r)
+    exp = A.to_affine(curve, A.scalar_point(curve, np.concatenate([g, one]), np.array(B.int_to_limbs(B.to_mont(s, cm.r)), dtype=np.uint64)))
+    assert same_affine(k.to_affine(curve, got), exp)
+    bases.free()
+
+
 def _dot_mod(ks, sc, r):
     tot = 0
     for a, b in zip(ks, sc):

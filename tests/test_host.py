@@ -31,6 +31,8 @@ EMU_CASES = [
     (0, 500, 11, 64, 16, 3, 11), (1, 64, 13, 16, 16, 1, 12), (0, 700, 10, 256, 4, 1, 13), (1, 333, 12, 1, 16, 2, 14),
     # running_sum_stop > 1: the weighting pass + tree sum close the reduction; small chunks + skew: hot-bucket worklist
     (0, 300, 8, 16, 4, 0, 15, 16), (1, 300, 9, 2, 2, 1, 16, 64), (0, 400, 6, 3, 4, 2, 17, 4096), (0, 600, 10, 2, 16, 1, 18, 8),
+    # mode + 10: window-collapsed mode on a precomputed table (kgr_bases_precompute)
+    (0, 200, 7, 16, 16, 10, 19, 4096), (1, 150, 5, 4, 4, 11, 20, 8), (0, 120, 11, 32, 16, 12, 21, 1), (1, 90, 3, 8, 2, 13, 22, 4096),
 ]
 
 
