@@ -19,13 +19,13 @@ __global__ void __launch_bounds__(TPB_SCALAR) k_fill(MsmShape sh, const uint32_t
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_ACC, 4) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                                                        XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail) {
-    body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail);
+                                                        XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
+    body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
-                                                   const XyzzPt<C> *tail, uint32_t *worklist, uint32_t *worklist_len) {
-    body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+                                                   const XyzzPt<C> *tail, const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
+    body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);
 }
 
 // XYZZ points in shared memory, word-major (word k of thread t at sm[k * TPB + t]): conflict-free.
@@ -72,8 +72,8 @@ __global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_reduce(uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
-                                                    const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a) {
-    body_reduce<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a);
+                                                    const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a, const uint32_t *bucket_offsets) {
+    body_reduce<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a, bucket_offsets);
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_weight(uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const XyzzPt<C> *in_s, const XyzzPt<C> *in_a,

@@ -21,20 +21,21 @@ void Launch<C>::fill(cudaStream_t st, const MsmShape &sh, const uint32_t *scalar
 }
 template <class C>
 void Launch<C>::accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks, const A *bases, const uint32_t *offsets, const uint32_t *entries, X *bucket_acc,
-                           X *head, X *tail) {
-    k_accumulate<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, bases, offsets, entries, bucket_acc, head, tail);
+                           X *head, X *tail, uint32_t *tail_bucket) {
+    k_accumulate<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
 template <class C>
-void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail, uint32_t *worklist,
-                      uint32_t *worklist_len) {
-    k_fixup<C><<<cdiv(sh.G, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
+                      const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
+    k_fixup<C><<<cdiv(chunks, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);
     unsigned blocks = sh.G < 4u * (unsigned)sm_count ? sh.G : 4u * (unsigned)sm_count;
     k_fixup_long<C><<<blocks, TPB_TREE, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
 }
 template <class C>
-void Launch<C>::reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a) {
+void Launch<C>::reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a,
+                       const uint32_t *bucket_offsets) {
     uint32_t threads = n_windows * ((cnt_in + K - 1) / K);
-    k_reduce<C><<<cdiv(threads, TPB_RED), TPB_RED, 0, st>>>(n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a);
+    k_reduce<C><<<cdiv(threads, TPB_RED), TPB_RED, 0, st>>>(n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a, bucket_offsets);
 }
 template <class C> void Launch<C>::weight(cudaStream_t st, uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const X *in_s, const X *in_a, X *out) {
     k_weight<C><<<cdiv((size_t)n_windows * cnt, TPB_RED), TPB_RED, 0, st>>>(n_windows, cnt, m_log2, in_s, in_a, out);

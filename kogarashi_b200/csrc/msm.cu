@@ -77,7 +77,7 @@ struct Engine {
     cudaEvent_t ev_sc = nullptr;      // scalars of the current call are on the device (orders the two uploads)
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
-    DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist;
+    DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket;
     DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
@@ -112,7 +112,7 @@ struct Engine {
         if (dev < 0) return;
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
-        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release();
+        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release();
         bucket_acc.release(); head.release(); tail.release(); result.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
@@ -236,6 +236,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     }
     e.result.ensure(sizeof(X));
     e.worklist.ensure((size_t)sh.G + 2);
+    e.tail_bucket.ensure((size_t)chunks + 1);
     if (e.counts_zeroed < G1) {
         CK(cudaMemsetAsync(e.counts.p, 0, e.counts.cap * sizeof(uint32_t), e.st));
         e.counts_zeroed = e.counts.cap;
@@ -254,10 +255,11 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
         e.wait_pts = false;
     }
-    K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p);
+    K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
     CK(cudaEventRecord(e.ev[EV_ACC], e.st));
     CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
-    K::fixup(e.st, sh, e.sm_count, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.worklist.p + 1, e.worklist.p);
+    K::fixup(e.st, sh, chunks, e.sm_count, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1,
+             e.worklist.p);
     CK(cudaEventRecord(e.ev[EV_FIXUP], e.st));
     // Reduce.  Running-sum levels (fan-in K) while many elements per window remain (throughput regime),
     // then one fully parallel weighting pass and block-level tree sums (latency regime).
@@ -268,7 +270,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     do {
         uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
         X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
-        K::reduce(e.st, nwin, cnt, sh.K, m_log2, in_s, in_a, os, oa);
+        K::reduce(e.st, nwin, cnt, sh.K, m_log2, in_s, in_a, os, oa, in_a ? nullptr : e.offsets.p);
         e.launches++;
         in_s = os;
         in_a = oa;

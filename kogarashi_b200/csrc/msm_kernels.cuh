@@ -142,7 +142,9 @@ template <class C> KGR_HD void body_count(uint32_t i, const MsmShape &sh, const 
 }
 
 // counts[] is consumed back to zero (positions are handed out from the end of each bucket), so
-// the histogram buffer is clean for the next MSM without a memset.
+// the histogram buffer is clean for the next MSM without a memset.  Windows are processed eight at
+// a time: eight digits, then eight independent atomics, then eight independent stores, so that the
+// L2 round trips of one scalar overlap instead of forming a chain.
 template <class C>
 KGR_HD void body_fill(uint32_t i, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets,
                       uint32_t *entries) {
@@ -150,11 +152,39 @@ KGR_HD void body_fill(uint32_t i, const MsmShape &sh, const uint32_t *scalars, i
     if (i < sh.n) {
         uint32_t s[8];
         load_scalar<C>(scalars, i, is_mont, s);
-        top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t sign) {
-            uint32_t g = w * sh.gstride + b;
-            uint32_t k = atomic_sub_u32(&counts[g], 1u) - 1u;
-            entries[offsets[g] + k] = (w * sh.pstride + sh.poff + i) | (sign << 31);
-        });
+        uint32_t carry = 0;
+        for (uint32_t w0 = 0; w0 < sh.W; w0 += 8) {
+            uint32_t g[8], pay[8], pos[8];
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++) {
+                uint32_t w = w0 + j;
+                g[j] = NO_DIGIT;
+                pay[j] = 0;
+                if (w < sh.W) {
+                    uint32_t d = window_raw(s, w * sh.c, sh.c) + carry;
+                    carry = 0;
+                    uint32_t sign = 0;
+                    if (d > sh.B) {
+                        d = (1u << sh.c) - d;
+                        sign = 1;
+                        carry = 1;
+                    }
+                    if (d != 0) {
+                        if (w + 1 == sh.W) top = (d - 1) | (sign << 31);
+                        else {
+                            g[j] = w * sh.gstride + d - 1;
+                            pay[j] = (w * sh.pstride + sh.poff + i) | (sign << 31);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++)
+                if (g[j] != NO_DIGIT) pos[j] = offsets[g[j]] + atomic_sub_u32(&counts[g[j]], 1u) - 1u;
+#pragma unroll
+            for (uint32_t j = 0; j < 8; j++)
+                if (g[j] != NO_DIGIT) entries[pos[j]] = pay[j];
+        }
     }
     uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.gstride + (top & 0x7fffffffu);
     uint32_t k = warp_aggregated_take(counts, key, true);
@@ -208,18 +238,24 @@ KGR_HD uint32_t bucket_of_position(const uint32_t *offsets, uint32_t G, uint32_t
     return lo;
 }
 
+// A segment that started before this chunk goes to head[t]; one that started here and continues past
+// the chunk goes to tail[t] (at most one per thread: the last segment) and its bucket id is returned
+// so that the fix-up pass can start from the chunks instead of scanning every bucket.
 template <class C>
-KGR_HD void flush_segment(uint32_t t, uint32_t g, uint32_t s, uint32_t e, const uint32_t *offsets, const XyzzPt<C> &acc, XyzzPt<C> *bucket_acc,
-                          XyzzPt<C> *head, XyzzPt<C> *tail) {
+KGR_HD uint32_t flush_segment(uint32_t t, uint32_t g, uint32_t s, uint32_t e, const uint32_t *offsets, const XyzzPt<C> &acc, XyzzPt<C> *bucket_acc,
+                              XyzzPt<C> *head, XyzzPt<C> *tail) {
     uint32_t lo = offsets[g], hi = offsets[g + 1];
     if (lo < s) store_xyzz(&head[t], acc);
-    else if (hi > e) store_xyzz(&tail[t], acc);
-    else store_xyzz(&bucket_acc[g], acc);
+    else if (hi > e) {
+        store_xyzz(&tail[t], acc);
+        return g;
+    } else store_xyzz(&bucket_acc[g], acc);
+    return NO_DIGIT;
 }
 
 template <class C>
 KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                            XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail) {
+                            XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
     uint32_t M = offsets[sh.G];
     uint64_t s64 = (uint64_t)t * sh.L;
     if (s64 >= M) return;
@@ -239,7 +275,7 @@ KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *b
             pt_next = load_affine(bases, ent_next & 0x7fffffffu);
         }
         if (pos >= g_end) {
-            flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);
+            (void)flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);  // ends inside the chunk: never a tail
             acc = xyzz_identity<C>();
             do {
                 g++;
@@ -251,31 +287,29 @@ KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *b
         ent = ent_next;
         pt = pt_next;
     }
-    flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);
+    tail_bucket[t] = flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);
 }
 
-// One thread per bucket: empty buckets become the identity, buckets cut by chunk boundaries get
-// their pieces summed (tail of the first chunk, heads of the following ones).  Buckets cut into
-// more than FIXUP_INLINE_MAX pieces (a hot bucket: skewed scalars, or the thin top window) are
-// queued for the block-cooperative kernel instead of being walked by one thread.
+// One thread per chunk: a chunk whose last segment continues into the following chunks owns that bucket
+// and sums its pieces (its own tail slot, then the head slots of the following chunks).  Buckets cut
+// into more than FIXUP_INLINE_MAX pieces (a hot bucket: skewed scalars, or a thin top window) are
+// queued for the block-cooperative kernel instead of being walked by one thread.  Empty buckets are
+// never written: the first reduce level recognises them from offsets[].
 constexpr uint32_t FIXUP_INLINE_MAX = 6;
 template <class C>
-KGR_HD void body_fixup(uint32_t g, const MsmShape &sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
-                       const XyzzPt<C> *tail, uint32_t *worklist, uint32_t *worklist_len) {
-    if (g >= sh.G) return;
-    uint32_t lo = offsets[g], hi = offsets[g + 1];
-    if (lo == hi) {
-        store_xyzz(&bucket_acc[g], xyzz_identity<C>());
-        return;
-    }
-    uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L;
-    if (t0 == t1) return;
-    if (t1 - t0 > FIXUP_INLINE_MAX && worklist) {
+KGR_HD void body_fixup(uint32_t t, const MsmShape &sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
+                       const XyzzPt<C> *tail, const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
+    uint32_t M = offsets[sh.G];
+    if ((uint64_t)t * sh.L >= M) return;
+    uint32_t g = tail_bucket[t];
+    if (g == NO_DIGIT) return;
+    uint32_t t1 = (offsets[g + 1] - 1) / sh.L;
+    if (t1 - t > FIXUP_INLINE_MAX && worklist) {
         worklist[atomic_add_u32(worklist_len, 1u)] = g;
         return;
     }
-    XyzzPt<C> acc = tail[t0];
-    for (uint32_t t = t0 + 1; t <= t1; t++) xyzz_add(acc, head[t]);
+    XyzzPt<C> acc = tail[t];
+    for (uint32_t u = t + 1; u <= t1; u++) xyzz_add(acc, head[u]);
     store_xyzz(&bucket_acc[g], acc);
 }
 
@@ -309,19 +343,21 @@ template <class C> KGR_HD void body_precompute(uint32_t i, uint32_t n, uint32_t 
 // Level 0 has a_i == s_i == bucket i (in_a == nullptr).
 template <class C>
 KGR_HD void body_reduce(uint32_t tid, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
-                        const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a) {
+                        const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a, const uint32_t *bucket_offsets) {
     uint32_t cnt_out = (cnt_in + K - 1) / K;
     if (tid >= n_windows * cnt_out) return;
     uint32_t w = tid / cnt_out, gi = tid % cnt_out;
     uint32_t base = gi * K;
     uint32_t k = (cnt_in - base < K) ? cnt_in - base : K;
     const XyzzPt<C> *s_in = in_s + (size_t)w * cnt_in + base;
+    // level 0 only: bucket_offsets != nullptr, an empty bucket (never written by accumulate / fixup) is the identity
+    const uint32_t *off = bucket_offsets ? bucket_offsets + (size_t)w * cnt_in + base : nullptr;
     XyzzPt<C> run = xyzz_identity<C>(), T = xyzz_identity<C>();
     for (uint32_t i = k; i-- > 1;) {
-        xyzz_add(run, s_in[i]);
+        if (!off || off[i] != off[i + 1]) xyzz_add(run, s_in[i]);
         xyzz_add(T, run);
     }
-    xyzz_add(run, s_in[0]);  // run = S
+    if (!off || off[0] != off[1]) xyzz_add(run, s_in[0]);  // run = S
     XyzzPt<C> A;
     if (in_a) {
         const XyzzPt<C> *a_in = in_a + (size_t)w * cnt_in + base;

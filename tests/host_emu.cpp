@@ -112,10 +112,11 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memset(bucket_acc.data(), 0xAB, bucket_acc.size() * sizeof(XyzzPt<C>));
     memset(head.data(), 0xCD, head.size() * sizeof(XyzzPt<C>));
     memset(tail.data(), 0xEF, tail.size() * sizeof(XyzzPt<C>));
-    for (uint32_t t = 0; t < chunks; t++) body_accumulate<C>(t, sh, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data());
+    std::vector<uint32_t> tail_bucket(chunks, 0x12345678u);
+    for (uint32_t t = 0; t < chunks; t++) body_accumulate<C>(t, sh, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
     std::vector<uint32_t> worklist(sh.G + 1);
     uint32_t wl_len = 0;
-    for (uint32_t g = 0; g < sh.G; g++) body_fixup<C>(g, sh, offsets.data(), bucket_acc.data(), head.data(), tail.data(), worklist.data(), &wl_len);
+    for (uint32_t t = 0; t < chunks; t++) body_fixup<C>(t, sh, offsets.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data(), worklist.data(), &wl_len);
     for (uint32_t i = 0; i < wl_len; i++) {  // k_fixup_long: lanes cooperate, then a tree sum
         const uint32_t lanes = 5;
         XyzzPt<C> tot = xyzz_identity<C>();
@@ -134,7 +135,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     int pp = 0;
     for (;;) {
         uint32_t cnt_out = (cnt + K - 1) / K;
-        for (uint32_t t = 0; t < nwin * cnt_out; t++) body_reduce<C>(t, nwin, cnt, K, m_log2, in_s, in_a, ls[pp].data(), la[pp].data());
+        for (uint32_t t = 0; t < nwin * cnt_out; t++) body_reduce<C>(t, nwin, cnt, K, m_log2, in_s, in_a, ls[pp].data(), la[pp].data(), in_a ? nullptr : offsets.data());
         in_s = ls[pp].data(); in_a = la[pp].data();
         cnt = cnt_out; m_log2 += klog; pp ^= 1;
         if (cnt <= rs_stop) break;
