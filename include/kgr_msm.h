@@ -97,6 +97,18 @@ int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]);
 /* a + b on the host for two projective points (used to combine per-GPU / per-rank partial sums). */
 int kgr_proj_add(int curve, const uint64_t a[12], const uint64_t b[12], uint64_t out[12]);
 
+/* ---- Fr NTT (next row N2: groth16/src/fft.rs) --------------------------------------------------
+ * Radix-2 transforms over bn254 Fr on a domain of size 2^log_n, semantics of groth16/src/fft.rs:92-127:
+ * op 0 dft, 1 idft, 2 coset_dft, 3 coset_idft.  in: n_in <= 2^log_n Montgomery elements (zero padded like
+ * prepare_fft, fft.rs:157-162); out: 2^log_n elements; *n_out: length after Coefficients::new stripped the
+ * trailing zeros (idft variants, poly.rs:61-63), else 2^log_n.  Host buffers. */
+int kgr_ntt(unsigned log_n, int op, const uint64_t *in, size_t n_in, uint64_t *out, size_t *n_out);
+/* Same transform in place on 2^log_n elements already in device memory (no stripping). */
+int kgr_ntt_device(unsigned log_n, int op, void *d_data);
+/* groth16/src/prover.rs:36-47 in one call: q = coset_idft((coset_dft(idft(a)) * coset_dft(idft(b)) - coset_dft(idft(c))) / Z).
+ * a, b, c: the m R1CS evaluations each (host, Montgomery); out: 2^log_n elements, *n_out after stripping. */
+int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, uint64_t *out, size_t *n_out);
+
 /* Tuning knobs: "window_bits" (0 = auto), "chunk" (entries per accumulate thread, 0 = auto),
  * "reduce_fanin" (power of two), "running_sum_stop" (elements per window below which the reduce
  * switches from running sums to the parallel weighting pass), "final_on_device" (1: Horner over

@@ -17,7 +17,7 @@ EXPORTS = [
     "kgr_bases_len", "kgr_msm", "kgr_msm_oneshot", "kgr_msm_device", "kgr_pedersen_commit", "kgr_to_affine",
     "kgr_proj_add", "kgr_set_param", "kgr_last_timing", "kgr_test_field_op", "kgr_test_point_op",
     "kgr_fixed_base_mul", "kgr_bases_generate", "kgr_microbench", "kgr_bases_download", "kgr_event_record",
-    "kgr_event_elapsed_ms", "kgr_launch_count", "kgr_bases_precompute",
+    "kgr_event_elapsed_ms", "kgr_launch_count", "kgr_bases_precompute", "kgr_ntt", "kgr_ntt_device", "kgr_groth16_h",
 ]
 
 
@@ -52,6 +52,9 @@ def lib():
     L.kgr_bases_register.argtypes = [ci, u64p, u8p, sz, ctypes.POINTER(vp)]
     L.kgr_bases_free.argtypes = [vp]
     L.kgr_bases_precompute.argtypes = [vp, ci]
+    L.kgr_ntt.argtypes = [ctypes.c_uint, ci, u64p, sz, u64p, ctypes.POINTER(sz)]
+    L.kgr_ntt_device.argtypes = [ctypes.c_uint, ci, vp]
+    L.kgr_groth16_h.argtypes = [ctypes.c_uint, u64p, u64p, u64p, sz, u64p, ctypes.POINTER(sz)]
     L.kgr_bases_len.argtypes = [vp]
     L.kgr_bases_len.restype = sz
     L.kgr_msm.argtypes = [vp, sz, u64p, ci, sz, u64p]

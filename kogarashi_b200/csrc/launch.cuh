@@ -4,6 +4,8 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstring>
+
 #include "msm_kernels.cuh"
 
 namespace kgr {
@@ -46,6 +48,15 @@ struct LaunchUtil {
     static void ubench_fmul(cudaStream_t st, int blocks, void *sink, int iters);
     static void ubench_madd(cudaStream_t st, int blocks, void *sink, const AffinePt<Bn254G1> &p, const AffinePt<Bn254G1> &q, int iters);
     static void clock_probe(cudaStream_t st, uint64_t *out2);
+};
+
+// Fr NTT (kernels_ntt.cu).  Field elements are passed as opaque 32-byte Montgomery values.
+struct LaunchNtt {
+    static int passes(uint32_t k);
+    static void pow_table(cudaStream_t st, void *out, const void *base32, uint32_t n);
+    static void scale(cudaStream_t st, void *d, const void *table, const void *c32, uint32_t n);
+    static void h_pointwise(cudaStream_t st, void *a, const void *b, const void *c, const void *zinv32, uint32_t n);
+    static int transform(cudaStream_t st, void *d, const void *tw, uint32_t k);
 };
 
 }  // namespace kgr

@@ -14,6 +14,8 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <memory>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -66,6 +68,16 @@ template <class T> struct DevBuf {
     }
 };
 
+// Radix-2 domain over bn254 Fr (groth16/src/fft.rs:27-90): tables live in HBM, built once per size.
+struct NttDomain {
+    uint32_t k = 0;
+    DevBuf<uint8_t> tw, inv_tw, cosets, inv_cosets;  // omega^i (n/2), omega^-i (n/2), 7^i (n), 7^-i (n)
+    Fp<FrP> n_inv, z_inv;                            // 1/n (fft.rs:86), 1/(7^n - 1) (fft.rs:139-153)
+    ~NttDomain() {
+        tw.release(); inv_tw.release(); cosets.release(); inv_cosets.release();
+    }
+};
+
 enum { EV_START, EV_H2D, EV_COUNT, EV_SCAN, EV_FILL, EV_ACC, EV_FIXUP, EV_END, EV_N };
 
 struct Engine {
@@ -91,6 +103,8 @@ struct Engine {
     uint64_t launches = 0;            // kernels of this library launched on this engine since init
     cudaEvent_t user_ev[4] = {};      // kgr_event_record / kgr_event_elapsed_ms
     DevBuf<uint8_t> oneshot_pts, oneshot_inf;  // device copy of the bases of kgr_msm_oneshot
+    std::map<uint32_t, std::shared_ptr<struct NttDomain>> ntt_domains;  // per log2(n): twiddle / coset tables in HBM
+    DevBuf<uint8_t> ntt_buf[3];
 
     void init(int device) {
         dev = device;
@@ -120,6 +134,8 @@ struct Engine {
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : user_ev) if (e) cudaEventDestroy(e);
         oneshot_pts.release(); oneshot_inf.release();
+        ntt_domains.clear();
+        for (auto &b : ntt_buf) b.release();
         if (st) cudaStreamDestroy(st);
         if (st_copy) cudaStreamDestroy(st_copy);
         if (ev_pts) cudaEventDestroy(ev_pts);
@@ -624,6 +640,78 @@ static double ubench_mode(Engine &e, int mode, uint32_t *sink, double ops_per_th
     return (double)blocks * tpb * iters * ops_per_thread_iter / (ms * 1e-3) / 1e9;
 }
 
+// ---- Fr NTT -----------------------------------------------------------------------
+static Fp<FrP> fr_from_u64(uint64_t v) {
+    Fp<FrP> x = fp_zero<FrP>();
+    x.v[0] = (uint32_t)v;
+    x.v[1] = (uint32_t)(v >> 32);
+    return fp_to_mont(x);
+}
+static Fp<FrP> fr_pow2k(Fp<FrP> x, uint32_t squarings) {
+    for (uint32_t i = 0; i < squarings; i++) x = fp_sqr(x);
+    return x;
+}
+static NttDomain &ntt_domain(Engine &e, uint32_t k) {
+    auto it = e.ntt_domains.find(k);
+    if (it != e.ntt_domains.end()) return *it->second;
+    auto d = std::make_shared<NttDomain>();
+    d->k = k;
+    const uint32_t n = 1u << k;
+    // fr.rs:60-65 ROOT_OF_UNITY = to_mont_form(limbs); S = 28 (fr.rs:53); omega = root^(2^(S-k)) (fft.rs:35)
+    Fp<FrP> root = fp_zero<FrP>();
+    const uint64_t rl[4] = {0xd34f1ed960c37c9cULL, 0x3215cf6dd39329c8ULL, 0x98865ea93dd31f74ULL, 0x03ddb9f5166d18b7ULL};
+    std::memcpy(root.v, rl, 32);
+    root = fp_to_mont(root);
+    Fp<FrP> omega = fr_pow2k(root, 28 - k), omega_inv = fp_inv(omega);
+    Fp<FrP> g = fr_from_u64(7), g_inv = fp_inv(g);  // MULTIPLICATIVE_GENERATOR (fr.rs:18,21)
+    d->n_inv = fp_inv(fr_from_u64(n));
+    Fp<FrP> gn = fr_pow2k(g, k);                     // 7^(2^k)
+    d->z_inv = fp_inv(fp_sub(gn, fp_one<FrP>()));
+    d->tw.ensure((size_t)std::max(1u, n / 2) * 32);
+    d->inv_tw.ensure((size_t)std::max(1u, n / 2) * 32);
+    d->cosets.ensure((size_t)n * 32);
+    d->inv_cosets.ensure((size_t)n * 32);
+    LaunchNtt::pow_table(e.st, d->tw.p, &omega, std::max(1u, n / 2));
+    LaunchNtt::pow_table(e.st, d->inv_tw.p, &omega_inv, std::max(1u, n / 2));
+    LaunchNtt::pow_table(e.st, d->cosets.p, &g, n);
+    LaunchNtt::pow_table(e.st, d->inv_cosets.p, &g_inv, n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(e.st));
+    e.launches += 4;
+    e.ntt_domains[k] = d;
+    return *d;
+}
+// op: 0 dft, 1 idft, 2 coset_dft, 3 coset_idft (fft.rs:92-127), in place on 2^k device elements
+static void ntt_enqueue(Engine &e, NttDomain &d, void *buf, int op) {
+    const uint32_t n = 1u << d.k;
+    switch (op) {
+        case 0: e.launches += LaunchNtt::transform(e.st, buf, d.tw.p, d.k); break;
+        case 1:
+            e.launches += LaunchNtt::transform(e.st, buf, d.inv_tw.p, d.k);
+            LaunchNtt::scale(e.st, buf, nullptr, &d.n_inv, n);
+            e.launches++;
+            break;
+        case 2:
+            LaunchNtt::scale(e.st, buf, d.cosets.p, nullptr, n);
+            e.launches += 1 + LaunchNtt::transform(e.st, buf, d.tw.p, d.k);
+            break;
+        default:
+            e.launches += LaunchNtt::transform(e.st, buf, d.inv_tw.p, d.k);
+            LaunchNtt::scale(e.st, buf, d.inv_cosets.p, &d.n_inv, n);
+            e.launches++;
+            break;
+    }
+}
+static size_t stripped_len(const uint64_t *v, size_t n) {  // Coefficients::new (poly.rs:61-63)
+    while (n && !(v[4 * (n - 1)] | v[4 * (n - 1) + 1] | v[4 * (n - 1) + 2] | v[4 * (n - 1) + 3])) n--;
+    return n;
+}
+static void upload_padded(Engine &e, void *dbuf, const uint64_t *src, size_t n_in, size_t n) {
+    size_t m = std::min(n_in, n);
+    if (m) CK(cudaMemcpyAsync(dbuf, src, m * 32, cudaMemcpyHostToDevice, e.st));
+    if (m < n) CK(cudaMemsetAsync((uint8_t *)dbuf + m * 32, 0, (n - m) * 32, e.st));
+}
+
 static int guarded(const std::function<int()> &f) {
     try {
         return f();
@@ -884,6 +972,93 @@ int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int fmt, size_
     int rc = kgr_msm(ck, 0, scalars, fmt, pairs, proj);
     if (rc) return rc;
     return kgr_to_affine(ck->curve, proj, out);
+}
+
+int kgr_ntt(unsigned log_n, int op, const uint64_t *in, size_t n_in, uint64_t *out, size_t *n_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (log_n < 1 || log_n > 28 || op < 0 || op > 3 || !out || (!in && n_in)) return fail(KGR_E_ARG, "bad argument");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        NttDomain &d = ntt_domain(e, log_n);
+        const size_t n = (size_t)1 << log_n;
+        e.ntt_buf[0].ensure(n * 32);
+        CK(cudaEventRecord(e.ev[EV_START], e.st));
+        upload_padded(e, e.ntt_buf[0].p, in, n_in, n);
+        CK(cudaEventRecord(e.ev[EV_H2D], e.st));
+        ntt_enqueue(e, d, e.ntt_buf[0].p, op);
+        CK(cudaEventRecord(e.ev[EV_ACC], e.st));
+        CK(cudaMemcpyAsync(out, e.ntt_buf[0].p, n * 32, cudaMemcpyDeviceToHost, e.st));
+        CK(cudaEventRecord(e.ev[EV_END], e.st));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e.st));
+        std::memset(e.last_ms, 0, sizeof e.last_ms);
+        cudaEventElapsedTime(&e.last_ms[0], e.ev[EV_START], e.ev[EV_END]);
+        cudaEventElapsedTime(&e.last_ms[7], e.ev[EV_START], e.ev[EV_H2D]);
+        cudaEventElapsedTime(&e.last_ms[4], e.ev[EV_H2D], e.ev[EV_ACC]);
+        if (n_out) *n_out = (op == 1 || op == 3) ? stripped_len(out, n) : n;
+        return KGR_OK;
+    });
+}
+
+int kgr_ntt_device(unsigned log_n, int op, void *d_data) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (log_n < 1 || log_n > 28 || op < 0 || op > 3 || !d_data) return fail(KGR_E_ARG, "bad argument");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        NttDomain &d = ntt_domain(e, log_n);
+        CK(cudaEventRecord(e.ev[EV_START], e.st));
+        ntt_enqueue(e, d, d_data, op);
+        CK(cudaEventRecord(e.ev[EV_END], e.st));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e.st));
+        std::memset(e.last_ms, 0, sizeof e.last_ms);
+        cudaEventElapsedTime(&e.last_ms[0], e.ev[EV_START], e.ev[EV_END]);
+        e.last_ms[4] = e.last_ms[0];
+        return KGR_OK;
+    });
+}
+
+int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, uint64_t *out, size_t *n_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (log_n < 1 || log_n > 28 || !a || !b || !c || !out) return fail(KGR_E_ARG, "bad argument");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        NttDomain &d = ntt_domain(e, log_n);
+        const size_t n = (size_t)1 << log_n;
+        const uint64_t *src[3] = {a, b, c};
+        CK(cudaEventRecord(e.ev[EV_START], e.st));
+        for (int i = 0; i < 3; i++) {
+            e.ntt_buf[i].ensure(n * 32);
+            upload_padded(e, e.ntt_buf[i].p, src[i], m, n);
+        }
+        CK(cudaEventRecord(e.ev[EV_H2D], e.st));
+        for (int i = 0; i < 3; i++) {
+            // idft then coset_dft (prover.rs:36-41); the 1/n and coset scalings are one elementwise pass
+            e.launches += LaunchNtt::transform(e.st, e.ntt_buf[i].p, d.inv_tw.p, d.k);
+            LaunchNtt::scale(e.st, e.ntt_buf[i].p, d.cosets.p, &d.n_inv, (uint32_t)n);
+            e.launches += 1 + LaunchNtt::transform(e.st, e.ntt_buf[i].p, d.tw.p, d.k);
+        }
+        LaunchNtt::h_pointwise(e.st, e.ntt_buf[0].p, e.ntt_buf[1].p, e.ntt_buf[2].p, &d.z_inv, (uint32_t)n);  // prover.rs:43-46
+        e.launches++;
+        ntt_enqueue(e, d, e.ntt_buf[0].p, 3);                                                             // coset_idft, prover.rs:47
+        CK(cudaEventRecord(e.ev[EV_ACC], e.st));
+        CK(cudaMemcpyAsync(out, e.ntt_buf[0].p, n * 32, cudaMemcpyDeviceToHost, e.st));
+        CK(cudaEventRecord(e.ev[EV_END], e.st));
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e.st));
+        std::memset(e.last_ms, 0, sizeof e.last_ms);
+        cudaEventElapsedTime(&e.last_ms[0], e.ev[EV_START], e.ev[EV_END]);
+        cudaEventElapsedTime(&e.last_ms[7], e.ev[EV_START], e.ev[EV_H2D]);
+        cudaEventElapsedTime(&e.last_ms[4], e.ev[EV_H2D], e.ev[EV_ACC]);
+        if (n_out) *n_out = stripped_len(out, n);
+        return KGR_OK;
+    });
 }
 
 int kgr_last_timing(int dev, float ms[8], uint32_t shape[6]) {

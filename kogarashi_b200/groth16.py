@@ -1,26 +1,23 @@
-"""G1 side of the reference's Groth16 prover on the GPU MSM engine.
+"""G1 side of the reference's Groth16 prover on the GPU engine (SURVEY.md §8f rows N1 + N2).
 
-Reference: groth16/src/prover.rs:49-92.  After the FFTs, `create_proof` issues six G1 MSMs
-(h, l, a x2, b_g1 x2; :51-62), two G2 MSMs (:64-65, out of scope: they stay on the reference CPU path)
-and then assembles
-    A = r*delta + alpha + a_answer                                   (:75,81-82)
-    C = r*s*delta + s*alpha + r*beta + s*a_answer + r*b1_answer + q + l   (:77,84,90-92)
-Everything on the right is a linear combination of fixed CRS points, so with the CRS resident on the GPU
-(`kgr_bases_register`, once per prover) A and C are ONE MSM each over the concatenated vectors
-    A: [delta, alpha, a...]                       scalars [r, 1, z...]
-    C: [delta, alpha, beta, a..., b_g1..., h..., l...]   scalars [r*s, s, r, s*z..., r*z..., q..., aux...]
-where z = inputs ++ aux.  This is the fusion N1 asks for (pairs a_inputs/a_aux and b_g1_inputs/b_g1_aux fused,
-blinding terms folded in).  Scalar products are taken mod r on the host; they are passed in canonical form.
-FFT / witness generation (rows N2) and G2 (N3) are not part of this module: the caller supplies q, inputs, aux.
+Reference: groth16/src/prover.rs:32-92.  `create_proof` runs seven FFTs (:36-47), six G1 MSMs (h, l, a x2, b_g1 x2;
+:51-62), two G2 MSMs (:64-65 — out of scope, they stay on the reference CPU path) and assembles
+    A = r*delta + alpha + a_answer                                          (:75,81-82)
+    C = r*s*delta + s*alpha + r*beta + s*a_answer + r*b1_answer + q + l     (:77,84,90-92)
+Here the G1 CRS (`Parameters::{h, l, a, b_g1}`, groth16/src/params.rs:7-29) is registered on the GPU once per prover;
+per proof the H coefficients come from the device NTT (kogarashi_b200.fft) and the `a_inputs / a_aux` and
+`b_g1_inputs / b_g1_aux` pairs are fused into one MSM each over z = inputs ++ aux (the prover splits them only because
+of its slice layout, :58-62).  The blinding terms are a five-point MSM, so no curve arithmetic is done in Python.
 """
 import numpy as np
 
-from .msm import BN254_G1, SCALARS_CANONICAL, Bases, msm_curve_addition, to_affine
+from .fft import Fft
+from .msm import BN254_G1, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Bases, msm_curve_addition, proj_add, to_affine
 
 FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001  # bn254/src/fr.rs:11-16
 
 
-def _scalars(vals):
+def _canonical(vals):
     out = np.zeros((len(vals), 4), dtype=np.uint64)
     for i, v in enumerate(vals):
         v %= FR
@@ -30,34 +27,45 @@ def _scalars(vals):
 
 
 class Groth16G1Prover:
-    """Holds the G1 part of `Parameters` (groth16/src/params.rs:7-29) on the GPU.
-
-    Points are (n, 8) uint64 Montgomery arrays with (n,) uint8 infinity flags (CRS entries may be the identity,
+    """Points are (n, 8) uint64 Montgomery arrays with (n,) uint8 infinity flags (CRS entries may be the identity,
     groth16/src/zksnark.rs:62-66,177-185)."""
 
-    def __init__(self, delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf):
-        one = np.zeros(1, dtype=np.uint8)
+    def __init__(self, delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, precompute=False):
         pt = lambda p: np.ascontiguousarray(p, dtype=np.uint64).reshape(1, 8)
-        self.n_var = len(a)
-        self.n_h, self.n_l = len(h), len(l)
-        a_pts = np.concatenate([pt(delta_g1), pt(alpha_g1), a])
-        a_flags = np.concatenate([one, one, a_inf])
-        c_pts = np.concatenate([pt(delta_g1), pt(alpha_g1), pt(beta_g1), a, b_g1, h, l])
-        c_flags = np.concatenate([one, one, one, a_inf, b_g1_inf, h_inf, l_inf])
-        self.crs_a = Bases(BN254_G1, a_pts, a_flags)
-        self.crs_c = Bases(BN254_G1, c_pts, c_flags)
+        self.vk = np.concatenate([pt(delta_g1), pt(alpha_g1), pt(beta_g1)])
+        self.a, self.b_g1, self.h, self.l = (Bases(BN254_G1, p, f) for p, f in ((a, a_inf), (b_g1, b_g1_inf), (h, h_inf), (l, l_inf)))
+        if precompute:
+            for b in (self.a, self.b_g1, self.h, self.l):
+                b.precompute(0)
+
+    def prove_g1(self, q, inputs, aux, r, s, scalar_fmt=SCALARS_MONTGOMERY):
+        """q, inputs, aux: (len, 4) uint64 scalars in `scalar_fmt`; r, s: Python ints (the prover's blinding factors, prover.rs:71-72).
+        -> (A, C) as (9,) uint64 affine [x, y, is_infinity] = Proof.a / Proof.c after `.into()` (prover.rs:94-98)."""
+        z = np.concatenate([np.asarray(inputs, dtype=np.uint64).reshape(-1, 4), np.asarray(aux, dtype=np.uint64).reshape(-1, 4)])
+        a_answer = msm_curve_addition(self.a, z, scalar_fmt=scalar_fmt)              # a_inputs + a_aux       (:58-59, :80)
+        b1_answer = msm_curve_addition(self.b_g1, z, scalar_fmt=scalar_fmt)          # b_g1_inputs + b_g1_aux (:61-62, :86)
+        q_pt = msm_curve_addition(self.h, q, scalar_fmt=scalar_fmt)                  # :51
+        l_pt = msm_curve_addition(self.l, aux, scalar_fmt=scalar_fmt)                # :56
+        delta, alpha, beta = self.vk
+        blind_a = msm_curve_addition(np.stack([delta, alpha]), _canonical([r, 1]), curve=BN254_G1, scalar_fmt=SCALARS_CANONICAL)
+        g_a = proj_add(BN254_G1, blind_a, a_answer)
+        aa, ba = to_affine(BN254_G1, a_answer), to_affine(BN254_G1, b1_answer)
+        pts = np.stack([aa[:8], ba[:8], delta, alpha, beta])
+        inf = np.array([aa[8], ba[8], 0, 0, 0], dtype=np.uint8)
+        blind_c = msm_curve_addition(pts, _canonical([s, r, r * s, s, r]), curve=BN254_G1, inf=inf, scalar_fmt=SCALARS_CANONICAL)
+        g_c = proj_add(BN254_G1, proj_add(BN254_G1, blind_c, q_pt), l_pt)
+        return to_affine(BN254_G1, g_a), to_affine(BN254_G1, g_c)
+
+    def prove_from_evaluations(self, log_n, a_evals, b_evals, c_evals, inputs, aux, r, s):
+        """The whole G1 side of create_proof from the R1CS evaluations (prover.rs:33): device NTTs for H, then the MSMs.
+        All scalars are Montgomery arrays (the reference's in-memory form)."""
+        q = Fft(log_n).h_coefficients(a_evals, b_evals, c_evals)
+        return self.prove_g1(q, inputs, aux, r, s) + (q,)
 
     def commitments(self, q, inputs, aux, r, s):
-        """-> (A, C) as (9,) uint64 affine [x, y, is_infinity] (Proof.a / Proof.c after `.into()`, prover.rs:94-98)."""
-        z = list(inputs) + list(aux)
-        assert len(z) <= self.n_var and len(q) <= self.n_h and len(aux) <= self.n_l
-        zpad = z + [0] * (self.n_var - len(z))
-        sa = [r, 1] + zpad
-        sc = [r * s, s, r] + [s * v for v in zpad] + [r * v for v in zpad] + list(q) + [0] * (self.n_h - len(q)) + list(aux) + [0] * (self.n_l - len(aux))
-        A = msm_curve_addition(self.crs_a, _scalars(sa), scalar_fmt=SCALARS_CANONICAL)
-        C = msm_curve_addition(self.crs_c, _scalars(sc), scalar_fmt=SCALARS_CANONICAL)
-        return to_affine(BN254_G1, A), to_affine(BN254_G1, C)
+        """Same as prove_g1 for scalars given as Python integers."""
+        return self.prove_g1(_canonical(list(q)), _canonical(list(inputs)), _canonical(list(aux)), r, s, scalar_fmt=SCALARS_CANONICAL)
 
     def free(self):
-        self.crs_a.free()
-        self.crs_c.free()
+        for b in (self.a, self.b_g1, self.h, self.l):
+            b.free()

@@ -160,6 +160,95 @@ def example_circuit(x, o):
     return cs
 
 
+def chain_circuit(steps, x0):
+    """The example's function iterated (the map nova/src/test.rs:16-29 iterates): x_{i+1} = x_i^3 + x_i + 5,
+    three constraints per step, public input x0 and public output x_steps (enforced like simple.rs:47)."""
+    out = x0 % R
+    for _ in range(steps):
+        out = (out * out * out + out + 5) % R
+    cs = R1cs()
+    xv, ov = cs.instance(x0), cs.instance(out)
+    c5 = cs.constant(5)
+    cur = xv
+    for _ in range(steps):
+        sym1 = cs.mul(cur, cur)
+        y = cs.mul(sym1, cur)
+        sym2 = cs.add(y, cur)
+        cur = cs.row_add(sym2, c5)
+    cs.enforce_eq(cur, ov)
+    return cs, out
+
+
+def lagrange_at(n, omega, tau):
+    """L_j(tau) for the size-n domain in closed form, = idft of the powers of tau (zksnark.rs:60): omega^j (tau^n - 1) / (n (tau - omega^j))."""
+    zt = (pow(tau, n, R) - 1) % R
+    ninv = pow(n, -1, R)
+    w, ws, dens = 1, [], []
+    for _ in range(n):
+        ws.append(w)
+        dens.append((tau - w) % R)
+        w = w * omega % R
+    pref, acc = [], 1
+    for d in dens:  # batch inversion
+        pref.append(acc)
+        acc = acc * d % R
+    inv = pow(acc, -1, R)
+    out = [0] * n
+    for j in range(n - 1, -1, -1):
+        out[j] = ws[j] * zt % R * ninv % R * (inv * pref[j] % R) % R
+        inv = inv * dens[j] % R
+    return out
+
+
+def crs_exponents(cs, rng):
+    """Discrete logs of every G1 CRS element of zksnark.rs:17-127 for constraint system `cs` (so that the points can be produced by
+    any fixed-base multiplication), plus the toxic waste and the per-variable (u, v, w)(tau)."""
+    k = max(1, (1 << (cs.m - 1).bit_length()).bit_length() - 1)
+    n = 1 << k
+    omega = pow(ROOT_OF_UNITY, 1 << (S - k), R)
+    alpha, beta, gamma, delta, tau = (rng.random_field(R) for _ in range(5))
+    gamma_inv, delta_inv = pow(gamma, -1, R), pow(delta, -1, R)
+    coeff = (pow(tau, n, R) - 1) * delta_inv % R
+    h, p = [], 1
+    for _ in range(cs.m - 1):
+        h.append(p * coeff % R)
+        p = p * tau % R
+    lagr = lagrange_at(n, omega, tau)
+    (ax, aw), (bx, bw), (cx, cw) = cs.columns(cs.a), cs.columns(cs.b), cs.columns(cs.c)
+    ev = lambda col: sum(lagr[idx] * co for co, idx in col) % R
+    a, b, ic, l, uvw = [], [], [], [], []
+    for cols, ext, inv in (((ax, bx, cx), ic, gamma_inv), ((aw, bw, cw), l, delta_inv)):
+        for ca, cb, cc in zip(*cols):
+            at, bt, ct = ev(ca), ev(cb), ev(cc)
+            uvw.append((at, bt, ct))
+            a.append(at)
+            b.append(bt)
+            ext.append((at * beta + bt * alpha + ct) * inv % R)
+    trap = dict(alpha=alpha, beta=beta, gamma=gamma, delta=delta, tau=tau)
+    return dict(k=k, n=n, h=h, a=a, b_g1=b, ic=ic, l=l), trap, uvw
+
+
+def expected_exponents(trap, uvw, inputs, aux, q, n, r, s):
+    """Discrete logs of proof.a, proof.b and proof.c (prover.rs:75-92) and the Groth16 equation in the exponent."""
+    al, be, ga, de, tau = (trap[k] for k in ("alpha", "beta", "gamma", "delta", "tau"))
+    z = list(inputs) + list(aux)
+    l = len(inputs)
+    u = sum(zi * t[0] for zi, t in zip(z, uvw)) % R
+    v = sum(zi * t[1] for zi, t in zip(z, uvw)) % R
+    ht, p = 0, 1
+    for qi in q:
+        ht = (ht + qi * p) % R
+        p = p * tau % R
+    ht = ht * (pow(tau, n, R) - 1) % R
+    a_exp = (al + r * de + u) % R
+    b_exp = (be + s * de + v) % R
+    aux_part = sum(zi * (be * t[0] + al * t[1] + t[2]) for zi, t in zip(z[l:], uvw[l:])) % R
+    in_part = sum(zi * (be * t[0] + al * t[1] + t[2]) for zi, t in zip(z[:l], uvw[:l])) % R
+    c_exp = ((aux_part + ht) * pow(de, -1, R) + s * a_exp + r * b_exp - r * s * de) % R
+    pairing_ok = (a_exp * b_exp - (al * be + in_part + c_exp * de)) % R == 0
+    return a_exp, b_exp, c_exp, pairing_ok
+
+
 # ---- radix-2 domain (fft.rs) -----------------------------------------------------------------------
 class Fft:
     def __init__(self, k):

@@ -51,6 +51,8 @@ def lib():
         L.zko_random_field.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, u64p]
         L.zko_random_points.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
         L.zko_xorshift_u64.argtypes = [u8p, ctypes.c_size_t, u64p]
+        L.zko_fft.argtypes = [ctypes.c_size_t, ctypes.c_int, u64p, ctypes.c_size_t, u64p, ctypes.POINTER(ctypes.c_size_t)]
+        L.zko_groth16_h.argtypes = [ctypes.c_size_t, u64p, u64p, u64p, ctypes.c_size_t, u64p, ctypes.POINTER(ctypes.c_size_t)]
         L.zko_window_bits.argtypes = [ctypes.c_size_t]
         L.zko_window_bits.restype = ctypes.c_size_t
         L.zko_get_at.argtypes = [ctypes.c_size_t, ctypes.c_size_t, u8p]
@@ -158,6 +160,27 @@ def xorshift_u64(n, seed=DEFAULT_SEED):
     s = _seed(seed)
     assert lib().zko_xorshift_u64(_u8(s), n, _u64(out)) == 0
     return out
+
+
+FFT_OPS = dict(dft=0, idft=1, coset_dft=2, coset_idft=3)
+
+
+def fft(k, op, values):
+    """groth16/src/fft.rs on Fr: returns (2^k, 4) uint64 and the stripped length (idft variants drop trailing zeros)."""
+    v = _c(values).reshape(-1, 4)
+    out = np.zeros((1 << k, 4), dtype=np.uint64)
+    n_out = ctypes.c_size_t()
+    assert lib().zko_fft(k, FFT_OPS[op], _u64(v), v.shape[0], _u64(out), ctypes.byref(n_out)) == 0
+    return out, int(n_out.value)
+
+
+def groth16_h(k, a, b, c):
+    """prover.rs:36-47: H coefficients from the R1CS evaluation vectors."""
+    a, b, c = (_c(x).reshape(-1, 4) for x in (a, b, c))
+    out = np.zeros((1 << k, 4), dtype=np.uint64)
+    n_out = ctypes.c_size_t()
+    assert lib().zko_groth16_h(k, _u64(a), _u64(b), _u64(c), a.shape[0], _u64(out), ctypes.byref(n_out)) == 0
+    return out, int(n_out.value)
 
 
 def window_bits(n):

@@ -258,6 +258,31 @@ int zko_xorshift_u64(const uint8_t seed[16], size_t n, uint64_t *out) {
     return 0;
 }
 
+// groth16/src/fft.rs on bn254 Fr.  op: 0 dft, 1 idft, 2 coset_dft, 3 coset_idft.  in: n_in x 4 u64 (Montgomery), out: 2^k x 4 u64,
+// *n_out = number of meaningful elements (idft variants strip trailing zeros like Coefficients::new).
+int zko_fft(size_t k, int op, const uint64_t *in, size_t n_in, uint64_t *out, size_t *n_out) {
+    FrFft f(k);
+    std::vector<Limbs> v = load_scalars(in, n_in), r;
+    switch (op) {
+        case 0: r = f.dft(v); break;
+        case 1: r = f.idft(v); break;
+        case 2: r = f.coset_dft(v); break;
+        case 3: r = f.coset_idft(v); break;
+        default: return -1;
+    }
+    *n_out = r.size();
+    for (size_t i = 0; i < f.n; i++) st4(out + 4 * i, i < r.size() ? r[i] : Limbs{0, 0, 0, 0});
+    return 0;
+}
+// prover.rs:36-47: coefficients of H from the R1CS evaluations (each m x 4 u64); out 2^k x 4 u64, *n_out after stripping
+int zko_groth16_h(size_t k, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, uint64_t *out, size_t *n_out) {
+    FrFft f(k);
+    std::vector<Limbs> r = f.h_coefficients(load_scalars(a, m), load_scalars(b, m), load_scalars(c, m));
+    *n_out = r.size();
+    for (size_t i = 0; i < f.n; i++) st4(out + 4 * i, i < r.size() ? r[i] : Limbs{0, 0, 0, 0});
+    return 0;
+}
+
 size_t zko_window_bits(size_t n_bases) { return window_bits(n_bases); }
 size_t zko_get_at(size_t segment, size_t c, const uint8_t bytes[32]) { return get_at(segment, c, bytes); }
 

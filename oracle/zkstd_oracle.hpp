@@ -437,4 +437,119 @@ struct XorShift128 {
     }
 };
 
+
+// ----- groth16/src/fft.rs (Fr only) --------------------------------------------------------------
+// Radix-2 domain of size n = 2^k over bn254 Fr (S = 28, fr.rs:53-66; multiplicative generator 7, fr.rs:18).
+struct FrFft {
+    typedef Field<FrParams> F;
+    size_t n, k;
+    std::vector<Limbs> twiddles, inv_twiddles, cosets, inv_cosets;
+    Limbs n_inv;
+    std::vector<std::pair<size_t, size_t>> bit_reverse;
+
+    static Limbs root_of_unity() {  // fr.rs:60-65 (to_mont_form of these limbs)
+        return F::to_mont_form(Limbs{0xd34f1ed960c37c9cULL, 0x3215cf6dd39329c8ULL, 0x98865ea93dd31f74ULL, 0x03ddb9f5166d18b7ULL});
+    }
+    static Limbs mul_gen() { return F::to_mont_form(Limbs{7, 0, 0, 0}); }
+
+    // fft.rs:27-90
+    explicit FrFft(size_t k_) : n((size_t)1 << k_), k(k_) {
+        size_t half_n = n >> 1;
+        Limbs g = root_of_unity();
+        for (size_t i = 0; i < 28 - k; i++) g = F::square(g);
+        Limbs g_inv, mg_inv, ninv;
+        F::invert(g, g_inv);
+        auto powers = [](const Limbs &base, size_t count) {
+            std::vector<Limbs> v(count);
+            Limbs w = F::one();
+            for (size_t i = 0; i < count; i++) {
+                v[i] = w;
+                w = F::mul(w, base);
+            }
+            return v;
+        };
+        twiddles = powers(g, half_n);
+        inv_twiddles = powers(g_inv, half_n);
+        cosets = powers(mul_gen(), n);
+        F::invert(mul_gen(), mg_inv);
+        inv_cosets = powers(mg_inv, n);
+        F::invert(F::to_mont_form(Limbs{(uint64_t)n, 0, 0, 0}), ninv);
+        n_inv = ninv;
+        for (uint64_t i = 0; i < n; i++) {
+            uint64_t r = 0;
+            for (size_t b = 0; b < k; b++) r |= ((i >> b) & 1) << (k - 1 - b);  // i.reverse_bits() >> (64 - k)
+            if (i < r) bit_reverse.emplace_back((size_t)i, (size_t)r);
+        }
+    }
+    // fft.rs:195-218
+    static void butterfly(Limbs *left, Limbs *right, size_t half, size_t chunk, const std::vector<Limbs> &tw) {
+        Limbs t = right[0];
+        right[0] = left[0];
+        left[0] = F::add(left[0], t);
+        right[0] = F::sub(right[0], t);
+        for (size_t i = 1; i < half; i++) {
+            Limbs t2 = F::mul(right[i], tw[i * chunk]);
+            right[i] = left[i];
+            left[i] = F::add(left[i], t2);
+            right[i] = F::sub(right[i], t2);
+        }
+    }
+    // fft.rs:166-192
+    static void classic(Limbs *c, size_t m, size_t chunk, const std::vector<Limbs> &tw) {
+        if (m == 2) {
+            Limbs t = c[1];
+            c[1] = c[0];
+            c[0] = F::add(c[0], t);
+            c[1] = F::sub(c[1], t);
+        } else {
+            classic(c, m / 2, chunk * 2, tw);
+            classic(c + m / 2, m / 2, chunk * 2, tw);
+            butterfly(c, c + m / 2, m / 2, chunk, tw);
+        }
+    }
+    void prepare(std::vector<Limbs> &v) const {  // fft.rs:157-162
+        v.resize(n, F::zero());
+        for (auto &p : bit_reverse) std::swap(v[p.second], v[p.first]);
+    }
+    // fft.rs:92-127; `strip` = Coefficients::new (poly.rs:61-63)
+    static void strip(std::vector<Limbs> &v) {
+        while (!v.empty() && F::is_zero(v.back())) v.pop_back();
+    }
+    std::vector<Limbs> dft(std::vector<Limbs> v) const {
+        prepare(v);
+        classic(v.data(), n, 1, twiddles);
+        return v;
+    }
+    std::vector<Limbs> idft(std::vector<Limbs> v) const {
+        prepare(v);
+        classic(v.data(), n, 1, inv_twiddles);
+        for (auto &x : v) x = F::mul(x, n_inv);
+        strip(v);
+        return v;
+    }
+    std::vector<Limbs> coset_dft(std::vector<Limbs> v) const {
+        for (size_t i = 0; i < v.size() && i < n; i++) v[i] = F::mul(v[i], cosets[i]);
+        return dft(v);
+    }
+    std::vector<Limbs> coset_idft(std::vector<Limbs> v) const {
+        v = idft(v);
+        for (size_t i = 0; i < v.size(); i++) v[i] = F::mul(v[i], inv_cosets[i]);
+        strip(v);
+        return v;
+    }
+    Limbs z_on_coset() const {  // fft.rs:139-144
+        Limbs e{(uint64_t)n, 0, 0, 0};
+        return F::sub(F::pow(mul_gen(), e, F::one()), F::one());
+    }
+    // prover.rs:36-47: q = coset_idft( (coset_dft(idft(a)) * coset_dft(idft(b)) - coset_dft(idft(c))) / Z )
+    std::vector<Limbs> h_coefficients(const std::vector<Limbs> &a, const std::vector<Limbs> &b, const std::vector<Limbs> &c) const {
+        std::vector<Limbs> ea = coset_dft(idft(a)), eb = coset_dft(idft(b)), ec = coset_dft(idft(c));
+        Limbs zi;
+        F::invert(z_on_coset(), zi);
+        std::vector<Limbs> h(n);
+        for (size_t i = 0; i < n; i++) h[i] = F::mul(F::sub(F::mul(ea[i], eb[i]), ec[i]), zi);
+        return coset_idft(h);
+    }
+};
+
 }  // namespace zko

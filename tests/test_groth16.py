@@ -47,6 +47,26 @@ def test_reference_prover_restatement_verifies(fixture):
     assert not G.exponent_check(trap, uvw, bad_int, bad)[1]
 
 
+def test_closed_form_lagrange_and_chain_circuit():
+    f = G.Fft(3)
+    tau = 123456789123456789
+    by_idft = f.idft([pow(tau, i, G.R) for i in range(8)])
+    assert G.lagrange_at(8, f.omega, tau) == by_idft + [0] * (8 - len(by_idft))
+    cs, out = G.chain_circuit(5, 3)
+    assert (cs.m, cs.l, cs.m_l_1) == (16, 3, 15)
+    a, b, c = cs.evaluate()
+    assert all((ai * bi - ci) % G.R == 0 for ai, bi, ci in zip(a, b, c))
+    # one step of the chain is the reference's example circuit
+    cs1, out1 = G.chain_circuit(1, 3)
+    ex = G.example_circuit(3, 35)
+    assert out1 == 35 and (cs1.a, cs1.b, cs1.c, cs1.x, cs1.w) == (ex.a, ex.b, ex.c, ex.x, ex.w)
+    # exponent bookkeeping agrees with the point-based setup on the example
+    E, trap, uvw = G.crs_exponents(ex, B.XorShift128(SETUP_SEED))
+    P, trap2, uvw2 = G.setup(B.XorShift128(SETUP_SEED))
+    assert trap == trap2 and uvw == uvw2
+    assert [G.G1.mul(G.G1.g, e) if e else None for e in E["a"]] == P["a"] and [G.G1.mul(G.G1.g, e) for e in E["h"]] == P["h"]
+
+
 def _pts(points):
     xy = np.zeros((len(points), 8), dtype=np.uint64)
     inf = np.zeros(len(points), dtype=np.uint8)
@@ -89,4 +109,46 @@ def test_proof_bytes_identical_with_g1_msms_on_gpu(fixture):
         got = k.to_affine(k.BN254_G1, k.msm_curve_addition(xy, sc(coeffs), curve=k.BN254_G1, inf=inf))
         exp = G.G1.msm(pts, coeffs)
         assert enc(got) == G.encode_g1(exp)
+    prover.free()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("steps,precompute", [(341, False), (1365, True)])
+def test_scaled_prover_g1_side_on_gpu(steps, precompute):
+    """The example's function chained to 2^10 / 2^12 constraints.  CRS points come from the device fixed-base
+    multiplication of the exponents, H from the device NTT, A and C from the device MSMs; both are checked against their
+    discrete logs computed from the toxic waste (and the Groth16 equation in the exponent), i.e. against an oracle that
+    shares no code with the GPU path."""
+    import kogarashi_b200 as k
+    from kogarashi_b200 import msm as M
+    from kogarashi_b200.groth16 import Groth16G1Prover
+    from oracle import oracle as A_
+    k.init()
+    cs, out = G.chain_circuit(steps, 3)
+    E, trap, uvw = G.crs_exponents(cs, B.XorShift128(SETUP_SEED))
+    mont = lambda vals: np.array([B.int_to_limbs(B.to_mont(v, B.FR)) for v in vals], dtype=np.uint64).reshape(-1, 4)
+
+    def points(exps):
+        xy = M.fixed_base_mul(k.BN254_G1, mont(exps))           # e * G on the device; exponent 0 -> identity -> (0, 0)
+        inf = np.array([1 if e == 0 else 0 for e in exps], dtype=np.uint8)
+        return xy, inf
+
+    vk = points([trap["delta"], trap["alpha"], trap["beta"]])[0]
+    prover = Groth16G1Prover(vk[0], vk[1], vk[2], *points(E["a"]), *points(E["b_g1"]), *points(E["h"]), *points(E["l"]), precompute=precompute)
+    a_ev, b_ev, c_ev = (mont(v) for v in cs.evaluate())
+    rng = B.XorShift128(PROVE_SEED)
+    r, s = rng.random_field(B.FR), rng.random_field(B.FR)
+    A, C, q = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, mont(cs.x), mont(cs.w), r, s)
+    # H coefficients: device NTT pipeline == restated reference FFT pipeline
+    q_ref, n_ref = A_.groth16_h(E["k"], a_ev, b_ev, c_ev)
+    assert q.shape[0] == n_ref and (q == q_ref[:n_ref]).all()
+    q_int = [B.from_mont(B.limbs_to_int(x), B.FR) for x in q]
+    a_exp, b_exp, c_exp, pairing_ok = G.expected_exponents(trap, uvw, cs.x, cs.w, q_int, E["n"], r, s)
+    assert pairing_ok
+
+    def enc(aff):
+        return np.asarray(aff[:8], dtype="<u8").tobytes() + bytes([int(aff[8])])
+
+    assert enc(A) == G.encode_g1(G.G1.mul(G.G1.g, a_exp))
+    assert enc(C) == G.encode_g1(G.G1.mul(G.G1.g, c_exp))
     prover.free()

@@ -1,0 +1,122 @@
+"""Measurement harness for the "next" rows N2 (Fr NTT) and N1 (G1 side of the Groth16 prover) — not the headline bench.
+Uses the oracle exactly like bench.py does: as the checker and as the CPU baseline timed on the host cores.
+Writes gpurun_out/next_rows_<tag>.json."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import kogarashi_b200 as k  # noqa: E402
+from kogarashi_b200 import msm as M  # noqa: E402
+from kogarashi_b200.groth16 import Groth16G1Prover  # noqa: E402
+from oracle import groth16_ref as G  # noqa: E402
+from oracle import oracle as A  # noqa: E402
+from oracle import pyref as B  # noqa: E402
+
+IMAD_PEAK = 148 * 64 * 1.965e9
+
+
+def bench_ntt(logn, out):
+    import torch
+    n = 1 << logn
+    x = A.random_field(A.FIELD_FR, n, seed=bytes(range(16)))
+    f = k.Fft(logn)
+    d = torch.from_numpy(x.view(np.int64)).cuda()
+    torch.cuda.synchronize()
+    f.transform_device("dft", d.data_ptr())
+    best = min(_timed(lambda: f.transform_device("dft", d.data_ptr())) for _ in range(10))
+    # parity at this size: device dft == restated reference dft
+    t0 = time.perf_counter()
+    exp, _ = A.fft(logn, "dft", x)
+    cpu_s = time.perf_counter() - t0
+    got = f.dft(x)
+    e2e = min(_wall(lambda: f.dft(x)) for _ in range(3))
+    butterflies = n // 2 * logn
+    rec = {"row": "N2 Fr NTT (groth16/src/fft.rs dft)", "log_n": logn, "device_ms": best, "melem_per_s": n / best / 1e3,
+           "bit_exact_with_oracle": bool((got == exp).all()),
+           "e2e_host_buffers_ms": e2e * 1e3, "cpu_baseline": {"seconds": cpu_s, "cores": 1, "kind": "port", "melem_per_s": n / cpu_s / 1e6},
+           "roofline": {"bound": "imad", "algorithmic_imads": butterflies * 264, "achieved_T_per_s": butterflies * 264 / (best * 1e-3) / 1e12,
+                        "peak_T_per_s": IMAD_PEAK / 1e12, "frac": butterflies * 264 / (best * 1e-3) / IMAD_PEAK,
+                        "hbm_gbs_algorithmic": 64 * n / (best * 1e-3) / 1e9,
+                        "note": "one 254-bit Montgomery product (264 IMAD) per butterfly, n/2*log2(n) butterflies; 64 B/element algorithmic traffic: multiplier-bound, not HBM-bound"}}
+    out.append(rec)
+    print(json.dumps(rec), flush=True)
+
+
+def _timed(fn):
+    fn()
+    return k.last_timing(0)[0]["total"]
+
+
+def _wall(fn):
+    t0 = time.perf_counter()
+    fn()
+    return time.perf_counter() - t0
+
+
+def bench_groth16(logm, out):
+    steps = ((1 << logm) - 1) // 3
+    t0 = time.perf_counter()
+    cs, _ = G.chain_circuit(steps, 3)
+    E, trap, uvw = G.crs_exponents(cs, B.XorShift128(A.DEFAULT_SEED))
+    setup_s = time.perf_counter() - t0
+    mont = lambda vals: np.array([B.int_to_limbs(B.to_mont(v, B.FR)) for v in vals], dtype=np.uint64).reshape(-1, 4)
+
+    def points(exps):
+        return M.fixed_base_mul(k.BN254_G1, mont(exps)), np.array([1 if e == 0 else 0 for e in exps], dtype=np.uint8)
+
+    vk = points([trap["delta"], trap["alpha"], trap["beta"]])[0]
+    crs = [points(E[name]) for name in ("a", "b_g1", "h", "l")]
+    a_ev, b_ev, c_ev = (mont(v) for v in cs.evaluate())
+    xs, ws = mont(cs.x), mont(cs.w)
+    rng = B.XorShift128(bytes(range(1, 17)))
+    r, s = rng.random_field(B.FR), rng.random_field(B.FR)
+    res = {}
+    for pre in (False, True):
+        prover = Groth16G1Prover(vk[0], vk[1], vk[2], *crs[0], *crs[1], *crs[2], *crs[3], precompute=pre)
+        prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)
+        wall = min(_wall(lambda: prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)) for _ in range(3))
+        Ap, Cp, q = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)
+        res["precomputed" if pre else "normal"] = wall * 1e3
+        prover.free()
+    q_int = [B.from_mont(B.limbs_to_int(x), B.FR) for x in q]
+    a_exp, b_exp, c_exp, pairing_ok = G.expected_exponents(trap, uvw, cs.x, cs.w, q_int, E["n"], r, s)
+    enc = lambda aff: np.asarray(aff[:8], dtype="<u8").tobytes() + bytes([int(aff[8])])
+    ok = pairing_ok and enc(Ap) == G.encode_g1(G.G1.mul(G.G1.g, a_exp)) and enc(Cp) == G.encode_g1(G.G1.mul(G.G1.g, c_exp))
+    # CPU baseline: the same G1-side work with the restated reference code (7 FFTs + the six G1 MSMs of prover.rs:51-62)
+    cores = os.cpu_count() or 1
+    l = cs.l
+    t0 = time.perf_counter()
+    q_ref, n_ref = A.groth16_h(E["k"], a_ev, b_ev, c_ev)
+    fft_s = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    for pts_inf, sc in ((crs[2], q_ref[:n_ref]), (crs[3], ws), (crs[0], xs), ((crs[0][0][l:], crs[0][1][l:]), ws), (crs[1], xs), ((crs[1][0][l:], crs[1][1][l:]), ws)):
+        A.msm(A.BN254_G1, pts_inf[0], sc, inf=pts_inf[1], threads=cores)
+    msm_s = time.perf_counter() - t0
+    rec = {"row": "N1 Groth16 create_proof, G1 side (7 FFTs + G1 MSMs + assembly of A and C; G2 and witness generation excluded)",
+           "constraints": cs.m, "log_n": E["k"], "gpu_wall_ms": res, "checked_against_discrete_logs": bool(ok),
+           "h_bit_exact_with_oracle": bool(q.shape[0] == n_ref and (q == q_ref[:n_ref]).all()),
+           "cpu_baseline": {"fft_seconds": fft_s, "msm_seconds": msm_s, "total_seconds": fft_s + msm_s, "cores": cores, "kind": "port",
+                            "note": "restated reference FFT (single thread) + six reference-algorithm MSMs on all cores"},
+           "speedup_vs_cpu_baseline": {m: (fft_s + msm_s) * 1e3 / v for m, v in res.items()}, "setup_python_s": setup_s}
+    out.append(rec)
+    print(json.dumps(rec), flush=True)
+
+
+def main():
+    tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+    os.makedirs("gpurun_out", exist_ok=True)
+    k.init([0])
+    out = []
+    for logn in (16, 20, 22):
+        bench_ntt(logn, out)
+    for logm in (12, 16):
+        bench_groth16(logm, out)
+    json.dump(out, open(f"gpurun_out/next_rows_{tag}.json", "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
