@@ -9,8 +9,13 @@
 namespace kgr {
 
 
-template <class C> __global__ void __launch_bounds__(TPB_SCALAR) k_count(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
-    body_count<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts);
+template <class C>
+__global__ void __launch_bounds__(TPB_SCALAR) k_count(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts, uint32_t *digits) {
+    body_count<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts, digits);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_SCALAR) k_fill_window(MsmShape sh, const uint32_t *digits, uint32_t *counts, const uint32_t *offsets, uint32_t *entries) {
+    body_fill_window<C>(blockIdx.x * blockDim.x + threadIdx.x, blockIdx.y, sh, digits, counts, offsets, entries);
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_SCALAR) k_fill(MsmShape sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets,

@@ -20,7 +20,8 @@ template <class C> struct Launch {
     typedef AffinePt<C> A;
     typedef Fp<typename C::Scalar> S;
     static int accumulate_blocks_per_sm();
-    static void count(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts);
+    static void count(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, uint32_t *digits);
+    static void fill_window(cudaStream_t st, const MsmShape &sh, const uint32_t *digits, uint32_t *counts, const uint32_t *offsets, uint32_t *entries);
     static void fill(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets, uint32_t *entries);
     static void accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks, const A *bases, const uint32_t *offsets, const uint32_t *entries, X *bucket_acc,
                            X *head, X *tail, uint32_t *tail_bucket);

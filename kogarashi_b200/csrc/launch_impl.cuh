@@ -12,8 +12,12 @@ template <class C> int Launch<C>::accumulate_blocks_per_sm() {
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accumulate<C>, TPB_ACC, 0);
     return nb;
 }
-template <class C> void Launch<C>::count(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
-    k_count<C><<<cdiv(sh.n, TPB_SCALAR), TPB_SCALAR, 0, st>>>(sh, scalars, is_mont, counts);
+template <class C> void Launch<C>::count(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, uint32_t *digits) {
+    k_count<C><<<cdiv(sh.n, TPB_SCALAR), TPB_SCALAR, 0, st>>>(sh, scalars, is_mont, counts, digits);
+}
+template <class C>
+void Launch<C>::fill_window(cudaStream_t st, const MsmShape &sh, const uint32_t *digits, uint32_t *counts, const uint32_t *offsets, uint32_t *entries) {
+    k_fill_window<C><<<dim3(cdiv(sh.n, TPB_SCALAR), sh.W), TPB_SCALAR, 0, st>>>(sh, digits, counts, offsets, entries);
 }
 template <class C>
 void Launch<C>::fill(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets, uint32_t *entries) {

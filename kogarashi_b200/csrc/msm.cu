@@ -45,7 +45,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1;
 };
 static Params g_params;
 
@@ -89,7 +89,7 @@ struct Engine {
     cudaEvent_t ev_sc = nullptr;      // scalars of the current call are on the device (orders the two uploads)
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
-    DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket;
+    DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
     DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
@@ -126,7 +126,7 @@ struct Engine {
         if (dev < 0) return;
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
-        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release();
+        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
         bucket_acc.release(); head.release(); tail.release(); result.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
@@ -260,12 +260,17 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
 
     CK(cudaEventRecord(e.ev[EV_H2D], e.st));
     typedef Launch<C> K;
-    K::count(e.st, sh, d_scalars, is_mont, e.counts.p);
+    // sort_mode 1: window-major fill from stored digits (scatter region per window stays in L2); 0: one thread per scalar
+    // recodes again and scatters into all windows; -1 (auto): window-major once the entry array outgrows the L2
+    const bool window_major = g_params.sort_mode == 1 || (g_params.sort_mode < 0 && (uint64_t)Mmax * 4 > (96ull << 20));
+    if (window_major) e.digits.ensure((size_t)Mmax + 1);
+    K::count(e.st, sh, d_scalars, is_mont, e.counts.p, window_major ? e.digits.p : nullptr);
     CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
     LaunchUtil::exclusive_scan(e.st, e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p);
     e.launches += LaunchUtil::scan_launches((uint32_t)G1);
     CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
-    K::fill(e.st, sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
+    if (window_major) K::fill_window(e.st, sh, e.digits.p, e.counts.p, e.offsets.p, e.entries.p);
+    else K::fill(e.st, sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
     CK(cudaEventRecord(e.ev[EV_FILL], e.st));
     if (e.wait_pts) {
         CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
@@ -789,6 +794,7 @@ int kgr_set_param(const char *name, long value) {
         g_params.reduce_fanin = value;
     } else if (s == "final_on_device") g_params.final_on_device = value;
     else if (s == "running_sum_stop") g_params.running_sum_stop = std::max<long>(1, value);
+    else if (s == "sort_mode") g_params.sort_mode = value;
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
 }

@@ -130,12 +130,35 @@ KGR_HD uint32_t warp_aggregated_take(uint32_t *counters, uint32_t key, bool sub)
 
 // ---- count / fill ---------------------------------------------------------------------------
 // i may be >= n (whole warps run so that the warp-aggregated top window sees all 32 lanes).
-template <class C> KGR_HD void body_count(uint32_t i, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts) {
+// digits != nullptr: also store every window's digit word (bucket | sign << 31, NO_DIGIT for zero) window-major at
+// digits[w * n + i], so that the fill pass can run window by window without recoding (body_fill_window).
+template <class C>
+KGR_HD void body_count(uint32_t i, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, uint32_t *digits) {
     uint32_t top = NO_DIGIT;
     if (i < sh.n) {
         uint32_t s[8];
         load_scalar<C>(scalars, i, is_mont, s);
-        top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t) { atomic_add_u32(&counts[w * sh.gstride + b], 1u); });
+        if (digits) {
+            uint32_t carry = 0;
+            for (uint32_t w = 0; w < sh.W; w++) {
+                uint32_t d = window_raw(s, w * sh.c, sh.c) + carry;
+                carry = 0;
+                uint32_t sign = 0;
+                if (d > sh.B) {
+                    d = (1u << sh.c) - d;
+                    sign = 1;
+                    carry = 1;
+                }
+                uint32_t word = d ? ((d - 1) | (sign << 31)) : NO_DIGIT;
+                digits[(size_t)w * sh.n + i] = word;
+                if (d) {
+                    if (w + 1 == sh.W) top = word;
+                    else atomic_add_u32(&counts[w * sh.gstride + d - 1], 1u);
+                }
+            }
+        } else {
+            top = for_each_digit(s, sh, [&](uint32_t w, uint32_t b, uint32_t) { atomic_add_u32(&counts[w * sh.gstride + b], 1u); });
+        }
     }
     uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.gstride + (top & 0x7fffffffu);
     (void)warp_aggregated_take(counts, key, false);
@@ -189,6 +212,23 @@ KGR_HD void body_fill(uint32_t i, const MsmShape &sh, const uint32_t *scalars, i
     uint32_t key = top == NO_DIGIT ? NO_DIGIT : (sh.W - 1) * sh.gstride + (top & 0x7fffffffu);
     uint32_t k = warp_aggregated_take(counts, key, true);
     if (key != NO_DIGIT) entries[offsets[key] + k] = ((sh.W - 1) * sh.pstride + sh.poff + i) | (top & 0x80000000u);
+}
+
+// Window-major fill: thread (i, w) places the entry of scalar i for window w.  All CTAs that run at the same
+// time work on the same one or two windows, so the scattered 4-byte stores land in a region of n * 4 bytes
+// (L2 resident up to n ~ 2^24) and are merged there instead of costing a DRAM sector each.
+template <class C>
+KGR_HD void body_fill_window(uint32_t i, uint32_t w, const MsmShape &sh, const uint32_t *digits, uint32_t *counts, const uint32_t *offsets,
+                             uint32_t *entries) {
+    uint32_t d = (i < sh.n) ? digits[(size_t)w * sh.n + i] : NO_DIGIT;
+    uint32_t key = d == NO_DIGIT ? NO_DIGIT : w * sh.gstride + (d & 0x7fffffffu);
+    uint32_t pay = (w * sh.pstride + sh.poff + i) | (d & 0x80000000u);
+    if (w + 1 == sh.W) {  // structurally hot window: warp-aggregated (all 32 lanes call it)
+        uint32_t k = warp_aggregated_take(counts, key, true);
+        if (key != NO_DIGIT) entries[offsets[key] + k] = pay;
+    } else if (key != NO_DIGIT) {
+        entries[offsets[key] + atomic_sub_u32(&counts[key], 1u) - 1u] = pay;
+    }
 }
 
 // ---- accumulate -----------------------------------------------------------------------------

@@ -108,10 +108,11 @@ def test_msm_golden_under_forced_shapes(k, golden, c, chunk):
         k.set_param("chunk", 0)
 
 
-@pytest.mark.parametrize("param,value", [("final_on_device", 1), ("running_sum_stop", 1), ("running_sum_stop", 1 << 20), ("reduce_fanin", 4)])
+@pytest.mark.parametrize("param,value", [("final_on_device", 1), ("running_sum_stop", 1), ("running_sum_stop", 1 << 20), ("reduce_fanin", 4), ("sort_mode", 0),
+                                         ("sort_mode", 1)])
 def test_msm_golden_under_reduce_variants(k, golden, param, value):
     """Device-side Horner, pure running-sum reduction, pure weighting-pass reduction, small fan-in: same element."""
-    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16}
+    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1}
     k.set_param(param, value)
     try:
         for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96", "gr_cancel_32", "gr_uniform_100"):
