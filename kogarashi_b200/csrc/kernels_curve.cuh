@@ -93,6 +93,76 @@ template <class C> __global__ void __launch_bounds__(TPB_TREE) k_tree_sum(const 
     v = block_tree_sum<C>(v, sm);
     if (threadIdx.x == 0) store_xyzz(&out[(size_t)w * gridDim.x + blockIdx.x], v);
 }
+// ---- fold reduce ----------------------------------------------------------------------------------------
+// Window sum S = sum_i (i + 1) * X_i over B = 2^nb buckets, written as S = T0 + sum_b 2^b * V_b with T0 = sum of all buckets
+// and V_b = sum of the buckets whose index has bit b set.  Folding the array in half (Y_i = X_i + X_{i+m}) keeps T0 and
+// every lower V_b and exposes V_{log2 m} as the plain sum of the upper half, so nb fully parallel fold levels (B adds in
+// total) plus plain sums of the upper halves (B adds) replace the serial running sums; every level is one add deep.
+// Level l (m = B >> l) reads Y^(l-1) (the buckets for l = 1) and writes Y^(l) at offset B - 2m of the window's row in F.
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *in, uint32_t in_off, XyzzPt<C> *out, uint32_t out_off, uint32_t B, uint32_t m,
+                                                  uint32_t n_windows, const uint32_t *bucket_offsets) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_windows * m) return;
+    uint32_t w = t / m, i = t % m;
+    size_t e = (size_t)w * B + in_off + i;
+    bool lo_ok = true, hi_ok = true;
+    if (bucket_offsets) {  // level 1: empty buckets were never written, they show as equal offsets
+        lo_ok = bucket_offsets[e] != bucket_offsets[e + 1];
+        hi_ok = bucket_offsets[e + m] != bucket_offsets[e + m + 1];
+    }
+    XyzzPt<C> a = lo_ok ? in[e] : xyzz_identity<C>();
+    if (hi_ok) {
+        XyzzPt<C> b = in[e + m];
+        xyzz_add(a, b);
+    }
+    store_xyzz(&out[(size_t)w * B + out_off + i], a);
+}
+// Partial sums of the upper halves: grid (chunk, level - 1, window); a CTA sums up to 8 * TPB_TREE elements of one upper half.
+template <class C>
+__global__ void __launch_bounds__(TPB_TREE) k_vsum1(const XyzzPt<C> *buckets, const XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t chunks_max,
+                                                    const uint32_t *bucket_offsets, XyzzPt<C> *partial) {
+    __shared__ uint32_t sm[32 * TPB_TREE];
+    const uint32_t chunk = blockIdx.x, l = blockIdx.y + 1, w = blockIdx.z;
+    const uint32_t m = B >> l;
+    if (chunk * 8u * TPB_TREE >= m) return;  // uniform per CTA
+    const XyzzPt<C> *src = (l == 1) ? buckets + (size_t)w * B + m : F + (size_t)w * B + (B - (B >> (l - 2))) + m;
+    const uint32_t *off = (l == 1 && bucket_offsets) ? bucket_offsets + (size_t)w * B + m : nullptr;
+    XyzzPt<C> acc = xyzz_identity<C>();
+#pragma unroll 1
+    for (uint32_t k = 0; k < 8; k++) {
+        uint32_t i = chunk * 8u * TPB_TREE + k * TPB_TREE + threadIdx.x;
+        if (i < m && (!off || off[i] != off[i + 1])) xyzz_add(acc, src[i]);
+    }
+    acc = block_tree_sum<C>(acc, sm);
+    if (threadIdx.x == 0) store_xyzz(&partial[((size_t)w * nb + (l - 1)) * chunks_max + chunk], acc);
+}
+// grid (level - 1, window): V[w][bit] = sum of that level's partials, bit = nb - level
+template <class C> __global__ void __launch_bounds__(TPB_TREE) k_vsum2(const XyzzPt<C> *partial, uint32_t B, uint32_t nb, uint32_t chunks_max, XyzzPt<C> *V) {
+    __shared__ uint32_t sm[32 * TPB_TREE];
+    const uint32_t l = blockIdx.x + 1, w = blockIdx.y;
+    const uint32_t m = B >> l;
+    const uint32_t cnt = (m + 8u * TPB_TREE - 1) / (8u * TPB_TREE);
+    const XyzzPt<C> *src = partial + ((size_t)w * nb + (l - 1)) * chunks_max;
+    XyzzPt<C> acc = xyzz_identity<C>();
+    for (uint32_t i = threadIdx.x; i < cnt; i += TPB_TREE) xyzz_add(acc, src[i]);
+    acc = block_tree_sum<C>(acc, sm);
+    if (threadIdx.x == 0) store_xyzz(&V[(size_t)w * nb + (nb - l)], acc);
+}
+// grid (window): out[w] = T0 + sum_b 2^b V[w][b]; lane b doubles V_b b times, then a CTA tree sum.
+template <class C> __global__ void __launch_bounds__(TPB_TREE) k_fold_combine(const XyzzPt<C> *F, const XyzzPt<C> *V, uint32_t B, uint32_t nb, XyzzPt<C> *out) {
+    __shared__ uint32_t sm[32 * TPB_TREE];
+    const uint32_t w = blockIdx.x, t = threadIdx.x;
+    XyzzPt<C> acc = xyzz_identity<C>();
+    if (t < nb) {
+        acc = V[(size_t)w * nb + t];
+        for (uint32_t d = 0; d < t; d++) acc = xyzz_dbl(acc);
+    } else if (t == nb) {
+        acc = F[(size_t)w * B + (B - 2)];  // Y^(nb): the single element of the last fold level = T0
+    }
+    acc = block_tree_sum<C>(acc, sm);
+    if (t == 0) store_xyzz(&out[w], acc);
+}
 // Horner over windows on the device (kept for kgr_set_param("final_on_device", 1)); one thread.
 template <class C> __global__ void k_final(MsmShape sh, const XyzzPt<C> *win_a, XyzzPt<C> *out) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;

@@ -31,6 +31,10 @@ template <class C> struct Launch {
                        const uint32_t *bucket_offsets);
     static void weight(cudaStream_t st, uint32_t n_windows, uint32_t cnt, uint32_t m_log2, const X *in_s, const X *in_a, X *out);
     static void tree_sum(cudaStream_t st, uint32_t n_windows, const X *in, uint32_t cnt_in, X *out);
+    // fold reduce (B >= 256): returns the number of kernels launched; F: n_windows * B points, partial: n_windows * nb * chunks_max,
+    // V: n_windows * nb, out: n_windows
+    static int fold_reduce(cudaStream_t st, uint32_t n_windows, uint32_t B, const X *buckets, const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out);
+    static uint32_t fold_chunks_max(uint32_t B);
     static void final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out);
     static void fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n);
     static void precompute(cudaStream_t st, uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const A *pts, A *table);

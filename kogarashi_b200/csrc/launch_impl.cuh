@@ -47,6 +47,26 @@ template <class C> void Launch<C>::weight(cudaStream_t st, uint32_t n_windows, u
 template <class C> void Launch<C>::tree_sum(cudaStream_t st, uint32_t n_windows, const X *in, uint32_t cnt_in, X *out) {
     k_tree_sum<C><<<dim3(cdiv(cnt_in, TPB_TREE), n_windows), TPB_TREE, 0, st>>>(in, cnt_in, out);
 }
+template <class C> uint32_t Launch<C>::fold_chunks_max(uint32_t B) { return ((B >> 1) + 8u * TPB_TREE - 1) / (8u * TPB_TREE); }
+template <class C>
+int Launch<C>::fold_reduce(cudaStream_t st, uint32_t n_windows, uint32_t B, const X *buckets, const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out) {
+    uint32_t nb = 0;
+    while ((1u << nb) < B) nb++;
+    int launches = 0;
+    for (uint32_t l = 1; l <= nb; l++) {
+        uint32_t m = B >> l;
+        const X *in = (l == 1) ? buckets : F;
+        uint32_t in_off = (l == 1) ? 0 : B - (B >> (l - 2));
+        uint32_t out_off = B - (B >> (l - 1));
+        k_fold<C><<<cdiv((size_t)n_windows * m, TPB_RED), TPB_RED, 0, st>>>(in, in_off, F, out_off, B, m, n_windows, l == 1 ? bucket_offsets : nullptr);
+        launches++;
+    }
+    uint32_t chunks_max = fold_chunks_max(B);
+    k_vsum1<C><<<dim3(chunks_max, nb, n_windows), TPB_TREE, 0, st>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial);
+    k_vsum2<C><<<dim3(nb, n_windows), TPB_TREE, 0, st>>>(partial, B, nb, chunks_max, V);
+    k_fold_combine<C><<<n_windows, TPB_TREE, 0, st>>>(F, V, B, nb, out);
+    return launches + 3;
+}
 template <class C> void Launch<C>::final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out) { k_final<C><<<1, 32, 0, st>>>(sh, win_a, out); }
 template <class C> void Launch<C>::fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n) { k_fold_inf<C><<<cdiv(n, 256), 256, 0, st>>>(pts, inf, n); }
 template <class C> void Launch<C>::precompute(cudaStream_t st, uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const A *pts, A *table) {

@@ -45,7 +45,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1;
 };
 static Params g_params;
 
@@ -90,7 +90,7 @@ struct Engine {
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
-    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result;  // raw bytes, cast per curve
+    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
     uint32_t result_c = 0;                                                // window bits to apply between them (0: already combined)
@@ -127,7 +127,7 @@ struct Engine {
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
         counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
-        bucket_acc.release(); head.release(); tail.release(); result.release();
+        bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
         if (h_stage) cudaFreeHost(h_stage);
@@ -282,40 +282,52 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     K::fixup(e.st, sh, chunks, e.sm_count, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1,
              e.worklist.p);
     CK(cudaEventRecord(e.ev[EV_FIXUP], e.st));
-    // Reduce.  Running-sum levels (fan-in K) while many elements per window remain (throughput regime),
-    // then one fully parallel weighting pass and block-level tree sums (latency regime).
-    uint32_t cnt = sh.B, m_log2 = 0, klog = 0;
-    while ((1u << klog) < sh.K) klog++;
-    const X *in_s = (const X *)e.bucket_acc.p, *in_a = nullptr;
-    int pp = 0;
-    do {
-        uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
-        X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
-        K::reduce(e.st, nwin, cnt, sh.K, m_log2, in_s, in_a, os, oa, in_a ? nullptr : e.offsets.p);
-        e.launches++;
-        in_s = os;
-        in_a = oa;
-        cnt = cnt_out;
-        m_log2 += klog;
-        pp ^= 1;
-    } while (cnt > (uint32_t)g_params.running_sum_stop);
-    const X *win = in_a;  // [W] once cnt == 1
-    if (cnt > 1) {
-        X *v = (X *)e.lvl_s[pp].p;
-        K::weight(e.st, nwin, cnt, m_log2, in_s, in_a, v);
-        e.launches++;
-        const X *tin = v;
-        X *tout = (X *)e.lvl_a[pp].p;
-        while (cnt > 1) {
-            uint32_t blocks = (cnt + TPB_TREE - 1) / TPB_TREE;
-            K::tree_sum(e.st, nwin, tin, cnt, tout);
+    // Reduce.  reduce_mode 1 (default, B >= 256): fold reduce — parallel halving folds + plain sums of the upper halves
+    // (kernels_curve.cuh).  reduce_mode 0: running-sum levels (fan-in K) while many elements per window remain, then one
+    // parallel weighting pass and block-level tree sums.
+    const X *win = nullptr;
+    if (g_params.reduce_mode == 1 && sh.B >= 256) {
+        uint32_t nb = sh.c - 1, chunks_max = K::fold_chunks_max(sh.B);
+        e.fold_f.ensure((size_t)nwin * sh.B * sizeof(X));
+        e.fold_partial.ensure((size_t)nwin * nb * chunks_max * sizeof(X));
+        e.fold_v.ensure((size_t)nwin * nb * sizeof(X));
+        e.launches += K::fold_reduce(e.st, nwin, sh.B, (const X *)e.bucket_acc.p, e.offsets.p, (X *)e.fold_f.p, (X *)e.fold_partial.p, (X *)e.fold_v.p,
+                                     (X *)e.lvl_a[0].p);
+        win = (const X *)e.lvl_a[0].p;
+    } else {
+        uint32_t cnt = sh.B, m_log2 = 0, klog = 0;
+        while ((1u << klog) < sh.K) klog++;
+        const X *in_s = (const X *)e.bucket_acc.p, *in_a = nullptr;
+        int pp = 0;
+        do {
+            uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
+            X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
+            K::reduce(e.st, nwin, cnt, sh.K, m_log2, in_s, in_a, os, oa, in_a ? nullptr : e.offsets.p);
             e.launches++;
-            cnt = blocks;
-            X *nxt = (X *)tin;
-            tin = tout;
-            tout = nxt;
+            in_s = os;
+            in_a = oa;
+            cnt = cnt_out;
+            m_log2 += klog;
+            pp ^= 1;
+        } while (cnt > (uint32_t)g_params.running_sum_stop);
+        win = in_a;  // [nwin] once cnt == 1
+        if (cnt > 1) {
+            X *v = (X *)e.lvl_s[pp].p;
+            K::weight(e.st, nwin, cnt, m_log2, in_s, in_a, v);
+            e.launches++;
+            const X *tin = v;
+            X *tout = (X *)e.lvl_a[pp].p;
+            while (cnt > 1) {
+                uint32_t blocks = (cnt + TPB_TREE - 1) / TPB_TREE;
+                K::tree_sum(e.st, nwin, tin, cnt, tout);
+                e.launches++;
+                cnt = blocks;
+                X *nxt = (X *)tin;
+                tin = tout;
+                tout = nxt;
+            }
+            win = tin;
         }
-        win = tin;
     }
     if (g_params.final_on_device && !table_c) {
         K::final_horner(e.st, sh, win, (X *)e.result.p);
@@ -795,6 +807,7 @@ int kgr_set_param(const char *name, long value) {
     } else if (s == "final_on_device") g_params.final_on_device = value;
     else if (s == "running_sum_stop") g_params.running_sum_stop = std::max<long>(1, value);
     else if (s == "sort_mode") g_params.sort_mode = value;
+    else if (s == "reduce_mode") g_params.reduce_mode = value;
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
 }

@@ -109,18 +109,21 @@ def test_msm_golden_under_forced_shapes(k, golden, c, chunk):
 
 
 @pytest.mark.parametrize("param,value", [("final_on_device", 1), ("running_sum_stop", 1), ("running_sum_stop", 1 << 20), ("reduce_fanin", 4), ("sort_mode", 0),
-                                         ("sort_mode", 1)])
+                                         ("sort_mode", 1), ("reduce_mode", 0), ("reduce_mode", 1)])
 def test_msm_golden_under_reduce_variants(k, golden, param, value):
     """Device-side Horner, pure running-sum reduction, pure weighting-pass reduction, small fan-in: same element."""
-    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1}
+    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1, "reduce_mode": 1}
     k.set_param(param, value)
     try:
-        for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96", "gr_cancel_32", "gr_uniform_100"):
-            curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
-            pts, sc, inf, aff = (golden[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
-            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve, inf=inf)), aff), (name, param, value)
+        for cbits in (0, 10):  # c = 10: 512 buckets per window, enough for the fold reduce to engage
+            k.set_param("window_bits", cbits)
+            for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96", "gr_cancel_32", "gr_uniform_100"):
+                curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
+                pts, sc, inf, aff = (golden[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
+                assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve, inf=inf)), aff), (name, param, value, cbits)
     finally:
         k.set_param(param, defaults[param])
+        k.set_param("window_bits", 0)
 
 
 @pytest.mark.parametrize("curve,logn", [(A.BN254_G1, 10), (A.GRUMPKIN, 12), (A.BN254_G1, 16)])
