@@ -132,7 +132,7 @@ int kgr_launch_count(int dev, uint64_t *count);
 
 /* ---- test / bench utilities (exercise the same device code the MSM uses) ------------------- */
 /* Elementwise field ops on the device: field 0 = Fq, 1 = Fr; op 0 add 1 sub 2 mul 3 sqr 4 neg
- * 5 from_mont 6 to_mont 7 inv 8 dbl.  a, b, out: host arrays of n x 4 uint64. */
+ * 5 from_mont 6 to_mont 7 inv (Fermat) 8 dbl 9 inv (safegcd divsteps).  a, b, out: host arrays of n x 4 uint64. */
 int kgr_test_field_op(int field, int op, const uint64_t *a, const uint64_t *b, size_t n, uint64_t *out);
 /* Elementwise point ops: op 0: proj(a_xyzz-from-affine madd b_affine), i.e. a + b for affine inputs with flags
  * (inf bytes may be NULL); out n x 12 projective. op 1: a + a.  op 2: a + b computed through xyzz_add. */

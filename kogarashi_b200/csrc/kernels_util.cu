@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 
 #include "launch.cuh"
+#include "modinv.cuh"
 #include "scan.cuh"
 
 namespace kgr {
@@ -19,6 +20,7 @@ template <class P> __global__ void k_field_op(int op, const Fp<P> *a, const Fp<P
         case 5: r = fp_from_mont(x); break;
         case 6: r = fp_to_mont(x); break;
         case 7: r = fp_inv(x); break;
+        case 9: r = fp_inv_fast(x); break;
         default: r = fp_dbl(x); break;
     }
     out[i] = r;

@@ -573,10 +573,11 @@ template <class F, int FIELD_ID> static int test_field_op(Engine &e, int op, con
     Fp<F> *da = nullptr, *db = nullptr, *dout = nullptr;
     CK(cudaMalloc(&da, n * 32));
     CK(cudaMalloc(&dout, n * 32));
-    CK(cudaMemcpy(da, a, n * 32, cudaMemcpyHostToDevice));
+    // uploads go on the engine stream: it is non-blocking, so a legacy-stream cudaMemcpy from pageable memory would not be ordered before the kernel
+    CK(cudaMemcpyAsync(da, a, n * 32, cudaMemcpyHostToDevice, e.st));
     if (b) {
         CK(cudaMalloc(&db, n * 32));
-        CK(cudaMemcpy(db, b, n * 32, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(db, b, n * 32, cudaMemcpyHostToDevice, e.st));
     }
     LaunchUtil::field_op(e.st, FIELD_ID, op, da, db, dout, (uint32_t)n);
     CK(cudaGetLastError());
@@ -1118,7 +1119,7 @@ int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy)
         void *dk = nullptr, *dp = nullptr;
         CK(cudaMalloc(&dk, n * 32 + 32));
         CK(cudaMalloc(&dp, n * 64 + 64));
-        CK(cudaMemcpy(dk, k, n * 32, cudaMemcpyHostToDevice));
+        CK(cudaMemcpyAsync(dk, k, n * 32, cudaMemcpyHostToDevice, e.st));
 #define CALL(C) Launch<C>::fixed_base(e.st, (const Fp<C::Scalar> *)dk, generator_affine<C>(), (uint32_t)n, (AffinePt<C> *)dp)
         DISPATCH(curve, CALL);
 #undef CALL

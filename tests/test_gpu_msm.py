@@ -26,6 +26,23 @@ FIELD_OPS = {"add": 0, "sub": 1, "mul": 2, "square": 3, "neg": 4, "mont_reduce":
 
 
 @pytest.mark.parametrize("fid", [A.FIELD_FQ, A.FIELD_FR])
+def test_safegcd_inverse_bit_exact(k, fid):
+    """modinv.cuh (batched divsteps) against the reference's Fermat inversion (normal.rs:256-287) and against a * a^-1 = 1."""
+    from kogarashi_b200 import msm as M
+    p = B.FQ if fid == A.FIELD_FQ else B.FR
+    n = 1 << 14
+    a = A.random_field(fid, n, seed=bytes(range(30, 46)))
+    for i, v in enumerate([0, 1, 2, p - 1, p - 2, (1 << 253) % p, 3 << 200]):
+        a[i] = B.int_to_limbs(v % p)
+    fast = M.test_field_op(fid, 9, a)
+    fermat = M.test_field_op(fid, 7, a)
+    assert (fast == fermat).all()
+    for i in list(range(0, n, 257)) + list(range(8)):
+        exp = A.field_op(fid, "invert", a[i])
+        assert (fast[i] == (exp if exp is not None else np.zeros(4, dtype=np.uint64))).all(), i
+
+
+@pytest.mark.parametrize("fid", [A.FIELD_FQ, A.FIELD_FR])
 def test_field_ops_bit_exact(k, fid):
     """The PTX carry chains (field.cuh) against zkstd's limb arithmetic on 2^16 random + edge operands."""
     from kogarashi_b200 import msm as M
