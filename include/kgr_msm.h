@@ -114,7 +114,8 @@ int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const ui
  * switches from running sums to the parallel weighting pass), "final_on_device" (1: Horner over
  * windows in a one-thread kernel and one point per GPU in the D2H copy; 0 (default): the W window
  * sums come back in one D2H copy and the host applies the doublings), "sort_mode" (-1 auto, 0 per-scalar fill,
- * 1 window-major fill from stored digits). */
+ * 1 window-major fill from stored digits), "reduce_mode" (1 fold reduce, 0 running sums), "affine_rounds" (0: XYZZ bucket
+ * accumulation; r > 0: the first r levels of every bucket sum are a pairwise tree of batched affine additions). */
 int kgr_set_param(const char *name, long value);
 
 /* Per-phase time (ms) of the last MSM on device slot `dev`, CUDA events on the engine's stream:

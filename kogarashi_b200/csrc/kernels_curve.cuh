@@ -28,6 +28,13 @@ __global__ void __launch_bounds__(TPB_ACC, 4) k_accumulate(MsmShape sh, const Af
     body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
 template <class C>
+__global__ void __launch_bounds__(TPB_ACC) k_accumulate_affine(MsmShape sh, uint32_t rounds, const AffinePt<C> *bases, const uint32_t *offsets,
+                                                               const uint32_t *entries, XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail,
+                                                               uint32_t *tail_bucket, AffinePt<C> *scratch_nodes, Fp<typename C::Base> *scratch_suffix) {
+    body_accumulate_affine<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, rounds, bases, offsets, entries, bucket_acc, head, tail, tail_bucket, scratch_nodes,
+                              scratch_suffix);
+}
+template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
                                                    const XyzzPt<C> *tail, const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
     body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);

@@ -28,6 +28,17 @@ void Launch<C>::accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks,
                            X *head, X *tail, uint32_t *tail_bucket) {
     k_accumulate<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
+template <class C> int Launch<C>::accumulate_affine_blocks_per_sm() {
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accumulate_affine<C>, TPB_ACC, 0);
+    return nb;
+}
+template <class C>
+void Launch<C>::accumulate_affine(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
+                                  const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix) {
+    k_accumulate_affine<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, rounds, bases, offsets, entries, bucket_acc, head, tail, tail_bucket,
+                                                                      (A *)scratch_nodes, (Fp<typename C::Base> *)scratch_suffix);
+}
 template <class C>
 void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
                       const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {

@@ -190,12 +190,12 @@ template <class P> KGR_HD void modinv_int(const uint32_t a[8], uint32_t out[8]) 
         int32_t neg = d.v[8] >> 31;
         int64_t c = 0;
 #pragma unroll
-        for (int i = 0; i < 9; i++) {
+        for (int i = 0; i < 8; i++) {
             c += (int64_t)d.v[i] + (m.v[i] & neg);
             d.v[i] = (int32_t)(c & 0x3fffffff);
             c >>= 30;
         }
-        d.v[8] |= (int32_t)(c << 30);  // keep the sign in the top limb
+        d.v[8] = (int32_t)(c + d.v[8] + (m.v[8] & neg));  // the top limb stays signed
     }
     if (sf) {  // d <- p - d  (d in [0, p)); 0 stays 0
         int32_t nz = 0;

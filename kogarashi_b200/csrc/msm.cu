@@ -45,7 +45,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0;
 };
 static Params g_params;
 
@@ -90,7 +90,7 @@ struct Engine {
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
-    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v;  // raw bytes, cast per curve
+    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v, aff_nodes, aff_suffix;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
     uint32_t result_c = 0;                                                // window bits to apply between them (0: already combined)
@@ -99,7 +99,7 @@ struct Engine {
     size_t counts_zeroed = 0;  // counts[0..counts_zeroed) are known to be zero
     float last_ms[9] = {};
     uint32_t last_shape[6] = {};
-    int acc_blocks_per_sm[2] = {0, 0};
+    int acc_blocks_per_sm[2] = {0, 0}, aff_blocks_per_sm[2] = {0, 0};
     uint64_t launches = 0;            // kernels of this library launched on this engine since init
     cudaEvent_t user_ev[4] = {};      // kgr_event_record / kgr_event_elapsed_ms
     DevBuf<uint8_t> oneshot_pts, oneshot_inf;  // device copy of the bases of kgr_msm_oneshot
@@ -121,13 +121,15 @@ struct Engine {
         CK(cudaMallocHost(&h_result, 256 * 32 * sizeof(uint32_t)));
         acc_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_blocks_per_sm();
         acc_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_blocks_per_sm();
+        aff_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_affine_blocks_per_sm();
+        aff_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_affine_blocks_per_sm();
     }
     void destroy() {
         if (dev < 0) return;
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
         counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
-        bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release();
+        bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release(); aff_nodes.release(); aff_suffix.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
         if (h_stage) cudaFreeHost(h_stage);
@@ -213,7 +215,8 @@ static MsmShape make_shape(uint32_t n, int blocks_per_sm, int sm_count, uint32_t
         uint64_t concurrent = (uint64_t)std::max(1, blocks_per_sm) * TPB_ACC * std::max(1, sm_count);
         double best = 1e300;
         uint32_t bestL = 32;
-        for (uint32_t L = 16; L <= 256; L += 4) {
+        // batched-affine accumulate: every thread shares one inversion per tree level among its ~L/2 pairs, so long chunks pay
+        for (uint32_t L = (g_params.affine_rounds > 0 ? 160 : 16); L <= 256; L += 4) {
             uint64_t chunks = (M + L - 1) / L;
             uint64_t waves = (chunks + concurrent - 1) / concurrent;
             double cost = (double)waves * (L + 2.0);
@@ -229,7 +232,8 @@ template <class C>
 static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d_scalars, int is_mont, uint32_t n, uint32_t table_c = 0,
                         uint32_t table_stride = 0, uint32_t table_off = 0) {
     typedef XyzzPt<C> X;
-    MsmShape sh = make_shape(n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
+    const bool affine = g_params.affine_rounds > 0;
+    MsmShape sh = make_shape(n, affine ? e.aff_blocks_per_sm[C::ID] : e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
     const uint32_t nwin = table_c ? 1u : sh.W;  // independent bucket sets to reduce
     uint64_t M64 = (uint64_t)n * sh.W;
     if (M64 >= (1ull << 32) - 1) throw CudaError{cudaErrorInvalidValue, "n * windows exceeds 2^32 entries", __LINE__};
@@ -276,7 +280,14 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
         e.wait_pts = false;
     }
-    K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
+    if (affine && sh.L <= AFF_MAX_L) {
+        e.aff_nodes.ensure((size_t)chunks * sh.L * sizeof(AffinePt<C>));
+        e.aff_suffix.ensure((size_t)chunks * ((sh.L + 1) / 2) * 32);
+        K::accumulate_affine(e.st, sh, chunks, (uint32_t)g_params.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
+                             (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p);
+    }
+    else
+        K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
     CK(cudaEventRecord(e.ev[EV_ACC], e.st));
     CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
     K::fixup(e.st, sh, chunks, e.sm_count, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1,
@@ -809,6 +820,7 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "running_sum_stop") g_params.running_sum_stop = std::max<long>(1, value);
     else if (s == "sort_mode") g_params.sort_mode = value;
     else if (s == "reduce_mode") g_params.reduce_mode = value;
+    else if (s == "affine_rounds") g_params.affine_rounds = std::min<long>(std::max<long>(value, 0), 6);
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
 }

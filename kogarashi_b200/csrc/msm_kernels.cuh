@@ -19,6 +19,7 @@
 // identical logic on the CPU.
 #pragma once
 #include "curve.cuh"
+#include "modinv.cuh"
 
 namespace kgr {
 
@@ -328,6 +329,217 @@ KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *b
         pt = pt_next;
     }
     tail_bucket[t] = flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);
+}
+
+// ---- batched-affine accumulate (experimental, kgr_set_param("affine_rounds", r)) ------------------------------
+// Same chunking and the same outputs as body_accumulate, but the first `rounds` levels of every bucket's sum are
+// done as a pairwise tree in affine coordinates: all pairs of a level (about L/2, L/4, ... per thread) share ONE
+// modular inversion (Montgomery's trick: suffix products backwards, recovery forwards), so an addition costs
+// 1 (product) + 2 (recovery) + 3 (lambda, lambda^2, y3) = 6 field multiplications plus its share of the inversion
+// (safegcd, ~80 multiplications' worth, modinv.cuh) instead of the 10 of the XYZZ mixed add.  What is left of each
+// bucket segment after `rounds` levels is summed with XYZZ mixed adds and flushed exactly like before.
+// Level-0 nodes are read straight from the base array (x only for the denominators, then the full point); later
+// levels live in a per-thread slice of global scratch.  All special cases keep the group law exact: identity
+// operands, equal points (tangent, denominator 2y), opposite points (result identity).
+// Measured (profiles/r01_affine.md): the multiplier work drops by 25 % but the loops become chains of dependent
+// gathers (long_scoreboard), so on B200 it is not faster than the XYZZ kernel yet: off by default.
+constexpr uint32_t AFF_MAX_L = 256;
+
+// x coordinate only (32 bytes): all the chord denominators of phase 1 need
+template <class C> KGR_HD Fp<typename C::Base> load_x(const AffinePt<C> *p) {
+    Fp<typename C::Base> x;
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint4 a = __ldg(q), b = __ldg(q + 1);
+    x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
+    x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
+#else
+    x = p->x;
+#endif
+    return x;
+}
+template <class C> KGR_HD AffinePt<C> load_node0(const AffinePt<C> *bases, uint32_t ent) {
+    AffinePt<C> p = load_affine(bases, ent & 0x7fffffffu);
+    p.y = fp_cneg(p.y, (ent >> 31) != 0);
+    return p;
+}
+// case of the pair (a, b) and its denominator: 0 chord (xb - xa), 1 tangent (2 ya), 2 result a, 3 result b, 4 result identity
+template <class C> KGR_HD int pair_case(const AffinePt<C> &a, const AffinePt<C> &b, Fp<typename C::Base> &den) {
+    typedef typename C::Base F;
+    den = fp_one<F>();
+    if (affine_is_identity(b)) return 2;
+    if (affine_is_identity(a)) return 3;
+    Fp<F> dx = fp_sub(b.x, a.x);
+    if (!fp_is_zero(dx)) {
+        den = dx;
+        return 0;
+    }
+    if (fp_eq(a.y, b.y) && !fp_is_zero(a.y)) {
+        den = fp_dbl(a.y);
+        return 1;
+    }
+    return 4;
+}
+template <class C> KGR_HD AffinePt<C> pair_sum(int code, const AffinePt<C> &a, const AffinePt<C> &b, const Fp<typename C::Base> &den_inv) {
+    typedef typename C::Base F;
+    if (code == 2) return a;
+    if (code == 3) return b;
+    AffinePt<C> r;
+    if (code == 4) {
+        r.x = fp_zero<F>();
+        r.y = fp_zero<F>();
+        return r;
+    }
+    Fp<F> num;
+    if (code == 0) num = fp_sub(b.y, a.y);
+    else {
+        Fp<F> xx = fp_sqr(a.x);
+        num = fp_add(fp_dbl(xx), xx);
+    }
+    Fp<F> lam = fp_mul(num, den_inv);
+    r.x = fp_sub(fp_sub(fp_sqr(lam), a.x), b.x);
+    r.y = fp_sub(fp_mul(lam, fp_sub(a.x, r.x)), a.y);
+    return r;
+}
+
+template <class C>
+KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t rounds, const AffinePt<C> *bases, const uint32_t *offsets,
+                                   const uint32_t *entries, XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket,
+                                   AffinePt<C> *scratch_nodes, Fp<typename C::Base> *scratch_suffix) {
+    typedef typename C::Base F;
+    uint32_t M = offsets[sh.G];
+    uint64_t s64 = (uint64_t)t * sh.L;
+    if (s64 >= M) return;
+    const uint32_t s = (uint32_t)s64;
+    const uint32_t e = (M - s > sh.L) ? s + sh.L : M;
+    // segments of this chunk: bucket id and node count
+    uint32_t seg_g[AFF_MAX_L];
+    uint16_t seg_len[AFF_MAX_L];
+    uint32_t nseg = 0, n_pairs = 0;
+    {
+        uint32_t g = bucket_of_position(offsets, sh.G, s), pos = s;
+        while (pos < e) {
+            uint32_t g_end = offsets[g + 1];
+            if (g_end <= pos) {
+                g++;
+                continue;
+            }
+            uint32_t len = (g_end < e ? g_end : e) - pos;
+            seg_g[nseg] = g;
+            seg_len[nseg] = (uint16_t)len;
+            n_pairs += len >> 1;
+            nseg++;
+            pos += len;
+            g++;
+        }
+    }
+    // Per-thread scratch lives in global memory, one contiguous slice per thread (L nodes, L/2 suffix products): the node
+    // indices differ from lane to lane, which would turn interleaved local memory into 4-byte scattered accesses, while a
+    // thread-major slice gives every lane whole 32-byte sectors (worst case, all segments odd, a level keeps all its nodes).
+    AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
+    Fp<F> *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
+    uint32_t n_nodes = e - s;
+    bool in_R = false;  // nodes still are the gathered base points until the first level has run
+    for (uint32_t round = 0; round < rounds && n_pairs > 0; round++) {
+        // Both phases are FLAT loops over "steps" (a pair, or the odd last node of a segment): every lane runs about
+        // n_nodes / 2 steps whatever its bucket boundaries are, so the warp stays converged.
+        // phase 1, backwards: suffix[i] = product of the denominators of the pairs after i
+        Fp<F> run = fp_one<F>();
+        {
+            uint32_t pos = n_nodes, pidx = n_pairs, j = nseg, rem = 0;
+            while (pos > 0) {
+                if (rem == 0) rem = seg_len[--j];
+                if (rem & 1) {  // odd node at the end of the segment: no pair
+                    rem--;
+                    pos--;
+                    continue;
+                }
+                pos -= 2;
+                rem -= 2;
+                // the chord denominator needs the two x coordinates only; the full points are fetched in the rare other cases
+                uint32_t ea = 0, eb = 0;
+                const AffinePt<C> *pa, *pb;
+                if (!in_R) {
+                    ea = entries[s + pos];
+                    eb = entries[s + pos + 1];
+                    pa = bases + (ea & 0x7fffffffu);
+                    pb = bases + (eb & 0x7fffffffu);
+                } else {
+                    pa = R + pos;
+                    pb = R + pos + 1;
+                }
+                Fp<F> xa = load_x(pa), xb = load_x(pb);
+                Fp<F> den = fp_sub(xb, xa);
+                if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {  // equal x, or x = 0 (maybe the identity encoding (0, 0))
+                    AffinePt<C> a = in_R ? *pa : load_node0(bases, ea), b = in_R ? *pb : load_node0(bases, eb);
+                    (void)pair_case(a, b, den);
+                }
+                pidx--;
+                suffix[pidx] = run;
+                run = fp_mul(run, den);
+            }
+        }
+        Fp<F> pre = fp_inv_fast(run);  // 1 / (product of all denominators)
+        // phase 2, forwards: 1/den_i = pre * suffix[i]; pre *= den_i.  Output index <= input index, so writing R in place is safe.
+        {
+            uint32_t pos = 0, out = 0, pidx = 0, j = 0, rem = 0, new_pairs = 0, seg_out = 0;
+            while (pos < n_nodes) {
+                if (rem == 0) {
+                    rem = seg_len[j];
+                    seg_out = 0;
+                }
+                if (rem >= 2) {
+                    AffinePt<C> a, b;
+                    if (!in_R) {
+                        a = load_node0(bases, entries[s + pos]);
+                        b = load_node0(bases, entries[s + pos + 1]);
+                    } else {
+                        a = R[pos];
+                        b = R[pos + 1];
+                    }
+                    Fp<F> den;
+                    int code = pair_case(a, b, den);
+                    Fp<F> den_inv = fp_mul(pre, suffix[pidx]);
+                    pre = fp_mul(pre, den);
+                    pidx++;
+                    R[out] = pair_sum(code, a, b, den_inv);
+                    pos += 2;
+                    rem -= 2;
+                } else {
+                    R[out] = in_R ? R[pos] : load_node0(bases, entries[s + pos]);
+                    pos += 1;
+                    rem -= 1;
+                }
+                out++;
+                seg_out++;
+                if (rem == 0) {
+                    seg_len[j] = (uint16_t)seg_out;
+                    new_pairs += seg_out >> 1;
+                    j++;
+                }
+            }
+            n_nodes = out;
+            n_pairs = new_pairs;
+        }
+        in_R = true;
+    }
+    // remaining nodes of every segment: XYZZ mixed adds in one flat loop over the nodes, flushing at segment ends
+    {
+        uint32_t tail_g = NO_DIGIT, j = 0, rem = nseg ? seg_len[0] : 0;
+        XyzzPt<C> acc = xyzz_identity<C>();
+        for (uint32_t pos = 0; pos < n_nodes; pos++) {
+            AffinePt<C> p = in_R ? R[pos] : load_node0(bases, entries[s + pos]);
+            xyzz_madd(acc, p);
+            if (--rem == 0) {
+                uint32_t r = flush_segment(t, seg_g[j], s, e, offsets, acc, bucket_acc, head, tail);
+                if (r != NO_DIGIT) tail_g = r;
+                acc = xyzz_identity<C>();
+                j++;
+                rem = (j < nseg) ? seg_len[j] : 0;
+            }
+        }
+        tail_bucket[t] = tail_g;
+    }
 }
 
 // One thread per chunk: a chunk whose last segment continues into the following chunks owns that bucket

@@ -120,7 +120,15 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memset(head.data(), 0xCD, head.size() * sizeof(XyzzPt<C>));
     memset(tail.data(), 0xEF, tail.size() * sizeof(XyzzPt<C>));
     std::vector<uint32_t> tail_bucket(chunks, 0x12345678u);
-    for (uint32_t t = 0; t < chunks; t++) body_accumulate<C>(t, sh, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
+    std::vector<AffinePt<C>> aff_nodes((size_t)chunks * L);
+    std::vector<Fp<typename C::Base>> aff_suffix((size_t)chunks * ((L + 1) / 2));
+    const uint32_t affine_rounds = (seed >> 1) % 4;  // 0: XYZZ accumulate; 1..3: batched-affine tree levels first
+    for (uint32_t t = 0; t < chunks; t++) {
+        if (affine_rounds && L <= AFF_MAX_L)
+            body_accumulate_affine<C>(t, sh, affine_rounds, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data(), aff_nodes.data(), aff_suffix.data());
+        else
+            body_accumulate<C>(t, sh, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
+    }
     std::vector<uint32_t> worklist(sh.G + 1);
     uint32_t wl_len = 0;
     for (uint32_t t = 0; t < chunks; t++) body_fixup<C>(t, sh, offsets.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data(), worklist.data(), &wl_len);
@@ -167,7 +175,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     zko::Affine got_aff = Cv::to_affine(got);
     bool ok = Cv::eq(got_aff, exp_aff) && (got_aff.inf || (got_aff.x == exp_aff.x && got_aff.y == exp_aff.y));
     (void)Fb::zero;
-    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf);
+    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_rounds=%u\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_rounds);
     return ok ? 0 : 1;
 }
 

@@ -126,10 +126,10 @@ def test_msm_golden_under_forced_shapes(k, golden, c, chunk):
 
 
 @pytest.mark.parametrize("param,value", [("final_on_device", 1), ("running_sum_stop", 1), ("running_sum_stop", 1 << 20), ("reduce_fanin", 4), ("sort_mode", 0),
-                                         ("sort_mode", 1), ("reduce_mode", 0), ("reduce_mode", 1)])
+                                         ("sort_mode", 1), ("reduce_mode", 0), ("reduce_mode", 1), ("affine_rounds", 1), ("affine_rounds", 2), ("affine_rounds", 4)])
 def test_msm_golden_under_reduce_variants(k, golden, param, value):
     """Device-side Horner, pure running-sum reduction, pure weighting-pass reduction, small fan-in: same element."""
-    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1, "reduce_mode": 1}
+    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1, "reduce_mode": 1, "affine_rounds": 0}
     k.set_param(param, value)
     try:
         for cbits in (0, 10):  # c = 10: 512 buckets per window, enough for the fold reduce to engage
