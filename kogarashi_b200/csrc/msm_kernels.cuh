@@ -542,6 +542,165 @@ KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t roun
     }
 }
 
+// ---- batched-affine accumulate, split into one kernel per phase (affine_split = 1) -----------------------------------
+// The fused body above needs ~120 registers for its XYZZ tail, so only 4 warps per sub-partition hide the dependent
+// gathers of the affine phases.  Here each phase is its own small body (launched at high occupancy); the segment
+// structure is re-derived from offsets[] on the fly: a segment with len0 level-0 nodes has (len0 + 2^r - 1) >> r nodes
+// at level r, so nothing but the nodes, the suffix products and one inverse per thread lives in global scratch.
+struct ChunkSpan {
+    uint32_t s, e, g_first;
+    bool valid;
+};
+KGR_HD ChunkSpan chunk_span(uint32_t t, const MsmShape &sh, const uint32_t *offsets) {
+    ChunkSpan c;
+    uint32_t M = offsets[sh.G];
+    uint64_t s64 = (uint64_t)t * sh.L;
+    c.valid = s64 < M;
+    c.s = (uint32_t)s64;
+    c.e = c.valid ? ((M - c.s > sh.L) ? c.s + sh.L : M) : c.s;
+    c.g_first = c.valid ? bucket_of_position(offsets, sh.G, c.s) : 0;
+    return c;
+}
+KGR_HD uint32_t level_len(uint32_t len0, uint32_t r) { return (len0 + (1u << r) - 1u) >> r; }
+
+// phase 1 of level r (backwards): suffix products, then the inverse of the product of all denominators -> inv_out[t]
+template <class C>
+KGR_HD void body_affine_phase1(uint32_t t, const MsmShape &sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+                               const AffinePt<C> *scratch_nodes, Fp<typename C::Base> *scratch_suffix, Fp<typename C::Base> *inv_out) {
+    typedef typename C::Base F;
+    ChunkSpan c = chunk_span(t, sh, offsets);
+    if (!c.valid) return;
+    const AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
+    Fp<F> *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
+    // totals at this level
+    uint32_t n_nodes = 0, n_pairs = 0, g_last = c.g_first;
+    for (uint32_t g = c.g_first, pos = c.s; pos < c.e; g++) {
+        uint32_t g_end = offsets[g + 1];
+        if (g_end <= pos) continue;
+        uint32_t len = level_len((g_end < c.e ? g_end : c.e) - pos, r);
+        n_nodes += len;
+        n_pairs += len >> 1;
+        pos = g_end < c.e ? g_end : c.e;
+        g_last = g;
+    }
+    Fp<F> run = fp_one<F>();
+    uint32_t pos = n_nodes, pidx = n_pairs, rem = 0, g = g_last + 1, hi0 = c.e;
+    while (pos > 0) {
+        if (rem == 0) {  // previous non-empty bucket (backwards)
+            uint32_t lo;
+            do {
+                g--;
+                lo = offsets[g] > c.s ? offsets[g] : c.s;
+            } while (lo >= hi0);
+            rem = level_len(hi0 - lo, r);
+            hi0 = lo;
+        }
+        if (rem & 1) {
+            rem--;
+            pos--;
+            continue;
+        }
+        pos -= 2;
+        rem -= 2;
+        uint32_t ea = 0, eb = 0;
+        const AffinePt<C> *pa, *pb;
+        if (r == 0) {
+            ea = entries[c.s + pos];
+            eb = entries[c.s + pos + 1];
+            pa = bases + (ea & 0x7fffffffu);
+            pb = bases + (eb & 0x7fffffffu);
+        } else {
+            pa = R + pos;
+            pb = R + pos + 1;
+        }
+        Fp<F> xa = load_x(pa), xb = load_x(pb);
+        Fp<F> den = fp_sub(xb, xa);
+        if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {
+            AffinePt<C> a = r ? *pa : load_node0(bases, ea), b = r ? *pb : load_node0(bases, eb);
+            (void)pair_case(a, b, den);
+        }
+        pidx--;
+        suffix[pidx] = run;
+        run = fp_mul(run, den);
+    }
+    inv_out[t] = fp_inv_fast(run);
+}
+
+// phase 2 of level r (forwards): recover the inverses, write the level r+1 nodes in place
+template <class C>
+KGR_HD void body_affine_phase2(uint32_t t, const MsmShape &sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+                               AffinePt<C> *scratch_nodes, const Fp<typename C::Base> *scratch_suffix, const Fp<typename C::Base> *inv_in) {
+    typedef typename C::Base F;
+    ChunkSpan c = chunk_span(t, sh, offsets);
+    if (!c.valid) return;
+    AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
+    const Fp<F> *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
+    Fp<F> pre = inv_in[t];
+    uint32_t pos = 0, out = 0, pidx = 0, rem = 0, g = c.g_first, lo0 = c.s;
+    bool more = true;
+    while (more) {
+        if (rem == 0) {  // next non-empty bucket
+            uint32_t hi;
+            for (;;) {
+                hi = offsets[g + 1] < c.e ? offsets[g + 1] : c.e;
+                if (hi > lo0) break;
+                g++;
+            }
+            rem = level_len(hi - lo0, r);
+            lo0 = hi;
+            g++;
+        }
+        if (rem >= 2) {
+            AffinePt<C> a, b;
+            if (r == 0) {
+                a = load_node0(bases, entries[c.s + pos]);
+                b = load_node0(bases, entries[c.s + pos + 1]);
+            } else {
+                a = R[pos];
+                b = R[pos + 1];
+            }
+            Fp<F> den;
+            int code = pair_case(a, b, den);
+            Fp<F> den_inv = fp_mul(pre, suffix[pidx]);
+            pre = fp_mul(pre, den);
+            pidx++;
+            R[out] = pair_sum(code, a, b, den_inv);
+            pos += 2;
+            rem -= 2;
+        } else {
+            R[out] = r ? R[pos] : load_node0(bases, entries[c.s + pos]);
+            pos += 1;
+            rem -= 1;
+        }
+        out++;
+        more = !(rem == 0 && lo0 >= c.e);
+    }
+}
+
+// XYZZ tail: the level-`r` nodes of every segment are summed with mixed adds and flushed like body_accumulate does
+template <class C>
+KGR_HD void body_affine_tail(uint32_t t, const MsmShape &sh, uint32_t r, const uint32_t *offsets, const AffinePt<C> *scratch_nodes, XyzzPt<C> *bucket_acc,
+                             XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
+    ChunkSpan c = chunk_span(t, sh, offsets);
+    if (!c.valid) return;
+    const AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
+    uint32_t tail_g = NO_DIGIT, pos = 0, g = c.g_first, lo0 = c.s;
+    while (lo0 < c.e) {
+        uint32_t hi = offsets[g + 1] < c.e ? offsets[g + 1] : c.e;
+        if (hi > lo0) {
+            uint32_t len = level_len(hi - lo0, r);
+            XyzzPt<C> acc = xyzz_identity<C>();
+            for (uint32_t k = 0; k < len; k++) xyzz_madd(acc, R[pos + k]);
+            pos += len;
+            uint32_t f = flush_segment(t, g, c.s, c.e, offsets, acc, bucket_acc, head, tail);
+            if (f != NO_DIGIT) tail_g = f;
+            lo0 = hi;
+        }
+        g++;
+    }
+    tail_bucket[t] = tail_g;
+}
+
 // One thread per chunk: a chunk whose last segment continues into the following chunks owns that bucket
 // and sums its pieces (its own tail slot, then the head slots of the following chunks).  Buckets cut
 // into more than FIXUP_INLINE_MAX pieces (a hot bucket: skewed scalars, or a thin top window) are

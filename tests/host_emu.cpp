@@ -123,6 +123,15 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     std::vector<AffinePt<C>> aff_nodes((size_t)chunks * L);
     std::vector<Fp<typename C::Base>> aff_suffix((size_t)chunks * ((L + 1) / 2));
     const uint32_t affine_rounds = (seed >> 1) % 4;  // 0: XYZZ accumulate; 1..3: batched-affine tree levels first
+    const bool affine_split = ((seed >> 3) & 1) != 0;  // one body per phase, structure re-derived from offsets
+    if (affine_rounds && affine_split) {
+        std::vector<Fp<typename C::Base>> aff_inv(chunks);
+        for (uint32_t r = 0; r < affine_rounds; r++) {
+            for (uint32_t t = 0; t < chunks; t++) body_affine_phase1<C>(t, sh, r, acc_bases, offsets.data(), entries.data(), aff_nodes.data(), aff_suffix.data(), aff_inv.data());
+            for (uint32_t t = 0; t < chunks; t++) body_affine_phase2<C>(t, sh, r, acc_bases, offsets.data(), entries.data(), aff_nodes.data(), aff_suffix.data(), aff_inv.data());
+        }
+        for (uint32_t t = 0; t < chunks; t++) body_affine_tail<C>(t, sh, affine_rounds, offsets.data(), aff_nodes.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
+    } else
     for (uint32_t t = 0; t < chunks; t++) {
         if (affine_rounds && L <= AFF_MAX_L)
             body_accumulate_affine<C>(t, sh, affine_rounds, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data(), aff_nodes.data(), aff_suffix.data());
@@ -175,7 +184,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     zko::Affine got_aff = Cv::to_affine(got);
     bool ok = Cv::eq(got_aff, exp_aff) && (got_aff.inf || (got_aff.x == exp_aff.x && got_aff.y == exp_aff.y));
     (void)Fb::zero;
-    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_rounds=%u\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_rounds);
+    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_rounds=%u split=%d\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_rounds, (int)affine_split);
     return ok ? 0 : 1;
 }
 
