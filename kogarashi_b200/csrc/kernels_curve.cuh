@@ -35,6 +35,21 @@ __global__ void __launch_bounds__(TPB_ACC) k_accumulate_affine(MsmShape sh, uint
                               scratch_suffix);
 }
 template <class C>
+__global__ void __launch_bounds__(TPB_ACC) k_affine_phase1(MsmShape sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+                                                           const AffinePt<C> *nodes, Fp<typename C::Base> *suffix, Fp<typename C::Base> *inv) {
+    body_affine_phase1<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, bases, offsets, entries, nodes, suffix, inv);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_ACC) k_affine_phase2(MsmShape sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+                                                           AffinePt<C> *nodes, const Fp<typename C::Base> *suffix, const Fp<typename C::Base> *inv) {
+    body_affine_phase2<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, bases, offsets, entries, nodes, suffix, inv);
+}
+template <class C>
+__global__ void __launch_bounds__(TPB_ACC, 4) k_affine_tail(MsmShape sh, uint32_t r, const uint32_t *offsets, const AffinePt<C> *nodes, XyzzPt<C> *bucket_acc,
+                                                            XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
+    body_affine_tail<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, offsets, nodes, bucket_acc, head, tail, tail_bucket);
+}
+template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
                                                    const XyzzPt<C> *tail, const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
     body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);

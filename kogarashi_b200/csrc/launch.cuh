@@ -28,6 +28,10 @@ template <class C> struct Launch {
     static int accumulate_affine_blocks_per_sm();
     static void accumulate_affine(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
                                   const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix);
+    // one kernel per phase (2 * rounds + 1 launches); inv: one field element per chunk
+    static int accumulate_affine_split(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
+                                       const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix,
+                                       void *scratch_inv);
     static void fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
                       const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len);
     static void reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a,

@@ -40,6 +40,18 @@ void Launch<C>::accumulate_affine(cudaStream_t st, const MsmShape &sh, uint32_t 
                                                                       (A *)scratch_nodes, (Fp<typename C::Base> *)scratch_suffix);
 }
 template <class C>
+int Launch<C>::accumulate_affine_split(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
+                                       const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix,
+                                       void *scratch_inv) {
+    typedef Fp<typename C::Base> F;
+    for (uint32_t r = 0; r < rounds; r++) {
+        k_affine_phase1<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, r, bases, offsets, entries, (const A *)scratch_nodes, (F *)scratch_suffix, (F *)scratch_inv);
+        k_affine_phase2<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, r, bases, offsets, entries, (A *)scratch_nodes, (const F *)scratch_suffix, (const F *)scratch_inv);
+    }
+    k_affine_tail<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, rounds, offsets, (const A *)scratch_nodes, bucket_acc, head, tail, tail_bucket);
+    return 2 * (int)rounds + 1;
+}
+template <class C>
 void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
                       const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
     k_fixup<C><<<cdiv(chunks, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);

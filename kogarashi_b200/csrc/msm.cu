@@ -45,7 +45,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0, affine_split = 1;
 };
 static Params g_params;
 
@@ -90,7 +90,7 @@ struct Engine {
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
-    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v, aff_nodes, aff_suffix;  // raw bytes, cast per curve
+    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v, aff_nodes, aff_suffix, aff_inv;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
     uint32_t result_c = 0;                                                // window bits to apply between them (0: already combined)
@@ -129,7 +129,7 @@ struct Engine {
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
         counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
-        bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release(); aff_nodes.release(); aff_suffix.release();
+        bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release(); aff_nodes.release(); aff_suffix.release(); aff_inv.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
         if (h_stage) cudaFreeHost(h_stage);
@@ -283,8 +283,14 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     if (affine && sh.L <= AFF_MAX_L) {
         e.aff_nodes.ensure((size_t)chunks * sh.L * sizeof(AffinePt<C>));
         e.aff_suffix.ensure((size_t)chunks * ((sh.L + 1) / 2) * 32);
-        K::accumulate_affine(e.st, sh, chunks, (uint32_t)g_params.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
-                             (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p);
+        if (g_params.affine_split) {
+            e.aff_inv.ensure((size_t)chunks * 32);
+            e.launches += K::accumulate_affine_split(e.st, sh, chunks, (uint32_t)g_params.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p,
+                                                     (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p, e.aff_inv.p) - 1;
+        } else {
+            K::accumulate_affine(e.st, sh, chunks, (uint32_t)g_params.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
+                                 (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p);
+        }
     }
     else
         K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
@@ -820,6 +826,7 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "running_sum_stop") g_params.running_sum_stop = std::max<long>(1, value);
     else if (s == "sort_mode") g_params.sort_mode = value;
     else if (s == "reduce_mode") g_params.reduce_mode = value;
+    else if (s == "affine_split") g_params.affine_split = value;
     else if (s == "affine_rounds") g_params.affine_rounds = std::min<long>(std::max<long>(value, 0), 6);
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;

@@ -684,19 +684,36 @@ KGR_HD void body_affine_tail(uint32_t t, const MsmShape &sh, uint32_t r, const u
     ChunkSpan c = chunk_span(t, sh, offsets);
     if (!c.valid) return;
     const AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    uint32_t tail_g = NO_DIGIT, pos = 0, g = c.g_first, lo0 = c.s;
-    while (lo0 < c.e) {
-        uint32_t hi = offsets[g + 1] < c.e ? offsets[g + 1] : c.e;
-        if (hi > lo0) {
-            uint32_t len = level_len(hi - lo0, r);
-            XyzzPt<C> acc = xyzz_identity<C>();
-            for (uint32_t k = 0; k < len; k++) xyzz_madd(acc, R[pos + k]);
-            pos += len;
-            uint32_t f = flush_segment(t, g, c.s, c.e, offsets, acc, bucket_acc, head, tail);
-            if (f != NO_DIGIT) tail_g = f;
+    // flat loop over the nodes (the warp stays converged), flushing at segment ends
+    uint32_t tail_g = NO_DIGIT, g = c.g_first, lo0 = c.s, rem = 0, n_nodes = 0;
+    for (uint32_t gg = c.g_first, pos0 = c.s; pos0 < c.e; gg++) {
+        uint32_t g_end = offsets[gg + 1];
+        if (g_end <= pos0) continue;
+        uint32_t hi = g_end < c.e ? g_end : c.e;
+        n_nodes += level_len(hi - pos0, r);
+        pos0 = hi;
+    }
+    XyzzPt<C> acc = xyzz_identity<C>();
+    uint32_t cur_g = g;
+    for (uint32_t pos = 0; pos < n_nodes; pos++) {
+        if (rem == 0) {
+            uint32_t hi;
+            for (;;) {
+                hi = offsets[g + 1] < c.e ? offsets[g + 1] : c.e;
+                if (hi > lo0) break;
+                g++;
+            }
+            rem = level_len(hi - lo0, r);
             lo0 = hi;
+            cur_g = g;
+            g++;
         }
-        g++;
+        xyzz_madd(acc, R[pos]);
+        if (--rem == 0) {
+            uint32_t f = flush_segment(t, cur_g, c.s, c.e, offsets, acc, bucket_acc, head, tail);
+            if (f != NO_DIGIT) tail_g = f;
+            acc = xyzz_identity<C>();
+        }
     }
     tail_bucket[t] = tail_g;
 }
