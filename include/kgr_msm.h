@@ -34,7 +34,10 @@
 extern "C" {
 #endif
 
-enum { KGR_CURVE_BN254_G1 = 0, KGR_CURVE_GRUMPKIN = 1 };
+/* KGR_CURVE_BN254_G2 (next row N3; bn254/src/g2.rs:15-21, the b_g2 queries of groth16/src/prover.rs:64-65): coordinates are
+ * Fq2 elements c0 || c1 (fqn.rs), so wherever a size below says 4 limbs per coordinate G2 uses 8: points n x 16 uint64,
+ * projective results 24, affine results 17 (x[8] y[8] is_infinity). */
+enum { KGR_CURVE_BN254_G1 = 0, KGR_CURVE_GRUMPKIN = 1, KGR_CURVE_BN254_G2 = 2 };
 enum { KGR_SCALARS_MONTGOMERY = 0, KGR_SCALARS_CANONICAL = 1 };
 enum {
     KGR_OK = 0,
@@ -71,17 +74,17 @@ int kgr_bases_precompute(kgr_bases_t *bases, int window_bits);
 
 /* sum_{i<n} scalars[i] * bases[base_off + i]   (replaces msm_curve_addition, groth16/src/msm.rs:6-48).
  * Host scalars; the H2D copy of the scalars and the 96-byte D2H of the result are part of the call. */
-int kgr_msm(kgr_bases_t *bases, size_t base_off, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t out[12]);
+int kgr_msm(kgr_bases_t *bases, size_t base_off, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t *out /* [12] */);
 
 /* Same with everything passed from host memory each call; pairs = min(n_bases, n_scalars) exactly
  * like coeffs.iter().zip(bases.iter()) (msm.rs:25). */
 int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, int scalar_fmt,
-                    size_t n_scalars, uint64_t out[12]);
+                    size_t n_scalars, uint64_t *out /* [12] */);
 
 /* Scalars already resident on the device that holds the bases (single-device contexts only):
  * d_scalars is a device pointer to n x 4 uint64.  Used for kernel-only timing and by callers
  * that produce scalars on the GPU. */
-int kgr_msm_device(kgr_bases_t *bases, size_t base_off, const void *d_scalars, int scalar_fmt, size_t n, uint64_t out[12]);
+int kgr_msm_device(kgr_bases_t *bases, size_t base_off, const void *d_scalars, int scalar_fmt, size_t n, uint64_t *out /* [12] */);
 
 /* Copy n registered points starting at `off` back to the host (x||y Montgomery; identity entries
  * come back as (0, 0), the device encoding). */
@@ -89,13 +92,13 @@ int kgr_bases_download(const kgr_bases_t *bases, size_t off, size_t n, uint64_t 
 
 /* PedersenCommitment::commit (nova/src/pedersen.rs:15-20): MSM followed by to_affine.
  * out = x[4] y[4] is_infinity (identity -> (0, R, 1) as in group.rs:22-26). */
-int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t out[9]);
+int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t *out /* [9] */);
 
 /* Projective -> affine normalisation on the host (zkstd/src/macros/curve/weierstrass.rs:57-66);
  * out = x[4] y[4] is_infinity. */
-int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]);
+int kgr_to_affine(int curve, const uint64_t *in, uint64_t *out);
 /* a + b on the host for two projective points (used to combine per-GPU / per-rank partial sums). */
-int kgr_proj_add(int curve, const uint64_t a[12], const uint64_t b[12], uint64_t out[12]);
+int kgr_proj_add(int curve, const uint64_t *a, const uint64_t *b, uint64_t *out);
 
 /* ---- Fr NTT (next row N2: groth16/src/fft.rs) --------------------------------------------------
  * Radix-2 transforms over bn254 Fr on a domain of size 2^log_n, semantics of groth16/src/fft.rs:92-127:
@@ -115,7 +118,8 @@ int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const ui
  * windows in a one-thread kernel and one point per GPU in the D2H copy; 0 (default): the W window
  * sums come back in one D2H copy and the host applies the doublings), "sort_mode" (-1 auto, 0 per-scalar fill,
  * 1 window-major fill from stored digits), "reduce_mode" (1 fold reduce, 0 running sums), "affine_rounds" (0: XYZZ bucket
- * accumulation; r > 0: the first r levels of every bucket sum are a pairwise tree of batched affine additions). */
+ * accumulation; r > 0: the first r levels of every bucket sum are a pairwise tree of batched affine additions; experimental, see profiles/r01_affine.md), "affine_split" (with affine_rounds > 0:
+ * 1 one kernel per phase, 0 one fused kernel). */
 int kgr_set_param(const char *name, long value);
 
 /* Per-phase time (ms) of the last MSM on device slot `dev`, CUDA events on the engine's stream:

@@ -17,33 +17,42 @@ namespace kgr {
 struct Bn254G1 {
     typedef FqP Base;
     typedef FrP Scalar;
+    typedef Fp<FqP> Elem;
     static constexpr int ID = 0;
 };
 // grumpkin/src/curve.rs:11-15 / params.rs:4-19 : coordinates in Fr, scalars in Fq, b = -17
 struct GrumpkinC {
     typedef FrP Base;
     typedef FqP Scalar;
+    typedef Fp<FrP> Elem;
     static constexpr int ID = 1;
 };
+// bn254/src/g2.rs:15-21 / params.rs:14-56 : coordinates in Fq2 = Fq[u]/(u^2+1), scalars in Fr, b = 3/(9+u)
+struct Bn254G2 {
+    typedef FqP Base;
+    typedef FrP Scalar;
+    typedef Fp2<FqP> Elem;
+    static constexpr int ID = 2;
+};
 
-// Device-side affine point, 64 bytes.  The reference carries a separate is_infinity flag
+// Device-side affine point, 64 bytes (128 for G2).  The reference carries a separate is_infinity flag
 // (g1.rs:21); on the device the identity is encoded as (0, 0), which is on neither curve
 // (b != 0), so the flag array is folded into the coordinates when bases are registered.
 template <class C> struct alignas(16) AffinePt {
-    Fp<typename C::Base> x, y;
+    typename C::Elem x, y;
 };
 template <class C> struct alignas(16) XyzzPt {
-    Fp<typename C::Base> x, y, zz, zzz;
+    typename C::Elem x, y, zz, zzz;
 };
 
 template <class C> KGR_HD bool affine_is_identity(const AffinePt<C> &p) { return fp_is_zero(p.x) && fp_is_zero(p.y); }
 template <class C> KGR_HD bool xyzz_is_identity(const XyzzPt<C> &p) { return fp_is_zero(p.zz); }
 template <class C> KGR_HD XyzzPt<C> xyzz_identity() {
     XyzzPt<C> r;
-    r.x = fp_zero<typename C::Base>();
-    r.y = fp_one<typename C::Base>();
-    r.zz = fp_zero<typename C::Base>();
-    r.zzz = fp_zero<typename C::Base>();
+    r.x = El<typename C::Elem>::zero();
+    r.y = El<typename C::Elem>::one();
+    r.zz = El<typename C::Elem>::zero();
+    r.zzz = El<typename C::Elem>::zero();
     return r;
 }
 template <class C> KGR_HD XyzzPt<C> xyzz_from_affine(const AffinePt<C> &p) {
@@ -51,22 +60,22 @@ template <class C> KGR_HD XyzzPt<C> xyzz_from_affine(const AffinePt<C> &p) {
     XyzzPt<C> r;
     r.x = p.x;
     r.y = p.y;
-    r.zz = fp_one<typename C::Base>();
-    r.zzz = fp_one<typename C::Base>();
+    r.zz = El<typename C::Elem>::one();
+    r.zzz = El<typename C::Elem>::one();
     return r;
 }
 
 // 2*(x, y) for an affine point (mdbl-2008-s-1, a = 0): 3M + 2S... (U^2, U*V, x*V, x^2, M^2, M*(..), W*y)
 template <class C> KGR_HD XyzzPt<C> xyzz_dbl_affine(const AffinePt<C> &p) {
-    typedef typename C::Base F;
+    typedef typename C::Elem E;
     if (affine_is_identity(p)) return xyzz_identity<C>();
     XyzzPt<C> r;
-    Fp<F> u = fp_dbl(p.y);
-    Fp<F> v = fp_sqr(u);
-    Fp<F> w = fp_mul(u, v);
-    Fp<F> s = fp_mul(p.x, v);
-    Fp<F> xx = fp_sqr(p.x);
-    Fp<F> m = fp_add(fp_dbl(xx), xx);
+    E u = fp_dbl(p.y);
+    E v = fp_sqr(u);
+    E w = fp_mul(u, v);
+    E s = fp_mul(p.x, v);
+    E xx = fp_sqr(p.x);
+    E m = fp_add(fp_dbl(xx), xx);
     r.x = fp_sub(fp_sqr(m), fp_dbl(s));
     r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
     r.zz = v;
@@ -77,15 +86,15 @@ template <class C> KGR_HD XyzzPt<C> xyzz_dbl_affine(const AffinePt<C> &p) {
 // 2*P (dbl-2008-s-1, a = 0).  y == 0 would give zz = 0 = identity, which is the right answer
 // for a 2-torsion point (neither curve has one: both groups have prime order).
 template <class C> KGR_HD XyzzPt<C> xyzz_dbl(const XyzzPt<C> &p) {
-    typedef typename C::Base F;
+    typedef typename C::Elem E;
     if (xyzz_is_identity(p)) return p;
     XyzzPt<C> r;
-    Fp<F> u = fp_dbl(p.y);
-    Fp<F> v = fp_sqr(u);
-    Fp<F> w = fp_mul(u, v);
-    Fp<F> s = fp_mul(p.x, v);
-    Fp<F> xx = fp_sqr(p.x);
-    Fp<F> m = fp_add(fp_dbl(xx), xx);
+    E u = fp_dbl(p.y);
+    E v = fp_sqr(u);
+    E w = fp_mul(u, v);
+    E s = fp_mul(p.x, v);
+    E xx = fp_sqr(p.x);
+    E m = fp_add(fp_dbl(xx), xx);
     r.x = fp_sub(fp_sqr(m), fp_dbl(s));
     r.y = fp_sub(fp_mul(m, fp_sub(s, r.x)), fp_mul(w, p.y));
     r.zz = fp_mul(v, p.zz);
@@ -95,26 +104,26 @@ template <class C> KGR_HD XyzzPt<C> xyzz_dbl(const XyzzPt<C> &p) {
 
 // acc += q for an affine q (madd-2008-s): 8M + 2S on the generic path.
 template <class C> KGR_HD void xyzz_madd(XyzzPt<C> &acc, const AffinePt<C> &q) {
-    typedef typename C::Base F;
+    typedef typename C::Elem E;
     if (affine_is_identity(q)) return;
     if (xyzz_is_identity(acc)) {
         acc = xyzz_from_affine(q);
         return;
     }
-    Fp<F> u2 = fp_mul(q.x, acc.zz);
-    Fp<F> s2 = fp_mul(q.y, acc.zzz);
-    Fp<F> p = fp_sub(u2, acc.x);
-    Fp<F> r = fp_sub(s2, acc.y);
+    E u2 = fp_mul(q.x, acc.zz);
+    E s2 = fp_mul(q.y, acc.zzz);
+    E p = fp_sub(u2, acc.x);
+    E r = fp_sub(s2, acc.y);
     if (fp_is_zero(p)) {
         if (fp_is_zero(r)) acc = xyzz_dbl_affine(q);
         else acc = xyzz_identity<C>();
         return;
     }
-    Fp<F> pp = fp_sqr(p);
-    Fp<F> ppp = fp_mul(p, pp);
-    Fp<F> qq = fp_mul(acc.x, pp);
-    Fp<F> x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-    Fp<F> y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(acc.y, ppp));
+    E pp = fp_sqr(p);
+    E ppp = fp_mul(p, pp);
+    E qq = fp_mul(acc.x, pp);
+    E x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
+    E y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(acc.y, ppp));
     acc.x = x3;
     acc.y = y3;
     acc.zz = fp_mul(acc.zz, pp);
@@ -123,28 +132,28 @@ template <class C> KGR_HD void xyzz_madd(XyzzPt<C> &acc, const AffinePt<C> &q) {
 
 // acc += q (add-2008-s): 12M + 2S on the generic path.
 template <class C> KGR_HD void xyzz_add(XyzzPt<C> &acc, const XyzzPt<C> &q) {
-    typedef typename C::Base F;
+    typedef typename C::Elem E;
     if (xyzz_is_identity(q)) return;
     if (xyzz_is_identity(acc)) {
         acc = q;
         return;
     }
-    Fp<F> u1 = fp_mul(acc.x, q.zz);
-    Fp<F> u2 = fp_mul(q.x, acc.zz);
-    Fp<F> s1 = fp_mul(acc.y, q.zzz);
-    Fp<F> s2 = fp_mul(q.y, acc.zzz);
-    Fp<F> p = fp_sub(u2, u1);
-    Fp<F> r = fp_sub(s2, s1);
+    E u1 = fp_mul(acc.x, q.zz);
+    E u2 = fp_mul(q.x, acc.zz);
+    E s1 = fp_mul(acc.y, q.zzz);
+    E s2 = fp_mul(q.y, acc.zzz);
+    E p = fp_sub(u2, u1);
+    E r = fp_sub(s2, s1);
     if (fp_is_zero(p)) {
         if (fp_is_zero(r)) acc = xyzz_dbl(acc);
         else acc = xyzz_identity<C>();
         return;
     }
-    Fp<F> pp = fp_sqr(p);
-    Fp<F> ppp = fp_mul(p, pp);
-    Fp<F> qq = fp_mul(u1, pp);
-    Fp<F> x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
-    Fp<F> y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(s1, ppp));
+    E pp = fp_sqr(p);
+    E ppp = fp_mul(p, pp);
+    E qq = fp_mul(u1, pp);
+    E x3 = fp_sub(fp_sub(fp_sqr(r), ppp), fp_dbl(qq));
+    E y3 = fp_sub(fp_mul(r, fp_sub(qq, x3)), fp_mul(s1, ppp));
     acc.x = x3;
     acc.y = y3;
     acc.zz = fp_mul(fp_mul(acc.zz, q.zz), pp);
@@ -153,12 +162,12 @@ template <class C> KGR_HD void xyzz_add(XyzzPt<C> &acc, const XyzzPt<C> &q) {
 
 // XYZZ -> the reference's homogeneous projective (X : Y : Z), x = X/Z, y = Y/Z
 // (zkstd/src/macros/curve/weierstrass/group.rs:106-110 identity = (0, 1, 0)).
-template <class C> KGR_HD void xyzz_to_projective(const XyzzPt<C> &p, Fp<typename C::Base> out[3]) {
-    typedef typename C::Base F;
+template <class C> KGR_HD void xyzz_to_projective(const XyzzPt<C> &p, typename C::Elem out[3]) {
+    typedef typename C::Elem E;
     if (xyzz_is_identity(p)) {
-        out[0] = fp_zero<F>();
-        out[1] = fp_one<F>();
-        out[2] = fp_zero<F>();
+        out[0] = El<E>::zero();
+        out[1] = El<E>::one();
+        out[2] = El<E>::zero();
         return;
     }
     out[0] = fp_mul(p.x, p.zzz);
@@ -168,17 +177,17 @@ template <class C> KGR_HD void xyzz_to_projective(const XyzzPt<C> &p, Fp<typenam
 
 // XYZZ -> affine (x, y) or (0,0) for the identity: one inversion (macros/curve/weierstrass.rs:57-66 semantics)
 template <class C> KGR_HD AffinePt<C> xyzz_to_affine(const XyzzPt<C> &p) {
-    typedef typename C::Base F;
+    typedef typename C::Elem E;
     AffinePt<C> r;
     if (xyzz_is_identity(p)) {
-        r.x = fp_zero<F>();
-        r.y = fp_zero<F>();
+        r.x = El<E>::zero();
+        r.y = El<E>::zero();
         return r;
     }
     // 1/zzz ; 1/zz = zzz^-1 * ... : zz^3 = zzz^2  =>  1/zz = zz^2 / zzz^2 = (zz / zzz)^2 ... use one inversion of zz*zzz
-    Fp<F> t = fp_inv(fp_mul(p.zz, p.zzz));
-    Fp<F> izz = fp_mul(t, p.zzz);
-    Fp<F> izzz = fp_mul(t, p.zz);
+    E t = fp_inv(fp_mul(p.zz, p.zzz));
+    E izz = fp_mul(t, p.zzz);
+    E izzz = fp_mul(t, p.zz);
     r.x = fp_mul(p.x, izz);
     r.y = fp_mul(p.y, izzz);
     return r;

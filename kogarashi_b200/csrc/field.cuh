@@ -425,4 +425,52 @@ template <class P> KGR_HD Fp<P> fp_inv(const Fp<P> &a) {
     return acc;
 }
 
+// ---- Fq2 = Fq[u] / (u^2 + 1)  (bn254/src/fqn.rs:347-370; limbs.rs tower macros) -------------
+// The coordinates of G2.  Products use three base-field multiplications (Karatsuba) and squares two
+// ((a0+a1)(a0-a1), 2 a0 a1) where the reference spends four and three: same field element, fewer multiplier cycles.
+template <class P> struct Fp2 {
+    Fp<P> c0, c1;
+};
+template <class P> KGR_HD bool fp_is_zero(const Fp2<P> &a) { return fp_is_zero(a.c0) && fp_is_zero(a.c1); }
+template <class P> KGR_HD bool fp_eq(const Fp2<P> &a, const Fp2<P> &b) { return fp_eq(a.c0, b.c0) && fp_eq(a.c1, b.c1); }
+template <class P> KGR_HD Fp2<P> fp_add(const Fp2<P> &a, const Fp2<P> &b) { return Fp2<P>{fp_add(a.c0, b.c0), fp_add(a.c1, b.c1)}; }
+template <class P> KGR_HD Fp2<P> fp_sub(const Fp2<P> &a, const Fp2<P> &b) { return Fp2<P>{fp_sub(a.c0, b.c0), fp_sub(a.c1, b.c1)}; }
+template <class P> KGR_HD Fp2<P> fp_dbl(const Fp2<P> &a) { return Fp2<P>{fp_dbl(a.c0), fp_dbl(a.c1)}; }
+template <class P> KGR_HD Fp2<P> fp_neg(const Fp2<P> &a) { return Fp2<P>{fp_neg(a.c0), fp_neg(a.c1)}; }
+template <class P> KGR_HD Fp2<P> fp_cneg(const Fp2<P> &a, bool sign) { return Fp2<P>{fp_cneg(a.c0, sign), fp_cneg(a.c1, sign)}; }
+// fqn.rs:359-363
+template <class P> KGR_HD Fp2<P> fp_mul(const Fp2<P> &a, const Fp2<P> &b) {
+    Fp<P> t0 = fp_mul(a.c0, b.c0);
+    Fp<P> t1 = fp_mul(a.c1, b.c1);
+    Fp<P> t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
+    return Fp2<P>{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
+}
+// fqn.rs:365-369
+template <class P> KGR_HD Fp2<P> fp_sqr(const Fp2<P> &a) {
+    Fp<P> t = fp_mul(a.c0, a.c1);
+    return Fp2<P>{fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1)), fp_dbl(t)};
+}
+// fqn.rs:348-357: conj(a) / (a0^2 + a1^2); zero maps to zero
+template <class P> KGR_HD Fp2<P> fp_inv(const Fp2<P> &a) {
+    Fp<P> t = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+    return Fp2<P>{fp_mul(t, a.c0), fp_mul(t, fp_neg(a.c1))};
+}
+
+// Element traits so the group law and the MSM pipeline are written once for Fp and Fp2 coordinates.
+template <class E> struct El;
+template <class P> struct El<Fp<P>> {
+    static constexpr int WORDS = 8;
+    static KGR_HD Fp<P> zero() { return fp_zero<P>(); }
+    static KGR_HD Fp<P> one() { return fp_one<P>(); }
+    static KGR_HD uint32_t &word(Fp<P> &a, int i) { return a.v[i]; }
+    static KGR_HD uint32_t word(const Fp<P> &a, int i) { return a.v[i]; }
+};
+template <class P> struct El<Fp2<P>> {
+    static constexpr int WORDS = 16;
+    static KGR_HD Fp2<P> zero() { return Fp2<P>{fp_zero<P>(), fp_zero<P>()}; }
+    static KGR_HD Fp2<P> one() { return Fp2<P>{fp_one<P>(), fp_zero<P>()}; }
+    static KGR_HD uint32_t &word(Fp2<P> &a, int i) { return i < 8 ? a.c0.v[i] : a.c1.v[i - 8]; }
+    static KGR_HD uint32_t word(const Fp2<P> &a, int i) { return i < 8 ? a.c0.v[i] : a.c1.v[i - 8]; }
+};
+
 }  // namespace kgr

@@ -1,5 +1,5 @@
 // kernels_curve.cuh — __global__ wrappers of the per-thread bodies (msm_kernels.cuh), templated on the curve.
-// Included only by launch_impl.cuh, which is compiled once per curve (kernels_g1.cu, kernels_grumpkin.cu).
+// Included only by launch_impl.cuh, which is compiled once per curve (kernels_g1.cu, kernels_grumpkin.cu, kernels_g2_*.cu).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -7,6 +7,11 @@
 #include "msm_kernels.cuh"
 
 namespace kgr {
+
+// resident CTAs per SM the accumulate kernels are compiled for: 4 (128 registers) with 8-word coordinates, 2 (255 registers) for G2,
+// whose XYZZ accumulator alone is 64 registers
+template <class C> constexpr int xyzz_words() { return (int)(sizeof(XyzzPt<C>) / 4); }
+template <class C> constexpr int acc_min_blocks() { return El<typename C::Elem>::WORDS == 8 ? 4 : 2; }
 
 
 template <class C>
@@ -23,29 +28,29 @@ __global__ void __launch_bounds__(TPB_SCALAR) k_fill(MsmShape sh, const uint32_t
     body_fill<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, scalars, is_mont, counts, offsets, entries);
 }
 template <class C>
-__global__ void __launch_bounds__(TPB_ACC, 4) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
+__global__ void __launch_bounds__(TPB_ACC, acc_min_blocks<C>()) k_accumulate(MsmShape sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
                                                         XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
     body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_ACC) k_accumulate_affine(MsmShape sh, uint32_t rounds, const AffinePt<C> *bases, const uint32_t *offsets,
                                                                const uint32_t *entries, XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail,
-                                                               uint32_t *tail_bucket, AffinePt<C> *scratch_nodes, Fp<typename C::Base> *scratch_suffix) {
+                                                               uint32_t *tail_bucket, AffinePt<C> *scratch_nodes, typename C::Elem *scratch_suffix) {
     body_accumulate_affine<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, rounds, bases, offsets, entries, bucket_acc, head, tail, tail_bucket, scratch_nodes,
                               scratch_suffix);
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_ACC) k_affine_phase1(MsmShape sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                                                           const AffinePt<C> *nodes, Fp<typename C::Base> *suffix, Fp<typename C::Base> *inv) {
+                                                           const AffinePt<C> *nodes, typename C::Elem *suffix, typename C::Elem *inv) {
     body_affine_phase1<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, bases, offsets, entries, nodes, suffix, inv);
 }
 template <class C>
 __global__ void __launch_bounds__(TPB_ACC) k_affine_phase2(MsmShape sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                                                           AffinePt<C> *nodes, const Fp<typename C::Base> *suffix, const Fp<typename C::Base> *inv) {
+                                                           AffinePt<C> *nodes, const typename C::Elem *suffix, const typename C::Elem *inv) {
     body_affine_phase2<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, bases, offsets, entries, nodes, suffix, inv);
 }
 template <class C>
-__global__ void __launch_bounds__(TPB_ACC, 4) k_affine_tail(MsmShape sh, uint32_t r, const uint32_t *offsets, const AffinePt<C> *nodes, XyzzPt<C> *bucket_acc,
+__global__ void __launch_bounds__(TPB_ACC, acc_min_blocks<C>()) k_affine_tail(MsmShape sh, uint32_t r, const uint32_t *offsets, const AffinePt<C> *nodes, XyzzPt<C> *bucket_acc,
                                                             XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
     body_affine_tail<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, offsets, nodes, bucket_acc, head, tail, tail_bucket);
 }
@@ -59,13 +64,13 @@ __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *
 template <class C> __device__ __forceinline__ void sm_put(uint32_t *sm, int t, const XyzzPt<C> &p) {
     const uint32_t *w = reinterpret_cast<const uint32_t *>(&p);
 #pragma unroll
-    for (int k = 0; k < 32; k++) sm[k * TPB_TREE + t] = w[k];
+    for (int k = 0; k < xyzz_words<C>(); k++) sm[k * TPB_TREE + t] = w[k];
 }
 template <class C> __device__ __forceinline__ XyzzPt<C> sm_get(const uint32_t *sm, int t) {
     XyzzPt<C> p;
     uint32_t *w = reinterpret_cast<uint32_t *>(&p);
 #pragma unroll
-    for (int k = 0; k < 32; k++) w[k] = sm[k * TPB_TREE + t];
+    for (int k = 0; k < xyzz_words<C>(); k++) w[k] = sm[k * TPB_TREE + t];
     return p;
 }
 // Sum of the TPB_TREE per-thread points of a CTA, returned in thread 0 (log2(TPB_TREE) add latencies).
@@ -87,7 +92,7 @@ template <class C> __device__ __forceinline__ XyzzPt<C> block_tree_sum(XyzzPt<C>
 template <class C>
 __global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
                                                          const XyzzPt<C> *tail, const uint32_t *worklist, const uint32_t *worklist_len) {
-    __shared__ uint32_t sm[32 * TPB_TREE];
+    __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     uint32_t n = *worklist_len;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
         uint32_t g = worklist[i];
@@ -109,7 +114,7 @@ __global__ void __launch_bounds__(TPB_RED) k_weight(uint32_t n_windows, uint32_t
 }
 // grid (ceil(cnt_in / TPB_TREE), windows): out[w][block] = sum of in[w][block * TPB_TREE ...]
 template <class C> __global__ void __launch_bounds__(TPB_TREE) k_tree_sum(const XyzzPt<C> *in, uint32_t cnt_in, XyzzPt<C> *out) {
-    __shared__ uint32_t sm[32 * TPB_TREE];
+    __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     uint32_t i = blockIdx.x * TPB_TREE + threadIdx.x, w = blockIdx.y;
     XyzzPt<C> v = (i < cnt_in) ? in[(size_t)w * cnt_in + i] : xyzz_identity<C>();
     v = block_tree_sum<C>(v, sm);
@@ -144,7 +149,7 @@ __global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *in, uint32_t 
 template <class C>
 __global__ void __launch_bounds__(TPB_TREE) k_vsum1(const XyzzPt<C> *buckets, const XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t chunks_max,
                                                     const uint32_t *bucket_offsets, XyzzPt<C> *partial) {
-    __shared__ uint32_t sm[32 * TPB_TREE];
+    __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     const uint32_t chunk = blockIdx.x, l = blockIdx.y + 1, w = blockIdx.z;
     const uint32_t m = B >> l;
     if (chunk * 8u * TPB_TREE >= m) return;  // uniform per CTA
@@ -161,7 +166,7 @@ __global__ void __launch_bounds__(TPB_TREE) k_vsum1(const XyzzPt<C> *buckets, co
 }
 // grid (level - 1, window): V[w][bit] = sum of that level's partials, bit = nb - level
 template <class C> __global__ void __launch_bounds__(TPB_TREE) k_vsum2(const XyzzPt<C> *partial, uint32_t B, uint32_t nb, uint32_t chunks_max, XyzzPt<C> *V) {
-    __shared__ uint32_t sm[32 * TPB_TREE];
+    __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     const uint32_t l = blockIdx.x + 1, w = blockIdx.y;
     const uint32_t m = B >> l;
     const uint32_t cnt = (m + 8u * TPB_TREE - 1) / (8u * TPB_TREE);
@@ -173,7 +178,7 @@ template <class C> __global__ void __launch_bounds__(TPB_TREE) k_vsum2(const Xyz
 }
 // grid (window): out[w] = T0 + sum_b 2^b V[w][b]; lane b doubles V_b b times, then a CTA tree sum.
 template <class C> __global__ void __launch_bounds__(TPB_TREE) k_fold_combine(const XyzzPt<C> *F, const XyzzPt<C> *V, uint32_t B, uint32_t nb, XyzzPt<C> *out) {
-    __shared__ uint32_t sm[32 * TPB_TREE];
+    __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     const uint32_t w = blockIdx.x, t = threadIdx.x;
     XyzzPt<C> acc = xyzz_identity<C>();
     if (t < nb) {
@@ -202,8 +207,8 @@ __global__ void __launch_bounds__(128) k_precompute(uint32_t n, uint32_t c, uint
 template <class C> __global__ void k_fold_inf(AffinePt<C> *pts, const uint8_t *inf, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || !inf[i]) return;
-    pts[i].x = fp_zero<typename C::Base>();
-    pts[i].y = fp_zero<typename C::Base>();
+    pts[i].x = El<typename C::Elem>::zero();
+    pts[i].y = El<typename C::Elem>::zero();
 }
 
 template <class C> __global__ void k_point_op(int op, const AffinePt<C> *a, const AffinePt<C> *b, uint32_t *out24, uint32_t n) {
@@ -219,10 +224,11 @@ template <class C> __global__ void k_point_op(int op, const AffinePt<C> *a, cons
         xyzz_madd(t, b[i]);             // 3b  (non-unit zz)
         xyzz_add(acc, t);               // a + 3b
     }
-    Fp<typename C::Base> o[3];
+    typename C::Elem o[3];
     xyzz_to_projective(acc, o);
+    constexpr int NW = El<typename C::Elem>::WORDS;
     for (int k = 0; k < 3; k++)
-        for (int j = 0; j < 8; j++) out24[24 * (size_t)i + 8 * k + j] = o[k].v[j];
+        for (int j = 0; j < NW; j++) out24[3 * NW * (size_t)i + NW * k + j] = El<typename C::Elem>::word(o[k], j);
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {

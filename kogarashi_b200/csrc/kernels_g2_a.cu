@@ -1,0 +1,4 @@
+// BN254 G2 (coordinates in Fq2): scalar side, accumulate and fixup kernels + launchers.
+#define KGR_PART 1
+#include "launch_impl.cuh"
+template struct kgr::Launch<kgr::Bn254G2>;

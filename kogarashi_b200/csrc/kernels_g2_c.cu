@@ -1,0 +1,4 @@
+// BN254 G2 (coordinates in Fq2): fold reduce kernels + launchers.
+#define KGR_PART 8
+#include "launch_impl.cuh"
+template struct kgr::Launch<kgr::Bn254G2>;

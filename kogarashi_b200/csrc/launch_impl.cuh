@@ -1,5 +1,11 @@
 // launch_impl.cuh — definitions of Launch<C>; include once per curve and instantiate explicitly.
+// KGR_PART selects which member groups a translation unit defines (an explicit instantiation of the class instantiates only the
+// members defined at that point), so a curve whose kernels compile slowly (G2) can be spread over several TUs:
+// 1 scalar side + accumulate + fixup, 2 experimental batched-affine accumulate, 4 running-sum reduce, 8 fold reduce, 16 utilities.
 #pragma once
+#ifndef KGR_PART
+#define KGR_PART 31
+#endif
 #include "kernels_curve.cuh"
 #include "launch.cuh"
 
@@ -7,6 +13,7 @@ namespace kgr {
 
 static inline unsigned cdiv(size_t a, unsigned b) { return (unsigned)((a + b - 1) / b); }
 
+#if KGR_PART & 1
 template <class C> int Launch<C>::accumulate_blocks_per_sm() {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accumulate<C>, TPB_ACC, 0);
@@ -28,6 +35,8 @@ void Launch<C>::accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks,
                            X *head, X *tail, uint32_t *tail_bucket) {
     k_accumulate<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
+#endif
+#if KGR_PART & 2
 template <class C> int Launch<C>::accumulate_affine_blocks_per_sm() {
     int nb = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accumulate_affine<C>, TPB_ACC, 0);
@@ -37,13 +46,13 @@ template <class C>
 void Launch<C>::accumulate_affine(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
                                   const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix) {
     k_accumulate_affine<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, rounds, bases, offsets, entries, bucket_acc, head, tail, tail_bucket,
-                                                                      (A *)scratch_nodes, (Fp<typename C::Base> *)scratch_suffix);
+                                                                      (A *)scratch_nodes, (typename C::Elem *)scratch_suffix);
 }
 template <class C>
 int Launch<C>::accumulate_affine_split(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
                                        const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix,
                                        void *scratch_inv) {
-    typedef Fp<typename C::Base> F;
+    typedef typename C::Elem F;
     for (uint32_t r = 0; r < rounds; r++) {
         k_affine_phase1<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, r, bases, offsets, entries, (const A *)scratch_nodes, (F *)scratch_suffix, (F *)scratch_inv);
         k_affine_phase2<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, r, bases, offsets, entries, (A *)scratch_nodes, (const F *)scratch_suffix, (const F *)scratch_inv);
@@ -51,6 +60,8 @@ int Launch<C>::accumulate_affine_split(cudaStream_t st, const MsmShape &sh, uint
     k_affine_tail<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, rounds, offsets, (const A *)scratch_nodes, bucket_acc, head, tail, tail_bucket);
     return 2 * (int)rounds + 1;
 }
+#endif
+#if KGR_PART & 1
 template <class C>
 void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
                       const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
@@ -58,6 +69,8 @@ void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int 
     unsigned blocks = sh.G < 4u * (unsigned)sm_count ? sh.G : 4u * (unsigned)sm_count;
     k_fixup_long<C><<<blocks, TPB_TREE, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
 }
+#endif
+#if KGR_PART & 4
 template <class C>
 void Launch<C>::reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a,
                        const uint32_t *bucket_offsets) {
@@ -70,6 +83,8 @@ template <class C> void Launch<C>::weight(cudaStream_t st, uint32_t n_windows, u
 template <class C> void Launch<C>::tree_sum(cudaStream_t st, uint32_t n_windows, const X *in, uint32_t cnt_in, X *out) {
     k_tree_sum<C><<<dim3(cdiv(cnt_in, TPB_TREE), n_windows), TPB_TREE, 0, st>>>(in, cnt_in, out);
 }
+#endif
+#if KGR_PART & 8
 template <class C> uint32_t Launch<C>::fold_chunks_max(uint32_t B) { return ((B >> 1) + 8u * TPB_TREE - 1) / (8u * TPB_TREE); }
 template <class C>
 int Launch<C>::fold_reduce(cudaStream_t st, uint32_t n_windows, uint32_t B, const X *buckets, const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out) {
@@ -90,7 +105,11 @@ int Launch<C>::fold_reduce(cudaStream_t st, uint32_t n_windows, uint32_t B, cons
     k_fold_combine<C><<<n_windows, TPB_TREE, 0, st>>>(F, V, B, nb, out);
     return launches + 3;
 }
+#endif
+#if KGR_PART & 4
 template <class C> void Launch<C>::final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out) { k_final<C><<<1, 32, 0, st>>>(sh, win_a, out); }
+#endif
+#if KGR_PART & 16
 template <class C> void Launch<C>::fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n) { k_fold_inf<C><<<cdiv(n, 256), 256, 0, st>>>(pts, inf, n); }
 template <class C> void Launch<C>::precompute(cudaStream_t st, uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const A *pts, A *table) {
     k_precompute<C><<<cdiv(n, 128), 128, 0, st>>>(n, c, W, stride, pts, table);
@@ -102,5 +121,6 @@ template <class C> void Launch<C>::gen_scalars(cudaStream_t st, uint64_t seed, u
     k_gen_scalars<C><<<cdiv(n, 256), 256, 0, st>>>(seed, first, n, out);
 }
 template <class C> void Launch<C>::fixed_base(cudaStream_t st, const S *k, const A &g, uint32_t n, A *out) { k_fixed_base<C><<<cdiv(n, 128), 128, 0, st>>>(k, g, n, out); }
+#endif
 
 }  // namespace kgr

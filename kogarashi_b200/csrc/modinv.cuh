@@ -223,4 +223,9 @@ template <class P> KGR_HD Fp<P> fp_inv_fast(const Fp<P> &a) {
     return fp_mul(x, r3);     // a^-1 R^-1 * R^3 * R^-1 = a^-1 R
 }
 
+template <class P> KGR_HD Fp2<P> fp_inv_fast(const Fp2<P> &a) {
+    Fp<P> t = fp_inv_fast(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));
+    return Fp2<P>{fp_mul(t, a.c0), fp_mul(t, fp_neg(a.c1))};
+}
+
 }  // namespace kgr

@@ -99,7 +99,7 @@ struct Engine {
     size_t counts_zeroed = 0;  // counts[0..counts_zeroed) are known to be zero
     float last_ms[9] = {};
     uint32_t last_shape[6] = {};
-    int acc_blocks_per_sm[2] = {0, 0}, aff_blocks_per_sm[2] = {0, 0};
+    int acc_blocks_per_sm[3] = {0, 0, 0}, aff_blocks_per_sm[3] = {0, 0, 0};
     uint64_t launches = 0;            // kernels of this library launched on this engine since init
     cudaEvent_t user_ev[4] = {};      // kgr_event_record / kgr_event_elapsed_ms
     DevBuf<uint8_t> oneshot_pts, oneshot_inf;  // device copy of the bases of kgr_msm_oneshot
@@ -118,11 +118,12 @@ struct Engine {
         CK(cudaEventCreateWithFlags(&ev_sc, cudaEventDisableTiming));
         for (auto &e : ev) CK(cudaEventCreate(&e));
         for (auto &e : user_ev) CK(cudaEventCreate(&e));
-        CK(cudaMallocHost(&h_result, 256 * 32 * sizeof(uint32_t)));
+        CK(cudaMallocHost(&h_result, 256 * 64 * sizeof(uint32_t)));  // up to 255 window sums of the widest XYZZ point (G2)
         acc_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_blocks_per_sm();
         acc_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_blocks_per_sm();
         aff_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_affine_blocks_per_sm();
         aff_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_affine_blocks_per_sm();
+        acc_blocks_per_sm[2] = Launch<Bn254G2>::accumulate_blocks_per_sm();
     }
     void destroy() {
         if (dev < 0) return;
@@ -232,7 +233,7 @@ template <class C>
 static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d_scalars, int is_mont, uint32_t n, uint32_t table_c = 0,
                         uint32_t table_stride = 0, uint32_t table_off = 0) {
     typedef XyzzPt<C> X;
-    const bool affine = g_params.affine_rounds > 0;
+    const bool affine = g_params.affine_rounds > 0 && C::ID != Bn254G2::ID;  // the experimental batched-affine path is built for 8-word coordinates only
     MsmShape sh = make_shape(n, affine ? e.aff_blocks_per_sm[C::ID] : e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
     const uint32_t nwin = table_c ? 1u : sh.W;  // independent bucket sets to reduce
     uint64_t M64 = (uint64_t)n * sh.W;
@@ -280,6 +281,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
         e.wait_pts = false;
     }
+    if constexpr (C::ID != Bn254G2::ID) {
     if (affine && sh.L <= AFF_MAX_L) {
         e.aff_nodes.ensure((size_t)chunks * sh.L * sizeof(AffinePt<C>));
         e.aff_suffix.ensure((size_t)chunks * ((sh.L + 1) / 2) * 32);
@@ -292,7 +294,8 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
                                  (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p);
         }
     }
-    else
+    }
+    if (!(affine && sh.L <= AFF_MAX_L))
         K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
     CK(cudaEventRecord(e.ev[EV_ACC], e.st));
     CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
@@ -402,7 +405,7 @@ template <class C> static void upload_shard(Engine &e, Shard &s, const uint64_t 
     CK(cudaSetDevice(e.dev));
     CK(cudaMalloc(&s.d_pts, std::max<size_t>(s.count, 1) * sizeof(AffinePt<C>)));
     if (s.count == 0) return;
-    CK(cudaMemcpyAsync(s.d_pts, xy + 8 * s.first, s.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st));
+    CK(cudaMemcpyAsync(s.d_pts, xy + (sizeof(AffinePt<C>) / 8) * s.first, s.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st));
     if (inf) {
         uint8_t *d_inf = nullptr;
         CK(cudaMalloc(&d_inf, s.count));
@@ -433,23 +436,24 @@ struct Partial {
     const uint32_t *pts;
     uint32_t count, c;
 };
-template <class C> static void combine_partials(const std::vector<Partial> &parts, uint64_t out[12]) {
+template <class C> static void combine_partials(const std::vector<Partial> &parts, uint64_t *out) {
+    constexpr size_t XW = sizeof(XyzzPt<C>) / 4;  // words per XYZZ point
     XyzzPt<C> acc = xyzz_identity<C>();
     for (const Partial &p : parts) {
         if (!p.count) continue;
         XyzzPt<C> r;
-        std::memcpy(&r, p.pts + 32 * (size_t)(p.count - 1), sizeof r);
+        std::memcpy(&r, p.pts + XW * (size_t)(p.count - 1), sizeof r);
         for (uint32_t w = p.count - 1; w-- > 0;) {
             for (uint32_t d = 0; d < p.c; d++) r = xyzz_dbl(r);
             XyzzPt<C> q;
-            std::memcpy(&q, p.pts + 32 * (size_t)w, sizeof q);
+            std::memcpy(&q, p.pts + XW * (size_t)w, sizeof q);
             xyzz_add(r, q);
         }
         xyzz_add(acc, r);
     }
-    Fp<typename C::Base> o[3];
+    typename C::Elem o[3];
     xyzz_to_projective(acc, o);
-    std::memcpy(out, o, 96);
+    std::memcpy(out, o, sizeof o);
 }
 
 struct HostPts {
@@ -461,7 +465,7 @@ struct HostPts {
 // hp != nullptr: the bases themselves come from host memory for this call only (kgr_msm_oneshot);
 // each GPU uploads its shard into a cached buffer on its own stream before the pipeline.
 template <class C>
-static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t out[12],
+static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t *out,
                     const HostPts *hp) {
     struct Job {
         Engine *e;
@@ -508,7 +512,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 e.oneshot_pts.ensure(jb.count * sizeof(AffinePt<C>));
                 CK(cudaEventRecord(e.ev_sc, e.st));
                 CK(cudaStreamWaitEvent(e.st_copy, e.ev_sc, 0));
-                CK(cudaMemcpyAsync(e.oneshot_pts.p, hp->xy + 8 * jb.pt_first, jb.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st_copy));
+                CK(cudaMemcpyAsync(e.oneshot_pts.p, hp->xy + (sizeof(AffinePt<C>) / 8) * jb.pt_first, jb.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st_copy));
                 if (hp->inf) {
                     e.oneshot_inf.ensure(jb.count);
                     CK(cudaMemcpyAsync(e.oneshot_inf.p, hp->inf + jb.pt_first, jb.count, cudaMemcpyHostToDevice, e.st_copy));
@@ -549,33 +553,36 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
     }
 }
 
-template <class C> static void proj_to_affine_host(const uint64_t in[12], uint64_t out[9]) {
-    typedef typename C::Base F;
-    Fp<F> x, y, z;
-    std::memcpy(&x, in, 32);
-    std::memcpy(&y, in + 4, 32);
-    std::memcpy(&z, in + 8, 32);
+// in: 3 coordinates, out: x, y (Montgomery) and one trailing word = is_infinity
+template <class C> static void proj_to_affine_host(const uint64_t *in, uint64_t *out) {
+    typedef typename C::Elem E;
+    constexpr size_t EB = sizeof(E), EL = sizeof(E) / 8;
+    E x, y, z;
+    std::memcpy(&x, in, EB);
+    std::memcpy(&y, in + EL, EB);
+    std::memcpy(&z, in + 2 * EL, EB);
     if (fp_is_zero(z)) {
-        Fp<F> zero = fp_zero<F>(), one = fp_one<F>();
-        std::memcpy(out, &zero, 32);
-        std::memcpy(out + 4, &one, 32);
-        out[8] = 1;
+        E zero = El<E>::zero(), one = El<E>::one();
+        std::memcpy(out, &zero, EB);
+        std::memcpy(out + EL, &one, EB);
+        out[2 * EL] = 1;
         return;
     }
-    Fp<F> zi = fp_inv(z);
-    Fp<F> ax = fp_mul(x, zi), ay = fp_mul(y, zi);
-    std::memcpy(out, &ax, 32);
-    std::memcpy(out + 4, &ay, 32);
-    out[8] = 0;
+    E zi = fp_inv(z);
+    E ax = fp_mul(x, zi), ay = fp_mul(y, zi);
+    std::memcpy(out, &ax, EB);
+    std::memcpy(out + EL, &ay, EB);
+    out[2 * EL] = 0;
 }
 
 // (X : Y : Z) homogeneous -> XYZZ with zz = Z^2, zzz = Z^3, X' = X*Z, Y' = Y*Z^2
-template <class C> static XyzzPt<C> proj_to_xyzz_host(const uint64_t in[12]) {
-    typedef typename C::Base F;
-    Fp<F> x, y, z;
-    std::memcpy(&x, in, 32);
-    std::memcpy(&y, in + 4, 32);
-    std::memcpy(&z, in + 8, 32);
+template <class C> static XyzzPt<C> proj_to_xyzz_host(const uint64_t *in) {
+    typedef typename C::Elem E;
+    constexpr size_t EB = sizeof(E), EL = sizeof(E) / 8;
+    E x, y, z;
+    std::memcpy(&x, in, EB);
+    std::memcpy(&y, in + EL, EB);
+    std::memcpy(&z, in + 2 * EL, EB);
     if (fp_is_zero(z)) return xyzz_identity<C>();
     XyzzPt<C> r;
     r.zz = fp_sqr(z);
@@ -614,11 +621,12 @@ static int test_point_op(Engine &e, int op, const uint64_t *a, const uint8_t *ai
     upload_shard<C>(e, sa, a, ainf);
     upload_shard<C>(e, sb, b, binf);
     uint32_t *dout = nullptr;
-    CK(cudaMalloc(&dout, n * 96));
+    const size_t PB = 3 * sizeof(typename C::Elem);  // bytes per projective result
+    CK(cudaMalloc(&dout, n * PB));
     Launch<C>::point_op(e.st, op, (AffinePt<C> *)sa.d_pts, (AffinePt<C> *)sb.d_pts, dout, (uint32_t)n);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e.st));
-    CK(cudaMemcpy(out, dout, n * 96, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, dout, n * PB, cudaMemcpyDeviceToHost));
     cudaFree(dout);
     cudaFree(sa.d_pts);
     cudaFree(sb.d_pts);
@@ -639,6 +647,22 @@ template <> AffinePt<GrumpkinC> generator_affine<GrumpkinC>() {  // grumpkin/src
     g.x = fp_one<FrP>();
     const uint64_t gy[4] = {0x11b2dff1448c41d8ULL, 0x23d3446f21c77dc3ULL, 0xaa7b8cf435dfafbbULL, 0x14b34cf69dc25d68ULL};
     std::memcpy(&g.y, gy, 32);
+    return g;
+}
+
+template <> AffinePt<Bn254G2> generator_affine<Bn254G2>() {  // bn254/src/params.rs:15-42 (canonical limbs there; Montgomery here)
+    const uint64_t c[4][4] = {{0x46debd5cd992f6edULL, 0x674322d4f75edaddULL, 0x426a00665e5c4479ULL, 0x1800deef121f1e76ULL},
+                              {0x97e485b7aef312c2ULL, 0xf1aa493335a9e712ULL, 0x7260bfb731fb5d25ULL, 0x198e9393920d483aULL},
+                              {0x4ce6cc0166fa7daaULL, 0xe3d1e7690c43d37bULL, 0x4aab71808dcb408fULL, 0x12c85ea5db8c6debULL},
+                              {0x55acdadcd122975bULL, 0xbc4b313370b38ef3ULL, 0xec9e99ad690c3395ULL, 0x090689d0585ff075ULL}};
+    Fp<FqP> m[4];
+    for (int i = 0; i < 4; i++) {
+        std::memcpy(&m[i], c[i], 32);
+        m[i] = fp_to_mont(m[i]);
+    }
+    AffinePt<Bn254G2> g;
+    g.x = Fp2<FqP>{m[0], m[1]};
+    g.y = Fp2<FqP>{m[2], m[3]};
     return g;
 }
 
@@ -762,10 +786,13 @@ static int guarded(const std::function<int()> &f) {
     }
 }
 
+static inline size_t affine_bytes(int curve) { return curve == KGR_CURVE_BN254_G2 ? 128 : 64; }  // x || y
+
 #define DISPATCH(curve, CALL)                                              \
     do {                                                                   \
         if ((curve) == KGR_CURVE_BN254_G1) { CALL(Bn254G1); }              \
         else if ((curve) == KGR_CURVE_GRUMPKIN) { CALL(GrumpkinC); }       \
+        else if ((curve) == KGR_CURVE_BN254_G2) { CALL(Bn254G2); }         \
         else return fail(KGR_E_ARG, "unknown curve id");                   \
     } while (0)
 
@@ -881,7 +908,7 @@ int kgr_bases_precompute(kgr_bases_t *b, int window_bits) {
             if (s.d_table) CK(cudaFree(s.d_table));
             s.d_table = nullptr;
             s.table_c = 0;
-            CK(cudaMalloc(&s.d_table, (size_t)W * s.count * 64));
+            CK(cudaMalloc(&s.d_table, (size_t)W * s.count * affine_bytes(b->curve)));
 #define CALL(C) Launch<C>::precompute(e.st, (uint32_t)s.count, c, W, (uint32_t)s.count, (const AffinePt<C> *)s.d_pts, (AffinePt<C> *)s.d_table)
             DISPATCH(b->curve, CALL);
 #undef CALL
@@ -893,7 +920,7 @@ int kgr_bases_precompute(kgr_bases_t *b, int window_bits) {
     });
 }
 
-static int msm_common(kgr_bases_t *b, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t out[12]) {
+static int msm_common(kgr_bases_t *b, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t *out) {
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     if (!b || !out || (!scalars && n)) return fail(KGR_E_ARG, "null pointer");
     if (off > b->n || n > b->n - off) return fail(KGR_E_ARG, "range exceeds the registered vector");
@@ -906,18 +933,18 @@ static int msm_common(kgr_bases_t *b, size_t off, const uint64_t *scalars, bool 
     });
 }
 
-int kgr_msm(kgr_bases_t *b, size_t off, const uint64_t *scalars, int fmt, size_t n, uint64_t out[12]) {
+int kgr_msm(kgr_bases_t *b, size_t off, const uint64_t *scalars, int fmt, size_t n, uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
     return msm_common(b, off, scalars, false, fmt, n, out);
 }
 
-int kgr_msm_device(kgr_bases_t *b, size_t off, const void *d_scalars, int fmt, size_t n, uint64_t out[12]) {
+int kgr_msm_device(kgr_bases_t *b, size_t off, const void *d_scalars, int fmt, size_t n, uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
     return msm_common(b, off, (const uint64_t *)d_scalars, true, fmt, n, out);
 }
 
 int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, int fmt, size_t n_scalars,
-                    uint64_t out[12]) {
+                    uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     size_t n = std::min(n_bases, n_scalars);  // zip semantics, groth16/src/msm.rs:25
@@ -944,7 +971,8 @@ int kgr_bases_download(const kgr_bases_t *b, size_t off, size_t n, uint64_t *xy_
             size_t lo = std::max(off, s.first), hi = std::min(off + n, s.first + s.count);
             if (lo >= hi) continue;
             CK(cudaSetDevice(g_engines[s.eng].dev));
-            CK(cudaMemcpy(xy_out + 8 * (lo - off), (const uint8_t *)s.d_pts + 64 * (lo - s.first), 64 * (hi - lo), cudaMemcpyDeviceToHost));
+            const size_t ab = affine_bytes(b->curve);
+            CK(cudaMemcpy(xy_out + (ab / 8) * (lo - off), (const uint8_t *)s.d_pts + ab * (lo - s.first), ab * (hi - lo), cudaMemcpyDeviceToHost));
         }
         return KGR_OK;
     });
@@ -981,7 +1009,7 @@ int kgr_launch_count(int dev, uint64_t *count) {
     return KGR_OK;
 }
 
-int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]) {
+int kgr_to_affine(int curve, const uint64_t *in, uint64_t *out) {
     if (!in || !out) return fail(KGR_E_ARG, "null pointer");
 #define CALL(C) proj_to_affine_host<C>(in, out)
     DISPATCH(curve, CALL);
@@ -989,24 +1017,24 @@ int kgr_to_affine(int curve, const uint64_t in[12], uint64_t out[9]) {
     return KGR_OK;
 }
 
-int kgr_proj_add(int curve, const uint64_t a[12], const uint64_t b[12], uint64_t out[12]) {
+int kgr_proj_add(int curve, const uint64_t *a, const uint64_t *b, uint64_t *out) {
     if (!a || !b || !out) return fail(KGR_E_ARG, "null pointer");
 #define CALL(C)                                                   \
     {                                                             \
         XyzzPt<C> x = proj_to_xyzz_host<C>(a), y = proj_to_xyzz_host<C>(b); \
         xyzz_add(x, y);                                           \
-        Fp<typename C::Base> o[3];                                \
+        typename C::Elem o[3];                                    \
         xyzz_to_projective(x, o);                                 \
-        std::memcpy(out, o, 96);                                  \
+        std::memcpy(out, o, sizeof o);                            \
     }
     DISPATCH(curve, CALL);
 #undef CALL
     return KGR_OK;
 }
 
-int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int fmt, size_t n, uint64_t out[9]) {
+int kgr_pedersen_commit(kgr_bases_t *ck, const uint64_t *scalars, int fmt, size_t n, uint64_t *out) {
     if (!ck) return fail(KGR_E_ARG, "null pointer");
-    uint64_t proj[12];
+    uint64_t proj[24];
     size_t pairs = std::min(n, ck->n);  // m.iter().zip(self.g.iter()), nova/src/pedersen.rs:16-17
     int rc = kgr_msm(ck, 0, scalars, fmt, pairs, proj);
     if (rc) return rc;
@@ -1137,14 +1165,15 @@ int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy)
         CK(cudaSetDevice(e.dev));
         void *dk = nullptr, *dp = nullptr;
         CK(cudaMalloc(&dk, n * 32 + 32));
-        CK(cudaMalloc(&dp, n * 64 + 64));
+        const size_t ab = affine_bytes(curve);
+        CK(cudaMalloc(&dp, n * ab + ab));
         CK(cudaMemcpyAsync(dk, k, n * 32, cudaMemcpyHostToDevice, e.st));
 #define CALL(C) Launch<C>::fixed_base(e.st, (const Fp<C::Scalar> *)dk, generator_affine<C>(), (uint32_t)n, (AffinePt<C> *)dp)
         DISPATCH(curve, CALL);
 #undef CALL
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e.st));
-        CK(cudaMemcpy(out_xy, dp, n * 64, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(out_xy, dp, n * ab, cudaMemcpyDeviceToHost));
         cudaFree(dk);
         cudaFree(dp);
         return KGR_OK;

@@ -233,39 +233,41 @@ KGR_HD void body_fill_window(uint32_t i, uint32_t w, const MsmShape &sh, const u
 }
 
 // ---- accumulate -----------------------------------------------------------------------------
+// 16-byte loads / stores of whole field elements (8 words, or 16 for Fq2) between global memory and registers
+template <class E> KGR_HD void el_load(E &e, const void *src) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int k = 0; k < El<E>::WORDS / 4; k++) {
+        uint4 a = __ldg(q + k);
+        El<E>::word(e, 4 * k) = a.x; El<E>::word(e, 4 * k + 1) = a.y; El<E>::word(e, 4 * k + 2) = a.z; El<E>::word(e, 4 * k + 3) = a.w;
+    }
+#else
+    e = *reinterpret_cast<const E *>(src);
+#endif
+}
+template <class E> KGR_HD void el_store(void *dst, const E &e) {
+#if defined(__CUDA_ARCH__)
+    uint4 *q = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int k = 0; k < El<E>::WORDS / 4; k++)
+        q[k] = make_uint4(El<E>::word(e, 4 * k), El<E>::word(e, 4 * k + 1), El<E>::word(e, 4 * k + 2), El<E>::word(e, 4 * k + 3));
+#else
+    *reinterpret_cast<E *>(dst) = e;
+#endif
+}
 template <class C> KGR_HD AffinePt<C> load_affine(const AffinePt<C> *bases, uint32_t idx) {
     AffinePt<C> p;
-#if defined(__CUDA_ARCH__)
-    const uint4 *q = reinterpret_cast<const uint4 *>(bases + idx);
-    uint4 a = __ldg(q), b = __ldg(q + 1), c = __ldg(q + 2), d = __ldg(q + 3);
-    p.x.v[0] = a.x; p.x.v[1] = a.y; p.x.v[2] = a.z; p.x.v[3] = a.w;
-    p.x.v[4] = b.x; p.x.v[5] = b.y; p.x.v[6] = b.z; p.x.v[7] = b.w;
-    p.y.v[0] = c.x; p.y.v[1] = c.y; p.y.v[2] = c.z; p.y.v[3] = c.w;
-    p.y.v[4] = d.x; p.y.v[5] = d.y; p.y.v[6] = d.z; p.y.v[7] = d.w;
-#else
-    p = bases[idx];
-#endif
+    el_load(p.x, &bases[idx].x);
+    el_load(p.y, &bases[idx].y);
     return p;
 }
 
 template <class C> KGR_HD void store_xyzz(XyzzPt<C> *dst, const XyzzPt<C> &p) {
-#if defined(__CUDA_ARCH__)
-    uint4 *q = reinterpret_cast<uint4 *>(dst);
-    const uint32_t *s = p.x.v;
-    q[0] = make_uint4(s[0], s[1], s[2], s[3]);
-    q[1] = make_uint4(s[4], s[5], s[6], s[7]);
-    s = p.y.v;
-    q[2] = make_uint4(s[0], s[1], s[2], s[3]);
-    q[3] = make_uint4(s[4], s[5], s[6], s[7]);
-    s = p.zz.v;
-    q[4] = make_uint4(s[0], s[1], s[2], s[3]);
-    q[5] = make_uint4(s[4], s[5], s[6], s[7]);
-    s = p.zzz.v;
-    q[6] = make_uint4(s[0], s[1], s[2], s[3]);
-    q[7] = make_uint4(s[4], s[5], s[6], s[7]);
-#else
-    *dst = p;
-#endif
+    el_store(&dst->x, p.x);
+    el_store(&dst->y, p.y);
+    el_store(&dst->zz, p.zz);
+    el_store(&dst->zzz, p.zzz);
 }
 
 // first g with offsets[g+1] > pos  (offsets is non-decreasing, offsets[G] = M > pos)
@@ -346,16 +348,9 @@ KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *b
 constexpr uint32_t AFF_MAX_L = 256;
 
 // x coordinate only (32 bytes): all the chord denominators of phase 1 need
-template <class C> KGR_HD Fp<typename C::Base> load_x(const AffinePt<C> *p) {
-    Fp<typename C::Base> x;
-#if defined(__CUDA_ARCH__)
-    const uint4 *q = reinterpret_cast<const uint4 *>(p);
-    uint4 a = __ldg(q), b = __ldg(q + 1);
-    x.v[0] = a.x; x.v[1] = a.y; x.v[2] = a.z; x.v[3] = a.w;
-    x.v[4] = b.x; x.v[5] = b.y; x.v[6] = b.z; x.v[7] = b.w;
-#else
-    x = p->x;
-#endif
+template <class C> KGR_HD typename C::Elem load_x(const AffinePt<C> *p) {
+    typename C::Elem x;
+    el_load(x, &p->x);
     return x;
 }
 template <class C> KGR_HD AffinePt<C> load_node0(const AffinePt<C> *bases, uint32_t ent) {
@@ -364,12 +359,12 @@ template <class C> KGR_HD AffinePt<C> load_node0(const AffinePt<C> *bases, uint3
     return p;
 }
 // case of the pair (a, b) and its denominator: 0 chord (xb - xa), 1 tangent (2 ya), 2 result a, 3 result b, 4 result identity
-template <class C> KGR_HD int pair_case(const AffinePt<C> &a, const AffinePt<C> &b, Fp<typename C::Base> &den) {
-    typedef typename C::Base F;
-    den = fp_one<F>();
+template <class C> KGR_HD int pair_case(const AffinePt<C> &a, const AffinePt<C> &b, typename C::Elem &den) {
+    typedef typename C::Elem E;
+    den = El<E>::one();
     if (affine_is_identity(b)) return 2;
     if (affine_is_identity(a)) return 3;
-    Fp<F> dx = fp_sub(b.x, a.x);
+    E dx = fp_sub(b.x, a.x);
     if (!fp_is_zero(dx)) {
         den = dx;
         return 0;
@@ -380,23 +375,23 @@ template <class C> KGR_HD int pair_case(const AffinePt<C> &a, const AffinePt<C> 
     }
     return 4;
 }
-template <class C> KGR_HD AffinePt<C> pair_sum(int code, const AffinePt<C> &a, const AffinePt<C> &b, const Fp<typename C::Base> &den_inv) {
-    typedef typename C::Base F;
+template <class C> KGR_HD AffinePt<C> pair_sum(int code, const AffinePt<C> &a, const AffinePt<C> &b, const typename C::Elem &den_inv) {
+    typedef typename C::Elem E;
     if (code == 2) return a;
     if (code == 3) return b;
     AffinePt<C> r;
     if (code == 4) {
-        r.x = fp_zero<F>();
-        r.y = fp_zero<F>();
+        r.x = El<E>::zero();
+        r.y = El<E>::zero();
         return r;
     }
-    Fp<F> num;
+    E num;
     if (code == 0) num = fp_sub(b.y, a.y);
     else {
-        Fp<F> xx = fp_sqr(a.x);
+        E xx = fp_sqr(a.x);
         num = fp_add(fp_dbl(xx), xx);
     }
-    Fp<F> lam = fp_mul(num, den_inv);
+    E lam = fp_mul(num, den_inv);
     r.x = fp_sub(fp_sub(fp_sqr(lam), a.x), b.x);
     r.y = fp_sub(fp_mul(lam, fp_sub(a.x, r.x)), a.y);
     return r;
@@ -405,8 +400,8 @@ template <class C> KGR_HD AffinePt<C> pair_sum(int code, const AffinePt<C> &a, c
 template <class C>
 KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t rounds, const AffinePt<C> *bases, const uint32_t *offsets,
                                    const uint32_t *entries, XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket,
-                                   AffinePt<C> *scratch_nodes, Fp<typename C::Base> *scratch_suffix) {
-    typedef typename C::Base F;
+                                   AffinePt<C> *scratch_nodes, typename C::Elem *scratch_suffix) {
+    typedef typename C::Elem E;
     uint32_t M = offsets[sh.G];
     uint64_t s64 = (uint64_t)t * sh.L;
     if (s64 >= M) return;
@@ -437,14 +432,14 @@ KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t roun
     // indices differ from lane to lane, which would turn interleaved local memory into 4-byte scattered accesses, while a
     // thread-major slice gives every lane whole 32-byte sectors (worst case, all segments odd, a level keeps all its nodes).
     AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    Fp<F> *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
+    E *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
     uint32_t n_nodes = e - s;
     bool in_R = false;  // nodes still are the gathered base points until the first level has run
     for (uint32_t round = 0; round < rounds && n_pairs > 0; round++) {
         // Both phases are FLAT loops over "steps" (a pair, or the odd last node of a segment): every lane runs about
         // n_nodes / 2 steps whatever its bucket boundaries are, so the warp stays converged.
         // phase 1, backwards: suffix[i] = product of the denominators of the pairs after i
-        Fp<F> run = fp_one<F>();
+        E run = El<E>::one();
         {
             uint32_t pos = n_nodes, pidx = n_pairs, j = nseg, rem = 0;
             while (pos > 0) {
@@ -468,8 +463,8 @@ KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t roun
                     pa = R + pos;
                     pb = R + pos + 1;
                 }
-                Fp<F> xa = load_x(pa), xb = load_x(pb);
-                Fp<F> den = fp_sub(xb, xa);
+                E xa = load_x(pa), xb = load_x(pb);
+                E den = fp_sub(xb, xa);
                 if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {  // equal x, or x = 0 (maybe the identity encoding (0, 0))
                     AffinePt<C> a = in_R ? *pa : load_node0(bases, ea), b = in_R ? *pb : load_node0(bases, eb);
                     (void)pair_case(a, b, den);
@@ -479,7 +474,7 @@ KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t roun
                 run = fp_mul(run, den);
             }
         }
-        Fp<F> pre = fp_inv_fast(run);  // 1 / (product of all denominators)
+        E pre = fp_inv_fast(run);  // 1 / (product of all denominators)
         // phase 2, forwards: 1/den_i = pre * suffix[i]; pre *= den_i.  Output index <= input index, so writing R in place is safe.
         {
             uint32_t pos = 0, out = 0, pidx = 0, j = 0, rem = 0, new_pairs = 0, seg_out = 0;
@@ -497,9 +492,9 @@ KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t roun
                         a = R[pos];
                         b = R[pos + 1];
                     }
-                    Fp<F> den;
+                    E den;
                     int code = pair_case(a, b, den);
-                    Fp<F> den_inv = fp_mul(pre, suffix[pidx]);
+                    E den_inv = fp_mul(pre, suffix[pidx]);
                     pre = fp_mul(pre, den);
                     pidx++;
                     R[out] = pair_sum(code, a, b, den_inv);
@@ -566,12 +561,12 @@ KGR_HD uint32_t level_len(uint32_t len0, uint32_t r) { return (len0 + (1u << r) 
 // phase 1 of level r (backwards): suffix products, then the inverse of the product of all denominators -> inv_out[t]
 template <class C>
 KGR_HD void body_affine_phase1(uint32_t t, const MsmShape &sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                               const AffinePt<C> *scratch_nodes, Fp<typename C::Base> *scratch_suffix, Fp<typename C::Base> *inv_out) {
-    typedef typename C::Base F;
+                               const AffinePt<C> *scratch_nodes, typename C::Elem *scratch_suffix, typename C::Elem *inv_out) {
+    typedef typename C::Elem E;
     ChunkSpan c = chunk_span(t, sh, offsets);
     if (!c.valid) return;
     const AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    Fp<F> *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
+    E *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
     // totals at this level
     uint32_t n_nodes = 0, n_pairs = 0, g_last = c.g_first;
     for (uint32_t g = c.g_first, pos = c.s; pos < c.e; g++) {
@@ -583,7 +578,7 @@ KGR_HD void body_affine_phase1(uint32_t t, const MsmShape &sh, uint32_t r, const
         pos = g_end < c.e ? g_end : c.e;
         g_last = g;
     }
-    Fp<F> run = fp_one<F>();
+    E run = El<E>::one();
     uint32_t pos = n_nodes, pidx = n_pairs, rem = 0, g = g_last + 1, hi0 = c.e;
     while (pos > 0) {
         if (rem == 0) {  // previous non-empty bucket (backwards)
@@ -613,8 +608,8 @@ KGR_HD void body_affine_phase1(uint32_t t, const MsmShape &sh, uint32_t r, const
             pa = R + pos;
             pb = R + pos + 1;
         }
-        Fp<F> xa = load_x(pa), xb = load_x(pb);
-        Fp<F> den = fp_sub(xb, xa);
+        E xa = load_x(pa), xb = load_x(pb);
+        E den = fp_sub(xb, xa);
         if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {
             AffinePt<C> a = r ? *pa : load_node0(bases, ea), b = r ? *pb : load_node0(bases, eb);
             (void)pair_case(a, b, den);
@@ -629,13 +624,13 @@ KGR_HD void body_affine_phase1(uint32_t t, const MsmShape &sh, uint32_t r, const
 // phase 2 of level r (forwards): recover the inverses, write the level r+1 nodes in place
 template <class C>
 KGR_HD void body_affine_phase2(uint32_t t, const MsmShape &sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                               AffinePt<C> *scratch_nodes, const Fp<typename C::Base> *scratch_suffix, const Fp<typename C::Base> *inv_in) {
-    typedef typename C::Base F;
+                               AffinePt<C> *scratch_nodes, const typename C::Elem *scratch_suffix, const typename C::Elem *inv_in) {
+    typedef typename C::Elem E;
     ChunkSpan c = chunk_span(t, sh, offsets);
     if (!c.valid) return;
     AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    const Fp<F> *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
-    Fp<F> pre = inv_in[t];
+    const E *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
+    E pre = inv_in[t];
     uint32_t pos = 0, out = 0, pidx = 0, rem = 0, g = c.g_first, lo0 = c.s;
     bool more = true;
     while (more) {
@@ -659,9 +654,9 @@ KGR_HD void body_affine_phase2(uint32_t t, const MsmShape &sh, uint32_t r, const
                 a = R[pos];
                 b = R[pos + 1];
             }
-            Fp<F> den;
+            E den;
             int code = pair_case(a, b, den);
-            Fp<F> den_inv = fp_mul(pre, suffix[pidx]);
+            E den_inv = fp_mul(pre, suffix[pidx]);
             pre = fp_mul(pre, den);
             pidx++;
             R[out] = pair_sum(code, a, b, den_inv);
@@ -831,10 +826,11 @@ template <class C> KGR_HD void body_final(const MsmShape &sh, const XyzzPt<C> *w
         for (uint32_t d = 0; d < sh.c; d++) r = xyzz_dbl(r);
         xyzz_add(r, win_a[w]);
     }
-    Fp<typename C::Base> o[3];
+    typename C::Elem o[3];
     xyzz_to_projective(r, o);
+    constexpr int NW = El<typename C::Elem>::WORDS;
     for (int k = 0; k < 3; k++)
-        for (int i = 0; i < 8; i++) out24[8 * k + i] = o[k].v[i];
+        for (int i = 0; i < NW; i++) out24[NW * k + i] = El<typename C::Elem>::word(o[k], i);
 }
 
 }  // namespace kgr

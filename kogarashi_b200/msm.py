@@ -14,6 +14,7 @@ from . import _lib
 
 BN254_G1 = 0   # bn_254::G1Affine, scalars bn_254::Fr
 GRUMPKIN = 1   # grumpkin::Affine, scalars bn_254::Fq
+BN254_G2 = 2   # bn_254::G2Affine (coordinates in Fq2 = c0 || c1), scalars bn_254::Fr  (next row N3, groth16/src/prover.rs:64-65)
 SCALARS_MONTGOMERY = 0
 SCALARS_CANONICAL = 1
 
@@ -29,6 +30,11 @@ def _c(a, dtype=np.uint64):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+def coord_limbs(curve):
+    """uint64 limbs per coordinate: 4, or 8 for G2 (an Fq2 element c0 || c1)."""
+    return 8 if curve == BN254_G2 else 4
+
+
 class Bases:
     """A base vector resident on the GPU(s) (kgr_bases_register): a Groth16 CRS query or a Pedersen ck."""
 
@@ -38,7 +44,7 @@ class Bases:
         if _handle is not None:
             self._h, self.n = _handle, _n
             return
-        pts = _c(points).reshape(-1, 8)
+        pts = _c(points).reshape(-1, 2 * coord_limbs(curve))
         self.n = pts.shape[0]
         h = ctypes.c_void_p()
         infp = None
@@ -70,7 +76,7 @@ class Bases:
     def download(self, off=0, n=None):
         """Copy registered points back to the host as (n, 8) uint64 (identity entries read (0, 0))."""
         n = self.n - off if n is None else n
-        out = np.zeros((n, 8), dtype=np.uint64)
+        out = np.zeros((n, 2 * coord_limbs(self.curve)), dtype=np.uint64)
         _lib.check(_lib.lib().kgr_bases_download(self._h, off, n, _u64(out)))
         return out
 
@@ -93,13 +99,15 @@ def msm_curve_addition(bases, coeffs, curve=BN254_G1, inf=None, scalar_fmt=SCALA
     (n, 8) uint64 array (uploaded for this call, like the reference's by-slice signature)."""
     _lib.ensure_init()
     sc = _c(coeffs).reshape(-1, 4)
-    out = np.zeros(12, dtype=np.uint64)
+    if isinstance(bases, Bases):
+        curve = bases.curve
+    out = np.zeros(3 * coord_limbs(curve), dtype=np.uint64)
     L = _lib.lib()
     if isinstance(bases, Bases):
         n = min(sc.shape[0], bases.n - base_off)
         _lib.check(L.kgr_msm(bases._h, base_off, _u64(sc), scalar_fmt, n, _u64(out)))
     else:
-        pts = _c(bases).reshape(-1, 8)
+        pts = _c(bases).reshape(-1, 2 * coord_limbs(curve))
         infp = None
         if inf is not None:
             inf = _c(inf, np.uint8)
@@ -110,22 +118,22 @@ def msm_curve_addition(bases, coeffs, curve=BN254_G1, inf=None, scalar_fmt=SCALA
 
 def msm_device(bases, d_scalars_ptr, n, scalar_fmt=SCALARS_MONTGOMERY, base_off=0):
     """MSM with the scalars already in device memory (raw pointer, n x 4 uint64)."""
-    out = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(3 * coord_limbs(bases.curve), dtype=np.uint64)
     _lib.check(_lib.lib().kgr_msm_device(bases._h, base_off, ctypes.c_void_p(d_scalars_ptr), scalar_fmt, n, _u64(out)))
     return out
 
 
 def to_affine(curve, proj):
-    """BNProjective::to_affine (zkstd/src/macros/curve/weierstrass.rs:57-66) -> (9,) x, y, is_infinity."""
+    """BNProjective::to_affine (zkstd/src/macros/curve/weierstrass.rs:57-66) -> (9,) x, y, is_infinity ((17,) for G2)."""
     proj = _c(proj)
-    out = np.zeros(9, dtype=np.uint64)
+    out = np.zeros(2 * coord_limbs(curve) + 1, dtype=np.uint64)
     _lib.check(_lib.lib().kgr_to_affine(curve, _u64(proj), _u64(out)))
     return out
 
 
 def proj_add(curve, a, b):
     a, b = _c(a), _c(b)
-    out = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(3 * coord_limbs(curve), dtype=np.uint64)
     _lib.check(_lib.lib().kgr_proj_add(curve, _u64(a), _u64(b), _u64(out)))
     return out
 
@@ -156,7 +164,7 @@ def launch_count(dev=0):
 
 def msm_oneshot_ptr(curve, xy_ptr, n_bases, sc_ptr, n_scalars, scalar_fmt=SCALARS_MONTGOMERY):
     """kgr_msm_oneshot on raw host pointers (e.g. pinned torch tensors): bases and scalars are uploaded inside the call."""
-    out = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(3 * coord_limbs(curve), dtype=np.uint64)
     L = _lib.lib()
     _lib.check(L.kgr_msm_oneshot(curve, ctypes.cast(xy_ptr, _u64p), None, n_bases, ctypes.cast(sc_ptr, _u64p), scalar_fmt, n_scalars, _u64(out)))
     return out
@@ -164,7 +172,7 @@ def msm_oneshot_ptr(curve, xy_ptr, n_bases, sc_ptr, n_scalars, scalar_fmt=SCALAR
 
 def msm_host_ptr(bases, sc_ptr, n, scalar_fmt=SCALARS_MONTGOMERY, base_off=0):
     """kgr_msm on a raw host pointer to the scalars (registered bases)."""
-    out = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(3 * coord_limbs(bases.curve), dtype=np.uint64)
     _lib.check(_lib.lib().kgr_msm(bases._h, base_off, ctypes.cast(sc_ptr, _u64p), scalar_fmt, n, _u64(out)))
     return out
 
@@ -195,8 +203,9 @@ def test_field_op(field, op, a, b=None):
 
 def test_point_op(curve, op, a, b, a_inf=None, b_inf=None):
     _lib.ensure_init()
-    a, b = _c(a).reshape(-1, 8), _c(b).reshape(-1, 8)
-    out = np.zeros((a.shape[0], 12), dtype=np.uint64)
+    cl = coord_limbs(curve)
+    a, b = _c(a).reshape(-1, 2 * cl), _c(b).reshape(-1, 2 * cl)
+    out = np.zeros((a.shape[0], 3 * cl), dtype=np.uint64)
     ai = _c(a_inf, np.uint8) if a_inf is not None else None
     bi = _c(b_inf, np.uint8) if b_inf is not None else None
     _lib.check(_lib.lib().kgr_test_point_op(curve, op, _u64(a), ai.ctypes.data_as(_u8p) if ai is not None else None, _u64(b),
@@ -207,6 +216,6 @@ def test_point_op(curve, op, a, b, a_inf=None, b_inf=None):
 def fixed_base_mul(curve, k):
     _lib.ensure_init()
     k = _c(k).reshape(-1, 4)
-    out = np.zeros((k.shape[0], 8), dtype=np.uint64)
+    out = np.zeros((k.shape[0], 2 * coord_limbs(curve)), dtype=np.uint64)
     _lib.check(_lib.lib().kgr_fixed_base_mul(curve, _u64(k), k.shape[0], _u64(out)))
     return out

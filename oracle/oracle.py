@@ -3,6 +3,7 @@
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs import
 this.  Array conventions equal include/kgr_msm.h: points (n, 8) uint64 = x||y Montgomery limbs,
 optional (n,) uint8 infinity flags, scalars (n, 4) uint64 Montgomery, projective result (12,).
+For BN254_G2 every coordinate is 8 limbs (c0 || c1): points (n, 16), projective (24,), affine (17,).
 """
 import ctypes
 import os
@@ -13,11 +14,16 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "libzkstd_oracle.so")
 
-BN254_G1, GRUMPKIN = 0, 1
+BN254_G1, GRUMPKIN, BN254_G2 = 0, 1, 2
 FIELD_FQ, FIELD_FR = 0, 1
 # base / scalar field ids per curve
 BASE_FIELD = {BN254_G1: FIELD_FQ, GRUMPKIN: FIELD_FR}
-SCALAR_FIELD = {BN254_G1: FIELD_FR, GRUMPKIN: FIELD_FQ}
+SCALAR_FIELD = {BN254_G1: FIELD_FR, GRUMPKIN: FIELD_FQ, BN254_G2: FIELD_FR}
+
+
+def coord_limbs(curve):
+    """uint64 limbs per coordinate: 4, or 8 for G2 (Fq2 = c0 || c1, bn254/src/fqn.rs)."""
+    return 8 if curve == BN254_G2 else 4
 
 OPS = dict(add=0, sub=1, mul=2, square=3, double=4, neg=5, invert=6, mont_reduce=7, to_mont=8, from_u512=9)
 
@@ -94,8 +100,8 @@ def field_op(field_id, op, a, b=None):
 
 
 def msm(curve, points, scalars, inf=None, threads=None):
-    points, scalars = _c(points).reshape(-1, 8), _c(scalars).reshape(-1, 4)
-    out = np.zeros(12, dtype=np.uint64)
+    points, scalars = _c(points).reshape(-1, 2 * coord_limbs(curve)), _c(scalars).reshape(-1, 4)
+    out = np.zeros(3 * coord_limbs(curve), dtype=np.uint64)
     infp = _u8(_c(inf, np.uint8)) if inf is not None else None
     rc = lib().zko_msm(curve, _u64(points), infp, points.shape[0], _u64(scalars), scalars.shape[0],
                        threads or os.cpu_count() or 1, _u64(out))
@@ -104,38 +110,38 @@ def msm(curve, points, scalars, inf=None, threads=None):
 
 
 def pedersen_commit(curve, points, scalars, inf=None):
-    points, scalars = _c(points).reshape(-1, 8), _c(scalars).reshape(-1, 4)
-    out = np.zeros(9, dtype=np.uint64)
+    points, scalars = _c(points).reshape(-1, 2 * coord_limbs(curve)), _c(scalars).reshape(-1, 4)
+    out = np.zeros(2 * coord_limbs(curve) + 1, dtype=np.uint64)
     infp = _u8(_c(inf, np.uint8)) if inf is not None else None
     assert lib().zko_pedersen_commit(curve, _u64(points), infp, points.shape[0], _u64(scalars), scalars.shape[0], _u64(out)) == 0
     return out
 
 
 def to_affine(curve, proj):
-    """-> (9,) uint64: x(4) y(4) is_infinity."""
+    """-> (9,) uint64: x(4) y(4) is_infinity ((17,) for G2)."""
     proj = _c(proj)
-    out = np.zeros(9, dtype=np.uint64)
+    out = np.zeros(2 * coord_limbs(curve) + 1, dtype=np.uint64)
     assert lib().zko_to_affine(curve, _u64(proj), _u64(out)) == 0
     return out
 
 
-def point_op(curve, op, a, b=None, out_len=12):
+def point_op(curve, op, a, b=None, out_len=None):
     a = _c(a)
-    bb = _c(b) if b is not None else np.zeros(12, dtype=np.uint64)
-    out = np.zeros(out_len, dtype=np.uint64)
+    bb = _c(b) if b is not None else np.zeros(3 * coord_limbs(curve), dtype=np.uint64)
+    out = np.zeros(out_len or 3 * coord_limbs(curve), dtype=np.uint64)
     assert lib().zko_point_op(curve, op, _u64(a), _u64(bb), _u64(out)) == 0
     return out
 
 
 def scalar_point(curve, proj, scalar):
     proj, scalar = _c(proj), _c(scalar)
-    out = np.zeros(12, dtype=np.uint64)
+    out = np.zeros(3 * coord_limbs(curve), dtype=np.uint64)
     assert lib().zko_scalar_point(curve, _u64(proj), _u64(scalar), _u64(out)) == 0
     return out
 
 
 def generator(curve):
-    out = np.zeros(8, dtype=np.uint64)
+    out = np.zeros(2 * coord_limbs(curve), dtype=np.uint64)
     assert lib().zko_generator(curve, _u64(out)) == 0
     return out
 
@@ -148,7 +154,7 @@ def random_field(field_id, n, seed=DEFAULT_SEED):
 
 
 def random_points(curve, n, seed=DEFAULT_SEED, threads=None, return_scalars=False):
-    xy = np.zeros((n, 8), dtype=np.uint64)
+    xy = np.zeros((n, 2 * coord_limbs(curve)), dtype=np.uint64)
     ks = np.zeros((n, 4), dtype=np.uint64)
     s = _seed(seed)
     assert lib().zko_random_points(curve, _u8(s), n, threads or os.cpu_count() or 1, _u64(xy), _u64(ks)) == 0

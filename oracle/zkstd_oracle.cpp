@@ -14,6 +14,8 @@ namespace {
 template <class C> struct Msm {
     typedef Curve<C> Cv;
     typedef Field<typename C::Scalar> Fs;
+    typedef typename Cv::Affine Affine;
+    typedef typename Cv::Proj Proj;
 
     // groth16/src/msm.rs:50-73
     struct Bucket {
@@ -86,19 +88,39 @@ template <class C> struct Msm {
 
 inline Limbs ld4(const uint64_t *p) { return Limbs{p[0], p[1], p[2], p[3]}; }
 inline void st4(uint64_t *p, const Limbs &l) { for (int i = 0; i < 4; i++) p[i] = l[i]; }
-
-std::vector<Affine> load_affine(const uint64_t *xy, const uint8_t *inf, size_t n) {
-    std::vector<Affine> v(n);
-    for (size_t i = 0; i < n; i++) v[i] = Affine{ld4(xy + 8 * i), ld4(xy + 8 * i + 4), inf ? inf[i] != 0 : false};
-    return v;
-}
+// coordinate <-> limbs: 4 per Fq/Fr element, 8 (c0 || c1) per Fq2 element
+template <class E> struct Io;
+template <> struct Io<Limbs> {
+    static constexpr size_t N = 4;
+    static Limbs ld(const uint64_t *p) { return ld4(p); }
+    static void st(uint64_t *p, const Limbs &v) { st4(p, v); }
+};
+template <> struct Io<Fq2El> {
+    static constexpr size_t N = 8;
+    static Fq2El ld(const uint64_t *p) { return Fq2El{ld4(p), ld4(p + 4)}; }
+    static void st(uint64_t *p, const Fq2El &v) { st4(p, v.c0); st4(p + 4, v.c1); }
+};
+template <class C> struct PtIo {
+    typedef typename Curve<C>::El El;
+    typedef typename Curve<C>::Affine Affine;
+    typedef typename Curve<C>::Proj Proj;
+    static constexpr size_t N = Io<El>::N;
+    static std::vector<Affine> load_affine(const uint64_t *xy, const uint8_t *inf, size_t n) {
+        std::vector<Affine> v(n);
+        for (size_t i = 0; i < n; i++) v[i] = Affine{Io<El>::ld(xy + 2 * N * i), Io<El>::ld(xy + 2 * N * i + N), inf ? inf[i] != 0 : false};
+        return v;
+    }
+    // x, y and a trailing is_infinity word
+    static Affine affine1(const uint64_t *p) { return Affine{Io<El>::ld(p), Io<El>::ld(p + N), p[2 * N] != 0}; }
+    static void store_affine1(uint64_t *out, const Affine &a) { Io<El>::st(out, a.x); Io<El>::st(out + N, a.y); out[2 * N] = a.inf; }
+    static void store_proj(uint64_t *out, const Proj &p) { Io<El>::st(out, p.x); Io<El>::st(out + N, p.y); Io<El>::st(out + 2 * N, p.z); }
+    static Proj load_proj(const uint64_t *in) { return Proj{Io<El>::ld(in), Io<El>::ld(in + N), Io<El>::ld(in + 2 * N)}; }
+};
 std::vector<Limbs> load_scalars(const uint64_t *s, size_t n) {
     std::vector<Limbs> v(n);
     for (size_t i = 0; i < n; i++) v[i] = ld4(s + 4 * i);
     return v;
 }
-void store_proj(uint64_t *out, const Proj &p) { st4(out, p.x); st4(out + 4, p.y); st4(out + 8, p.z); }
-Proj load_proj(const uint64_t *in) { return Proj{ld4(in), ld4(in + 4), ld4(in + 8)}; }
 
 template <class F> int field_op(int op, const uint64_t *a, const uint64_t *b, uint64_t *out) {
     typedef Field<F> Fd;
@@ -140,9 +162,10 @@ template <class C> void random_points(const uint8_t seed[16], size_t n, uint64_t
             size_t i = next.fetch_add(64);
             if (i >= n) break;
             for (size_t j = i; j < std::min(n, i + 64); j++) {
-                Affine a = Cv::to_affine(Cv::scalar_point(Cv::to_extended(Cv::generator()), k[j]));
-                st4(xy + 8 * j, a.x);
-                st4(xy + 8 * j + 4, a.y);
+                typename Cv::Affine a = Cv::to_affine(Cv::scalar_point(Cv::to_extended(Cv::generator()), k[j]));
+                constexpr size_t N = PtIo<C>::N;
+                Io<typename Cv::El>::st(xy + 2 * N * j, a.x);
+                Io<typename Cv::El>::st(xy + 2 * N * j + N, a.y);
             }
         }
     };
@@ -154,8 +177,14 @@ template <class C> void random_points(const uint8_t seed[16], size_t n, uint64_t
 
 }  // namespace
 
-#define DISPATCH_CURVE(curve, EXPR_G1, EXPR_GR) \
-    do { if ((curve) == 0) { EXPR_G1; } else if ((curve) == 1) { EXPR_GR; } else return -1; } while (0)
+// BODY is instantiated with C = the curve's parameter struct
+#define DISPATCH_CURVE(curve, BODY)                                   \
+    switch (curve) {                                                  \
+        case 0: { typedef Bn254G1 C; BODY; } break;                   \
+        case 1: { typedef Grumpkin C; BODY; } break;                  \
+        case 2: { typedef Bn254G2 C; BODY; } break;                   \
+        default: return -1;                                           \
+    }
 
 extern "C" {
 
@@ -166,68 +195,65 @@ int zko_field_op(int field_id, int op, const uint64_t *a, const uint64_t *b, uin
     return -1;
 }
 
-// curve: 0 = BN254 G1 (base Fq, scalar Fr), 1 = Grumpkin (base Fr, scalar Fq)
+// curve: 0 = BN254 G1 (base Fq, scalar Fr), 1 = Grumpkin (base Fr, scalar Fq), 2 = BN254 G2 (base Fq2, scalar Fr).
+// Point buffers hold N = 4 limbs per coordinate (8 for G2): affine xy n x 2N, projective 3N, affine result 2N + 1.
 int zko_msm(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, size_t n_scalars,
-            int threads, uint64_t out[12]) {
-    auto bases = load_affine(xy, inf, n_bases);
+            int threads, uint64_t *out) {
     auto sc = load_scalars(scalars, n_scalars);
-    DISPATCH_CURVE(curve, store_proj(out, Msm<Bn254G1>::run(bases.data(), n_bases, sc.data(), n_scalars, threads)),
-                   store_proj(out, Msm<Grumpkin>::run(bases.data(), n_bases, sc.data(), n_scalars, threads)));
+    DISPATCH_CURVE(curve, {
+        auto bases = PtIo<C>::load_affine(xy, inf, n_bases);
+        PtIo<C>::store_proj(out, Msm<C>::run(bases.data(), n_bases, sc.data(), n_scalars, threads));
+    });
     return 0;
 }
 
-// out = [x(4) y(4) inf(1 as u64)]
-int zko_pedersen_commit(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_g, const uint64_t *m, size_t n_m, uint64_t out[9]) {
-    auto g = load_affine(xy, inf, n_g);
+// out = [x y inf(1 as u64)]
+int zko_pedersen_commit(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_g, const uint64_t *m, size_t n_m, uint64_t *out) {
     auto sc = load_scalars(m, n_m);
-    Affine r;
-    DISPATCH_CURVE(curve, r = Msm<Bn254G1>::pedersen_commit(g.data(), n_g, sc.data(), n_m),
-                   r = Msm<Grumpkin>::pedersen_commit(g.data(), n_g, sc.data(), n_m));
-    st4(out, r.x); st4(out + 4, r.y); out[8] = r.inf;
+    DISPATCH_CURVE(curve, {
+        auto g = PtIo<C>::load_affine(xy, inf, n_g);
+        PtIo<C>::store_affine1(out, Msm<C>::pedersen_commit(g.data(), n_g, sc.data(), n_m));
+    });
     return 0;
 }
 
-int zko_to_affine(int curve, const uint64_t in[12], uint64_t out[9]) {
-    Affine r;
-    DISPATCH_CURVE(curve, r = Curve<Bn254G1>::to_affine(load_proj(in)), r = Curve<Grumpkin>::to_affine(load_proj(in)));
-    st4(out, r.x); st4(out + 4, r.y); out[8] = r.inf;
+int zko_to_affine(int curve, const uint64_t *in, uint64_t *out) {
+    DISPATCH_CURVE(curve, PtIo<C>::store_affine1(out, Curve<C>::to_affine(PtIo<C>::load_proj(in))));
     return 0;
 }
 
-// op: 0 add_proj(a,b), 1 double_proj(a), 2 add_mixed(affine b[x,y | inf in b[8]], proj a), 3 add_affine(a[0..8|inf a[8]], b[..]),
+// op: 0 add_proj(a,b), 1 double_proj(a), 2 add_mixed(affine b[x,y | inf], proj a), 3 add_affine(a[x,y | inf], b[..]),
 //     4 double_affine(a), 5 proj eq (out[0]), 6 is_on_curve(affine a) (out[0])
 int zko_point_op(int curve, int op, const uint64_t *a, const uint64_t *b, uint64_t *out) {
-    auto aff = [](const uint64_t *p) { return Affine{ld4(p), ld4(p + 4), p[8] != 0}; };
-#define BODY(C)                                                                         \
-    {                                                                                   \
-        typedef Curve<C> Cv;                                                            \
-        switch (op) {                                                                   \
-            case 0: store_proj(out, Cv::add_proj(load_proj(a), load_proj(b))); break;   \
-            case 1: store_proj(out, Cv::double_proj(load_proj(a))); break;              \
-            case 2: store_proj(out, Cv::add_mixed(aff(b), load_proj(a))); break;        \
-            case 3: store_proj(out, Cv::add_affine(aff(a), aff(b))); break;             \
-            case 4: store_proj(out, Cv::double_affine(aff(a))); break;                  \
-            case 5: out[0] = Cv::eq(load_proj(a), load_proj(b)); break;                 \
-            case 6: out[0] = Cv::is_on_curve(aff(a)); break;                            \
-            default: return -1;                                                         \
-        }                                                                               \
-    }
-    DISPATCH_CURVE(curve, BODY(Bn254G1), BODY(Grumpkin));
-#undef BODY
+    DISPATCH_CURVE(curve, {
+        typedef Curve<C> Cv;
+        typedef PtIo<C> P;
+        switch (op) {
+            case 0: P::store_proj(out, Cv::add_proj(P::load_proj(a), P::load_proj(b))); break;
+            case 1: P::store_proj(out, Cv::double_proj(P::load_proj(a))); break;
+            case 2: P::store_proj(out, Cv::add_mixed(P::affine1(b), P::load_proj(a))); break;
+            case 3: P::store_proj(out, Cv::add_affine(P::affine1(a), P::affine1(b))); break;
+            case 4: P::store_proj(out, Cv::double_affine(P::affine1(a))); break;
+            case 5: out[0] = Cv::eq(P::load_proj(a), P::load_proj(b)); break;
+            case 6: out[0] = Cv::is_on_curve(P::affine1(a)); break;
+            default: return -1;
+        }
+    });
     return 0;
 }
 
-// out = proj(12): point(a: proj 12) * scalar (Montgomery, scalar field of the curve)
-int zko_scalar_point(int curve, const uint64_t a[12], const uint64_t scalar[4], uint64_t out[12]) {
-    DISPATCH_CURVE(curve, store_proj(out, Curve<Bn254G1>::scalar_point(load_proj(a), ld4(scalar))),
-                   store_proj(out, Curve<Grumpkin>::scalar_point(load_proj(a), ld4(scalar))));
+// out = proj: point(a: proj) * scalar (Montgomery, scalar field of the curve)
+int zko_scalar_point(int curve, const uint64_t *a, const uint64_t scalar[4], uint64_t *out) {
+    DISPATCH_CURVE(curve, PtIo<C>::store_proj(out, Curve<C>::scalar_point(PtIo<C>::load_proj(a), ld4(scalar))));
     return 0;
 }
 
-int zko_generator(int curve, uint64_t out[8]) {
-    Affine g;
-    DISPATCH_CURVE(curve, g = Curve<Bn254G1>::generator(), g = Curve<Grumpkin>::generator());
-    st4(out, g.x); st4(out + 4, g.y);
+int zko_generator(int curve, uint64_t *out) {
+    DISPATCH_CURVE(curve, {
+        auto g = Curve<C>::generator();
+        Io<typename Curve<C>::El>::st(out, g.x);
+        Io<typename Curve<C>::El>::st(out + PtIo<C>::N, g.y);
+    });
     return 0;
 }
 
@@ -247,8 +273,7 @@ int zko_random_field(int field_id, const uint8_t seed[16], size_t n, uint64_t *o
 
 // n random points G * k_i (k_i from the sampler above); optionally returns the k_i (Montgomery).
 int zko_random_points(int curve, const uint8_t seed[16], size_t n, int threads, uint64_t *xy, uint64_t *scalars_out) {
-    DISPATCH_CURVE(curve, random_points<Bn254G1>(seed, n, xy, scalars_out, threads),
-                   random_points<Grumpkin>(seed, n, xy, scalars_out, threads));
+    DISPATCH_CURVE(curve, random_points<C>(seed, n, xy, scalars_out, threads));
     return 0;
 }
 

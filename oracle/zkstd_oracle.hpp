@@ -62,6 +62,7 @@ static inline uint64_t mac(uint64_t acc, uint64_t a, uint64_t b, uint64_t &carry
 }
 
 template <class F> struct Field {
+    typedef Limbs El;
     // conditional add-back of p under an all-ones/zero mask (normal.rs:22-29, 44-51, 73-80, 245-252)
     static inline Limbs add_masked_p(Limbs l, uint64_t mask) {
         uint64_t c = 0;
@@ -216,11 +217,49 @@ template <class F> struct Field {
     }
 };
 
+// ----- Fq2 = Fq[u]/(u^2 + 1)  (bn254/src/fqn.rs, zkstd/src/macros/extension_field.rs) ------------
+struct Fq2El {
+    Limbs c0, c1;
+    bool operator==(const Fq2El &o) const { return c0 == o.c0 && c1 == o.c1; }
+};
+struct Fq2Ops {
+    typedef Fq2El El;
+    typedef Field<FqParams> F;
+    static El zero() { return El{F::zero(), F::zero()}; }
+    static El one() { return El{F::one(), F::zero()}; }
+    static bool is_zero(const El &a) { return F::is_zero(a.c0) && F::is_zero(a.c1); }
+    static El add(const El &a, const El &b) { return El{F::add(a.c0, b.c0), F::add(a.c1, b.c1)}; }
+    static El sub(const El &a, const El &b) { return El{F::sub(a.c0, b.c0), F::sub(a.c1, b.c1)}; }
+    static El dbl(const El &a) { return El{F::dbl(a.c0), F::dbl(a.c1)}; }
+    static El neg(const El &a) { return El{F::neg(a.c0), F::neg(a.c1)}; }
+    // fqn.rs:359-363
+    static El mul(const El &a, const El &b) {
+        Limbs re = F::sub(F::mul(a.c0, b.c0), F::mul(a.c1, b.c1));
+        Limbs im = F::add(F::mul(a.c0, b.c1), F::mul(a.c1, b.c0));
+        return El{re, im};
+    }
+    // fqn.rs:365-369
+    static El square(const El &a) {
+        Limbs re = F::sub(F::square(a.c0), F::square(a.c1));
+        Limbs im = F::dbl(F::mul(a.c0, a.c1));
+        return El{re, im};
+    }
+    // fqn.rs:348-357
+    static bool invert(const El &a, El &out) {
+        if (is_zero(a)) return false;
+        Limbs t = F::add(F::square(a.c0), F::square(a.c1)), ti;
+        F::invert(t, ti);
+        out = El{F::mul(ti, a.c0), F::mul(ti, F::neg(a.c1))};
+        return true;
+    }
+};
+
 // ----- curves ------------------------------------------------------------------------------
 // Base = field of coordinates, Scalar = field of scalars, B3 = 3b in Montgomery form.
 struct Bn254G1 {
     typedef FqParams Base;
     typedef FrParams Scalar;
+    typedef Field<FqParams> BaseOps;
     // bn254/src/params.rs:8-12: generator (1,2), b = 3, 3b = 9 (Montgomery forms computed at init)
     static Limbs b3() { return Field<Base>::to_mont_form(Limbs{9, 0, 0, 0}); }
     static Limbs b() { return Field<Base>::to_mont_form(Limbs{3, 0, 0, 0}); }
@@ -230,19 +269,45 @@ struct Bn254G1 {
 struct Grumpkin {
     typedef FrParams Base;
     typedef FqParams Scalar;
+    typedef Field<FrParams> BaseOps;
     // grumpkin/src/params.rs:4-19 (Montgomery-form constants as stored by the reference)
     static Limbs b() { return Limbs{0xdd7056026000005aULL, 0x223fa97acb319311ULL, 0xcc388229877910c0ULL, 0x034394632b724eaaULL}; }
     static Limbs b3() { Limbs v = b(); return Field<Base>::add(Field<Base>::add(v, v), v); }
     static Limbs gx() { return Field<Base>::one(); }
     static Limbs gy() { return Limbs{0x11b2dff1448c41d8ULL, 0x23d3446f21c77dc3ULL, 0xaa7b8cf435dfafbbULL, 0x14b34cf69dc25d68ULL}; }
 };
+// bn254/src/g2.rs:12-21, params.rs:14-56 (canonical limbs there, to_mont_form applied as the reference does)
+struct Bn254G2 {
+    typedef FqParams Base;
+    typedef FrParams Scalar;
+    typedef Fq2Ops BaseOps;
+    static Limbs m(uint64_t a, uint64_t b, uint64_t c, uint64_t d) { return Field<Base>::to_mont_form(Limbs{a, b, c, d}); }
+    static Fq2El b() {
+        return Fq2El{m(0x3267e6dc24a138e5ULL, 0xb5b4c5e559dbefa3ULL, 0x81be18991be06ac3ULL, 0x2b149d40ceb8aaaeULL),
+                     m(0xe4a2bd0685c315d2ULL, 0xa74fa084e52d1852ULL, 0xcd2cafadeed8fdf4ULL, 0x009713b03af0fed4ULL)};
+    }
+    static Fq2El b3() { Fq2El v = b(); return Fq2Ops::add(Fq2Ops::add(v, v), v); }  // g2.rs:12
+    static Fq2El gx() {
+        return Fq2El{m(0x46debd5cd992f6edULL, 0x674322d4f75edaddULL, 0x426a00665e5c4479ULL, 0x1800deef121f1e76ULL),
+                     m(0x97e485b7aef312c2ULL, 0xf1aa493335a9e712ULL, 0x7260bfb731fb5d25ULL, 0x198e9393920d483aULL)};
+    }
+    static Fq2El gy() {
+        return Fq2El{m(0x4ce6cc0166fa7daaULL, 0xe3d1e7690c43d37bULL, 0x4aab71808dcb408fULL, 0x12c85ea5db8c6debULL),
+                     m(0x55acdadcd122975bULL, 0xbc4b313370b38ef3ULL, 0xec9e99ad690c3395ULL, 0x090689d0585ff075ULL)};
+    }
+};
 
-struct Affine { Limbs x, y; bool inf; };
-struct Proj { Limbs x, y, z; };
+template <class E> struct AffineT { E x, y; bool inf; };
+template <class E> struct ProjT { E x, y, z; };
+typedef AffineT<Limbs> Affine;
+typedef ProjT<Limbs> Proj;
 
 template <class C> struct Curve {
-    typedef Field<typename C::Base> Fb;
+    typedef typename C::BaseOps Fb;           // coordinate field operations (Field<Base>, or Fq2Ops for G2)
+    typedef typename Fb::El El;
     typedef Field<typename C::Scalar> Fs;
+    typedef AffineT<El> Affine;
+    typedef ProjT<El> Proj;
 
     // macros/curve/weierstrass/group.rs:22-26, 106-110
     static Affine affine_identity() { return Affine{Fb::zero(), Fb::one(), true}; }
@@ -256,7 +321,7 @@ template <class C> struct Curve {
     }
     // macros/curve/weierstrass.rs:57-66
     static Affine to_affine(const Proj &p) {
-        Limbs zi;
+        El zi;
         if (!Fb::invert(p.z, zi)) return affine_identity();
         return Affine{Fb::mul(p.x, zi), Fb::mul(p.y, zi), false};
     }
@@ -279,14 +344,14 @@ template <class C> struct Curve {
 
     // points/weierstrass.rs:39-59 (RCB Alg. 9, a = 0, from affine)
     static Proj double_affine(const Affine &pt) {
-        Limbs b3 = C::b3();
-        Limbs t0 = Fb::square(pt.y);
-        Limbs z3 = Fb::dbl(Fb::dbl(Fb::dbl(t0)));
-        Limbs x3 = Fb::mul(b3, z3);
-        Limbs y3 = Fb::add(t0, b3);
+        El b3 = C::b3();
+        El t0 = Fb::square(pt.y);
+        El z3 = Fb::dbl(Fb::dbl(Fb::dbl(t0)));
+        El x3 = Fb::mul(b3, z3);
+        El y3 = Fb::add(t0, b3);
         z3 = Fb::mul(pt.y, z3);
-        Limbs t1 = Fb::dbl(b3);
-        Limbs t2 = Fb::add(t1, b3);
+        El t1 = Fb::dbl(b3);
+        El t2 = Fb::add(t1, b3);
         t0 = Fb::sub(t0, t2);
         y3 = Fb::mul(t0, y3);
         y3 = Fb::add(x3, y3);
@@ -297,14 +362,14 @@ template <class C> struct Curve {
     }
     // points/weierstrass.rs:140-163
     static Proj double_proj(const Proj &p) {
-        Limbs b3 = C::b3();
-        Limbs t0 = Fb::square(p.y);
-        Limbs z3 = Fb::dbl(Fb::dbl(Fb::dbl(t0)));
-        Limbs t1 = Fb::mul(p.y, p.z);
-        Limbs t2 = Fb::square(p.z);
+        El b3 = C::b3();
+        El t0 = Fb::square(p.y);
+        El z3 = Fb::dbl(Fb::dbl(Fb::dbl(t0)));
+        El t1 = Fb::mul(p.y, p.z);
+        El t2 = Fb::square(p.z);
         t2 = Fb::mul(t2, b3);
-        Limbs x3 = Fb::mul(t2, z3);
-        Limbs y3 = Fb::add(t0, t2);
+        El x3 = Fb::mul(t2, z3);
+        El y3 = Fb::add(t0, t2);
         z3 = Fb::mul(t1, z3);
         t1 = Fb::dbl(t2);
         t2 = Fb::add(t1, t2);
@@ -324,58 +389,58 @@ template <class C> struct Curve {
             if (l.y == r.y) return double_affine(l);
             return proj_identity();
         }
-        Limbs s = Fb::sub(l.y, r.y);
-        Limbs u = Fb::sub(l.x, r.x);
-        Limbs uu = Fb::square(u);
-        Limbs w = Fb::sub(Fb::square(s), Fb::mul(uu, Fb::add(l.x, r.x)));
-        Limbs uuu = Fb::mul(uu, u);
-        Limbs x = Fb::mul(u, w);
-        Limbs y = Fb::sub(Fb::mul(s, Fb::sub(Fb::mul(l.x, uu), w)), Fb::mul(l.y, uuu));
+        El s = Fb::sub(l.y, r.y);
+        El u = Fb::sub(l.x, r.x);
+        El uu = Fb::square(u);
+        El w = Fb::sub(Fb::square(s), Fb::mul(uu, Fb::add(l.x, r.x)));
+        El uuu = Fb::mul(uu, u);
+        El x = Fb::mul(u, w);
+        El y = Fb::sub(Fb::mul(s, Fb::sub(Fb::mul(l.x, uu), w)), Fb::mul(l.y, uuu));
         return Proj{x, y, uuu};
     }
     // points/weierstrass.rs:63-97 (lhs affine, rhs projective)
     static Proj add_mixed(const Affine &l, const Proj &r) {
         if (l.inf) return r;
         if (is_identity(r)) return to_extended(l);
-        Limbs s1 = Fb::mul(l.y, r.z);
-        Limbs u1 = Fb::mul(l.x, r.z);
+        El s1 = Fb::mul(l.y, r.z);
+        El u1 = Fb::mul(l.x, r.z);
         if (u1 == r.x) {
             if (s1 == r.y) return double_affine(l);
             return to_extended(affine_identity());
         }
-        Limbs u = Fb::sub(s1, r.y);
-        Limbs uu = Fb::square(u);
-        Limbs v = Fb::sub(u1, r.x);
-        Limbs vv = Fb::square(v);
-        Limbs vvv = Fb::mul(vv, v);
-        Limbs rr = Fb::mul(vv, r.x);
-        Limbs a = Fb::sub(Fb::sub(Fb::mul(uu, r.z), vvv), Fb::dbl(rr));
-        Limbs x = Fb::mul(v, a);
-        Limbs y = Fb::sub(Fb::mul(u, Fb::sub(rr, a)), Fb::mul(vvv, r.y));
-        Limbs z = Fb::mul(vvv, r.z);
+        El u = Fb::sub(s1, r.y);
+        El uu = Fb::square(u);
+        El v = Fb::sub(u1, r.x);
+        El vv = Fb::square(v);
+        El vvv = Fb::mul(vv, v);
+        El rr = Fb::mul(vv, r.x);
+        El a = Fb::sub(Fb::sub(Fb::mul(uu, r.z), vvv), Fb::dbl(rr));
+        El x = Fb::mul(v, a);
+        El y = Fb::sub(Fb::mul(u, Fb::sub(rr, a)), Fb::mul(vvv, r.y));
+        El z = Fb::mul(vvv, r.z);
         return Proj{x, y, z};
     }
     // points/weierstrass.rs:101-136
     static Proj add_proj(const Proj &l, const Proj &r) {
         if (is_identity(l)) return r;
         if (is_identity(r)) return l;
-        Limbs s1 = Fb::mul(l.y, r.z);
-        Limbs s2 = Fb::mul(r.y, l.z);
-        Limbs u1 = Fb::mul(l.x, r.z);
-        Limbs u2 = Fb::mul(r.x, l.z);
+        El s1 = Fb::mul(l.y, r.z);
+        El s2 = Fb::mul(r.y, l.z);
+        El u1 = Fb::mul(l.x, r.z);
+        El u2 = Fb::mul(r.x, l.z);
         if (u1 == u2) {
             if (s1 == s2) return double_proj(l);
             return proj_identity();
         }
-        Limbs s = Fb::sub(s1, s2);
-        Limbs u = Fb::sub(u1, u2);
-        Limbs uu = Fb::square(u);
-        Limbs v = Fb::mul(l.z, r.z);
-        Limbs w = Fb::sub(Fb::mul(Fb::square(s), v), Fb::mul(uu, Fb::add(u1, u2)));
-        Limbs uuu = Fb::mul(uu, u);
-        Limbs x = Fb::mul(u, w);
-        Limbs y = Fb::sub(Fb::mul(s, Fb::sub(Fb::mul(u1, uu), w)), Fb::mul(s1, uuu));
-        Limbs z = Fb::mul(uuu, v);
+        El s = Fb::sub(s1, s2);
+        El u = Fb::sub(u1, u2);
+        El uu = Fb::square(u);
+        El v = Fb::mul(l.z, r.z);
+        El w = Fb::sub(Fb::mul(Fb::square(s), v), Fb::mul(uu, Fb::add(u1, u2)));
+        El uuu = Fb::mul(uu, u);
+        El x = Fb::mul(u, w);
+        El y = Fb::sub(Fb::mul(s, Fb::sub(Fb::mul(u1, uu), w)), Fb::mul(s1, uuu));
+        El z = Fb::mul(uuu, v);
         return Proj{x, y, z};
     }
     // points/weierstrass.rs:167-178; `res -= point` is by-value Sub = add(lhs, -rhs)

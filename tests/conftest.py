@@ -18,6 +18,16 @@ def golden():
     return np.load(os.path.join(ROOT, "tests", "golden", "msm_vectors.npz"))
 
 
+@pytest.fixture(scope="session")
+def golden_g2():
+    return np.load(os.path.join(ROOT, "tests", "golden", "g2_vectors.npz"))
+
+
+def golden_g2_case_names():
+    z = np.load(os.path.join(ROOT, "tests", "golden", "g2_vectors.npz"))
+    return sorted({k[: -len("_aff")] for k in z.files if k.endswith("_aff")})
+
+
 def golden_case_names(prefix=None):
     z = np.load(os.path.join(ROOT, "tests", "golden", "msm_vectors.npz"))
     names = sorted({k[: -len("_aff")] for k in z.files if k.endswith("_aff")})
@@ -27,6 +37,7 @@ def golden_case_names(prefix=None):
 def same_affine(a, b):
     """zkstd affine equality (macros/curve/weierstrass/group.rs:5-13): identities compare equal regardless of coordinates."""
     a, b = np.asarray(a, dtype=np.uint64), np.asarray(b, dtype=np.uint64)
-    if int(a[8]) or int(b[8]):
-        return bool(int(a[8]) and int(b[8]))
-    return bool((a[:8] == b[:8]).all())
+    assert a.shape == b.shape  # x, y, then the is_infinity word: (9,), or (17,) for G2
+    if int(a[-1]) or int(b[-1]):
+        return bool(int(a[-1]) and int(b[-1]))
+    return bool((a[:-1] == b[:-1]).all())

@@ -4,7 +4,7 @@
 // the pipeline LOGIC (recoding, counting sort, chunked accumulation, fix-up, hierarchical
 // reduction, Horner) without a GPU; the PTX bodies themselves are covered by the -m gpu tests.
 //
-// usage: host_emu <curve 0|1> <n> <c> <L> <K> <mode> <seed> [running_sum_stop]
+// usage: host_emu <curve 0|1|2> <n> <c> <L> <K> <mode> <seed> [running_sum_stop]
 //   mode 0 uniform scalars, 1 skewed (zeros/ones/r-1), 2 duplicate + opposite points + identity bases,
 //        3 canonical-format scalars; add 10 for the window-collapsed (precomputed table) mode
 #include <cstdio>
@@ -23,13 +23,16 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     if (collapsed) mode -= 10;
     typedef zko::Curve<OC> Cv;
     typedef zko::Field<typename OC::Scalar> Fs;
-    typedef zko::Field<typename OC::Base> Fb;
+    typedef typename Cv::Affine OAffine;
+    typedef typename Cv::Proj OProj;
+    constexpr size_t EB = sizeof(typename C::Elem);  // bytes per coordinate: 32, or 64 for G2 (c0 || c1)
+    static_assert(sizeof(typename Cv::El) == EB, "oracle and device coordinates have the same layout");
     std::mt19937_64 rng(seed);
     // points: small multiples of G built by repeated addition (cheap), shuffled
-    std::vector<zko::Affine> pts(n);
+    std::vector<OAffine> pts(n);
     {
-        zko::Proj acc = Cv::to_extended(Cv::generator());
-        zko::Proj step = Cv::double_proj(acc);
+        OProj acc = Cv::to_extended(Cv::generator());
+        OProj step = Cv::double_proj(acc);
         for (uint32_t i = 0; i < n; i++) {
             pts[i] = Cv::to_affine(acc);
             acc = Cv::add_proj(acc, step);
@@ -61,13 +64,13 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         pts[n - 1] = Cv::affine_identity();
     }
     // expected (oracle, reference algorithm)
-    zko::Proj exp;
+    OProj exp;
     {
         // inline copy of the reference structure through the naive sum: sum k_i P_i by scalar_point
         exp = Cv::proj_identity();
         for (uint32_t i = 0; i < n; i++) exp = Cv::add_proj(exp, Cv::scalar_point(Cv::to_extended(pts[i]), sc[i]));
     }
-    zko::Affine exp_aff = Cv::to_affine(exp);
+    OAffine exp_aff = Cv::to_affine(exp);
 
     // ---- device-format inputs
     std::vector<AffinePt<C>> bases(n);
@@ -75,8 +78,8 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         if (pts[i].inf) {
             memset(&bases[i], 0, sizeof bases[i]);
         } else {
-            memcpy(bases[i].x.v, pts[i].x.data(), 32);
-            memcpy(bases[i].y.v, pts[i].y.data(), 32);
+            memcpy(&bases[i].x, &pts[i].x, EB);
+            memcpy(&bases[i].y, &pts[i].y, EB);
         }
     }
     std::vector<uint32_t> scalars(8 * (size_t)n);
@@ -121,11 +124,11 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memset(tail.data(), 0xEF, tail.size() * sizeof(XyzzPt<C>));
     std::vector<uint32_t> tail_bucket(chunks, 0x12345678u);
     std::vector<AffinePt<C>> aff_nodes((size_t)chunks * L);
-    std::vector<Fp<typename C::Base>> aff_suffix((size_t)chunks * ((L + 1) / 2));
+    std::vector<typename C::Elem> aff_suffix((size_t)chunks * ((L + 1) / 2));
     const uint32_t affine_rounds = (seed >> 1) % 4;  // 0: XYZZ accumulate; 1..3: batched-affine tree levels first
     const bool affine_split = ((seed >> 3) & 1) != 0;  // one body per phase, structure re-derived from offsets
     if (affine_rounds && affine_split) {
-        std::vector<Fp<typename C::Base>> aff_inv(chunks);
+        std::vector<typename C::Elem> aff_inv(chunks);
         for (uint32_t r = 0; r < affine_rounds; r++) {
             for (uint32_t t = 0; t < chunks; t++) body_affine_phase1<C>(t, sh, r, acc_bases, offsets.data(), entries.data(), aff_nodes.data(), aff_suffix.data(), aff_inv.data());
             for (uint32_t t = 0; t < chunks; t++) body_affine_phase2<C>(t, sh, r, acc_bases, offsets.data(), entries.data(), aff_nodes.data(), aff_suffix.data(), aff_inv.data());
@@ -175,15 +178,14 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     } else {
         for (uint32_t w = 0; w < nwin; w++) win[w] = in_a[w];
     }
-    uint32_t out24[24];
+    uint32_t out24[48];
     MsmShape shf = sh;
     shf.W = nwin;  // collapsed: a single window sum, no doublings left
     body_final<C>(shf, win.data(), out24);
-    zko::Proj got;
-    memcpy(got.x.data(), out24, 32); memcpy(got.y.data(), out24 + 8, 32); memcpy(got.z.data(), out24 + 16, 32);
-    zko::Affine got_aff = Cv::to_affine(got);
+    OProj got;
+    memcpy(&got.x, out24, EB); memcpy(&got.y, out24 + EB / 4, EB); memcpy(&got.z, out24 + 2 * (EB / 4), EB);
+    OAffine got_aff = Cv::to_affine(got);
     bool ok = Cv::eq(got_aff, exp_aff) && (got_aff.inf || (got_aff.x == exp_aff.x && got_aff.y == exp_aff.y));
-    (void)Fb::zero;
     printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_rounds=%u split=%d\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_rounds, (int)affine_split);
     return ok ? 0 : 1;
 }
@@ -196,5 +198,6 @@ int main(int argc, char **argv) {
     uint64_t seed = strtoull(argv[7], nullptr, 10);
     uint32_t rs_stop = argc > 8 ? (uint32_t)atol(argv[8]) : 1;
     if (curve == 0) return run<Bn254G1, zko::Bn254G1>(n, c, L, K, mode, seed, rs_stop);
+    if (curve == 2) return run<Bn254G2, zko::Bn254G2>(n, c, L, K, mode, seed, rs_stop);
     return run<GrumpkinC, zko::Grumpkin>(n, c, L, K, mode, seed, rs_stop);
 }

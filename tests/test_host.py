@@ -18,7 +18,7 @@ EMU = os.path.join(ROOT, "tests", "_build", "host_emu")
 def host_emu():
     os.makedirs(os.path.dirname(EMU), exist_ok=True)
     src = os.path.join(ROOT, "tests", "host_emu.cpp")
-    deps = [src] + [os.path.join(ROOT, "kogarashi_b200", "csrc", f) for f in ("field.cuh", "curve.cuh", "msm_kernels.cuh")]
+    deps = [src] + [os.path.join(ROOT, "kogarashi_b200", "csrc", f) for f in ("field.cuh", "modinv.cuh", "curve.cuh", "msm_kernels.cuh")]
     if not os.path.exists(EMU) or any(os.path.getmtime(d) > os.path.getmtime(EMU) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-o", EMU, src])
     return EMU
@@ -33,6 +33,9 @@ EMU_CASES = [
     (0, 300, 8, 16, 4, 0, 15, 16), (1, 300, 9, 2, 2, 1, 16, 64), (0, 400, 6, 3, 4, 2, 17, 4096), (0, 600, 10, 2, 16, 1, 18, 8),
     # mode + 10: window-collapsed mode on a precomputed table (kgr_bases_precompute)
     (0, 200, 7, 16, 16, 10, 19, 4096), (1, 150, 5, 4, 4, 11, 20, 8), (0, 120, 11, 32, 16, 12, 21, 1), (1, 90, 3, 8, 2, 13, 22, 4096),
+    # curve 2: BN254 G2 (Fq2 coordinates) through the same bodies
+    (2, 1, 4, 16, 16, 0, 32), (2, 150, 7, 16, 4, 0, 33), (2, 200, 6, 5, 8, 2, 34), (2, 180, 8, 8, 16, 1, 35, 16), (2, 100, 5, 4, 4, 12, 36, 8),
+    (2, 120, 9, 32, 2, 3, 48),
 ]
 
 
