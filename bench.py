@@ -49,13 +49,18 @@ def ref_window_bits(n):  # groth16/src/msm.rs:7-14
     return (n.bit_length() * 69) // 100 + 2
 
 
-def algorithmic_imads(n):
+CURVE_IDS = {"bn254_g1": 0, "grumpkin": 1, "bn254_g2": 2}
+METRICS = {"bn254_g1": METRIC, "grumpkin": "grumpkin_msm_throughput", "bn254_g2": "bn254_g2_msm_throughput"}
+
+
+def algorithmic_imads(n, curve_name="bn254_g1"):
     """SURVEY.md §8(d): A(n) = n*W + 2*(2^c - 1)*W point adds with the reference's c and W = ceil(254/c);
-    11 field multiplications per add (reference mixed add 9M+2S); 264 32-bit IMADs per multiplication."""
+    11 field multiplications per add (reference mixed add 9M+2S); 264 32-bit IMADs per multiplication.
+    G2: the same adds over Fq2 — 9 Fq2 products at 3 Fq multiplications + 2 Fq2 squares at 2 = 31 per add."""
     c = ref_window_bits(n)
     W = math.ceil(254 / c)
     adds = n * W + 2 * ((1 << c) - 1) * W
-    return adds * 11 * 264
+    return adds * (31 if curve_name == "bn254_g2" else 11) * 264
 
 
 def random_scalars(n, seed):
@@ -138,7 +143,7 @@ def run_reference(args, rank, world):
     n_full = 1 << args.logn
     # calibrate, then bound the per-step sample so that the whole run stays within a few minutes
     cal_n = 1 << 13
-    cid = 0 if args.curve == "bn254_g1" else 1
+    cid = CURVE_IDS[args.curve]
     pool = A.random_points(cid, cal_n, seed=bytes(range(16)))
     sc_cal = random_scalars(cal_n, 1)
     rate, _, _ = cpu_msm_rate(pool, sc_cal, cores, curve=cid)
@@ -156,7 +161,7 @@ def run_reference(args, rank, world):
     dt = time.perf_counter() - t0
     value = n_s * args.steps / dt / 1e6
     sample = f"{args.steps} x MSM of 2^{int(math.log2(n_s))} {args.curve} points (workload 2^{args.logn}); {cal_n} distinct points tiled, uniform scalars"
-    line = {"impl": "reference", "metric": METRIC if cid == 0 else "grumpkin_msm_throughput", "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"impl": "reference", "metric": METRICS[args.curve], "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 limbs (Montgomery Fq/Fr)",
             "data": "synthetic", "config": {"workload": f"{args.curve} MSM, 2^{args.logn} points per GPU", "sample_points_per_step": n_s},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -172,7 +177,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--logn", type=int, default=20, help="log2 of the points per GPU (BASELINE configs[1]: 2^20 on 1 B200)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--curve", default="bn254_g1", choices=["bn254_g1", "grumpkin"], help="grumpkin = BASELINE configs[2] (Nova secondary-curve commitment shape)")
+    ap.add_argument("--curve", default="bn254_g1", choices=["bn254_g1", "grumpkin", "bn254_g2"],
+                    help="grumpkin = BASELINE configs[2] (Nova secondary-curve commitment shape); bn254_g2 = next row N3 (the b_g2 MSMs of the Groth16 prover)")
     ap.add_argument("--cpu-sample-logn", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-precompute", action="store_true", help="skip the secondary measurement of the window-collapsed (precomputed table) mode")
@@ -200,8 +206,9 @@ def main():
     k.init([local_rank])
 
     n = 1 << args.logn
-    curve = k.BN254_G1 if args.curve == "bn254_g1" else k.GRUMPKIN
-    metric = METRIC if curve == k.BN254_G1 else "grumpkin_msm_throughput"
+    curve = CURVE_IDS[args.curve]
+    metric = METRICS[args.curve]
+    pt_bytes = 128 if curve == k.BN254_G2 else 64
     # this rank's shard of the (world * n)-point vector: bases k_i*G for global indices [rank*n, (rank+1)*n)
     bases, ks = k.Bases.generate(curve, n, seed=1000 + rank, return_scalars=True)
     sc = random_scalars(n, 77 + rank)
@@ -303,24 +310,24 @@ def main():
     except Exception:
         pass
     imad_peak_t = 148 * 64 * 1.965e9 / 1e12  # nominal = measured by kgr_microbench on this pool (profiles/r01_microbench.md): 18.5 T IMAD/s
-    alg = algorithmic_imads(n)
+    alg = algorithmic_imads(n, args.curve)
     achieved_t = alg / (ms_per_step * 1e-3) / 1e12
-    hbm_bytes = 96 * n  # 64 B point + 32 B scalar per pair
+    hbm_bytes = (pt_bytes + 32) * n  # 64 B point (128 B on G2) + 32 B scalar per pair
     roofline = {"bound": "imad", "achieved": achieved_t, "peak": imad_peak_t, "unit": "T IMAD/s", "frac": achieved_t / imad_peak_t, "traffic": None,
                 "peak_source": "148 SM x 64 IMAD/clk x 1.965 GHz; kgr_microbench measured 18.5 T mad.lo.u32/s on this pool (MEASURED_PEAKS.json has no integer figure)",
                 "kernel": "whole pipeline; k_accumulate is the dominant kernel (see phases_ms)",
                 "algorithmic_imads_per_launch": alg,
-                "hbm": {"achieved_gbs": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "note": "96 B/point algorithmic traffic; the path is multiply-bound, not HBM-bound"}}
+                "hbm": {"achieved_gbs": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "note": f"{pt_bytes + 32} B/point algorithmic traffic; the path is multiply-bound, not HBM-bound"}}
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq/Fr, 8x32-bit)", "data": "synthetic",
             "config": {"workload": f"{args.curve} MSM, 2^{args.logn} points per GPU ({world * n} total), uniform scalars, bases k_i*G", "l2": "flushed between steps (512 MiB write)",
                        "shape": shape, "timing": "sum of per-step CUDA-event durations on the engine stream; wall_ms_per_step includes the flush and host gaps"},
             "wall_ms_per_step": wall_ms / args.steps, "phases_ms": phases, "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": world * n / e2e_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": 96 * n, "d2h_bytes_per_step": 128, "ms_per_step": e2e_ms,
+            "e2e": {"value": world * n / e2e_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": (pt_bytes + 32) * n, "d2h_bytes_per_step": shape["W"] * 2 * pt_bytes, "ms_per_step": e2e_ms,
                     "call": "kgr_msm_oneshot (points + scalars uploaded from pinned host memory every call)"},
-            "e2e_registered": {"value": world * n / e2e_reg_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": 128, "ms_per_step": e2e_reg_ms,
+            "e2e_registered": {"value": world * n / e2e_reg_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": shape["W"] * 2 * pt_bytes, "ms_per_step": e2e_reg_ms,
                                "call": "kgr_msm (bases registered once, scalars uploaded every call)"},
-            "roofline": roofline, "result_is_identity": bool(int(total_aff[8]))}
+            "roofline": roofline, "result_is_identity": bool(int(total_aff[-1]))}
     if pre:
         line["precomputed_bases"] = {
             "note": "secondary numbers, NOT the headline: bases registered with kgr_bases_precompute (table 2^(c*w)*P_i built once, W x the memory); "
@@ -333,13 +340,14 @@ def main():
     if world == 1:
         from oracle import oracle as A  # checker only
         from oracle import pyref as B
-        r = B.CURVES[curve].r
+        r = B.FQ if curve == A.GRUMPKIN else B.FR
         acc = 0
         for a, b in zip(ks, sc):
             acc += B.from_mont(B.limbs_to_int(a), r) * B.from_mont(B.limbs_to_int(b), r)
         g = A.generator(curve)
-        one = A.field_op(A.BASE_FIELD[curve], "to_mont", np.array([1, 0, 0, 0], dtype=np.uint64))
-        exp = A.to_affine(curve, A.scalar_point(curve, np.concatenate([g, one]), np.array(B.int_to_limbs(B.to_mont(acc % r, r)), dtype=np.uint64)))
+        one = A.field_op(A.FIELD_FR if curve == A.GRUMPKIN else A.FIELD_FQ, "to_mont", np.array([1, 0, 0, 0], dtype=np.uint64))
+        z = np.concatenate([one, np.zeros(4, dtype=np.uint64)]) if curve == A.BN254_G2 else one  # Z = 1 (in Fq2: 1 + 0u)
+        exp = A.to_affine(curve, A.scalar_point(curve, np.concatenate([g, z]), np.array(B.int_to_limbs(B.to_mont(acc % r, r)), dtype=np.uint64)))
         line["checksum_ok"] = bool((exp == total_aff).all())
 
     # ---- cpu_baseline: the restated reference algorithm on the host cores, bounded sample ------------

@@ -439,17 +439,28 @@ template <class P> KGR_HD Fp2<P> fp_dbl(const Fp2<P> &a) { return Fp2<P>{fp_dbl(
 template <class P> KGR_HD Fp2<P> fp_neg(const Fp2<P> &a) { return Fp2<P>{fp_neg(a.c0), fp_neg(a.c1)}; }
 template <class P> KGR_HD Fp2<P> fp_cneg(const Fp2<P> &a, bool sign) { return Fp2<P>{fp_cneg(a.c0, sign), fp_cneg(a.c1, sign)}; }
 // fqn.rs:359-363
-template <class P> KGR_HD Fp2<P> fp_mul(const Fp2<P> &a, const Fp2<P> &b) {
+template <class P> KGR_HD Fp2<P> fp2_mul_inline(const Fp2<P> &a, const Fp2<P> &b) {
     Fp<P> t0 = fp_mul(a.c0, b.c0);
     Fp<P> t1 = fp_mul(a.c1, b.c1);
     Fp<P> t2 = fp_mul(fp_add(a.c0, a.c1), fp_add(b.c0, b.c1));
     return Fp2<P>{fp_sub(t0, t1), fp_sub(fp_sub(t2, t0), t1)};
 }
 // fqn.rs:365-369
-template <class P> KGR_HD Fp2<P> fp_sqr(const Fp2<P> &a) {
+template <class P> KGR_HD Fp2<P> fp2_sqr_inline(const Fp2<P> &a) {
     Fp<P> t = fp_mul(a.c0, a.c1);
     return Fp2<P>{fp_mul(fp_add(a.c0, a.c1), fp_sub(a.c0, a.c1)), fp_dbl(t)};
 }
+#if defined(__CUDA_ARCH__) && defined(KGR_FP2_CALLS)
+// One shared copy of the Fq2 product / square per kernel instead of ~30 inlined ones per point addition: the inlined G2 accumulate
+// loop is > 100 KB of SASS and stalls on instruction fetch (profiles/r01_g2.md).
+template <class P> __device__ __noinline__ Fp2<P> fp2_mul_call(Fp2<P> a, Fp2<P> b) { return fp2_mul_inline(a, b); }
+template <class P> __device__ __noinline__ Fp2<P> fp2_sqr_call(Fp2<P> a) { return fp2_sqr_inline(a); }
+template <class P> KGR_HD Fp2<P> fp_mul(const Fp2<P> &a, const Fp2<P> &b) { return fp2_mul_call(a, b); }
+template <class P> KGR_HD Fp2<P> fp_sqr(const Fp2<P> &a) { return fp2_sqr_call(a); }
+#else
+template <class P> KGR_HD Fp2<P> fp_mul(const Fp2<P> &a, const Fp2<P> &b) { return fp2_mul_inline(a, b); }
+template <class P> KGR_HD Fp2<P> fp_sqr(const Fp2<P> &a) { return fp2_sqr_inline(a); }
+#endif
 // fqn.rs:348-357: conj(a) / (a0^2 + a1^2); zero maps to zero
 template <class P> KGR_HD Fp2<P> fp_inv(const Fp2<P> &a) {
     Fp<P> t = fp_inv(fp_add(fp_sqr(a.c0), fp_sqr(a.c1)));

@@ -1,4 +1,5 @@
 // BN254 G2 (coordinates in Fq2): fold reduce kernels + launchers.
 #define KGR_PART 8
+#define KGR_FP2_CALLS 1
 #include "launch_impl.cuh"
 template struct kgr::Launch<kgr::Bn254G2>;

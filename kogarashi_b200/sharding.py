@@ -20,9 +20,10 @@ def shard_range(n, world, rank):
 
 def identity_projective(curve):
     """(0, R, 0): zkstd/src/macros/curve/weierstrass/group.rs:106-110."""
-    from .msm import to_affine
-    out = np.zeros(12, dtype=np.uint64)
-    out[4:8] = to_affine(curve, out)[4:8]  # to_affine of Z = 0 returns (0, R, inf)
+    from .msm import coord_limbs, to_affine
+    cl = coord_limbs(curve)
+    out = np.zeros(3 * cl, dtype=np.uint64)
+    out[cl:2 * cl] = to_affine(curve, out)[cl:2 * cl]  # to_affine of Z = 0 returns (0, R, inf)
     return out
 
 

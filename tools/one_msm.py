@@ -5,11 +5,15 @@ import kogarashi_b200 as k
 import torch
 k.init([0])
 logn = int(sys.argv[1]) if len(sys.argv) > 1 else 20
+curve = k.BN254_G1
 for kv in sys.argv[2:]:
     name, v = kv.split("=")
-    k.set_param(name, int(v))
+    if name == "curve":
+        curve = int(v)
+    else:
+        k.set_param(name, int(v))
 n = 1 << logn
-bases = k.Bases.generate(k.BN254_G1, n, seed=3)
+bases = k.Bases.generate(curve, n, seed=3)
 rng = np.random.default_rng(1)
 sc = rng.integers(0, 1 << 62, size=(n, 4), dtype=np.uint64)
 d_sc = torch.from_numpy(sc.view(np.int64)).cuda()
