@@ -1,9 +1,11 @@
-"""G1 side of the reference's Groth16 prover on the GPU engine (SURVEY.md §8f rows N1 + N2).
+"""The MSM / FFT part of the reference's Groth16 prover on the GPU engine (SURVEY.md §8f rows N1 + N2 + N3).
 
 Reference: groth16/src/prover.rs:32-92.  `create_proof` runs seven FFTs (:36-47), six G1 MSMs (h, l, a x2, b_g1 x2;
-:51-62), two G2 MSMs (:64-65 — out of scope, they stay on the reference CPU path) and assembles
+:51-62), two G2 MSMs (b_g2 x2, :64-65) and assembles
     A = r*delta + alpha + a_answer                                          (:75,81-82)
+    B = s*delta_g2 + beta_g2 + b2_answer                                    (:76,87-88)
     C = r*s*delta + s*alpha + r*beta + s*a_answer + r*b1_answer + q + l     (:77,84,90-92)
+`Groth16G1Prover` computes A and C; `Groth16Prover` adds B with the G2 MSM, i.e. the whole proof.
 Here the G1 CRS (`Parameters::{h, l, a, b_g1}`, groth16/src/params.rs:7-29) is registered on the GPU once per prover;
 per proof the H coefficients come from the device NTT (kogarashi_b200.fft) and the `a_inputs / a_aux` and
 `b_g1_inputs / b_g1_aux` pairs are fused into one MSM each over z = inputs ++ aux (the prover splits them only because
@@ -12,7 +14,7 @@ of its slice layout, :58-62).  The blinding terms are a five-point MSM, so no cu
 import numpy as np
 
 from .fft import Fft
-from .msm import BN254_G1, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Bases, msm_curve_addition, proj_add, to_affine
+from .msm import BN254_G1, BN254_G2, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Bases, msm_curve_addition, proj_add, to_affine
 
 FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001  # bn254/src/fr.rs:11-16
 
@@ -69,3 +71,35 @@ class Groth16G1Prover:
     def free(self):
         for b in (self.a, self.b_g1, self.h, self.l):
             b.free()
+
+
+class Groth16Prover(Groth16G1Prover):
+    """All three proof elements.  G2 points are (n, 16) uint64 = x.c0 x.c1 y.c0 y.c1 Montgomery (bn254/src/g2.rs:15-21)."""
+
+    def __init__(self, delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, delta_g2, beta_g2, b_g2, b_g2_inf, precompute=False):
+        super().__init__(delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, precompute=precompute)
+        pt = lambda p: np.ascontiguousarray(p, dtype=np.uint64).reshape(1, 16)
+        self.vk_g2 = np.concatenate([pt(delta_g2), pt(beta_g2)])
+        self.b_g2 = Bases(BN254_G2, b_g2, b_g2_inf)
+        if precompute:
+            self.b_g2.precompute(0)
+
+    def prove(self, q, inputs, aux, r, s, scalar_fmt=SCALARS_MONTGOMERY):
+        """-> (A, B, C): A, C (9,) uint64 and B (17,) uint64 affine [x, y, is_infinity] = Proof {a, b, c} (prover.rs:94-98)."""
+        g_a, g_c = self.prove_g1(q, inputs, aux, r, s, scalar_fmt=scalar_fmt)
+        z = np.concatenate([np.asarray(inputs, dtype=np.uint64).reshape(-1, 4), np.asarray(aux, dtype=np.uint64).reshape(-1, 4)])
+        b2_answer = msm_curve_addition(self.b_g2, z, scalar_fmt=scalar_fmt)          # b_g2_inputs + b_g2_aux (:64-65, :87)
+        blind_b = msm_curve_addition(self.vk_g2, _canonical([s, 1]), curve=BN254_G2, scalar_fmt=SCALARS_CANONICAL)
+        return g_a, to_affine(BN254_G2, proj_add(BN254_G2, blind_b, b2_answer)), g_c
+
+    def prove_from_evaluations(self, log_n, a_evals, b_evals, c_evals, inputs, aux, r, s):
+        q = Fft(log_n).h_coefficients(a_evals, b_evals, c_evals)
+        return self.prove(q, inputs, aux, r, s) + (q,)
+
+    def proof(self, q, inputs, aux, r, s):
+        """Scalars as Python integers."""
+        return self.prove(_canonical(list(q)), _canonical(list(inputs)), _canonical(list(aux)), r, s, scalar_fmt=SCALARS_CANONICAL)
+
+    def free(self):
+        super().free()
+        self.b_g2.free()

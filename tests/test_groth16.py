@@ -1,7 +1,7 @@
 """BASELINE config #4: Groth16 proof of the reference's example circuit (groth16/examples/simple.rs, x^3 + x + 5 = 35)
 under fixed randomness.  CPU part: the big-int restatement of setup + create_proof yields a proof that satisfies the
-Groth16 equation (checked in the exponent).  GPU part: the G1 commitments A and C computed by the CUDA MSM engine from the
-device-resident CRS are byte-identical to the all-CPU computation (B is a G2 element and stays on the CPU path)."""
+Groth16 equation (checked in the exponent).  GPU part: A, C (G1) and B (G2) computed by the CUDA MSM engine from the
+device-resident CRS are byte-identical to the all-CPU computation, i.e. the whole 259-byte proof."""
 import numpy as np
 import pytest
 
@@ -80,6 +80,48 @@ def _pts(points):
     return xy, inf
 
 
+def _pts_g2(points):
+    xy = np.zeros((len(points), 16), dtype=np.uint64)
+    inf = np.zeros(len(points), dtype=np.uint8)
+    for i, p in enumerate(points):
+        if p is None:
+            inf[i] = 1
+            xy[i, 8:12] = B.int_to_limbs(B.to_mont(1, B.FQ))
+        else:
+            for j, v in enumerate((p[0][0], p[0][1], p[1][0], p[1][1])):
+                xy[i, 4 * j:4 * j + 4] = B.int_to_limbs(B.to_mont(v, B.FQ))
+    return xy, inf
+
+
+def _enc(aff):
+    return np.asarray(aff[:-1], dtype="<u8").tobytes() + bytes([int(aff[-1])])
+
+
+@pytest.mark.gpu
+def test_whole_proof_bytes_identical_with_all_msms_on_gpu(fixture):
+    """prover.rs:51-98 with all eight MSMs (six G1, two G2) on the device: Proof {a, b, c} byte for byte."""
+    import kogarashi_b200 as k
+    from kogarashi_b200.groth16 import Groth16Prover
+    k.init()
+    P, trap, uvw, proof, internals = fixture
+    vk = P["vk"]
+    one = lambda p: _pts([p])[0][0]
+    one2 = lambda p: _pts_g2([p])[0][0]
+    prover = Groth16Prover(one(vk["delta_g1"]), one(vk["alpha_g1"]), one(vk["beta_g1"]), *_pts(P["a"]), *_pts(P["b_g1"]), *_pts(P["h"]), *_pts(P["l"]),
+                           one2(vk["delta_g2"]), one2(vk["beta_g2"]), *_pts_g2(P["b_g2"]))
+    A, Bp, C = prover.proof(internals["q"], internals["inputs"], internals["aux"], internals["r"], internals["s"])
+    assert _enc(Bp) == G.encode_g2(proof["b"])
+    assert _enc(A) + _enc(Bp) + _enc(C) == G.proof_bytes(proof)
+    # the two G2 MSMs of prover.rs:64-65 one by one (identity CRS entries, the `[l..]` slice)
+    l = internals["l"]
+    sc = lambda v: np.array([B.int_to_limbs(B.to_mont(x, B.FR)) for x in v], dtype=np.uint64).reshape(-1, 4)
+    for pts, coeffs in ((P["b_g2"], internals["inputs"]), (P["b_g2"][l:], internals["aux"])):
+        xy, inf = _pts_g2(pts)
+        got = k.to_affine(k.BN254_G2, k.msm_curve_addition(xy, sc(coeffs), curve=k.BN254_G2, inf=inf))
+        assert _enc(got) == G.encode_g2(G.g2_msm(pts, coeffs))
+    prover.free()
+
+
 @pytest.mark.gpu
 def test_proof_bytes_identical_with_g1_msms_on_gpu(fixture):
     import kogarashi_b200 as k
@@ -114,14 +156,14 @@ def test_proof_bytes_identical_with_g1_msms_on_gpu(fixture):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("steps,precompute", [(341, False), (1365, True)])
-def test_scaled_prover_g1_side_on_gpu(steps, precompute):
+def test_scaled_prover_on_gpu(steps, precompute):
     """The example's function chained to 2^10 / 2^12 constraints.  CRS points come from the device fixed-base
-    multiplication of the exponents, H from the device NTT, A and C from the device MSMs; both are checked against their
+    multiplication of the exponents, H from the device NTT, A, B and C from the device MSMs; all are checked against their
     discrete logs computed from the toxic waste (and the Groth16 equation in the exponent), i.e. against an oracle that
     shares no code with the GPU path."""
     import kogarashi_b200 as k
     from kogarashi_b200 import msm as M
-    from kogarashi_b200.groth16 import Groth16G1Prover
+    from kogarashi_b200.groth16 import Groth16Prover
     from oracle import oracle as A_
     k.init()
     cs, out = G.chain_circuit(steps, 3)
@@ -133,12 +175,17 @@ def test_scaled_prover_g1_side_on_gpu(steps, precompute):
         inf = np.array([1 if e == 0 else 0 for e in exps], dtype=np.uint8)
         return xy, inf
 
+    def points_g2(exps):
+        return M.fixed_base_mul(k.BN254_G2, mont(exps)), np.array([1 if e == 0 else 0 for e in exps], dtype=np.uint8)
+
     vk = points([trap["delta"], trap["alpha"], trap["beta"]])[0]
-    prover = Groth16G1Prover(vk[0], vk[1], vk[2], *points(E["a"]), *points(E["b_g1"]), *points(E["h"]), *points(E["l"]), precompute=precompute)
+    vk2 = points_g2([trap["delta"], trap["beta"]])[0]
+    prover = Groth16Prover(vk[0], vk[1], vk[2], *points(E["a"]), *points(E["b_g1"]), *points(E["h"]), *points(E["l"]),
+                           vk2[0], vk2[1], *points_g2(E["b_g1"]), precompute=precompute)   # b_g2 has the exponents of b_g1 on the G2 generator
     a_ev, b_ev, c_ev = (mont(v) for v in cs.evaluate())
     rng = B.XorShift128(PROVE_SEED)
     r, s = rng.random_field(B.FR), rng.random_field(B.FR)
-    A, C, q = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, mont(cs.x), mont(cs.w), r, s)
+    A, Bp, C, q = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, mont(cs.x), mont(cs.w), r, s)
     # H coefficients: device NTT pipeline == restated reference FFT pipeline
     q_ref, n_ref = A_.groth16_h(E["k"], a_ev, b_ev, c_ev)
     assert q.shape[0] == n_ref and (q == q_ref[:n_ref]).all()
@@ -151,4 +198,5 @@ def test_scaled_prover_g1_side_on_gpu(steps, precompute):
 
     assert enc(A) == G.encode_g1(G.G1.mul(G.G1.g, a_exp))
     assert enc(C) == G.encode_g1(G.G1.mul(G.G1.g, c_exp))
+    assert _enc(Bp) == G.encode_g2(G.g2_mul(G.G2_GEN, b_exp))
     prover.free()

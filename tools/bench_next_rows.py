@@ -11,7 +11,7 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import kogarashi_b200 as k  # noqa: E402
 from kogarashi_b200 import msm as M  # noqa: E402
-from kogarashi_b200.groth16 import Groth16G1Prover  # noqa: E402
+from kogarashi_b200.groth16 import Groth16Prover  # noqa: E402
 from oracle import groth16_ref as G  # noqa: E402
 from oracle import oracle as A  # noqa: E402
 from oracle import pyref as B  # noqa: E402
@@ -68,25 +68,31 @@ def bench_groth16(logm, out):
     def points(exps):
         return M.fixed_base_mul(k.BN254_G1, mont(exps)), np.array([1 if e == 0 else 0 for e in exps], dtype=np.uint8)
 
+    def points_g2(exps):
+        return M.fixed_base_mul(k.BN254_G2, mont(exps)), np.array([1 if e == 0 else 0 for e in exps], dtype=np.uint8)
+
     vk = points([trap["delta"], trap["alpha"], trap["beta"]])[0]
+    vk2 = points_g2([trap["delta"], trap["beta"]])[0]
     crs = [points(E[name]) for name in ("a", "b_g1", "h", "l")]
+    crs_g2 = points_g2(E["b_g1"])  # b_g2: the exponents of b_g1 on the G2 generator (zksnark.rs:177-185)
     a_ev, b_ev, c_ev = (mont(v) for v in cs.evaluate())
     xs, ws = mont(cs.x), mont(cs.w)
     rng = B.XorShift128(bytes(range(1, 17)))
     r, s = rng.random_field(B.FR), rng.random_field(B.FR)
     res = {}
     for pre in (False, True):
-        prover = Groth16G1Prover(vk[0], vk[1], vk[2], *crs[0], *crs[1], *crs[2], *crs[3], precompute=pre)
+        prover = Groth16Prover(vk[0], vk[1], vk[2], *crs[0], *crs[1], *crs[2], *crs[3], vk2[0], vk2[1], *crs_g2, precompute=pre)
         prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)
         wall = min(_wall(lambda: prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)) for _ in range(3))
-        Ap, Cp, q = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)
+        Ap, Bp, Cp, q = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)
         res["precomputed" if pre else "normal"] = wall * 1e3
         prover.free()
     q_int = [B.from_mont(B.limbs_to_int(x), B.FR) for x in q]
     a_exp, b_exp, c_exp, pairing_ok = G.expected_exponents(trap, uvw, cs.x, cs.w, q_int, E["n"], r, s)
-    enc = lambda aff: np.asarray(aff[:8], dtype="<u8").tobytes() + bytes([int(aff[8])])
-    ok = pairing_ok and enc(Ap) == G.encode_g1(G.G1.mul(G.G1.g, a_exp)) and enc(Cp) == G.encode_g1(G.G1.mul(G.G1.g, c_exp))
-    # CPU baseline: the same G1-side work with the restated reference code (7 FFTs + the six G1 MSMs of prover.rs:51-62)
+    enc = lambda aff: np.asarray(aff[:-1], dtype="<u8").tobytes() + bytes([int(aff[-1])])
+    ok = (pairing_ok and enc(Ap) == G.encode_g1(G.G1.mul(G.G1.g, a_exp)) and enc(Cp) == G.encode_g1(G.G1.mul(G.G1.g, c_exp))
+          and enc(Bp) == G.encode_g2(G.g2_mul(G.G2_GEN, b_exp)))
+    # CPU baseline: the same work with the restated reference code (7 FFTs + the six G1 and two G2 MSMs of prover.rs:51-65)
     cores = os.cpu_count() or 1
     l = cs.l
     t0 = time.perf_counter()
@@ -95,15 +101,49 @@ def bench_groth16(logm, out):
     t0 = time.perf_counter()
     for pts_inf, sc in ((crs[2], q_ref[:n_ref]), (crs[3], ws), (crs[0], xs), ((crs[0][0][l:], crs[0][1][l:]), ws), (crs[1], xs), ((crs[1][0][l:], crs[1][1][l:]), ws)):
         A.msm(A.BN254_G1, pts_inf[0], sc, inf=pts_inf[1], threads=cores)
+    for pts_inf, sc in ((crs_g2, xs), ((crs_g2[0][l:], crs_g2[1][l:]), ws)):
+        A.msm(A.BN254_G2, pts_inf[0], sc, inf=pts_inf[1], threads=cores)
     msm_s = time.perf_counter() - t0
-    rec = {"row": "N1 Groth16 create_proof, G1 side (7 FFTs + G1 MSMs + assembly of A and C; G2 and witness generation excluded)",
+    rec = {"row": "N1+N3 Groth16 create_proof after witness generation (7 FFTs + six G1 MSMs + two G2 MSMs + assembly of A, B, C)",
            "constraints": cs.m, "log_n": E["k"], "gpu_wall_ms": res, "checked_against_discrete_logs": bool(ok),
            "h_bit_exact_with_oracle": bool(q.shape[0] == n_ref and (q == q_ref[:n_ref]).all()),
            "cpu_baseline": {"fft_seconds": fft_s, "msm_seconds": msm_s, "total_seconds": fft_s + msm_s, "cores": cores, "kind": "port",
-                            "note": "restated reference FFT (single thread) + six reference-algorithm MSMs on all cores"},
+                            "note": "restated reference FFT (single thread) + the eight reference-algorithm MSMs on all cores"},
            "speedup_vs_cpu_baseline": {m: (fft_s + msm_s) * 1e3 / v for m, v in res.items()}, "setup_python_s": setup_s}
     out.append(rec)
     print(json.dumps(rec), flush=True)
+
+
+def bench_g2(logn, out):
+    """N3: one G2 MSM (prover.rs:64-65) with device-resident bases, host scalars; CPU baseline = the reference algorithm over Fq2."""
+    n = 1 << logn
+    bases, ks = k.Bases.generate(k.BN254_G2, n, seed=5, return_scalars=True)
+    sc = A.random_field(A.FIELD_FR, n, seed=bytes(range(16)))
+    k.msm_curve_addition(bases, sc)
+    best, phases, shape = None, None, None
+    for _ in range(5):
+        got = k.msm_curve_addition(bases, sc)
+        t, sh = k.last_timing(0)
+        dev = t["total"] - t["h2d"]
+        if best is None or dev < best:
+            best, phases, shape = dev, t, sh
+    wall = min(_wall(lambda: k.msm_curve_addition(bases, sc)) for _ in range(3)) * 1e3
+    cores = os.cpu_count() or 1
+    ns = min(n, 1 << 18)
+    pts = bases.download(0, ns)
+    t0 = time.perf_counter()
+    cpu = A.msm(A.BN254_G2, pts, sc[:ns], threads=cores)
+    cpu_s = time.perf_counter() - t0
+    same = bool((A.to_affine(A.BN254_G2, cpu) == k.to_affine(k.BN254_G2, k.msm_curve_addition(bases, sc[:ns]))).all()) if ns < n else \
+        bool((A.to_affine(A.BN254_G2, cpu) == k.to_affine(k.BN254_G2, got)).all())
+    rec = {"row": "N3 BN254 G2 MSM", "log_n": logn, "device_ms": best, "mpoints_per_s": n / best / 1e3, "e2e_registered_ms": wall, "shape": shape,
+           "phases_ms": {a: round(b, 3) for a, b in phases.items()}, "bit_exact_with_oracle_on_sample": same,
+           "cpu_baseline": {"mpoints_per_s": ns / cpu_s / 1e6, "cores": cores, "kind": "port", "sample": f"one MSM over the first 2^{int(np.log2(ns))} pairs, {cpu_s:.2f} s"},
+           "roofline": {"bound": "imad", "note": "madd over Fq2 = 8 products x 3 + 2 squares x 2 = 28 Fq multiplications (10 on G1)"}}
+    rec["speedup_vs_cpu_baseline"] = rec["mpoints_per_s"] / rec["cpu_baseline"]["mpoints_per_s"]
+    out.append(rec)
+    print(json.dumps(rec), flush=True)
+    bases.free()
 
 
 def main():
@@ -113,6 +153,8 @@ def main():
     out = []
     for logn in (16, 20, 22):
         bench_ntt(logn, out)
+    for logn in (16, 20):
+        bench_g2(logn, out)
     for logm in (12, 16):
         bench_groth16(logm, out)
     json.dump(out, open(f"gpurun_out/next_rows_{tag}.json", "w"), indent=1)
