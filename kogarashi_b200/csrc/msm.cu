@@ -179,18 +179,23 @@ static uint32_t choose_window_bits(uint32_t n) {
     return best_c;
 }
 
-// Window size for the collapsed mode: one bucket set shared by all windows, so the reduce term is B, not W * B
-// (constants fitted to profiles/r01_precompute.md: 0.16 ns per entry, single-window reduce 0.45 ms + 0.9 ns per bucket).
-static uint32_t choose_window_bits_collapsed(uint32_t n) {
+// Window size for the collapsed mode: one bucket set shared by all windows, so the reduce term depends on B, not W * B.
+// Fitted to the sweeps in profiles/r01_precompute.md (ns): accumulate 0.16 per entry (0.08 ms floor: one chunk of 16 adds);
+// count and fill are bound by atomics on the B shared counters — 0.245 per entry at B <= 256 falling like B^-0.6 to the
+// 0.008 streaming floor; single-window reduce 0.17 ms + 0.017 ms per bit of c (+ 0.9 per bucket beyond 2^16); a thin top
+// window (fewer leading bits than c) makes a few buckets hot and costs ~0.25 ms of fix-up.  `mul_weight`: field
+// multiplications per coordinate product (1, or 3 for G2) scales everything that is curve arithmetic.
+static uint32_t choose_window_bits_collapsed(uint32_t n, double mul_weight) {
     double best = 1e300;
-    uint32_t best_c = 1;
-    for (uint32_t c = 1; c <= 23; c++) {
-        double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1);
-        double lg = std::log2(B);
-        double sort_ns = 0.02 + (lg > 19 ? 0.008 * (lg - 19) : 0.0);
-        double cost = (double)n * W * (0.16 + sort_ns) + 0.9 * B + (B > 64 ? 0.45e6 : 0.1e6);
+    uint32_t best_c = 9;
+    for (uint32_t c = 9; c <= 23; c++) {  // below c = 9 all entries share <= 128 counters and buckets: never the fastest
+        double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1), entries = (double)n * W;
+        double atomic_ns = std::min(0.245, std::max(0.008, 0.072 * std::pow(1024.0 / B, 0.6)));
+        double acc = std::max(entries * 0.16, 0.08e6);
+        double reduce = 0.17e6 + 0.017e6 * c + 0.9 * std::max(0.0, B - 65536.0);
         int top_bits = 255 - (int)c * ((int)W - 1);
-        if (top_bits < 10 && top_bits < (int)c) cost += 0.03 * n * (10 - top_bits);
+        double hot = top_bits < (int)c ? std::min(0.25e6, entries * 0.05) : 0.0;
+        double cost = (acc + reduce + hot) * mul_weight + 2.0 * entries * atomic_ns;
         if (cost < best) { best = cost; best_c = c; }
     }
     return best_c;
@@ -902,7 +907,7 @@ int kgr_bases_precompute(kgr_bases_t *b, int window_bits) {
             if (!s.count) continue;
             Engine &e = g_engines[s.eng];
             CK(cudaSetDevice(e.dev));
-            uint32_t c = window_bits ? (uint32_t)window_bits : choose_window_bits_collapsed((uint32_t)s.count);
+            uint32_t c = window_bits ? (uint32_t)window_bits : choose_window_bits_collapsed((uint32_t)s.count, b->curve == KGR_CURVE_BN254_G2 ? 3.0 : 1.0);
             uint32_t W = (255 + c - 1) / c;
             if ((uint64_t)W * s.count >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "precomputed table would exceed 2^31 points");
             if (s.d_table) CK(cudaFree(s.d_table));
