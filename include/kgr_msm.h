@@ -112,6 +112,27 @@ int kgr_ntt_device(unsigned log_n, int op, void *d_data);
  * a, b, c: the m R1CS evaluations each (host, Montgomery); out: 2^log_n elements, *n_out after stripping. */
 int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, uint64_t *out, size_t *n_out);
 
+/* ---- Nova folding vector work (next row N4: nova/src/prover.rs:53-90, relaxed_r1cs/witness.rs:56-71) ----------------
+ * An R1CS shape: A, B, C as CSR over flat column indices into z = (u, x, w) — the caller resolves Wire::Instance(i) -> i and
+ * Wire::Witness(i) -> i + l (zkstd/src/matrix.rs:41-44) when it builds the arrays.  field: 0 = Fq (nova's GrumpkinDriver),
+ * 1 = Fr (Bn254Driver).  row_ptr[k]: m + 1 offsets, cols[k]: nnz column indices, coeffs[k]: nnz x 4 uint64 Montgomery; k = A, B, C.
+ * The shape lives on the first device of kgr_init. */
+typedef struct kgr_r1cs kgr_r1cs_t;
+int kgr_r1cs_register(int field, size_t m, size_t n_z, const uint32_t *const row_ptr[3], const uint32_t *const cols[3],
+                      const uint64_t *const coeffs[3], kgr_r1cs_t **out);
+int kgr_r1cs_free(kgr_r1cs_t *shape);
+/* SparseMatrix::prod (matrix.rs:36-48): out (m x 4) = M z, which = 0 A, 1 B, 2 C; z: n_z x 4 uint64 Montgomery, host buffers. */
+int kgr_r1cs_mul(kgr_r1cs_t *shape, int which, const uint64_t *z, uint64_t *out);
+/* compute_cross_term (prover.rs:53-90): T = AZ1 o BZ2 + AZ2 o BZ1 - u1 CZ2 - u2 CZ1 with u1 = z1[0], u2 = z2[0] (the reference passes
+ * z2 = (1, x2, w2)), in one fused kernel.  t_out (m x 4, host) may be NULL.  With ck != NULL the Pedersen commitment of T
+ * (prover.rs:35, `self.ck.commit(&t)`) is computed from the device-resident T without copying it: commit_out = x[4] y[4] is_infinity.
+ * ck must be registered on the first device only and its scalar field must equal `field`. */
+int kgr_nova_cross_term(kgr_r1cs_t *shape, const uint64_t *z1, const uint64_t *z2, uint64_t *t_out, kgr_bases_t *ck, uint64_t *commit_out);
+/* ms[0] H2D of z1 and z2, ms[1] cross-term kernel, ms[2] commitment MSM (device events + host finish) of the last kgr_nova_cross_term. */
+int kgr_r1cs_last_timing(const kgr_r1cs_t *shape, float ms[3]);
+/* RelaxedR1csWitness::fold (witness.rs:67-68): out[i] = a[i] + b[i] * r over `field`; host buffers, n x 4 uint64 Montgomery. */
+int kgr_vec_fold(int field, const uint64_t *a, const uint64_t *b, const uint64_t r[4], size_t n, uint64_t *out);
+
 /* Tuning knobs: "window_bits" (0 = auto), "chunk" (entries per accumulate thread, 0 = auto),
  * "reduce_fanin" (power of two), "running_sum_stop" (elements per window below which the reduce
  * switches from running sums to the parallel weighting pass), "final_on_device" (1: Horner over

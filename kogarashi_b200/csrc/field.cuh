@@ -484,4 +484,28 @@ template <class P> struct El<Fp2<P>> {
     static KGR_HD uint32_t word(const Fp2<P> &a, int i) { return i < 8 ? a.c0.v[i] : a.c1.v[i - 8]; }
 };
 
+// 16-byte loads / stores of whole field elements (8 words, or 16 for Fq2) between global memory and registers
+template <class E> KGR_HD void el_load(E &e, const void *src) {
+#if defined(__CUDA_ARCH__)
+    const uint4 *q = reinterpret_cast<const uint4 *>(src);
+#pragma unroll
+    for (int k = 0; k < El<E>::WORDS / 4; k++) {
+        uint4 a = __ldg(q + k);
+        El<E>::word(e, 4 * k) = a.x; El<E>::word(e, 4 * k + 1) = a.y; El<E>::word(e, 4 * k + 2) = a.z; El<E>::word(e, 4 * k + 3) = a.w;
+    }
+#else
+    e = *reinterpret_cast<const E *>(src);
+#endif
+}
+template <class E> KGR_HD void el_store(void *dst, const E &e) {
+#if defined(__CUDA_ARCH__)
+    uint4 *q = reinterpret_cast<uint4 *>(dst);
+#pragma unroll
+    for (int k = 0; k < El<E>::WORDS / 4; k++)
+        q[k] = make_uint4(El<E>::word(e, 4 * k), El<E>::word(e, 4 * k + 1), El<E>::word(e, 4 * k + 2), El<E>::word(e, 4 * k + 3));
+#else
+    *reinterpret_cast<E *>(dst) = e;
+#endif
+}
+
 }  // namespace kgr

@@ -71,4 +71,12 @@ struct LaunchNtt {
     static int transform(cudaStream_t st, void *d, const void *tw, uint32_t k);
 };
 
+// Nova folding vector work (kernels_r1cs.cu).  field: 0 Fq, 1 Fr.
+struct Csr;
+struct LaunchR1cs {
+    static void spmv(cudaStream_t st, int field, uint32_t m, const Csr &mat, const uint32_t *z, uint32_t *out);
+    static void cross_term(cudaStream_t st, int field, uint32_t m, const Csr &a, const Csr &b, const Csr &c, const uint32_t *z1, const uint32_t *z2, uint32_t *t);
+    static void vec_fold(cudaStream_t st, int field, uint32_t n, const uint32_t *a, const uint32_t *b, const uint32_t r8[8], uint32_t *out);
+};
+
 }  // namespace kgr

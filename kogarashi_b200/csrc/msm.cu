@@ -23,6 +23,7 @@
 
 #include "../../include/kgr_msm.h"
 #include "launch.cuh"
+#include "r1cs_kernels.cuh"
 
 namespace kgr {
 
@@ -402,6 +403,15 @@ struct kgr_bases {
     int curve = 0;
     size_t n = 0;
     std::vector<kgr::Shard> shards;
+};
+
+// An R1CS shape (A, B, C in CSR) resident on the first device (nova/src/relaxed_r1cs.rs R1csShape).
+struct kgr_r1cs {
+    int field = 0;
+    size_t m = 0, n_z = 0;
+    kgr::DevBuf<uint32_t> row_ptr[3], cols[3], coeffs[3], z1, z2, t;
+    float ms[3] = {0, 0, 0};  // last cross term: H2D of z1 / z2, kernel, commit MSM
+    kgr::Csr csr(int i) const { return kgr::Csr{row_ptr[i].p, cols[i].p, coeffs[i].p}; }
 };
 
 namespace kgr {
@@ -1199,6 +1209,149 @@ int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, ui
         DISPATCH(curve, CALL);
 #undef CALL
         *out = b;
+        return KGR_OK;
+    });
+}
+
+// ---- Nova folding vector work (row N4) ------------------------------------------------------------------------------
+int kgr_r1cs_register(int field, size_t m, size_t n_z, const uint32_t *const row_ptr[3], const uint32_t *const cols[3], const uint64_t *const coeffs[3],
+                      kgr_r1cs_t **out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if ((field != 0 && field != 1) || !row_ptr || !cols || !coeffs || !out) return fail(KGR_E_ARG, "bad argument");
+    if (m >= (1ull << 31) || n_z >= (1ull << 31) || n_z == 0) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 rows / columns, at least one column");
+    for (int k = 0; k < 3; k++) {
+        if (!row_ptr[k]) return fail(KGR_E_ARG, "null row_ptr");
+        if (row_ptr[k][0] != 0) return fail(KGR_E_ARG, "row_ptr must start at 0");
+        for (size_t i = 0; i < m; i++)
+            if (row_ptr[k][i + 1] < row_ptr[k][i]) return fail(KGR_E_ARG, "row_ptr must be non-decreasing");
+        size_t nnz = row_ptr[k][m];
+        if (nnz && (!cols[k] || !coeffs[k])) return fail(KGR_E_ARG, "null cols / coeffs");
+        for (size_t j = 0; j < nnz; j++)
+            if (cols[k][j] >= n_z) return fail(KGR_E_ARG, "column index out of range");
+    }
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        std::unique_ptr<kgr_r1cs> s(new kgr_r1cs);
+        s->field = field;
+        s->m = m;
+        s->n_z = n_z;
+        for (int k = 0; k < 3; k++) {
+            size_t nnz = row_ptr[k][m];
+            s->row_ptr[k].ensure(m + 1);
+            s->cols[k].ensure(std::max<size_t>(nnz, 1));
+            s->coeffs[k].ensure(std::max<size_t>(nnz, 1) * 8);
+            CK(cudaMemcpyAsync(s->row_ptr[k].p, row_ptr[k], (m + 1) * sizeof(uint32_t), cudaMemcpyHostToDevice, e.st));
+            if (nnz) {
+                CK(cudaMemcpyAsync(s->cols[k].p, cols[k], nnz * sizeof(uint32_t), cudaMemcpyHostToDevice, e.st));
+                CK(cudaMemcpyAsync(s->coeffs[k].p, coeffs[k], nnz * 32, cudaMemcpyHostToDevice, e.st));
+            }
+        }
+        s->z1.ensure(n_z * 8);
+        s->z2.ensure(n_z * 8);
+        s->t.ensure(std::max<size_t>(m, 1) * 8);
+        CK(cudaStreamSynchronize(e.st));
+        *out = s.release();
+        return KGR_OK;
+    });
+}
+
+int kgr_r1cs_free(kgr_r1cs_t *s) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!s) return KGR_OK;
+    if (!g_engines.empty()) cudaSetDevice(g_engines[0].dev);
+    for (int k = 0; k < 3; k++) { s->row_ptr[k].release(); s->cols[k].release(); s->coeffs[k].release(); }
+    s->z1.release(); s->z2.release(); s->t.release();
+    delete s;
+    return KGR_OK;
+}
+
+int kgr_r1cs_mul(kgr_r1cs_t *s, int which, const uint64_t *z, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (!s || which < 0 || which > 2 || !z || (!out && s->m)) return fail(KGR_E_ARG, "bad argument");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        CK(cudaMemcpyAsync(s->z1.p, z, s->n_z * 32, cudaMemcpyHostToDevice, e.st));
+        LaunchR1cs::spmv(e.st, s->field, (uint32_t)s->m, s->csr(which), s->z1.p, s->t.p);
+        e.launches++;
+        CK(cudaGetLastError());
+        if (s->m) CK(cudaMemcpyAsync(out, s->t.p, s->m * 32, cudaMemcpyDeviceToHost, e.st));
+        CK(cudaStreamSynchronize(e.st));
+        return KGR_OK;
+    });
+}
+
+int kgr_nova_cross_term(kgr_r1cs_t *s, const uint64_t *z1, const uint64_t *z2, uint64_t *t_out, kgr_bases_t *ck, uint64_t *commit_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (!s || !z1 || !z2 || (ck && !commit_out)) return fail(KGR_E_ARG, "bad argument");
+    if (ck) {
+        // the commitment key's scalar field must be the field of the constraint system (nova/src/driver.rs: Grumpkin <-> Fq, G1 <-> Fr)
+        int scalar_field = ck->curve == KGR_CURVE_GRUMPKIN ? 0 : 1;
+        if (scalar_field != s->field) return fail(KGR_E_ARG, "commitment key curve does not match the R1CS field");
+        if (ck->shards.size() != 1 || ck->shards[0].eng != 0) return fail(KGR_E_ARG, "the commitment key must live on the first device only");
+    }
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        CK(cudaEventRecord(e.user_ev[1], e.st));
+        CK(cudaMemcpyAsync(s->z1.p, z1, s->n_z * 32, cudaMemcpyHostToDevice, e.st));
+        CK(cudaMemcpyAsync(s->z2.p, z2, s->n_z * 32, cudaMemcpyHostToDevice, e.st));
+        CK(cudaEventRecord(e.user_ev[2], e.st));
+        LaunchR1cs::cross_term(e.st, s->field, (uint32_t)s->m, s->csr(0), s->csr(1), s->csr(2), s->z1.p, s->z2.p, s->t.p);
+        e.launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e.user_ev[3], e.st));
+        if (t_out && s->m) CK(cudaMemcpyAsync(t_out, s->t.p, s->m * 32, cudaMemcpyDeviceToHost, e.st));
+        CK(cudaStreamSynchronize(e.st));
+        cudaEventElapsedTime(&s->ms[0], e.user_ev[1], e.user_ev[2]);
+        cudaEventElapsedTime(&s->ms[1], e.user_ev[2], e.user_ev[3]);
+        s->ms[2] = 0;
+        if (ck) {
+            // PedersenCommitment::commit(&t) (nova/src/prover.rs:35) straight from the device-resident cross term: no H2D of scalars
+            uint64_t proj[24];
+            size_t pairs = std::min(s->m, ck->n);
+#define CALL(C) run_msm<C>(ck->shards, 0, reinterpret_cast<const uint64_t *>(s->t.p), true, KGR_SCALARS_MONTGOMERY, pairs, proj, nullptr)
+            DISPATCH(ck->curve, CALL);
+#undef CALL
+            s->ms[2] = e.last_ms[0];
+#define CALL(C) proj_to_affine_host<C>(proj, commit_out)
+            DISPATCH(ck->curve, CALL);
+#undef CALL
+        }
+        return KGR_OK;
+    });
+}
+
+int kgr_r1cs_last_timing(const kgr_r1cs_t *s, float ms[3]) {
+    if (!s || !ms) return fail(KGR_E_ARG, "null pointer");
+    for (int i = 0; i < 3; i++) ms[i] = s->ms[i];
+    return KGR_OK;
+}
+
+int kgr_vec_fold(int field, const uint64_t *a, const uint64_t *b, const uint64_t r[4], size_t n, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if ((field != 0 && field != 1) || !r || (n && (!a || !b || !out))) return fail(KGR_E_ARG, "bad argument");
+    if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 elements");
+    if (!n) return KGR_OK;
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        e.ntt_buf[0].ensure(n * 32);
+        e.ntt_buf[1].ensure(n * 32);
+        CK(cudaMemcpyAsync(e.ntt_buf[0].p, a, n * 32, cudaMemcpyHostToDevice, e.st));
+        CK(cudaMemcpyAsync(e.ntt_buf[1].p, b, n * 32, cudaMemcpyHostToDevice, e.st));
+        uint32_t r8[8];
+        std::memcpy(r8, r, 32);
+        LaunchR1cs::vec_fold(e.st, field, (uint32_t)n, (const uint32_t *)e.ntt_buf[0].p, (const uint32_t *)e.ntt_buf[1].p, r8, (uint32_t *)e.ntt_buf[0].p);
+        e.launches++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(out, e.ntt_buf[0].p, n * 32, cudaMemcpyDeviceToHost, e.st));
+        CK(cudaStreamSynchronize(e.st));
         return KGR_OK;
     });
 }

@@ -59,6 +59,11 @@ def lib():
         L.zko_xorshift_u64.argtypes = [u8p, ctypes.c_size_t, u64p]
         L.zko_fft.argtypes = [ctypes.c_size_t, ctypes.c_int, u64p, ctypes.c_size_t, u64p, ctypes.POINTER(ctypes.c_size_t)]
         L.zko_groth16_h.argtypes = [ctypes.c_size_t, u64p, u64p, u64p, ctypes.c_size_t, u64p, ctypes.POINTER(ctypes.c_size_t)]
+        u32p = ctypes.POINTER(ctypes.c_uint32)
+        L.zko_sparse_prod.argtypes = [ctypes.c_int, ctypes.c_size_t, u32p, u32p, u64p, u64p, ctypes.c_size_t, u64p]
+        L.zko_cross_term.argtypes = [ctypes.c_int, ctypes.c_size_t, ctypes.POINTER(u32p), ctypes.POINTER(u32p), ctypes.POINTER(u64p), u64p, u64p,
+                                     ctypes.c_size_t, u64p]
+        L.zko_vec_fold.argtypes = [ctypes.c_int, u64p, u64p, u64p, ctypes.c_size_t, u64p]
         L.zko_window_bits.argtypes = [ctypes.c_size_t]
         L.zko_window_bits.restype = ctypes.c_size_t
         L.zko_get_at.argtypes = [ctypes.c_size_t, ctypes.c_size_t, u8p]
@@ -187,6 +192,41 @@ def groth16_h(k, a, b, c):
     n_out = ctypes.c_size_t()
     assert lib().zko_groth16_h(k, _u64(a), _u64(b), _u64(c), a.shape[0], _u64(out), ctypes.byref(n_out)) == 0
     return out, int(n_out.value)
+
+
+def _u32(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))
+
+
+def sparse_prod(field_id, m, mat, z):
+    """zkstd/src/matrix.rs:36-48: mat = (row_ptr[m+1], cols[nnz], coeffs (nnz, 4)) over flat column indices; -> (m, 4)."""
+    rp, cl, cf = _c(mat[0], np.uint32), _c(mat[1], np.uint32), _c(mat[2]).reshape(-1, 4)
+    z = _c(z).reshape(-1, 4)
+    out = np.zeros((m, 4), dtype=np.uint64)
+    assert lib().zko_sparse_prod(field_id, m, _u32(rp), _u32(cl), _u64(cf), _u64(z), z.shape[0], _u64(out)) == 0
+    return out
+
+
+def cross_term(field_id, m, a, b, c, z1, z2):
+    """nova/src/prover.rs:53-90 compute_cross_term with z1 = (u1, x1, w1), z2 = (u2, x2, w2)."""
+    u32p, u64p = ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64)
+    keep = []
+    rp, cl, cf = (u32p * 3)(), (u32p * 3)(), (u64p * 3)()
+    for k, mat in enumerate((a, b, c)):
+        arrs = (_c(mat[0], np.uint32), _c(mat[1], np.uint32), _c(mat[2]).reshape(-1, 4))
+        keep.append(arrs)
+        rp[k], cl[k], cf[k] = _u32(arrs[0]), _u32(arrs[1]), _u64(arrs[2])
+    z1, z2 = _c(z1).reshape(-1, 4), _c(z2).reshape(-1, 4)
+    out = np.zeros((m, 4), dtype=np.uint64)
+    assert lib().zko_cross_term(field_id, m, rp, cl, cf, _u64(z1), _u64(z2), z1.shape[0], _u64(out)) == 0
+    return out
+
+
+def vec_fold(field_id, a, b, r):
+    a, b, r = _c(a).reshape(-1, 4), _c(b).reshape(-1, 4), _c(r).reshape(4)
+    out = np.zeros_like(a)
+    assert lib().zko_vec_fold(field_id, _u64(a), _u64(b), _u64(r), a.shape[0], _u64(out)) == 0
+    return out
 
 
 def window_bits(n):

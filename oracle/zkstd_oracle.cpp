@@ -308,6 +308,37 @@ int zko_groth16_h(size_t k, const uint64_t *a, const uint64_t *b, const uint64_t
     return 0;
 }
 
+// zkstd/src/matrix.rs:36-48 SparseMatrix::prod over `field_id` (0 Fq, 1 Fr): out (m x 4) = M z
+int zko_sparse_prod(int field_id, size_t m, const uint32_t *row_ptr, const uint32_t *cols, const uint64_t *coeffs, const uint64_t *z, size_t n_z, uint64_t *out) {
+    CsrRef mat{row_ptr, cols, coeffs};
+    std::vector<Limbs> zv = load_scalars(z, n_z), r;
+    if (field_id == 0) r = NovaVec<FqParams>::prod(m, mat, zv);
+    else if (field_id == 1) r = NovaVec<FrParams>::prod(m, mat, zv);
+    else return -1;
+    for (size_t i = 0; i < m; i++) st4(out + 4 * i, r[i]);
+    return 0;
+}
+// nova/src/prover.rs:53-90 compute_cross_term; row_ptr / cols / coeffs: A, B, C
+int zko_cross_term(int field_id, size_t m, const uint32_t *const row_ptr[3], const uint32_t *const cols[3], const uint64_t *const coeffs[3],
+                   const uint64_t *z1, const uint64_t *z2, size_t n_z, uint64_t *out) {
+    CsrRef a{row_ptr[0], cols[0], coeffs[0]}, b{row_ptr[1], cols[1], coeffs[1]}, c{row_ptr[2], cols[2], coeffs[2]};
+    std::vector<Limbs> v1 = load_scalars(z1, n_z), v2 = load_scalars(z2, n_z), r;
+    if (field_id == 0) r = NovaVec<FqParams>::cross_term(m, a, b, c, v1, v2);
+    else if (field_id == 1) r = NovaVec<FrParams>::cross_term(m, a, b, c, v1, v2);
+    else return -1;
+    for (size_t i = 0; i < m; i++) st4(out + 4 * i, r[i]);
+    return 0;
+}
+// nova/src/relaxed_r1cs/witness.rs:67-68: out = a + b * r
+int zko_vec_fold(int field_id, const uint64_t *a, const uint64_t *b, const uint64_t r[4], size_t n, uint64_t *out) {
+    std::vector<Limbs> av = load_scalars(a, n), bv = load_scalars(b, n), o;
+    if (field_id == 0) o = NovaVec<FqParams>::fold(av, bv, ld4(r));
+    else if (field_id == 1) o = NovaVec<FrParams>::fold(av, bv, ld4(r));
+    else return -1;
+    for (size_t i = 0; i < n; i++) st4(out + 4 * i, o[i]);
+    return 0;
+}
+
 size_t zko_window_bits(size_t n_bases) { return window_bits(n_bases); }
 size_t zko_get_at(size_t segment, size_t c, const uint8_t bytes[32]) { return get_at(segment, c, bytes); }
 

@@ -456,6 +456,47 @@ template <class C> struct Curve {
     }
 };
 
+// ----- zkstd/src/matrix.rs + nova folding vector work ------------------------------------------
+// A sparse matrix in CSR form over flat column indices into z (Wire::Instance(i) -> i, Wire::Witness(i) -> i + l, matrix.rs:41-44).
+struct CsrRef {
+    const uint32_t *row_ptr, *cols;
+    const uint64_t *coeffs;  // nnz x 4 limbs, Montgomery
+};
+template <class F> struct NovaVec {
+    typedef Field<F> Fd;
+    // matrix.rs:36-48 SparseMatrix::prod: fold(F::zero(), |sum, (wire, coeff)| sum + coeff * value)
+    static std::vector<Limbs> prod(size_t m, const CsrRef &mat, const std::vector<Limbs> &z) {
+        std::vector<Limbs> out(m, Fd::zero());
+        for (size_t i = 0; i < m; i++) {
+            Limbs sum = Fd::zero();
+            for (uint32_t j = mat.row_ptr[i]; j < mat.row_ptr[i + 1]; j++) {
+                Limbs coeff{mat.coeffs[4 * j], mat.coeffs[4 * j + 1], mat.coeffs[4 * j + 2], mat.coeffs[4 * j + 3]};
+                sum = Fd::add(sum, Fd::mul(coeff, z[mat.cols[j]]));
+            }
+            out[i] = sum;
+        }
+        return out;
+    }
+    // nova/src/prover.rs:53-90 compute_cross_term; z1 = (u1, x1, w1), z2 = (u2, x2, w2)
+    static std::vector<Limbs> cross_term(size_t m, const CsrRef &a, const CsrRef &b, const CsrRef &c, const std::vector<Limbs> &z1, const std::vector<Limbs> &z2) {
+        Limbs u1 = z1[0], u2 = z2[0];
+        std::vector<Limbs> az2 = prod(m, a, z2), bz1 = prod(m, b, z1), az1 = prod(m, a, z1), bz2 = prod(m, b, z2), cz2 = prod(m, c, z2), cz1 = prod(m, c, z1);
+        std::vector<Limbs> t(m);
+        for (size_t i = 0; i < m; i++) {
+            Limbs az2bz1 = Fd::mul(az2[i], bz1[i]), az1bz2 = Fd::mul(az1[i], bz2[i]);
+            Limbs c1cz2 = Fd::mul(cz2[i], u1), c2cz1 = Fd::mul(cz1[i], u2);
+            t[i] = Fd::sub(Fd::sub(Fd::add(az2bz1, az1bz2), c1cz2), c2cz1);   // :88
+        }
+        return t;
+    }
+    // nova/src/relaxed_r1cs/witness.rs:67-68: a + b * r
+    static std::vector<Limbs> fold(const std::vector<Limbs> &a, const std::vector<Limbs> &b, const Limbs &r) {
+        std::vector<Limbs> out(a.size());
+        for (size_t i = 0; i < a.size(); i++) out[i] = Fd::add(a[i], Fd::mul(b[i], r));
+        return out;
+    }
+};
+
 // ----- groth16/src/msm.rs -------------------------------------------------------------------
 // msm.rs:75-91
 static inline size_t get_at(size_t segment, size_t c, const uint8_t bytes[32]) {
