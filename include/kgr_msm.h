@@ -76,6 +76,20 @@ int kgr_bases_precompute(kgr_bases_t *bases, int window_bits);
  * Host scalars; the H2D copy of the scalars and the 96-byte D2H of the result are part of the call. */
 int kgr_msm(kgr_bases_t *bases, size_t base_off, const uint64_t *scalars, int scalar_fmt, size_t n, uint64_t *out /* [12] */);
 
+/* Several independent MSMs on registered vectors in one call — the prover's h, l, a, b_g1 and b_g2 queries (groth16/src/prover.rs:51-65,
+ * "overlap the MSMs on streams").  Same results as calling kgr_msm on each job in order.  With one device selected the
+ * jobs run on up to four independent lanes (stream + workspace) of that device, so the latency-bound tail of one MSM overlaps the
+ * bulk of the next; with several devices every MSM is already spread over all of them and the jobs run in sequence. */
+typedef struct kgr_msm_job {
+    kgr_bases_t *bases;
+    size_t base_off;
+    const uint64_t *scalars;
+    int scalar_fmt;
+    size_t n;
+    uint64_t *out; /* [12], or [24] for G2 */
+} kgr_msm_job_t;
+int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs);
+
 /* Same with everything passed from host memory each call; pairs = min(n_bases, n_scalars) exactly
  * like coeffs.iter().zip(bases.iter()) (msm.rs:25). */
 int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, int scalar_fmt,

@@ -159,6 +159,13 @@ struct Engine {
 
 static std::mutex g_mu;
 static std::vector<Engine> g_engines;
+// Extra engines (stream + workspaces) on the device of g_engines[0]: independent MSMs of one kgr_msm_batch call overlap on them.
+static std::vector<std::unique_ptr<Engine>> g_lanes;
+static constexpr size_t MAX_LANES = 4;
+static void destroy_lanes() {
+    for (auto &l : g_lanes) l->destroy();
+    g_lanes.clear();
+}
 
 // Cost model for the window size, fitted to the per-phase timings in profiles/r01_phase_sweep.md (ns):
 //   accumulate 0.174 per entry; counting sort 0.0155 per entry growing with the histogram size G
@@ -568,6 +575,26 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
     }
 }
 
+// ---- kgr_msm_batch: one single-shard MSM per lane, started without waiting and finished later --------------------------
+template <class C> static void lane_start(Engine &e, const Shard &s, size_t off, const uint64_t *scalars, int fmt, size_t n) {
+    CK(cudaSetDevice(e.dev));
+    CK(cudaEventRecord(e.ev[EV_START], e.st));
+    e.scalars.ensure(std::max<size_t>(n, 1) * 8);
+    if (n) CK(cudaMemcpyAsync(e.scalars.p, scalars, n * 32, cudaMemcpyHostToDevice, e.st));
+    size_t first = off - s.first;
+    if (s.d_table)
+        enqueue_msm<C>(e, (const AffinePt<C> *)s.d_table, e.scalars.p, fmt == KGR_SCALARS_MONTGOMERY, (uint32_t)n, s.table_c, (uint32_t)s.count, (uint32_t)first);
+    else
+        enqueue_msm<C>(e, (const AffinePt<C> *)s.d_pts + first, e.scalars.p, fmt == KGR_SCALARS_MONTGOMERY, (uint32_t)n);
+}
+template <class C> static void lane_finish(Engine &e, uint64_t *out) {
+    CK(cudaSetDevice(e.dev));
+    CK(cudaStreamSynchronize(e.st));
+    collect_timing(e);
+    std::vector<Partial> parts{Partial{e.h_result, e.n_result, e.result_c}};
+    combine_partials<C>(parts, out);
+}
+
 // in: 3 coordinates, out: x, y (Montgomery) and one trailing word = is_infinity
 template <class C> static void proj_to_affine_host(const uint64_t *in, uint64_t *out) {
     typedef typename C::Elem E;
@@ -828,6 +855,7 @@ int kgr_init(const int *devices, int n_devices) {
             cudaGetLastError();
             return fail(KGR_E_NO_DEVICE, std::string("no CUDA device: ") + cudaGetErrorString(ce));
         }
+        destroy_lanes();
         for (auto &e : g_engines) e.destroy();
         g_engines.clear();
         std::vector<int> devs;
@@ -849,6 +877,7 @@ int kgr_init(const int *devices, int n_devices) {
 
 int kgr_shutdown(void) {
     std::lock_guard<std::mutex> lk(g_mu);
+    destroy_lanes();
     for (auto &e : g_engines) e.destroy();
     g_engines.clear();
     return KGR_OK;
@@ -958,6 +987,76 @@ int kgr_msm_device(kgr_bases_t *b, size_t off, const void *d_scalars, int fmt, s
     return msm_common(b, off, (const uint64_t *)d_scalars, true, fmt, n, out);
 }
 
+int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
+    if (!jobs && n_jobs) return fail(KGR_E_ARG, "null pointer");
+    bool overlap;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+        overlap = g_engines.size() == 1 && n_jobs > 1;
+        for (size_t j = 0; j < n_jobs && overlap; j++) {
+            const kgr_msm_job_t &jb = jobs[j];
+            if (!jb.bases || jb.bases->shards.size() != 1) overlap = false;
+        }
+    }
+    if (!overlap) {  // several devices (every MSM is already spread over all of them) or a single job: plain sequence
+        for (size_t j = 0; j < n_jobs; j++) {
+            int rc = kgr_msm(jobs[j].bases, jobs[j].base_off, jobs[j].scalars, jobs[j].scalar_fmt, jobs[j].n, jobs[j].out);
+            if (rc) return rc;
+        }
+        return KGR_OK;
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t j = 0; j < n_jobs; j++) {
+        const kgr_msm_job_t &jb = jobs[j];
+        if (!jb.out || (!jb.scalars && jb.n)) return fail(KGR_E_ARG, "null pointer");
+        if (jb.base_off > jb.bases->n || jb.n > jb.bases->n - jb.base_off) return fail(KGR_E_ARG, "range exceeds the registered vector");
+        if (jb.scalar_fmt != KGR_SCALARS_MONTGOMERY && jb.scalar_fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
+    }
+    return guarded([&]() -> int {
+        size_t n_lanes = std::min(n_jobs, MAX_LANES);
+        while (g_lanes.size() + 1 < n_lanes) {
+            std::unique_ptr<Engine> l(new Engine);
+            l->init(g_engines[0].dev);
+            g_lanes.push_back(std::move(l));
+        }
+        auto lane = [&](size_t i) -> Engine & { return i == 0 ? g_engines[0] : *g_lanes[i - 1]; };
+        std::vector<long> in_flight(n_lanes, -1);  // job index running on each lane
+        auto finish = [&](size_t li) -> int {
+            const kgr_msm_job_t &jb = jobs[in_flight[li]];
+#define CALL(C) lane_finish<C>(lane(li), jb.out)
+            DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+            in_flight[li] = -1;
+            return KGR_OK;
+        };
+        for (size_t j = 0; j < n_jobs; j++) {
+            size_t li = j % n_lanes;
+            const kgr_msm_job_t &jb = jobs[j];
+            if (jb.n != 0 && in_flight[li] >= 0) {
+                int rc = finish(li);
+                if (rc) return rc;
+            }
+            if (jb.n == 0) {  // empty sum: the identity (msm.rs:45-47 folds nothing)
+#define CALL(C) combine_partials<C>(std::vector<Partial>(), jb.out)
+                DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+                continue;
+            }
+#define CALL(C) lane_start<C>(lane(li), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n)
+            DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+            in_flight[li] = (long)j;
+        }
+        for (size_t li = 0; li < n_lanes; li++)
+            if (in_flight[li] >= 0) {
+                int rc = finish(li);
+                if (rc) return rc;
+            }
+        return KGR_OK;
+    });
+}
+
 int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_bases, const uint64_t *scalars, int fmt, size_t n_scalars,
                     uint64_t *out) {
     std::lock_guard<std::mutex> lk(g_mu);
@@ -1021,6 +1120,8 @@ int kgr_launch_count(int dev, uint64_t *count) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (dev < 0 || dev >= (int)g_engines.size() || !count) return fail(KGR_E_ARG, "bad device slot");
     *count = g_engines[dev].launches;
+    if (dev == 0)
+        for (auto &l : g_lanes) *count += l->launches;
     return KGR_OK;
 }
 

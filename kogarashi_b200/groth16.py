@@ -14,7 +14,7 @@ of its slice layout, :58-62).  The blinding terms are a five-point MSM, so no cu
 import numpy as np
 
 from .fft import Fft
-from .msm import BN254_G1, BN254_G2, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Bases, msm_curve_addition, proj_add, to_affine
+from .msm import BN254_G1, BN254_G2, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Bases, msm_batch, msm_curve_addition, proj_add, to_affine
 
 FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001  # bn254/src/fr.rs:11-16
 
@@ -36,20 +36,23 @@ class Groth16G1Prover:
         pt = lambda p: np.ascontiguousarray(p, dtype=np.uint64).reshape(1, 8)
         self.vk = np.concatenate([pt(delta_g1), pt(alpha_g1), pt(beta_g1)])
         self.a, self.b_g1, self.h, self.l = (Bases(BN254_G1, p, f) for p, f in ((a, a_inf), (b_g1, b_g1_inf), (h, h_inf), (l, l_inf)))
+        self.vk_bases = Bases(BN254_G1, self.vk)
         if precompute:
             for b in (self.a, self.b_g1, self.h, self.l):
                 b.precompute(0)
 
-    def prove_g1(self, q, inputs, aux, r, s, scalar_fmt=SCALARS_MONTGOMERY):
-        """q, inputs, aux: (len, 4) uint64 scalars in `scalar_fmt`; r, s: Python ints (the prover's blinding factors, prover.rs:71-72).
-        -> (A, C) as (9,) uint64 affine [x, y, is_infinity] = Proof.a / Proof.c after `.into()` (prover.rs:94-98)."""
+    def _g1_jobs(self, q, inputs, aux, r, scalar_fmt):
+        """The G1 queries of prover.rs:51-62 as one batch (independent MSMs overlap on the device) + the blinding of A."""
         z = np.concatenate([np.asarray(inputs, dtype=np.uint64).reshape(-1, 4), np.asarray(aux, dtype=np.uint64).reshape(-1, 4)])
-        a_answer = msm_curve_addition(self.a, z, scalar_fmt=scalar_fmt)              # a_inputs + a_aux       (:58-59, :80)
-        b1_answer = msm_curve_addition(self.b_g1, z, scalar_fmt=scalar_fmt)          # b_g1_inputs + b_g1_aux (:61-62, :86)
-        q_pt = msm_curve_addition(self.h, q, scalar_fmt=scalar_fmt)                  # :51
-        l_pt = msm_curve_addition(self.l, aux, scalar_fmt=scalar_fmt)                # :56
+        return z, [(self.a, z, 0, scalar_fmt),                      # a_inputs + a_aux       (:58-59, :80)
+                   (self.b_g1, z, 0, scalar_fmt),                   # b_g1_inputs + b_g1_aux (:61-62, :86)
+                   (self.h, q, 0, scalar_fmt),                      # :51
+                   (self.l, aux, 0, scalar_fmt),                    # :56
+                   (self.vk_bases, _canonical([r, 1]), 0, SCALARS_CANONICAL)]   # r*delta + alpha (:75)
+
+    def _assemble_g1(self, res, r, s):
+        a_answer, b1_answer, q_pt, l_pt, blind_a = res[:5]
         delta, alpha, beta = self.vk
-        blind_a = msm_curve_addition(np.stack([delta, alpha]), _canonical([r, 1]), curve=BN254_G1, scalar_fmt=SCALARS_CANONICAL)
         g_a = proj_add(BN254_G1, blind_a, a_answer)
         aa, ba = to_affine(BN254_G1, a_answer), to_affine(BN254_G1, b1_answer)
         pts = np.stack([aa[:8], ba[:8], delta, alpha, beta])
@@ -57,6 +60,12 @@ class Groth16G1Prover:
         blind_c = msm_curve_addition(pts, _canonical([s, r, r * s, s, r]), curve=BN254_G1, inf=inf, scalar_fmt=SCALARS_CANONICAL)
         g_c = proj_add(BN254_G1, proj_add(BN254_G1, blind_c, q_pt), l_pt)
         return to_affine(BN254_G1, g_a), to_affine(BN254_G1, g_c)
+
+    def prove_g1(self, q, inputs, aux, r, s, scalar_fmt=SCALARS_MONTGOMERY):
+        """q, inputs, aux: (len, 4) uint64 scalars in `scalar_fmt`; r, s: Python ints (the prover's blinding factors, prover.rs:71-72).
+        -> (A, C) as (9,) uint64 affine [x, y, is_infinity] = Proof.a / Proof.c after `.into()` (prover.rs:94-98)."""
+        _, jobs = self._g1_jobs(q, inputs, aux, r, scalar_fmt)
+        return self._assemble_g1(msm_batch(jobs), r, s)
 
     def prove_from_evaluations(self, log_n, a_evals, b_evals, c_evals, inputs, aux, r, s):
         """The whole G1 side of create_proof from the R1CS evaluations (prover.rs:33): device NTTs for H, then the MSMs.
@@ -69,7 +78,7 @@ class Groth16G1Prover:
         return self.prove_g1(_canonical(list(q)), _canonical(list(inputs)), _canonical(list(aux)), r, s, scalar_fmt=SCALARS_CANONICAL)
 
     def free(self):
-        for b in (self.a, self.b_g1, self.h, self.l):
+        for b in (self.a, self.b_g1, self.h, self.l, self.vk_bases):
             b.free()
 
 
@@ -81,16 +90,19 @@ class Groth16Prover(Groth16G1Prover):
         pt = lambda p: np.ascontiguousarray(p, dtype=np.uint64).reshape(1, 16)
         self.vk_g2 = np.concatenate([pt(delta_g2), pt(beta_g2)])
         self.b_g2 = Bases(BN254_G2, b_g2, b_g2_inf)
+        self.vk_g2_bases = Bases(BN254_G2, self.vk_g2)
         if precompute:
             self.b_g2.precompute(0)
 
     def prove(self, q, inputs, aux, r, s, scalar_fmt=SCALARS_MONTGOMERY):
-        """-> (A, B, C): A, C (9,) uint64 and B (17,) uint64 affine [x, y, is_infinity] = Proof {a, b, c} (prover.rs:94-98)."""
-        g_a, g_c = self.prove_g1(q, inputs, aux, r, s, scalar_fmt=scalar_fmt)
-        z = np.concatenate([np.asarray(inputs, dtype=np.uint64).reshape(-1, 4), np.asarray(aux, dtype=np.uint64).reshape(-1, 4)])
-        b2_answer = msm_curve_addition(self.b_g2, z, scalar_fmt=scalar_fmt)          # b_g2_inputs + b_g2_aux (:64-65, :87)
-        blind_b = msm_curve_addition(self.vk_g2, _canonical([s, 1]), curve=BN254_G2, scalar_fmt=SCALARS_CANONICAL)
-        return g_a, to_affine(BN254_G2, proj_add(BN254_G2, blind_b, b2_answer)), g_c
+        """-> (A, B, C): A, C (9,) uint64 and B (17,) uint64 affine [x, y, is_infinity] = Proof {a, b, c} (prover.rs:94-98).
+        All eight MSMs of prover.rs:51-65 (pairs fused) and the two independent blinding sums go to the device as one batch."""
+        z, jobs = self._g1_jobs(q, inputs, aux, r, scalar_fmt)
+        jobs += [(self.b_g2, z, 0, scalar_fmt),                                           # b_g2_inputs + b_g2_aux (:64-65, :87)
+                 (self.vk_g2_bases, _canonical([s, 1]), 0, SCALARS_CANONICAL)]            # s*delta_g2 + beta_g2   (:76)
+        res = msm_batch(jobs)
+        g_a, g_c = self._assemble_g1(res, r, s)
+        return g_a, to_affine(BN254_G2, proj_add(BN254_G2, res[6], res[5])), g_c
 
     def prove_from_evaluations(self, log_n, a_evals, b_evals, c_evals, inputs, aux, r, s):
         q = Fft(log_n).h_coefficients(a_evals, b_evals, c_evals)
@@ -103,3 +115,4 @@ class Groth16Prover(Groth16G1Prover):
     def free(self):
         super().free()
         self.b_g2.free()
+        self.vk_g2_bases.free()

@@ -116,6 +116,29 @@ def msm_curve_addition(bases, coeffs, curve=BN254_G1, inf=None, scalar_fmt=SCALA
     return out
 
 
+class _Job(ctypes.Structure):
+    _fields_ = [("bases", ctypes.c_void_p), ("base_off", ctypes.c_size_t), ("scalars", _u64p), ("scalar_fmt", ctypes.c_int),
+                ("n", ctypes.c_size_t), ("out", _u64p)]
+
+
+def msm_batch(jobs, scalar_fmt=SCALARS_MONTGOMERY):
+    """kgr_msm_batch: jobs = [(Bases, coeffs[, base_off[, scalar_fmt]]), ...] -> list of projective results.  Independent MSMs
+    on registered vectors (the prover's h, l, a, b_g1, b_g2 queries, prover.rs:51-65) overlap on separate lanes of the device."""
+    _lib.ensure_init()
+    arr = (_Job * len(jobs))()
+    keep, outs = [], []
+    for i, job in enumerate(jobs):
+        bases, coeffs = job[0], _c(job[1]).reshape(-1, 4)
+        off = job[2] if len(job) > 2 else 0
+        fmt = job[3] if len(job) > 3 else scalar_fmt
+        out = np.zeros(3 * coord_limbs(bases.curve), dtype=np.uint64)
+        keep.append(coeffs)
+        outs.append(out)
+        arr[i] = _Job(bases._h.value if hasattr(bases._h, "value") else bases._h, off, _u64(coeffs), fmt, min(coeffs.shape[0], bases.n - off), _u64(out))
+    _lib.check(_lib.lib().kgr_msm_batch(ctypes.cast(arr, ctypes.c_void_p), len(jobs)))
+    return outs
+
+
 def msm_device(bases, d_scalars_ptr, n, scalar_fmt=SCALARS_MONTGOMERY, base_off=0):
     """MSM with the scalars already in device memory (raw pointer, n x 4 uint64)."""
     out = np.zeros(3 * coord_limbs(bases.curve), dtype=np.uint64)

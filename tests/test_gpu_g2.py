@@ -158,3 +158,34 @@ def test_msm_checksum_2p18(k):
     bases.precompute()
     assert same_affine(k.to_affine(C2, k.msm_curve_addition(bases, sc)), _k_times_g(s))
     bases.free()
+
+
+def test_msm_batch_equals_sequence(k, golden_g2, golden):
+    """kgr_msm_batch: mixed-curve jobs (G1, Grumpkin, G2, empty, offset, precomputed, canonical scalars) overlapped on the lanes of one
+    device give exactly the results of the same calls made one by one; more jobs than lanes reuse lanes in order."""
+    specs = [("g1_uniform_1024", 0), ("gr_skewed_128", 1), ("g2_uniform_128", 2), ("g1_dup_neg_96", 0), ("g2_identity_bases_24", 2),
+             ("gr_uniform_100", 1), ("g1_uniform_0", 0), ("g2_dup_neg_48", 2), ("g1_identity_bases_40", 0)]
+    jobs, expect, keep = [], [], []
+    for i, (name, curve) in enumerate(specs):
+        z = golden_g2 if curve == 2 else golden
+        pts, sc, inf, aff = (z[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
+        bases = k.Bases(curve, pts, inf)
+        if i == 3:
+            bases.precompute(6)
+        keep.append(bases)
+        jobs.append((bases, sc))
+        expect.append((curve, aff))
+    # an offset window and a canonical-format job on vectors already in the batch
+    pts, sc = golden["g1_uniform_1024_pts"], golden["g1_uniform_1024_sc"]
+    jobs.append((keep[0], sc[:1000], 24))
+    expect.append((0, A.to_affine(0, A.msm(0, pts[24:], sc[:1000]))))
+    canon = np.stack([A.field_op(A.FIELD_FR, "mont_reduce", s) for s in golden_g2["g2_uniform_128_sc"]])
+    jobs.append((keep[2], canon, 0, k.SCALARS_CANONICAL))
+    expect.append((2, golden_g2["g2_uniform_128_aff"]))
+    for _ in range(2):
+        got = k.msm_batch(jobs)
+        assert len(got) == len(jobs)
+        for g, (curve, aff) in zip(got, expect):
+            assert same_affine(k.to_affine(curve, g), aff)
+    for b in keep:
+        b.free()
