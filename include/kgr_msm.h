@@ -78,7 +78,7 @@ int kgr_msm(kgr_bases_t *bases, size_t base_off, const uint64_t *scalars, int sc
 
 /* Several independent MSMs on registered vectors in one call — the prover's h, l, a, b_g1 and b_g2 queries (groth16/src/prover.rs:51-65,
  * "overlap the MSMs on streams").  Same results as calling kgr_msm on each job in order.  With one device selected the
- * jobs run on up to four independent lanes (stream + workspace) of that device, so the latency-bound tail of one MSM overlaps the
+ * jobs run on up to eight independent lanes (stream + workspace) of that device, so the latency-bound tail of one MSM overlaps the
  * bulk of the next; with several devices every MSM is already spread over all of them and the jobs run in sequence. */
 typedef struct kgr_msm_job {
     kgr_bases_t *bases;

@@ -249,17 +249,49 @@ template <class C> __global__ void k_gen_scalars(uint64_t seed, uint64_t first, 
     }
     out[i] = fp_from_u512<typename C::Scalar>(w);
 }
-// out[i] = k[i] * G, affine.  MSB-first double-and-add on the canonical scalar, then one inversion.
-template <class C> __global__ void __launch_bounds__(128) k_fixed_base(const Fp<typename C::Scalar> *k, AffinePt<C> g, uint32_t n, AffinePt<C> *out) {
+// Fixed-base scalar multiplication k * G for many k (PedersenCommitment::new, nova/src/pedersen.rs:10-13; CRS setup,
+// groth16/src/zksnark.rs:55-57,172-193 — the reference pays one full double-and-add per point).  A table of
+// T[j][d] = d * 2^(8 j) * G (32 windows x 256 digits, affine, 512 KB on G1: L2-resident) turns every product into at most 32
+// mixed additions and one inversion.
+constexpr uint32_t FIXED_WINDOWS = 32, FIXED_DIGITS = 256;
+template <class C> KGR_HD AffinePt<C> xyzz_to_affine_fast(const XyzzPt<C> &p) {
+    typedef typename C::Elem E;
+    AffinePt<C> r;
+    if (xyzz_is_identity(p)) {
+        r.x = El<E>::zero();
+        r.y = El<E>::zero();
+        return r;
+    }
+    E t = fp_inv_fast(fp_mul(p.zz, p.zzz));  // safegcd inversion (modinv.cuh): same unique inverse as Fermat, ~4.5x cheaper
+    r.x = fp_mul(p.x, fp_mul(t, p.zzz));
+    r.y = fp_mul(p.y, fp_mul(t, p.zz));
+    return r;
+}
+// one thread per table entry (j, d): 8 j doublings of G, then d times that point
+template <class C> __global__ void __launch_bounds__(128) k_fixed_table(AffinePt<C> g, AffinePt<C> *table) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= FIXED_WINDOWS * FIXED_DIGITS) return;
+    uint32_t j = i / FIXED_DIGITS, d = i % FIXED_DIGITS;
+    XyzzPt<C> base = xyzz_from_affine(g);
+    for (uint32_t t = 0; t < 8 * j; t++) base = xyzz_dbl(base);
+    XyzzPt<C> acc = xyzz_identity<C>();
+    for (int bit = 7; bit >= 0; bit--) {
+        acc = xyzz_dbl(acc);
+        if ((d >> bit) & 1) xyzz_add(acc, base);
+    }
+    table[i] = xyzz_to_affine_fast(acc);
+}
+// out[i] = k[i] * G, affine: one table entry per non-zero byte of the canonical scalar
+template <class C> __global__ void __launch_bounds__(128) k_fixed_base(const Fp<typename C::Scalar> *k, const AffinePt<C> *table, uint32_t n, AffinePt<C> *out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Fp<typename C::Scalar> s = fp_from_mont(k[i]);
     XyzzPt<C> acc = xyzz_identity<C>();
-    for (int bit = 255; bit >= 0; bit--) {
-        acc = xyzz_dbl(acc);
-        if ((s.v[bit >> 5] >> (bit & 31)) & 1) xyzz_madd(acc, g);
+    for (uint32_t j = 0; j < FIXED_WINDOWS; j++) {
+        uint32_t d = (s.v[j >> 2] >> (8 * (j & 3))) & 0xffu;
+        if (d) xyzz_madd(acc, load_affine(table, j * FIXED_DIGITS + d));
     }
-    out[i] = xyzz_to_affine(acc);
+    out[i] = xyzz_to_affine_fast(acc);
 }
 
 

@@ -47,7 +47,9 @@ template <class C> struct Launch {
     static void precompute(cudaStream_t st, uint32_t n, uint32_t c, uint32_t W, uint32_t stride, const A *pts, A *table);
     static void point_op(cudaStream_t st, int op, const A *a, const A *b, uint32_t *out24, uint32_t n);
     static void gen_scalars(cudaStream_t st, uint64_t seed, uint64_t first, uint32_t n, S *out);
-    static void fixed_base(cudaStream_t st, const S *k, const A &g, uint32_t n, A *out);
+    static size_t fixed_table_points();  // entries of the table below
+    static void fixed_table(cudaStream_t st, const A &g, A *table);
+    static void fixed_base(cudaStream_t st, const S *k, const A *table, uint32_t n, A *out);
 };
 
 struct LaunchUtil {

@@ -120,7 +120,9 @@ template <class C> void Launch<C>::point_op(cudaStream_t st, int op, const A *a,
 template <class C> void Launch<C>::gen_scalars(cudaStream_t st, uint64_t seed, uint64_t first, uint32_t n, S *out) {
     k_gen_scalars<C><<<cdiv(n, 256), 256, 0, st>>>(seed, first, n, out);
 }
-template <class C> void Launch<C>::fixed_base(cudaStream_t st, const S *k, const A &g, uint32_t n, A *out) { k_fixed_base<C><<<cdiv(n, 128), 128, 0, st>>>(k, g, n, out); }
+template <class C> size_t Launch<C>::fixed_table_points() { return (size_t)FIXED_WINDOWS * FIXED_DIGITS; }
+template <class C> void Launch<C>::fixed_table(cudaStream_t st, const A &g, A *table) { k_fixed_table<C><<<cdiv(FIXED_WINDOWS * FIXED_DIGITS, 128), 128, 0, st>>>(g, table); }
+template <class C> void Launch<C>::fixed_base(cudaStream_t st, const S *k, const A *table, uint32_t n, A *out) { k_fixed_base<C><<<cdiv(n, 128), 128, 0, st>>>(k, table, n, out); }
 #endif
 
 }  // namespace kgr

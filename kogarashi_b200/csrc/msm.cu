@@ -9,6 +9,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -106,6 +107,7 @@ struct Engine {
     DevBuf<uint8_t> oneshot_pts, oneshot_inf;  // device copy of the bases of kgr_msm_oneshot
     std::map<uint32_t, std::shared_ptr<struct NttDomain>> ntt_domains;  // per log2(n): twiddle / coset tables in HBM
     DevBuf<uint8_t> ntt_buf[3];
+    DevBuf<uint8_t> fixed_table[3];   // per curve: d * 2^(8 j) * G, built on first use (kgr_fixed_base_mul / kgr_bases_generate)
 
     void init(int device) {
         dev = device;
@@ -132,6 +134,7 @@ struct Engine {
         cudaStreamSynchronize(st);
         counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
         bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release(); aff_nodes.release(); aff_suffix.release(); aff_inv.release();
+        for (auto &t : fixed_table) t.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
         if (h_stage) cudaFreeHost(h_stage);
@@ -161,7 +164,7 @@ static std::mutex g_mu;
 static std::vector<Engine> g_engines;
 // Extra engines (stream + workspaces) on the device of g_engines[0]: independent MSMs of one kgr_msm_batch call overlap on them.
 static std::vector<std::unique_ptr<Engine>> g_lanes;
-static constexpr size_t MAX_LANES = 4;
+static constexpr size_t MAX_LANES = 8;
 static void destroy_lanes() {
     for (auto &l : g_lanes) l->destroy();
     g_lanes.clear();
@@ -708,6 +711,18 @@ template <> AffinePt<Bn254G2> generator_affine<Bn254G2>() {  // bn254/src/params
     return g;
 }
 
+// The generator's window table on engine e (built once per curve and device).
+template <class C> static const AffinePt<C> *fixed_table(Engine &e) {
+    DevBuf<uint8_t> &buf = e.fixed_table[C::ID];
+    if (!buf.p) {
+        buf.ensure(Launch<C>::fixed_table_points() * sizeof(AffinePt<C>));
+        Launch<C>::fixed_table(e.st, generator_affine<C>(), (AffinePt<C> *)buf.p);
+        e.launches++;
+        CK(cudaGetLastError());
+    }
+    return (const AffinePt<C> *)buf.p;
+}
+
 template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed, uint64_t *k_out) {
     typedef Fp<typename C::Scalar> S;
     CK(cudaSetDevice(e.dev));
@@ -717,7 +732,7 @@ template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed
     CK(cudaMalloc(&dk, s.count * sizeof(S)));
     uint32_t n = (uint32_t)s.count;
     Launch<C>::gen_scalars(e.st, seed, (uint64_t)s.first, n, dk);
-    Launch<C>::fixed_base(e.st, dk, generator_affine<C>(), n, (AffinePt<C> *)s.d_pts);
+    Launch<C>::fixed_base(e.st, dk, fixed_table<C>(e), n, (AffinePt<C> *)s.d_pts);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e.st));
     if (k_out) CK(cudaMemcpy(k_out + 4 * s.first, dk, s.count * sizeof(S), cudaMemcpyDeviceToHost));
@@ -1012,6 +1027,7 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
         if (!jb.out || (!jb.scalars && jb.n)) return fail(KGR_E_ARG, "null pointer");
         if (jb.base_off > jb.bases->n || jb.n > jb.bases->n - jb.base_off) return fail(KGR_E_ARG, "range exceeds the registered vector");
         if (jb.scalar_fmt != KGR_SCALARS_MONTGOMERY && jb.scalar_fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
+        if (jb.bases->curve < KGR_CURVE_BN254_G1 || jb.bases->curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
     }
     return guarded([&]() -> int {
         size_t n_lanes = std::min(n_jobs, MAX_LANES);
@@ -1021,38 +1037,43 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
             g_lanes.push_back(std::move(l));
         }
         auto lane = [&](size_t i) -> Engine & { return i == 0 ? g_engines[0] : *g_lanes[i - 1]; };
-        std::vector<long> in_flight(n_lanes, -1);  // job index running on each lane
-        auto finish = [&](size_t li) -> int {
-            const kgr_msm_job_t &jb = jobs[in_flight[li]];
-#define CALL(C) lane_finish<C>(lane(li), jb.out)
-            DISPATCH(jb.bases->curve, CALL);
-#undef CALL
-            in_flight[li] = -1;
-            return KGR_OK;
-        };
-        for (size_t j = 0; j < n_jobs; j++) {
-            size_t li = j % n_lanes;
-            const kgr_msm_job_t &jb = jobs[j];
-            if (jb.n != 0 && in_flight[li] >= 0) {
-                int rc = finish(li);
-                if (rc) return rc;
-            }
-            if (jb.n == 0) {  // empty sum: the identity (msm.rs:45-47 folds nothing)
+        // one host thread per lane: it takes the next job, enqueues it on its lane (uploads + ~25 launches), waits and finishes it on the
+        // host (Horner over the window sums), so neither the enqueue work nor the host finish of one job delays another lane
+        std::atomic<size_t> next(0);
+        std::vector<CudaError> errs(n_lanes, CudaError{cudaSuccess, "", 0});
+        std::vector<int> rcs(n_lanes, KGR_OK);
+        auto worker = [&](size_t li) {
+            try {
+                for (;;) {
+                    size_t j = next.fetch_add(1);
+                    if (j >= n_jobs) break;
+                    const kgr_msm_job_t &jb = jobs[j];
+                    rcs[li] = [&]() -> int {
+                        if (jb.n == 0) {  // empty sum: the identity (msm.rs:45-47 folds nothing)
 #define CALL(C) combine_partials<C>(std::vector<Partial>(), jb.out)
-                DISPATCH(jb.bases->curve, CALL);
+                            DISPATCH(jb.bases->curve, CALL);
 #undef CALL
-                continue;
-            }
-#define CALL(C) lane_start<C>(lane(li), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n)
-            DISPATCH(jb.bases->curve, CALL);
+                            return KGR_OK;
+                        }
+#define CALL(C) lane_start<C>(lane(li), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n); lane_finish<C>(lane(li), jb.out)
+                        DISPATCH(jb.bases->curve, CALL);
 #undef CALL
-            in_flight[li] = (long)j;
-        }
-        for (size_t li = 0; li < n_lanes; li++)
-            if (in_flight[li] >= 0) {
-                int rc = finish(li);
-                if (rc) return rc;
+                        return KGR_OK;
+                    }();
+                    if (rcs[li]) break;
+                }
+            } catch (CudaError &ce) {
+                errs[li] = ce;
             }
+        };
+        std::vector<std::thread> th;
+        for (size_t li = 1; li < n_lanes; li++) th.emplace_back(worker, li);
+        worker(0);
+        for (auto &t : th) t.join();
+        for (auto &ce : errs)
+            if (ce.e != cudaSuccess) throw ce;
+        for (int rc : rcs)
+            if (rc) return rc;
         return KGR_OK;
     });
 }
@@ -1284,7 +1305,7 @@ int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy)
         const size_t ab = affine_bytes(curve);
         CK(cudaMalloc(&dp, n * ab + ab));
         CK(cudaMemcpyAsync(dk, k, n * 32, cudaMemcpyHostToDevice, e.st));
-#define CALL(C) Launch<C>::fixed_base(e.st, (const Fp<C::Scalar> *)dk, generator_affine<C>(), (uint32_t)n, (AffinePt<C> *)dp)
+#define CALL(C) Launch<C>::fixed_base(e.st, (const Fp<C::Scalar> *)dk, fixed_table<C>(e), (uint32_t)n, (AffinePt<C> *)dp)
         DISPATCH(curve, CALL);
 #undef CALL
         CK(cudaGetLastError());

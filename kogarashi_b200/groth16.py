@@ -98,11 +98,11 @@ class Groth16Prover(Groth16G1Prover):
         """-> (A, B, C): A, C (9,) uint64 and B (17,) uint64 affine [x, y, is_infinity] = Proof {a, b, c} (prover.rs:94-98).
         All eight MSMs of prover.rs:51-65 (pairs fused) and the two independent blinding sums go to the device as one batch."""
         z, jobs = self._g1_jobs(q, inputs, aux, r, scalar_fmt)
-        jobs += [(self.b_g2, z, 0, scalar_fmt),                                           # b_g2_inputs + b_g2_aux (:64-65, :87)
-                 (self.vk_g2_bases, _canonical([s, 1]), 0, SCALARS_CANONICAL)]            # s*delta_g2 + beta_g2   (:76)
+        # the G2 query is the longest job (3x the arithmetic per point): it goes first so that the G1 queries overlap with it
+        jobs = [(self.b_g2, z, 0, scalar_fmt)] + jobs + [(self.vk_g2_bases, _canonical([s, 1]), 0, SCALARS_CANONICAL)]   # :64-65,:87 / :76
         res = msm_batch(jobs)
-        g_a, g_c = self._assemble_g1(res, r, s)
-        return g_a, to_affine(BN254_G2, proj_add(BN254_G2, res[6], res[5])), g_c
+        g_a, g_c = self._assemble_g1(res[1:6], r, s)
+        return g_a, to_affine(BN254_G2, proj_add(BN254_G2, res[6], res[0])), g_c
 
     def prove_from_evaluations(self, log_n, a_evals, b_evals, c_evals, inputs, aux, r, s):
         q = Fft(log_n).h_coefficients(a_evals, b_evals, c_evals)

@@ -3,6 +3,10 @@
 //!
 //! UNTESTED: this file has never been compiled (no rustc/cargo in the development image).  The tested
 //! contract is the C ABI; tests/ exercise every marshalling step below through Python/ctypes instead.
+//!
+//! Covered here: the two 4-limb curves of the MSM hot path.  The later rows of the same library — G2 (`KGR_CURVE_BN254_G2`,
+//! 8 limbs per coordinate, needs an accessor for `Fq2`'s private array), `kgr_msm_batch`, `kgr_ntt`, `kgr_groth16_h`,
+//! `kgr_r1cs_register` / `kgr_nova_cross_term` / `kgr_vec_fold` — bind the same way; INTEGRATION.md §1 and §3 list the call sites.
 use core::ffi::c_char;
 use std::sync::Once;
 
