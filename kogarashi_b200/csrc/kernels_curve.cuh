@@ -145,20 +145,40 @@ __global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *in, uint32_t 
     }
     store_xyzz(&out[(size_t)w * B + out_off + i], a);
 }
-// Partial sums of the upper halves: grid (chunk, level - 1, window); a CTA sums up to 8 * TPB_TREE elements of one upper half.
+// Fold levels l_first .. nb of one window in one CTA (m = B >> l <= TPB_TAIL there): the deep levels are one add each and purely
+// latency-bound, so they are not worth a launch apiece.  Same reads and writes as k_fold; a level's output is the next level's input,
+// ordered by the CTA barrier.
+constexpr int TPB_TAIL = 256;
+constexpr uint32_t VSUM_ELEMS = 8;
+template <class C> __global__ void __launch_bounds__(TPB_TAIL) k_fold_tail(XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t l_first) {
+    const uint32_t w = blockIdx.x, i = threadIdx.x;
+    XyzzPt<C> *row = F + (size_t)w * B;
+    for (uint32_t l = l_first; l <= nb; l++) {
+        uint32_t m = B >> l;
+        uint32_t in_off = B - (B >> (l - 2)), out_off = B - (B >> (l - 1));  // l_first >= 2: the input is always a fold level in F
+        if (i < m) {
+            XyzzPt<C> a = row[in_off + i];
+            XyzzPt<C> b = row[in_off + i + m];
+            xyzz_add(a, b);
+            store_xyzz(&row[out_off + i], a);
+        }
+        __syncthreads();
+    }
+}
+// Partial sums of the upper halves: grid (chunk, level - l_first, window); a CTA sums up to 8 * TPB_TREE elements of one upper half.
 template <class C>
 __global__ void __launch_bounds__(TPB_TREE) k_vsum1(const XyzzPt<C> *buckets, const XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t chunks_max,
-                                                    const uint32_t *bucket_offsets, XyzzPt<C> *partial) {
+                                                    const uint32_t *bucket_offsets, XyzzPt<C> *partial, uint32_t l_first) {
     __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
-    const uint32_t chunk = blockIdx.x, l = blockIdx.y + 1, w = blockIdx.z;
+    const uint32_t chunk = blockIdx.x, l = blockIdx.y + l_first, w = blockIdx.z;
     const uint32_t m = B >> l;
-    if (chunk * 8u * TPB_TREE >= m) return;  // uniform per CTA
+    if (chunk * VSUM_ELEMS * TPB_TREE >= m) return;  // uniform per CTA
     const XyzzPt<C> *src = (l == 1) ? buckets + (size_t)w * B + m : F + (size_t)w * B + (B - (B >> (l - 2))) + m;
     const uint32_t *off = (l == 1 && bucket_offsets) ? bucket_offsets + (size_t)w * B + m : nullptr;
     XyzzPt<C> acc = xyzz_identity<C>();
 #pragma unroll 1
-    for (uint32_t k = 0; k < 8; k++) {
-        uint32_t i = chunk * 8u * TPB_TREE + k * TPB_TREE + threadIdx.x;
+    for (uint32_t k = 0; k < VSUM_ELEMS; k++) {
+        uint32_t i = chunk * VSUM_ELEMS * TPB_TREE + k * TPB_TREE + threadIdx.x;
         if (i < m && (!off || off[i] != off[i + 1])) xyzz_add(acc, src[i]);
     }
     acc = block_tree_sum<C>(acc, sm);
@@ -169,7 +189,7 @@ template <class C> __global__ void __launch_bounds__(TPB_TREE) k_vsum2(const Xyz
     __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     const uint32_t l = blockIdx.x + 1, w = blockIdx.y;
     const uint32_t m = B >> l;
-    const uint32_t cnt = (m + 8u * TPB_TREE - 1) / (8u * TPB_TREE);
+    const uint32_t cnt = (m + VSUM_ELEMS * TPB_TREE - 1) / (VSUM_ELEMS * TPB_TREE);
     const XyzzPt<C> *src = partial + ((size_t)w * nb + (l - 1)) * chunks_max;
     XyzzPt<C> acc = xyzz_identity<C>();
     for (uint32_t i = threadIdx.x; i < cnt; i += TPB_TREE) xyzz_add(acc, src[i]);

@@ -40,7 +40,10 @@ template <class C> struct Launch {
     static void tree_sum(cudaStream_t st, uint32_t n_windows, const X *in, uint32_t cnt_in, X *out);
     // fold reduce (B >= 256): returns the number of kernels launched; F: n_windows * B points, partial: n_windows * nb * chunks_max,
     // V: n_windows * nb, out: n_windows
-    static int fold_reduce(cudaStream_t st, uint32_t n_windows, uint32_t B, const X *buckets, const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out);
+    // st2 / ev_fork / ev_join: a second stream on which the sums of the big upper halves (levels 1..3, 7/8 of that work) overlap the deep,
+    // latency-bound fold levels
+    static int fold_reduce(cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join, uint32_t n_windows, uint32_t B, const X *buckets,
+                           const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out);
     static uint32_t fold_chunks_max(uint32_t B);
     static void final_horner(cudaStream_t st, const MsmShape &sh, const X *win_a, X *out);
     static void fold_inf(cudaStream_t st, A *pts, const uint8_t *inf, uint32_t n);

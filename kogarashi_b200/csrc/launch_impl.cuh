@@ -85,25 +85,49 @@ template <class C> void Launch<C>::tree_sum(cudaStream_t st, uint32_t n_windows,
 }
 #endif
 #if KGR_PART & 8
-template <class C> uint32_t Launch<C>::fold_chunks_max(uint32_t B) { return ((B >> 1) + 8u * TPB_TREE - 1) / (8u * TPB_TREE); }
+template <class C> uint32_t Launch<C>::fold_chunks_max(uint32_t B) { return ((B >> 1) + VSUM_ELEMS * TPB_TREE - 1) / (VSUM_ELEMS * TPB_TREE); }
 template <class C>
-int Launch<C>::fold_reduce(cudaStream_t st, uint32_t n_windows, uint32_t B, const X *buckets, const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out) {
+int Launch<C>::fold_reduce(cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join, uint32_t n_windows, uint32_t B, const X *buckets,
+                           const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out) {
     uint32_t nb = 0;
     while ((1u << nb) < B) nb++;
     int launches = 0;
-    for (uint32_t l = 1; l <= nb; l++) {
+    const uint32_t chunks_max = fold_chunks_max(B);
+    const uint32_t l_early = 3;  // upper halves of levels 1..3 are summed on st2 as soon as fold level 2 exists
+    bool forked = false;
+    uint32_t l = 1;
+    for (; l <= nb; l++) {
         uint32_t m = B >> l;
+        if (l >= 2 && m <= (uint32_t)TPB_TAIL) break;  // the rest in one kernel
         const X *in = (l == 1) ? buckets : F;
         uint32_t in_off = (l == 1) ? 0 : B - (B >> (l - 2));
         uint32_t out_off = B - (B >> (l - 1));
         k_fold<C><<<cdiv((size_t)n_windows * m, TPB_RED), TPB_RED, 0, st>>>(in, in_off, F, out_off, B, m, n_windows, l == 1 ? bucket_offsets : nullptr);
         launches++;
+        if (l + 1 == l_early && l_early < nb) {
+            cudaEventRecord(ev_fork, st);
+            cudaStreamWaitEvent(st2, ev_fork, 0);
+            k_vsum1<C><<<dim3(chunks_max, l_early, n_windows), TPB_TREE, 0, st2>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial, 1);
+            cudaEventRecord(ev_join, st2);
+            launches++;
+            forked = true;
+        }
     }
-    uint32_t chunks_max = fold_chunks_max(B);
-    k_vsum1<C><<<dim3(chunks_max, nb, n_windows), TPB_TREE, 0, st>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial);
+    if (l <= nb) {
+        k_fold_tail<C><<<n_windows, TPB_TAIL, 0, st>>>(F, B, nb, l);
+        launches++;
+    }
+    {
+        uint32_t first = forked ? l_early + 1 : 1;
+        uint32_t m = B >> first;
+        uint32_t chunks = (m + VSUM_ELEMS * TPB_TREE - 1) / (VSUM_ELEMS * TPB_TREE);
+        k_vsum1<C><<<dim3(chunks, nb - first + 1, n_windows), TPB_TREE, 0, st>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial, first);
+        launches++;
+    }
+    if (forked) cudaStreamWaitEvent(st, ev_join, 0);
     k_vsum2<C><<<dim3(nb, n_windows), TPB_TREE, 0, st>>>(partial, B, nb, chunks_max, V);
     k_fold_combine<C><<<n_windows, TPB_TREE, 0, st>>>(F, V, B, nb, out);
-    return launches + 3;
+    return launches + 2;
 }
 #endif
 #if KGR_PART & 4

@@ -89,6 +89,7 @@ struct Engine {
     cudaStream_t st_copy = nullptr;   // second stream: oneshot base upload overlaps count/scan/fill
     cudaEvent_t ev_pts = nullptr;     // bases of the current oneshot call are on the device
     cudaEvent_t ev_sc = nullptr;      // scalars of the current call are on the device (orders the two uploads)
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // fold reduce: the big upper-half sums run on st_copy beside the deep fold levels
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
@@ -119,6 +120,8 @@ struct Engine {
         CK(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ev_pts, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ev_sc, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         for (auto &e : ev) CK(cudaEventCreate(&e));
         for (auto &e : user_ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&h_result, 256 * 64 * sizeof(uint32_t)));  // up to 255 window sums of the widest XYZZ point (G2)
@@ -327,7 +330,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         e.fold_f.ensure((size_t)nwin * sh.B * sizeof(X));
         e.fold_partial.ensure((size_t)nwin * nb * chunks_max * sizeof(X));
         e.fold_v.ensure((size_t)nwin * nb * sizeof(X));
-        e.launches += K::fold_reduce(e.st, nwin, sh.B, (const X *)e.bucket_acc.p, e.offsets.p, (X *)e.fold_f.p, (X *)e.fold_partial.p, (X *)e.fold_v.p,
+        e.launches += K::fold_reduce(e.st, e.st_copy, e.ev_fork, e.ev_join, nwin, sh.B, (const X *)e.bucket_acc.p, e.offsets.p, (X *)e.fold_f.p, (X *)e.fold_partial.p, (X *)e.fold_v.p,
                                      (X *)e.lvl_a[0].p);
         win = (const X *)e.lvl_a[0].p;
     } else {

@@ -38,3 +38,28 @@ def test_sharded_msm_matches_oracle(curve):
         bases.free()
     finally:
         k.init()
+
+
+def test_g2_and_batch_on_several_devices():
+    """G2 through the sharded path, and kgr_msm_batch with several devices selected (jobs run in sequence, each spread over all GPUs)."""
+    ng = _ngpu()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import kogarashi_b200 as k
+    k.init(list(range(min(ng, 8))))
+    try:
+        n = 3001
+        p2 = np.tile(A.random_points(A.BN254_G2, 256, seed=bytes(range(3, 19))), (12, 1))[:n]
+        p1 = np.tile(A.random_points(A.BN254_G1, 256, seed=bytes(range(5, 21))), (12, 1))[:n]
+        sc = A.random_field(A.FIELD_FR, n, seed=bytes(range(4, 20)))
+        e2 = A.to_affine(A.BN254_G2, A.msm(A.BN254_G2, p2, sc))
+        e1 = A.to_affine(A.BN254_G1, A.msm(A.BN254_G1, p1, sc))
+        assert same_affine(k.to_affine(A.BN254_G2, k.msm_curve_addition(p2, sc, curve=A.BN254_G2)), e2)
+        b2, b1 = k.Bases(A.BN254_G2, p2), k.Bases(A.BN254_G1, p1)
+        got = k.msm_batch([(b2, sc), (b1, sc), (b1, sc[:100], 7)])
+        assert same_affine(k.to_affine(A.BN254_G2, got[0]), e2) and same_affine(k.to_affine(A.BN254_G1, got[1]), e1)
+        assert same_affine(k.to_affine(A.BN254_G1, got[2]), A.to_affine(A.BN254_G1, A.msm(A.BN254_G1, p1[7:], sc[:100])))
+        b1.free()
+        b2.free()
+    finally:
+        k.init()
