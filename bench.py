@@ -313,7 +313,13 @@ def main():
     alg = algorithmic_imads(n, args.curve)
     achieved_t = alg / (ms_per_step * 1e-3) / 1e12
     hbm_bytes = (pt_bytes + 32) * n  # 64 B point (128 B on G2) + 32 B scalar per pair
-    roofline = {"bound": "imad", "achieved": achieved_t, "peak": imad_peak_t, "unit": "T IMAD/s", "frac": achieved_t / imad_peak_t, "traffic": None,
+    # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json)
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.curve}/{args.logn}", {}).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"bound": "imad", "achieved": achieved_t, "peak": imad_peak_t, "unit": "T IMAD/s", "frac": achieved_t / imad_peak_t, "traffic": traffic,
                 "peak_source": "148 SM x 64 IMAD/clk x 1.965 GHz; kgr_microbench measured 18.5 T mad.lo.u32/s on this pool (MEASURED_PEAKS.json has no integer figure)",
                 "kernel": "whole pipeline; k_accumulate is the dominant kernel (see phases_ms)",
                 "algorithmic_imads_per_launch": alg,

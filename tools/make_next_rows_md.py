@@ -1,0 +1,70 @@
+"""profiles/r01_next_rows.md from the JSON that tools/bench_next_rows.py wrote: python tools/make_next_rows_md.py gpurun_out/next_rows_r01.json r01"""
+import json
+import shutil
+import sys
+
+src, tag = sys.argv[1], sys.argv[2]
+shutil.copy(src, f"profiles/{tag}_next_rows.json")
+r = json.load(open(src))
+ntt = [x for x in r if x["row"].startswith("N2")]
+g2 = [x for x in r if x["row"].startswith("N3")]
+pr = [x for x in r if x["row"].startswith("N1")]
+nv = [x for x in r if x["row"].startswith("N4")]
+md = [f'# Round {tag[1:]} — the "next" rows N2 (Fr NTT), N3 (G2 MSM), N1 (the Groth16 prover on top of them) and N4 (Nova folding vector work), one B200\n',
+      f"`python tools/bench_next_rows.py {tag}` (raw: `profiles/{tag}_next_rows.json`).  Device times are CUDA events on the engine stream, best of several;\n"
+      "the CPU baseline is the restated reference code from `oracle/` timed on the same box (16 host cores).\n",
+      "## N2 — `dft` of groth16/src/fft.rs on bn254 Fr (kernels_ntt.cu)\n",
+      "| log2 n | device ms | Melem/s | fraction of IMAD roofline | algorithmic HBM GB/s (64 B/elem) | host-buffer call ms | CPU restatement (1 thread) | bit-exact |\n|---|---|---|---|---|---|---|---|"]
+for x in ntt:
+    md.append(f"| {x['log_n']} | {x['device_ms']:.3f} | {x['melem_per_s']:.0f} | {x['roofline']['frac']:.2f} | {x['roofline']['hbm_gbs_algorithmic']:.0f} | "
+              f"{x['e2e_host_buffers_ms']:.2f} | {x['cpu_baseline']['seconds']:.3f} s | {x['bit_exact_with_oracle']} |")
+md.append("""
+The transform is multiplier-bound like the MSM (one 254-bit Montgomery product = 264 IMAD per butterfly, n/2·log2 n butterflies): at 2^22 it runs at 0.67
+of the measured 18.5 T IMAD/s while moving 273 GB/s of algorithmic traffic = 4 % of the measured HBM copy bandwidth (MEASURED_PEAKS.json: 6556 GB/s).
+The host-buffer call is dominated by the PCIe transfers of 32 B/element in each direction.
+""")
+md.append("## N3 — BN254 G2 MSM (`msm_curve_addition::<G2Affine>`, prover.rs:64-65): same pipeline, Fq2 coordinates\n")
+md.append("| log2 n | device ms | Mpoints/s | call with host scalars ms | CPU restatement (16 cores) | speed-up | bit-exact on the CPU sample |\n|---|---|---|---|---|---|---|")
+for x in g2:
+    md.append(f"| {x['log_n']} | {x['device_ms']:.2f} | {x['mpoints_per_s']:.1f} | {x['e2e_registered_ms']:.2f} | {x['cpu_baseline']['mpoints_per_s']:.3f} Mpoints/s "
+              f"({x['cpu_baseline']['sample']}) | {x['speedup_vs_cpu_baseline']:.0f} x | {x['bit_exact_with_oracle_on_sample']} |")
+md.append(f"""
+`bench.py --curve bn254_g2` (`{tag}_bench_g2_2p20.json`) gives the full bench line for this row (resident / host-buffer / registered / window-collapsed
+throughput, reference arm, checksum (sum k_i s_i)·G2, bit-exactness with the restated reference algorithm at the full 2^20).  Details and the ncu capture
+of the G2 accumulate kernel: `r01_g2.md`.
+""")
+md.append("## N1 (+ N3) — `create_proof` after witness generation: 7 NTTs + six G1 MSMs + two G2 MSMs + assembly of A, B, C (chained x^3 + x + 5 circuit)\n")
+md.append("| constraints | GPU wall ms (CRS registered) | GPU wall ms (CRS precomputed) | CPU restatement: FFTs (1 thread) + eight reference MSMs (16 cores) | speed-up | H bit-exact | A, B, C equal to their discrete logs |\n|---|---|---|---|---|---|---|")
+for x in pr:
+    c = x["cpu_baseline"]
+    md.append(f"| {x['constraints']} | {x['gpu_wall_ms']['normal']:.2f} | {x['gpu_wall_ms']['precomputed']:.2f} | {c['fft_seconds'] * 1e3:.0f} + {c['msm_seconds'] * 1e3:.0f} ms | "
+              f"{x['speedup_vs_cpu_baseline']['normal']:.1f} x / {x['speedup_vs_cpu_baseline']['precomputed']:.1f} x | {x['h_bit_exact_with_oracle']} | {x['checked_against_discrete_logs']} |")
+md.append("""
+All eight MSMs of prover.rs:51-65 and the seven FFTs run on the device (`kogarashi_b200.groth16.Groth16Prover`); the whole 259-byte proof of the
+reference's example circuit is byte-identical to the all-CPU computation (tests/test_groth16.py).  The five queries (pairs fused) and the two independent
+blinding sums are one `kgr_msm_batch` call whose jobs overlap on separate lanes of the device (history of the 2^16 row: 10.3 ms with one MSM after
+the other, 7.4 ms with the batch call, 5.6-5.8 ms with one host thread per lane; `tools/probe_prover.py`: H 0.94 ms, batch 3.9 ms against 7.4 ms for the
+same jobs one by one, dependent blinding MSM + host 0.34 ms).  Still excluded on both sides: witness generation (R1CS evaluation), so this is prove
+latency after synthesis.  The literal 4-constraint example is covered for byte identity only; its 3-point MSMs cannot be accelerated (SURVEY H7).
+""")
+md.append("## N4 — Nova `compute_cross_term` + `ck.commit(&t)` + witness fold (nova/src/prover.rs:33-47), Fq / Grumpkin, chained x^3 + x + 5 circuit\n")
+md.append("| constraints | non-zeros A / B / C | H2D of z1, z2 ms | cross-term kernel ms | algorithmic GB/s | commit MSM ms (T on the device) | whole call ms | CPU restatement: cross term (1 thread) | commit: reference naive fold / reference MSM (16 cores) | bit-exact |\n|---|---|---|---|---|---|---|---|---|---|")
+for x in nv:
+    g, c = x["gpu_ms"], x["cpu_baseline"]
+    md.append(f"| {x['constraints']} | {' / '.join(str(v) for v in x['nnz'])} | {g['h2d_z1_z2']:.2f} | {g['cross_term_kernel']:.3f} | {x['cross_term_algorithmic']['gb_per_s']:.0f} | "
+              f"{g['commit_msm']:.2f} | {g['call_wall']:.2f} | {c['cross_term_seconds'] * 1e3:.0f} ms | {c['commit_reference_naive_seconds_extrapolated']:.1f} s (extrapolated from 2048 elements) / "
+              f"{c['commit_as_reference_msm_seconds'] * 1e3:.0f} ms | {x['bit_exact_with_oracle']} |")
+md.append("""
+`kgr_nova_cross_term` uploads z1 = (u1, x1, w1) and z2, runs one fused kernel (thread per constraint: the six sparse products of a row and
+T[i] = AZ2·BZ1 + AZ1·BZ2 − u1·CZ2 − u2·CZ1 stay in registers; unit coefficients skip the multiplication) and feeds the device-resident T to the MSM
+pipeline, so the commitment needs no second H2D.  Algorithmic traffic = 100 B per non-zero (32 B coefficient, 4 B column, two 32 B z gathers) + 32 B per
+row: 3.0 TB/s at 2^20 constraints = 0.46 of the measured HBM copy bandwidth (the z gathers are served by L2); at this size the kernel is 2 % of the call —
+the PCIe upload of z (64 MB from pageable memory) and the commitment MSM dominate, so a caller that keeps the running z on the device pays ~3.5 ms.
+`kgr_vec_fold` (w1 + r·w2) with host buffers is PCIe-bound against the CPU loop's 100 ms at 2^20 elements.
+Checked in tests/test_gpu_nova.py: bit-exact products / T / fold against the restated reference loops, T's commitment equal to `PedersenCommitment::commit`
+of the oracle's T, and the folded (u, x, w, E) satisfying (A z)∘(B z) = u (C z) + E computed with the device products.
+Fixed-base batches (`PedersenCommitment::new`, CRS setup): `kgr_bases_generate` produces 2^20 G1 points k_i·G in 7.2 ms (146 Mpoints/s), 2^20 G2 points
+in 25 ms, from a 32 x 256 window table of the generator; the double-and-add kernel of the first half of the round took 85 ms for the G1 case.
+""")
+open(f"profiles/{tag}_next_rows.md", "w").write("\n".join(md))
+print("wrote", f"profiles/{tag}_next_rows.md")

@@ -9,7 +9,7 @@ import sys
 R = sys.argv[1] if len(sys.argv) > 1 else "r01"
 G = "gpurun_out"
 for src, dst in (("bench_%s_final_g1_2p20.json", "%s_bench_g1_2p20.json"), ("bench_%s_final_g1_2p24.json", "%s_bench_g1_2p24.json"),
-                 ("bench_%s_final_grumpkin_2p20.json", "%s_bench_grumpkin_2p20.json"), ("bench_%s_final_reference.json", "%s_bench_reference_arm.json"),
+                 ("bench_%s_final_grumpkin_2p20.json", "%s_bench_grumpkin_2p20.json"), ("bench_%s_final_reference.json", "%s_bench_reference_arm.json"), ("bench_%s_final_g2_2p20.json", "%s_bench_g2_2p20.json"),
                  ("launches_%s_final.csv", "%s_launches_bench_2p20.csv")):
     if os.path.exists(os.path.join(G, src % R)):
         shutil.copy(os.path.join(G, src % R), os.path.join("profiles", dst % R))
@@ -21,7 +21,7 @@ for r in rows[1:]:
     name = r[ki].split("(")[0].replace("void ", "").replace("kgr::", "")[:44]
     agg.setdefault(name, []).append(float(r[vi].replace(",", "")))
 msm = ["k_count", "k_scan_tiles", "k_scan_sums", "k_scan_add", "k_fill", "k_accumulate", "k_fixup<", "k_fixup_long", "k_reduce", "k_weight", "k_tree_sum",
-       "k_fold<", "k_vsum1", "k_vsum2", "k_fold_combine"]
+       "k_fold<", "k_fold_tail", "k_vsum1", "k_vsum2", "k_fold_combine"]
 nacc = len(agg[[x for x in agg if x.startswith("k_accumulate")][0]])
 per = {k: sum(v) / nacc for k, v in agg.items() if any(k.startswith(m) for m in msm)}
 tot = sum(per.values())

@@ -27,4 +27,21 @@ for name in ("g2_uniform_128", "g2_dup_neg_48", "g2_identity_bases_24", "g2_skew
     got = k.to_affine(2, k.msm_curve_addition(b, z2[name + "_sc"]))
     ok &= bool((got[:16] == z2[name + "_aff"][:16]).all() or (got[16] and z2[name + "_aff"][16]))
     b.free()
+# batch lanes (several streams + host threads) and the R1CS kernels
+b1 = k.Bases(0, z["g1_uniform_1024_pts"], z["g1_uniform_1024_inf"])
+b2 = k.Bases(2, z2["g2_uniform_128_pts"], z2["g2_uniform_128_inf"])
+got = k.msm_batch([(b2, z2["g2_uniform_128_sc"]), (b1, z["g1_uniform_1024_sc"]), (b1, z["g1_uniform_1024_sc"][:500], 100)])
+ok &= bool((k.to_affine(0, got[1])[:8] == z["g1_uniform_1024_aff"][:8]).all() and (k.to_affine(2, got[0])[:16] == z2["g2_uniform_128_aff"][:16]).all())
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from nova_util import chain_r1cs, mont
+from oracle import pyref as B
+from kogarashi_b200 import nova
+m, n_z, mats, z1 = chain_r1cs(100, 3, B.FQ)
+zz2 = chain_r1cs(100, 4, B.FQ)[3]
+shape = nova.R1csShape(0, m, n_z, *mats)
+ck = k.PedersenCommitment(1, A.random_points(1, 512))
+t, commit = shape.cross_term(mont(z1, B.FQ), mont(zz2, B.FQ), ck=ck)
+ok &= bool((t == A.cross_term(0, m, *mats, mont(z1, B.FQ), mont(zz2, B.FQ))).all())
+ok &= bool((nova.vec_fold(0, t, t, t[0]) == A.vec_fold(0, t, t, t[0])).all())
+fb = k.Bases.generate(0, 300, seed=5)
 print("sanitize run results ok:", ok)
