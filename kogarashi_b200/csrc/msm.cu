@@ -925,6 +925,7 @@ int kgr_bases_register(int curve, const uint64_t *xy, const uint8_t *inf, size_t
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     if (!out || (!xy && n)) return fail(KGR_E_ARG, "null pointer");
+    if (curve < KGR_CURVE_BN254_G1 || curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
     if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 bases per vector");
     return guarded([&]() -> int {
         kgr_bases *b = new kgr_bases;
@@ -1324,6 +1325,7 @@ int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, ui
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     if (!out) return fail(KGR_E_ARG, "null pointer");
+    if (curve < KGR_CURVE_BN254_G1 || curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
     if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 bases per vector");
     return guarded([&]() -> int {
         kgr_bases *b = new kgr_bases;

@@ -261,3 +261,31 @@ def test_skewed_scalars_large(k):
     s = _dot_mod(ks, sc, cm.r)
     exp = A.to_affine(curve, A.scalar_point(curve, np.concatenate([g, one]), np.array(B.int_to_limbs(B.to_mont(s, cm.r)), dtype=np.uint64)))
     assert same_affine(k.to_affine(curve, got), exp)
+
+
+def test_abi_error_codes(k, golden):
+    """Error behaviour at the C boundary: negative KGR_E_* codes with a message, no exception, engine usable afterwards."""
+    import ctypes
+    from kogarashi_b200 import _lib
+    L = _lib.lib()
+    u64p = ctypes.POINTER(ctypes.c_uint64)
+    pts, sc, aff = golden["g1_uniform_32_pts"], golden["g1_uniform_32_sc"], golden["g1_uniform_32_aff"]
+    out = np.zeros(12, dtype=np.uint64)
+    p = lambda a: a.ctypes.data_as(u64p)
+    bases = k.Bases(A.BN254_G1, pts)
+    E_ARG = -3
+    assert L.kgr_msm(bases._h, 30, p(sc), 0, 5, p(out)) == E_ARG and b"range" in L.kgr_last_error()        # off + n beyond the vector
+    assert L.kgr_msm(bases._h, 0, p(sc), 7, 32, p(out)) == E_ARG and b"scalar format" in L.kgr_last_error()
+    assert L.kgr_msm(bases._h, 0, None, 0, 32, p(out)) == E_ARG
+    assert L.kgr_msm(None, 0, p(sc), 0, 32, p(out)) == E_ARG
+    assert L.kgr_msm_oneshot(9, p(pts), None, 32, p(sc), 0, 32, p(out)) == E_ARG and b"curve" in L.kgr_last_error()
+    assert L.kgr_set_param(b"no_such_knob", 1) == E_ARG
+    assert L.kgr_set_param(b"reduce_fanin", 3) == E_ARG
+    assert L.kgr_bases_precompute(bases._h, 99) == E_ARG
+    h = ctypes.c_void_p()
+    assert L.kgr_bases_register(5, p(pts), None, 32, ctypes.byref(h)) != 0
+    # the engine still works and an empty MSM is the identity (msm.rs:45-47 folds nothing)
+    assert same_affine(k.to_affine(A.BN254_G1, k.msm_curve_addition(bases, sc)), aff)
+    assert L.kgr_msm(bases._h, 32, p(sc), 0, 0, p(out)) == 0
+    assert int(k.to_affine(A.BN254_G1, out)[8]) == 1
+    bases.free()
