@@ -323,6 +323,11 @@ def main():
                 "peak_source": "148 SM x 64 IMAD/clk x 1.965 GHz; kgr_microbench measured 18.5 T mad.lo.u32/s on this pool (MEASURED_PEAKS.json has no integer figure)",
                 "kernel": "whole pipeline; k_accumulate is the dominant kernel (see phases_ms)",
                 "algorithmic_imads_per_launch": alg,
+                # the dominant kernel on its own: the n*W bucket additions of the reference's inner loop (msm.rs:25-33) over k_accumulate's
+                # live CUDA-event duration (phases_ms.accumulate); the 2*(2^c - 1)*W running-sum additions belong to the reduce kernels
+                "dominant_kernel": (lambda adds: {"name": "k_accumulate", "ms": phases.get("accumulate"), "algorithmic_imads": adds,
+                                                  "achieved": adds / (phases["accumulate"] * 1e-3) / 1e12, "frac": adds / (phases["accumulate"] * 1e-3) / 1e12 / imad_peak_t})(
+                    n * math.ceil(254 / ref_window_bits(n)) * (31 if args.curve == "bn254_g2" else 11) * 264),
                 "hbm": {"achieved_gbs": hbm_bytes / (ms_per_step * 1e-3) / 1e9, "peak_gbs": peaks.get("hbm_gbs"), "note": f"{pt_bytes + 32} B/point algorithmic traffic; the path is multiply-bound, not HBM-bound"}}
     line = {"metric": metric, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq/Fr, 8x32-bit)", "data": "synthetic",
