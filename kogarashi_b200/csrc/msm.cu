@@ -180,13 +180,17 @@ static void destroy_lanes() {
 static uint32_t choose_window_bits(uint32_t n) {
     if (g_params.window_bits > 0) return (uint32_t)std::min<long>(std::max<long>(g_params.window_bits, 1), 24);
     double best = 1e300;
-    uint32_t best_c = 1;
-    for (uint32_t c = 1; c <= 22; c++) {
+    // c >= 9: with fewer than 256 buckets per window the bucket reduction falls back to serial running sums, which is never faster
+    // from 2^8 points on (sweeps in profiles/r01_phase_sweep.md); a handful of points (the prover's blinding sums) is cheapest with tiny windows
+    const uint32_t c_min = n < 64 ? 1 : 9;
+    uint32_t best_c = c_min;
+    for (uint32_t c = c_min; c <= 22; c++) {
         double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1), G = W * B;
         double lg = std::log2(G);
         double sort_ns = 0.0155 + (lg > 19 ? 0.008 * (lg - 19) : 0.0);
         double cost = (double)n * W * (0.174 + sort_ns) + 0.7 * G + (G > 64 ? 0.4e6 : 0.1e6);
         int top_bits = 255 - (int)c * ((int)W - 1);  // bits of the top window incl. the carry bit
+        if (top_bits < (int)c) cost += 0.08e6;       // a thin top window fills few buckets: the hot-bucket fix-up path runs
         if (top_bits < 8 && top_bits < (int)c) cost += 0.08 * n * (8 - top_bits);
         if (cost < best) { best = cost; best_c = c; }
     }
