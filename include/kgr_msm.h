@@ -154,7 +154,8 @@ int kgr_vec_fold(int field, const uint64_t *a, const uint64_t *b, const uint64_t
  * sums come back in one D2H copy and the host applies the doublings), "sort_mode" (-1 auto, 0 per-scalar fill,
  * 1 window-major fill from stored digits), "reduce_mode" (1 fold reduce, 0 running sums), "affine_rounds" (0: XYZZ bucket
  * accumulation; r > 0: the first r levels of every bucket sum are a pairwise tree of batched affine additions; experimental, see profiles/r01_affine.md), "affine_split" (with affine_rounds > 0:
- * 1 one kernel per phase, 0 one fused kernel). */
+ * 1 one kernel per phase, 0 one fused kernel), "oneshot_split" (pieces a large single-device kgr_msm_oneshot call is cut into so that uploads
+ * overlap the pipeline; 0 (default) = automatic: pieces of at least 2^19 pairs, at most 4; 1 = off). */
 int kgr_set_param(const char *name, long value);
 
 /* Per-phase time (ms) of the last MSM on device slot `dev`, CUDA events on the engine's stream:

@@ -47,7 +47,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0, affine_split = 1;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0, affine_split = 1, oneshot_split = 0;
 };
 static Params g_params;
 
@@ -504,6 +504,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         const AffinePt<C> *pts;
         size_t pt_first, sc_first, count;
         uint32_t table_c, table_stride, table_off;
+        Engine *after = nullptr;  // oneshot pieces: this piece's uploads start when the previous piece's are on the device
     };
     std::vector<Job> jobs;
     for (auto &s : shards) {
@@ -515,13 +516,44 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             jobs.push_back(Job{&g_engines[s.eng], hp ? nullptr : (const AffinePt<C> *)s.d_pts + (lo - s.first), lo, lo - off, hi - lo, 0, 0, 0});
     }
     if (on_device && jobs.size() > 1) throw CudaError{cudaErrorInvalidValue, "device-resident scalars need a single-device range", __LINE__};
+    // kgr_msm_oneshot on one device: the call is bound by PCIe upload + pipeline in sequence (the bucket accumulation needs every base).
+    // MSM is linear, so a large call is cut into pieces that run as independent MSMs on separate lanes: piece k + 1 uploads while piece k
+    // accumulates, and the latency-bound reduction of one piece hides under the accumulation of the next.  Uploads are chained with events so
+    // that the pieces do not share the link.
+    bool pieces = false;
+    // pieces of >= 2^19 pairs, at most 4 (measured: 2^20 5.50 -> 4.96 ms with 2, 2^24 69.3 -> 53.3 ms with 4; below 2^19 a cut only adds fixed costs)
+    size_t want = g_params.oneshot_split > 0 ? (size_t)g_params.oneshot_split : (jobs.size() == 1 ? std::min<size_t>(4, jobs[0].count >> 19) : 1);
+    if (hp && !on_device && jobs.size() == 1 && g_engines.size() == 1 && want > 1) {
+        size_t k = want;
+        while (g_lanes.size() + 1 < k) {
+            std::unique_ptr<Engine> l(new Engine);
+            l->init(g_engines[0].dev);
+            g_lanes.push_back(std::move(l));
+        }
+        Job whole = jobs[0];
+        jobs.clear();
+        size_t per = (whole.count + k - 1) / k;
+        for (size_t i = 0; i < k; i++) {
+            size_t lo = std::min(whole.count, i * per), hi = std::min(whole.count, (i + 1) * per);
+            if (lo >= hi) continue;
+            Job jb = whole;
+            jb.e = i == 0 ? &g_engines[0] : g_lanes[i - 1].get();
+            jb.pt_first = whole.pt_first + lo;
+            jb.sc_first = whole.sc_first + lo;
+            jb.count = hi - lo;
+            jb.after = jobs.empty() ? nullptr : jobs.back().e;
+            jobs.push_back(jb);
+        }
+        pieces = true;
+    }
     int is_mont = (fmt == KGR_SCALARS_MONTGOMERY);
     std::vector<CudaError> errs(jobs.size(), CudaError{cudaSuccess, "", 0});
-    auto launch = [&](size_t j) {
+    auto launch = [&](size_t j, bool wait) {
         try {
             Job &jb = jobs[j];
             Engine &e = *jb.e;
             CK(cudaSetDevice(e.dev));
+            if (jb.after) CK(cudaStreamWaitEvent(e.st, jb.after->ev_pts, 0));
             CK(cudaEventRecord(e.ev[EV_START], e.st));
             auto dbg_t0 = std::chrono::steady_clock::now();
             auto dbg = [&](const char *what) {
@@ -558,6 +590,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             }
             enqueue_msm<C>(e, jb.pts, d_sc, is_mont, (uint32_t)jb.count, jb.table_c, jb.table_stride, jb.table_off);
             dbg("pipeline enqueued");
+            if (!wait) return;
             CK(cudaStreamSynchronize(e.st));
             dbg("stream synchronized");
             collect_timing(e);
@@ -565,11 +598,19 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             errs[j] = ce;
         }
     };
-    if (jobs.size() <= 1) {
-        for (size_t j = 0; j < jobs.size(); j++) launch(j);
+    if (pieces) {
+        // one thread enqueues the pieces in order (the upload chain needs every ev_pts recorded before the next piece waits on it)
+        for (size_t j = 0; j < jobs.size(); j++) launch(j, false);
+        for (size_t j = 0; j < jobs.size(); j++) {
+            if (errs[j].e != cudaSuccess) continue;
+            if (cudaError_t ce = cudaStreamSynchronize(jobs[j].e->st); ce != cudaSuccess) errs[j] = CudaError{ce, "cudaStreamSynchronize", __LINE__};
+            else collect_timing(*jobs[j].e);
+        }
+    } else if (jobs.size() <= 1) {
+        for (size_t j = 0; j < jobs.size(); j++) launch(j, true);
     } else {
         std::vector<std::thread> th;
-        for (size_t j = 0; j < jobs.size(); j++) th.emplace_back(launch, j);
+        for (size_t j = 0; j < jobs.size(); j++) th.emplace_back(launch, j, true);
         for (auto &t : th) t.join();
     }
     for (auto &ce : errs)
@@ -920,6 +961,7 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "sort_mode") g_params.sort_mode = value;
     else if (s == "reduce_mode") g_params.reduce_mode = value;
     else if (s == "affine_split") g_params.affine_split = value;
+    else if (s == "oneshot_split") g_params.oneshot_split = std::min<long>(std::max<long>(value, 0), (long)MAX_LANES);
     else if (s == "affine_rounds") g_params.affine_rounds = std::min<long>(std::max<long>(value, 0), 6);
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;

@@ -289,3 +289,29 @@ def test_abi_error_codes(k, golden):
     assert L.kgr_msm(bases._h, 32, p(sc), 0, 0, p(out)) == 0
     assert int(k.to_affine(A.BN254_G1, out)[8]) == 1
     bases.free()
+
+
+@pytest.mark.parametrize("curve", [A.BN254_G1, A.BN254_G2])
+def test_oneshot_pieces_same_element(k, curve):
+    """Large kgr_msm_oneshot calls on one device are cut into pipelined pieces ("oneshot_split"): same group element as the
+    registered-bases call for 1, 2, 3 and 4 pieces, with identity bases and a ragged length."""
+    n = (1 << 18) + 12345
+    bases = k.Bases.generate(curve, n, seed=31)
+    pts = bases.download()
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[[0, 5, n // 2, n - 1]] = 1
+    pts_inf = pts.copy()
+    pts_inf[inf == 1] = 0
+    sc = A.random_field(A.FIELD_FR, n, seed=bytes(range(9, 25)))
+    ref = k.to_affine(curve, k.msm_curve_addition(bases, sc))
+    reg_inf = k.Bases(curve, pts_inf, inf)
+    ref_inf = k.to_affine(curve, k.msm_curve_addition(reg_inf, sc))
+    try:
+        for pieces in (1, 2, 3, 4, 0):
+            k.set_param("oneshot_split", pieces)
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), ref), pieces
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts_inf, sc, curve=curve, inf=inf)), ref_inf), pieces
+    finally:
+        k.set_param("oneshot_split", 0)
+    bases.free()
+    reg_inf.free()
