@@ -504,7 +504,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         const AffinePt<C> *pts;
         size_t pt_first, sc_first, count;
         uint32_t table_c, table_stride, table_off;
-        Engine *after = nullptr;  // oneshot pieces: this piece's uploads start when the previous piece's are on the device
+        cudaEvent_t after = nullptr;  // pieces of one call: this piece's uploads start when the previous piece's are on the device
     };
     std::vector<Job> jobs;
     for (auto &s : shards) {
@@ -522,8 +522,12 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
     // that the pieces do not share the link.
     bool pieces = false;
     // pieces of >= 2^19 pairs, at most 4 (measured: 2^20 5.50 -> 4.96 ms with 2, 2^24 69.3 -> 53.3 ms with 4; below 2^19 a cut only adds fixed costs)
-    size_t want = g_params.oneshot_split > 0 ? (size_t)g_params.oneshot_split : (jobs.size() == 1 ? std::min<size_t>(4, jobs[0].count >> 19) : 1);
-    if (hp && !on_device && jobs.size() == 1 && g_engines.size() == 1 && want > 1) {
+    size_t want = 1;
+    if (!on_device && jobs.size() == 1 && g_engines.size() == 1) {
+        if (g_params.oneshot_split > 0) want = (size_t)g_params.oneshot_split;
+        else want = std::min<size_t>(4, jobs[0].count >> (hp ? 19 : 21));  // scalars only (registered bases): a third of the traffic, larger pieces
+    }
+    if (want > 1) {
         size_t k = want;
         while (g_lanes.size() + 1 < k) {
             std::unique_ptr<Engine> l(new Engine);
@@ -541,7 +545,11 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             jb.pt_first = whole.pt_first + lo;
             jb.sc_first = whole.sc_first + lo;
             jb.count = hi - lo;
-            jb.after = jobs.empty() ? nullptr : jobs.back().e;
+            if (!hp) {
+                if (whole.table_c) jb.table_off = whole.table_off + (uint32_t)lo;   // window table: same base pointer, shifted column
+                else jb.pts = whole.pts + lo;
+            }
+            jb.after = jobs.empty() ? nullptr : (hp ? jobs.back().e->ev_pts : jobs.back().e->ev_sc);
             jobs.push_back(jb);
         }
         pieces = true;
@@ -553,7 +561,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             Job &jb = jobs[j];
             Engine &e = *jb.e;
             CK(cudaSetDevice(e.dev));
-            if (jb.after) CK(cudaStreamWaitEvent(e.st, jb.after->ev_pts, 0));
+            if (jb.after) CK(cudaStreamWaitEvent(e.st, jb.after, 0));
             CK(cudaEventRecord(e.ev[EV_START], e.st));
             auto dbg_t0 = std::chrono::steady_clock::now();
             auto dbg = [&](const char *what) {
@@ -565,6 +573,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             } else {
                 e.scalars.ensure(jb.count * 8);
                 CK(cudaMemcpyAsync(e.scalars.p, scalars + 4 * jb.sc_first, jb.count * 32, cudaMemcpyHostToDevice, e.st));
+                CK(cudaEventRecord(e.ev_sc, e.st));
                 d_sc = e.scalars.p;
                 dbg("scalars memcpyAsync returned");
             }
@@ -574,7 +583,6 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 // (the scalars go first on the link: the copy stream waits for them, otherwise the two uploads
                 // share the PCIe bandwidth and the scalar-only kernels start late)
                 e.oneshot_pts.ensure(jb.count * sizeof(AffinePt<C>));
-                CK(cudaEventRecord(e.ev_sc, e.st));
                 CK(cudaStreamWaitEvent(e.st_copy, e.ev_sc, 0));
                 CK(cudaMemcpyAsync(e.oneshot_pts.p, hp->xy + (sizeof(AffinePt<C>) / 8) * jb.pt_first, jb.count * sizeof(AffinePt<C>), cudaMemcpyHostToDevice, e.st_copy));
                 if (hp->inf) {

@@ -311,6 +311,17 @@ def test_oneshot_pieces_same_element(k, curve):
             k.set_param("oneshot_split", pieces)
             assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), ref), pieces
             assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts_inf, sc, curve=curve, inf=inf)), ref_inf), pieces
+            # registered bases, host scalars: the same cut (scalar uploads under the pipeline), also with an offset window
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(reg_inf, sc)), ref_inf), pieces
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc[: n - 77], base_off=77)),
+                               k.to_affine(curve, k.msm_curve_addition(pts[77:], sc[: n - 77], curve=curve))), pieces
+        if curve == A.BN254_G1:   # window-collapsed table: pieces index the same table at shifted columns
+            bases.precompute(0)
+            for pieces in (1, 3):
+                k.set_param("oneshot_split", pieces)
+                assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc)), ref), ("table", pieces)
+                assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc[: n - 77], base_off=77)),
+                                   k.to_affine(curve, k.msm_curve_addition(pts[77:], sc[: n - 77], curve=curve))), ("table", pieces)
     finally:
         k.set_param("oneshot_split", 0)
     bases.free()

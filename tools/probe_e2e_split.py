@@ -24,4 +24,11 @@ for pieces in (1, 2, 3, 4, 6, 8):
         out = k.msm_oneshot_ptr(curve, pts.data_ptr(), n, scp.data_ptr(), n)
     dt = (time.perf_counter() - t0) / 10
     ok = bool((k.to_affine(curve, out) == ref).all())
-    print(f"2^{logn} curve {curve} pieces {pieces}: {dt*1e3:.3f} ms = {n/dt/1e6:.1f} Mpoints/s ok={ok}", flush=True)
+    for _ in range(3):
+        out = k.msm_host_ptr(bases, scp.data_ptr(), n)
+    t0 = time.perf_counter()
+    for _ in range(10):
+        out = k.msm_host_ptr(bases, scp.data_ptr(), n)
+    dr = (time.perf_counter() - t0) / 10
+    ok = ok and bool((k.to_affine(curve, out) == ref).all())
+    print(f"2^{logn} curve {curve} pieces {pieces}: oneshot {dt*1e3:.3f} ms = {n/dt/1e6:.1f} Mpoints/s | registered bases {dr*1e3:.3f} ms = {n/dr/1e6:.1f} Mpoints/s ok={ok}", flush=True)
