@@ -161,7 +161,9 @@ int kgr_set_param(const char *name, long value);
 /* Per-phase time (ms) of the last MSM on device slot `dev`, CUDA events on the engine's stream:
  * [1] count, [2] scan, [3] fill, [4] accumulate, [5] fixup, [6] reduce (+ D2H of the window sums),
  * [7] H2D of scalars (and bases for oneshot); [8] host finish (Horner over windows + sum over GPUs,
- * host clock); [0] total = device events start..end + [8].  shape = {c, W, B, L, K, n}. */
+ * host clock); [0] total = device events start..end + [8].  shape = {c, W, B, L, K, n}.  For a host-buffer call that was cut into pipelined
+ * pieces ("oneshot_split") the phases are summed over the pieces (they overlap, so they can exceed the total), [0] spans the first piece's start
+ * to the last piece's end, and c, W, B, L describe the first piece. */
 int kgr_last_timing(int dev, float ms[9], uint32_t shape[6]);
 
 /* CUDA events on the engine's own stream (the stream every kernel of this library is launched

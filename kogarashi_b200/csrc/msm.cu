@@ -623,6 +623,14 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
     }
     for (auto &ce : errs)
         if (ce.e != cudaSuccess) throw ce;
+    if (pieces && jobs.size() > 1) {
+        // kgr_last_timing of a call cut into pieces: phases summed over the pieces, total = first start .. last end on the device, n = all pairs
+        Engine &e0 = *jobs[0].e;
+        for (size_t j = 1; j < jobs.size(); j++)
+            for (int i = 1; i <= 7; i++) e0.last_ms[i] += jobs[j].e->last_ms[i];
+        cudaEventElapsedTime(&e0.last_ms[0], e0.ev[EV_START], jobs.back().e->ev[EV_END]);
+        e0.last_shape[5] = (uint32_t)n;
+    }
     std::vector<Partial> parts;
     for (auto &jb : jobs) parts.push_back(Partial{jb.e->h_result, jb.e->n_result, jb.e->result_c});
     auto t0 = std::chrono::steady_clock::now();
