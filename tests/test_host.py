@@ -45,6 +45,24 @@ def test_pipeline_bodies_on_cpu(host_emu, case):
     assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
 
 
+@pytest.fixture(scope="module")
+def host_emu_r1cs():
+    exe = os.path.join(ROOT, "tests", "_build", "host_emu_r1cs")
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    src = os.path.join(ROOT, "tests", "host_emu_r1cs.cpp")
+    deps = [src] + [os.path.join(ROOT, "kogarashi_b200", "csrc", f) for f in ("field.cuh", "r1cs_kernels.cuh")] + [os.path.join(ROOT, "oracle", "zkstd_oracle.hpp")]
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-Wno-unknown-pragmas", "-o", exe, src])
+    return exe
+
+
+@pytest.mark.parametrize("case", [(0, 200, 57, 1), (1, 333, 90, 2), (1, 1, 1, 3), (0, 64, 300, 4)])
+def test_r1cs_bodies_on_cpu(host_emu_r1cs, case):
+    """Nova folding kernels' per-row bodies (sparse product, fused cross term, fold) executed on the host against the oracle's loops."""
+    out = subprocess.run([host_emu_r1cs] + [str(x) for x in case], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and out.stdout.startswith("OK"), out.stdout + out.stderr
+
+
 def test_library_exports_every_declared_symbol():
     from kogarashi_b200 import _lib
     _lib.build()
