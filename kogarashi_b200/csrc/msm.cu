@@ -166,12 +166,22 @@ struct Engine {
 static std::mutex g_mu;
 static std::vector<Engine> g_engines;
 // Extra engines (stream + workspaces) on the device of g_engines[0]: independent MSMs of one kgr_msm_batch call overlap on them.
-static std::vector<std::unique_ptr<Engine>> g_lanes;
+static std::vector<std::vector<std::unique_ptr<Engine>>> g_lanes;  // [engine index][lane - 1]; lane 0 of a device is g_engines[index] itself
 static constexpr size_t MAX_LANES = 8;
 static void destroy_lanes() {
-    for (auto &l : g_lanes) l->destroy();
+    for (auto &v : g_lanes)
+        for (auto &l : v) l->destroy();
     g_lanes.clear();
 }
+static void ensure_lanes(size_t eng, size_t k) {
+    if (g_lanes.size() < g_engines.size()) g_lanes.resize(g_engines.size());
+    while (g_lanes[eng].size() + 1 < k) {
+        std::unique_ptr<Engine> l(new Engine);
+        l->init(g_engines[eng].dev);
+        g_lanes[eng].push_back(std::move(l));
+    }
+}
+static Engine &lane_of(size_t eng, size_t i) { return i == 0 ? g_engines[eng] : *g_lanes[eng][i - 1]; }
 
 // Cost model for the window size, fitted to the per-phase timings in profiles/r01_phase_sweep.md (ns):
 //   accumulate 0.174 per entry; counting sort 0.0155 per entry growing with the histogram size G
@@ -505,6 +515,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         size_t pt_first, sc_first, count;
         uint32_t table_c, table_stride, table_off;
         cudaEvent_t after = nullptr;  // pieces of one call: this piece's uploads start when the previous piece's are on the device
+        size_t eng = 0;               // index of the device's engine (pieces of one device form a group)
     };
     std::vector<Job> jobs;
     for (auto &s : shards) {
@@ -514,6 +525,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             jobs.push_back(Job{&g_engines[s.eng], (const AffinePt<C> *)s.d_table, lo, lo - off, hi - lo, s.table_c, (uint32_t)s.count, (uint32_t)(lo - s.first)});
         else
             jobs.push_back(Job{&g_engines[s.eng], hp ? nullptr : (const AffinePt<C> *)s.d_pts + (lo - s.first), lo, lo - off, hi - lo, 0, 0, 0});
+        jobs.back().eng = (size_t)s.eng;
     }
     if (on_device && jobs.size() > 1) throw CudaError{cudaErrorInvalidValue, "device-resident scalars need a single-device range", __LINE__};
     // kgr_msm_oneshot on one device: the call is bound by PCIe upload + pipeline in sequence (the bucket accumulation needs every base).
@@ -521,38 +533,35 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
     // accumulates, and the latency-bound reduction of one piece hides under the accumulation of the next.  Uploads are chained with events so
     // that the pieces do not share the link.
     bool pieces = false;
-    // pieces of >= 2^19 pairs, at most 4 (measured: 2^20 5.50 -> 4.96 ms with 2, 2^24 69.3 -> 53.3 ms with 4; below 2^19 a cut only adds fixed costs)
-    size_t want = 1;
-    if (!on_device && jobs.size() == 1 && g_engines.size() == 1) {
-        if (g_params.oneshot_split > 0) want = (size_t)g_params.oneshot_split;
-        else want = std::min<size_t>(4, jobs[0].count >> (hp ? 19 : 21));  // scalars only (registered bases): a third of the traffic, larger pieces
-    }
-    if (want > 1) {
-        size_t k = want;
-        while (g_lanes.size() + 1 < k) {
-            std::unique_ptr<Engine> l(new Engine);
-            l->init(g_engines[0].dev);
-            g_lanes.push_back(std::move(l));
-        }
-        Job whole = jobs[0];
-        jobs.clear();
-        size_t per = (whole.count + k - 1) / k;
-        for (size_t i = 0; i < k; i++) {
-            size_t lo = std::min(whole.count, i * per), hi = std::min(whole.count, (i + 1) * per);
-            if (lo >= hi) continue;
-            Job jb = whole;
-            jb.e = i == 0 ? &g_engines[0] : g_lanes[i - 1].get();
-            jb.pt_first = whole.pt_first + lo;
-            jb.sc_first = whole.sc_first + lo;
-            jb.count = hi - lo;
-            if (!hp) {
-                if (whole.table_c) jb.table_off = whole.table_off + (uint32_t)lo;   // window table: same base pointer, shifted column
-                else jb.pts = whole.pts + lo;
+    // pieces of >= 2^19 pairs, at most 4 (measured: 2^20 5.50 -> 4.96 ms with 2, 2^24 69.3 -> 53.3 ms with 4; below 2^19 a cut only adds fixed costs);
+    // with several devices every device's shard is cut the same way on that device's own lanes
+    if (!on_device) {
+        std::vector<Job> cut;
+        for (const Job &whole : jobs) {
+            size_t k = g_params.oneshot_split > 0 ? (size_t)g_params.oneshot_split
+                                                  : std::max<size_t>(1, std::min<size_t>(4, whole.count >> (hp ? 19 : 21)));  // scalars only: a third of the traffic, larger pieces
+            if (k > 1) {
+                ensure_lanes(whole.eng, k);
+                pieces = true;
             }
-            jb.after = jobs.empty() ? nullptr : (hp ? jobs.back().e->ev_pts : jobs.back().e->ev_sc);
-            jobs.push_back(jb);
+            size_t per = (whole.count + k - 1) / k, first_of_group = cut.size();
+            for (size_t i = 0; i < k; i++) {
+                size_t lo = std::min(whole.count, i * per), hi = std::min(whole.count, (i + 1) * per);
+                if (lo >= hi) continue;
+                Job jb = whole;
+                jb.e = &lane_of(whole.eng, i);
+                jb.pt_first = whole.pt_first + lo;
+                jb.sc_first = whole.sc_first + lo;
+                jb.count = hi - lo;
+                if (!hp) {
+                    if (whole.table_c) jb.table_off = whole.table_off + (uint32_t)lo;   // window table: same base pointer, shifted column
+                    else jb.pts = whole.pts + lo;
+                }
+                jb.after = cut.size() == first_of_group ? nullptr : (hp ? cut.back().e->ev_pts : cut.back().e->ev_sc);
+                cut.push_back(jb);
+            }
         }
-        pieces = true;
+        if (pieces) jobs.swap(cut);
     }
     int is_mont = (fmt == KGR_SCALARS_MONTGOMERY);
     std::vector<CudaError> errs(jobs.size(), CudaError{cudaSuccess, "", 0});
@@ -607,12 +616,27 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         }
     };
     if (pieces) {
-        // one thread enqueues the pieces in order (the upload chain needs every ev_pts recorded before the next piece waits on it)
-        for (size_t j = 0; j < jobs.size(); j++) launch(j, false);
-        for (size_t j = 0; j < jobs.size(); j++) {
-            if (errs[j].e != cudaSuccess) continue;
-            if (cudaError_t ce = cudaStreamSynchronize(jobs[j].e->st); ce != cudaSuccess) errs[j] = CudaError{ce, "cudaStreamSynchronize", __LINE__};
-            else collect_timing(*jobs[j].e);
+        // per device one thread enqueues that device's pieces in order (the upload chain needs every event recorded before the next piece waits
+        // on it), then waits for them
+        auto run_group = [&](size_t eng) {
+            for (size_t j = 0; j < jobs.size(); j++)
+                if (jobs[j].eng == eng) launch(j, false);
+            for (size_t j = 0; j < jobs.size(); j++) {
+                if (jobs[j].eng != eng || errs[j].e != cudaSuccess) continue;
+                cudaSetDevice(jobs[j].e->dev);
+                if (cudaError_t ce = cudaStreamSynchronize(jobs[j].e->st); ce != cudaSuccess) errs[j] = CudaError{ce, "cudaStreamSynchronize", __LINE__};
+                else collect_timing(*jobs[j].e);
+            }
+        };
+        std::vector<size_t> groups;
+        for (auto &jb : jobs)
+            if (std::find(groups.begin(), groups.end(), jb.eng) == groups.end()) groups.push_back(jb.eng);
+        if (groups.size() == 1) {
+            run_group(groups[0]);
+        } else {
+            std::vector<std::thread> th;
+            for (size_t g : groups) th.emplace_back(run_group, g);
+            for (auto &t : th) t.join();
         }
     } else if (jobs.size() <= 1) {
         for (size_t j = 0; j < jobs.size(); j++) launch(j, true);
@@ -623,13 +647,22 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
     }
     for (auto &ce : errs)
         if (ce.e != cudaSuccess) throw ce;
-    if (pieces && jobs.size() > 1) {
-        // kgr_last_timing of a call cut into pieces: phases summed over the pieces, total = first start .. last end on the device, n = all pairs
-        Engine &e0 = *jobs[0].e;
-        for (size_t j = 1; j < jobs.size(); j++)
-            for (int i = 1; i <= 7; i++) e0.last_ms[i] += jobs[j].e->last_ms[i];
-        cudaEventElapsedTime(&e0.last_ms[0], e0.ev[EV_START], jobs.back().e->ev[EV_END]);
-        e0.last_shape[5] = (uint32_t)n;
+    if (pieces) {
+        // kgr_last_timing of a call cut into pieces: per device, phases summed over its pieces, total = first start .. last end, n = the device's pairs
+        for (size_t j = 0; j < jobs.size(); j++) {
+            if (jobs[j].e != &g_engines[jobs[j].eng]) continue;  // lane 0 of a device carries the device's figures
+            Engine &e0 = *jobs[j].e;
+            size_t pairs = jobs[j].count, last = j;
+            for (size_t i = 0; i < jobs.size(); i++) {
+                if (i == j || jobs[i].eng != jobs[j].eng) continue;
+                for (int q = 1; q <= 7; q++) e0.last_ms[q] += jobs[i].e->last_ms[q];
+                pairs += jobs[i].count;
+                last = std::max(last, i);
+            }
+            cudaSetDevice(e0.dev);
+            cudaEventElapsedTime(&e0.last_ms[0], e0.ev[EV_START], jobs[last].e->ev[EV_END]);
+            e0.last_shape[5] = (uint32_t)pairs;
+        }
     }
     std::vector<Partial> parts;
     for (auto &jb : jobs) parts.push_back(Partial{jb.e->h_result, jb.e->n_result, jb.e->result_c});
@@ -1097,12 +1130,8 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
     }
     return guarded([&]() -> int {
         size_t n_lanes = std::min(n_jobs, MAX_LANES);
-        while (g_lanes.size() + 1 < n_lanes) {
-            std::unique_ptr<Engine> l(new Engine);
-            l->init(g_engines[0].dev);
-            g_lanes.push_back(std::move(l));
-        }
-        auto lane = [&](size_t i) -> Engine & { return i == 0 ? g_engines[0] : *g_lanes[i - 1]; };
+        ensure_lanes(0, n_lanes);
+        auto lane = [&](size_t i) -> Engine & { return lane_of(0, i); };
         // one host thread per lane: it takes the next job, enqueues it on its lane (uploads + ~25 launches), waits and finishes it on the
         // host (Horner over the window sums), so neither the enqueue work nor the host finish of one job delays another lane
         std::atomic<size_t> next(0);
@@ -1207,8 +1236,8 @@ int kgr_launch_count(int dev, uint64_t *count) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (dev < 0 || dev >= (int)g_engines.size() || !count) return fail(KGR_E_ARG, "bad device slot");
     *count = g_engines[dev].launches;
-    if (dev == 0)
-        for (auto &l : g_lanes) *count += l->launches;
+    if ((size_t)dev < g_lanes.size())
+        for (auto &l : g_lanes[dev]) *count += l->launches;
     return KGR_OK;
 }
 

@@ -63,3 +63,32 @@ def test_g2_and_batch_on_several_devices():
         b2.free()
     finally:
         k.init()
+
+
+def test_pieces_on_every_device():
+    """A sharded call large enough for pipelined pieces on each device (forced piece counts and the automatic rule), registered and oneshot."""
+    ng = _ngpu()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import kogarashi_b200 as k
+    g = min(ng, 8)
+    k.init([0])
+    n = (1 << 19) + 333
+    one = k.Bases.generate(A.BN254_G1, n, seed=17)
+    pts = one.download()
+    sc = A.random_field(A.FIELD_FR, n, seed=bytes(range(11, 27)))
+    ref = k.to_affine(A.BN254_G1, k.msm_curve_addition(one, sc))
+    one.free()
+    k.init(list(range(g)))
+    try:
+        bases = k.Bases(A.BN254_G1, pts)
+        for pieces in (0, 1, 2, 3):
+            k.set_param("oneshot_split", pieces)
+            assert same_affine(k.to_affine(A.BN254_G1, k.msm_curve_addition(bases, sc)), ref), pieces
+            assert same_affine(k.to_affine(A.BN254_G1, k.msm_curve_addition(pts, sc, curve=A.BN254_G1)), ref), pieces
+            assert same_affine(k.to_affine(A.BN254_G1, k.msm_curve_addition(bases, sc[: n - 1000], base_off=1000)),
+                               k.to_affine(A.BN254_G1, k.msm_curve_addition(pts[1000:], sc[: n - 1000], curve=A.BN254_G1))), pieces
+        bases.free()
+    finally:
+        k.set_param("oneshot_split", 0)
+        k.init()
