@@ -6,6 +6,14 @@
 // thread per device, each GPU returns one XYZZ point, and the host adds them with the same
 // field/curve code compiled for the CPU (field.cuh host bodies).  No NCCL, no CPU fallback for
 // the MSM itself.
+//
+// Layout of this file:
+//   1. error plumbing, Params, DevBuf, NttDomain, Engine (one per GPU and per lane: stream, events, grow-only workspaces)
+//   2. window-size cost models, make_shape, enqueue_msm (the kernel pipeline of one MSM on one engine), collect_timing
+//   3. shards / handles, upload, combine_partials (host Horner + sum over GPUs), run_msm (sharding, pipelined pieces, oneshot uploads),
+//      lane_start / lane_finish (kgr_msm_batch), host conversions between the reference's projective form and XYZZ
+//   4. test hooks, generator constants, fixed-base table, NTT domain tables and enqueue
+//   5. extern "C": init / params / bases / msm / batch / oneshot / pedersen, NTT + Groth16 H, R1CS + Nova cross term, timing, test + bench hooks
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -105,6 +113,7 @@ struct Engine {
     int acc_blocks_per_sm[3] = {0, 0, 0}, aff_blocks_per_sm[3] = {0, 0, 0};
     uint64_t launches = 0;            // kernels of this library launched on this engine since init
     cudaEvent_t user_ev[4] = {};      // kgr_event_record / kgr_event_elapsed_ms
+    cudaEvent_t aux_ev[3] = {};       // phase marks of the R1CS calls (kgr_r1cs_last_timing)
     DevBuf<uint8_t> oneshot_pts, oneshot_inf;  // device copy of the bases of kgr_msm_oneshot
     std::map<uint32_t, std::shared_ptr<struct NttDomain>> ntt_domains;  // per log2(n): twiddle / coset tables in HBM
     DevBuf<uint8_t> ntt_buf[3];
@@ -124,6 +133,7 @@ struct Engine {
         CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
         for (auto &e : ev) CK(cudaEventCreate(&e));
         for (auto &e : user_ev) CK(cudaEventCreate(&e));
+        for (auto &e : aux_ev) CK(cudaEventCreate(&e));
         CK(cudaMallocHost(&h_result, 256 * 64 * sizeof(uint32_t)));  // up to 255 window sums of the widest XYZZ point (G2)
         acc_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_blocks_per_sm();
         acc_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_blocks_per_sm();
@@ -143,6 +153,7 @@ struct Engine {
         if (h_stage) cudaFreeHost(h_stage);
         for (auto &e : ev) if (e) cudaEventDestroy(e);
         for (auto &e : user_ev) if (e) cudaEventDestroy(e);
+        for (auto &e : aux_ev) if (e) cudaEventDestroy(e);
         oneshot_pts.release(); oneshot_inf.release();
         ntt_domains.clear();
         for (auto &b : ntt_buf) b.release();
@@ -1515,18 +1526,18 @@ int kgr_nova_cross_term(kgr_r1cs_t *s, const uint64_t *z1, const uint64_t *z2, u
     return guarded([&]() -> int {
         Engine &e = g_engines[0];
         CK(cudaSetDevice(e.dev));
-        CK(cudaEventRecord(e.user_ev[1], e.st));
+        CK(cudaEventRecord(e.aux_ev[0], e.st));
         CK(cudaMemcpyAsync(s->z1.p, z1, s->n_z * 32, cudaMemcpyHostToDevice, e.st));
         CK(cudaMemcpyAsync(s->z2.p, z2, s->n_z * 32, cudaMemcpyHostToDevice, e.st));
-        CK(cudaEventRecord(e.user_ev[2], e.st));
+        CK(cudaEventRecord(e.aux_ev[1], e.st));
         LaunchR1cs::cross_term(e.st, s->field, (uint32_t)s->m, s->csr(0), s->csr(1), s->csr(2), s->z1.p, s->z2.p, s->t.p);
         e.launches++;
         CK(cudaGetLastError());
-        CK(cudaEventRecord(e.user_ev[3], e.st));
+        CK(cudaEventRecord(e.aux_ev[2], e.st));
         if (t_out && s->m) CK(cudaMemcpyAsync(t_out, s->t.p, s->m * 32, cudaMemcpyDeviceToHost, e.st));
         CK(cudaStreamSynchronize(e.st));
-        cudaEventElapsedTime(&s->ms[0], e.user_ev[1], e.user_ev[2]);
-        cudaEventElapsedTime(&s->ms[1], e.user_ev[2], e.user_ev[3]);
+        cudaEventElapsedTime(&s->ms[0], e.aux_ev[0], e.aux_ev[1]);
+        cudaEventElapsedTime(&s->ms[1], e.aux_ev[1], e.aux_ev[2]);
         s->ms[2] = 0;
         if (ck) {
             // PedersenCommitment::commit(&t) (nova/src/prover.rs:35) straight from the device-resident cross term: no H2D of scalars
