@@ -334,7 +334,9 @@ def main():
             "config": {"workload": f"{args.curve} MSM, 2^{args.logn} points per GPU ({world * n} total), uniform scalars, bases k_i*G", "l2": "flushed between steps (512 MiB write)",
                        "shape": shape, "timing": "sum of per-step CUDA-event durations on the engine stream; wall_ms_per_step includes the flush and host gaps"},
             "wall_ms_per_step": wall_ms / args.steps, "phases_ms": phases, "clocks": clocks, "gpu_launches": launches,
-            "e2e": {"value": world * n / e2e_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": (pt_bytes + 32) * n, "d2h_bytes_per_step": shape["W"] * 2 * pt_bytes, "ms_per_step": e2e_ms,
+            "e2e": {"value": world * n / e2e_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": (pt_bytes + 32) * n,
+                    # the call cuts itself into min(4, n >> 19) pipelined pieces; every piece returns its W window sums (one XYZZ point each)
+                    "d2h_bytes_per_step": max(1, min(4, n >> 19)) * shape["W"] * 2 * pt_bytes, "ms_per_step": e2e_ms,
                     "call": "kgr_msm_oneshot (points + scalars uploaded from pinned host memory every call)"},
             "e2e_registered": {"value": world * n / e2e_reg_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": shape["W"] * 2 * pt_bytes, "ms_per_step": e2e_reg_ms,
                                "call": "kgr_msm (bases registered once, scalars uploaded every call)"},
