@@ -326,3 +326,47 @@ def test_oneshot_pieces_same_element(k, curve):
         k.set_param("oneshot_split", 0)
     bases.free()
     reg_inf.free()
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_shapes_vs_oracle(k, seed):
+    """Randomised configurations: curve, size, forced window / chunk, sort and reduce variants, scalar mix (zeros, ones, r - 1, uniform),
+    duplicated / opposite / identity bases, ragged lengths — each compared with the restated reference algorithm."""
+    rng = np.random.default_rng(1000 + seed)
+    curve = int(rng.integers(0, 3))
+    cl = 8 if curve == A.BN254_G2 else 4
+    n = int(rng.choice([1, 2, 3, 7, 33, 100, 257, 1000, 3000]))
+    pool = A.random_points(curve, min(n, 64), seed=bytes((seed + i) % 256 for i in range(16)))
+    pts = pool[rng.integers(0, pool.shape[0], size=n)]                 # repeated bases
+    fid = A.SCALAR_FIELD[curve]
+    sc = A.random_field(fid, n, seed=bytes((2 * seed + i) % 256 for i in range(16)))
+    one = A.field_op(fid, "to_mont", np.array([1, 0, 0, 0], dtype=np.uint64))
+    rm1 = A.field_op(fid, "neg", one)
+    kind = rng.integers(0, 4, size=n)
+    sc[kind == 0] = 0
+    sc[kind == 1] = one
+    if seed % 3 == 0:
+        sc[kind == 2] = rm1
+    inf = (rng.integers(0, 9, size=n) == 0).astype(np.uint8)
+    neg = rng.integers(0, 5, size=n) == 0                               # opposite points
+    bf = A.FIELD_FR if curve == A.GRUMPKIN else A.FIELD_FQ
+    for i in np.nonzero(neg)[0]:
+        for h in range(cl, 2 * cl, 4):
+            pts[i, h:h + 4] = A.field_op(bf, "neg", pts[i, h:h + 4])
+    m = n if seed % 4 else max(1, n - 3)                                # fewer scalars than bases
+    params = {"window_bits": int(rng.integers(0, 15)), "chunk": int(rng.choice([0, 1, 2, 5, 16, 64])), "sort_mode": int(rng.integers(-1, 2)),
+              "reduce_mode": int(rng.integers(0, 2)), "final_on_device": int(rng.integers(0, 2))}
+    defaults = {"window_bits": 0, "chunk": 0, "sort_mode": -1, "reduce_mode": 1, "final_on_device": 0}
+    exp = A.to_affine(curve, A.msm(curve, pts, sc[:m], inf=inf))
+    try:
+        for name, v in params.items():
+            k.set_param(name, v)
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc[:m], curve=curve, inf=inf)), exp), params
+        bases = k.Bases(curve, pts, inf)
+        if seed % 2:
+            bases.precompute(int(rng.integers(1, 12)))
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc[:m])), exp), params
+        bases.free()
+    finally:
+        for name, v in defaults.items():
+            k.set_param(name, v)
