@@ -211,6 +211,56 @@ static void upload_from_host(Engine &e, void *dst, const void *src, size_t bytes
         if (ce != cudaSuccess) throw CudaError{ce, "upload_from_host", __LINE__};
 }
 
+// Device -> host copy into a caller buffer, same staging for pageable destinations.  Returns when the data is in `dst` (it synchronises the copies
+// it issued; everything enqueued on st before the call has completed by then as well).
+static void download_to_host(Engine &e, void *dst, const void *src, size_t bytes, cudaStream_t st) {
+    if (!bytes) return;
+    cudaPointerAttributes at;
+    bool pageable = true;
+    if (cudaPointerGetAttributes(&at, dst) == cudaSuccess) pageable = (at.type == cudaMemoryTypeUnregistered);
+    else cudaGetLastError();
+    if (!pageable || bytes < 2 * STAGE_CHUNK) {
+        CK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return;
+    }
+    if (!e.h_stage) {
+        CK(cudaMallocHost(&e.h_stage, STAGE_CHUNK * STAGE_SLOTS));
+        for (auto &ev : e.stage_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    for (auto &ev : e.stage_ev) CK(cudaEventSynchronize(ev));  // no upload may still be reading a slot
+    const size_t n_chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
+    const size_t n_threads = std::min(STAGE_THREADS, n_chunks);
+    std::vector<cudaError_t> errs(n_threads, cudaSuccess);
+    auto worker = [&](size_t t) {
+        cudaError_t ce = cudaSetDevice(e.dev);
+        // two slots per thread: the copy of chunk i + 1 into one slot runs while chunk i is copied out of the other
+        size_t first = t, use = 0;
+        auto issue = [&](size_t c, size_t u) {
+            size_t slot = t + (u & 1) * STAGE_THREADS, off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+            cudaError_t r = cudaMemcpyAsync(e.h_stage + slot * STAGE_CHUNK, (const uint8_t *)src + off, len, cudaMemcpyDeviceToHost, st);
+            if (r == cudaSuccess) r = cudaEventRecord(e.stage_ev[slot], st);
+            return r;
+        };
+        if (first < n_chunks && ce == cudaSuccess) ce = issue(first, 0);
+        for (size_t c = first; c < n_chunks && ce == cudaSuccess; c += n_threads, use++) {
+            size_t nxt = c + n_threads;
+            if (nxt < n_chunks) ce = issue(nxt, use + 1);
+            if (ce != cudaSuccess) break;
+            size_t slot = t + (use & 1) * STAGE_THREADS, off = c * STAGE_CHUNK, len = std::min(STAGE_CHUNK, bytes - off);
+            ce = cudaEventSynchronize(e.stage_ev[slot]);
+            if (ce == cudaSuccess) std::memcpy((uint8_t *)dst + off, e.h_stage + slot * STAGE_CHUNK, len);
+        }
+        errs[t] = ce;
+    };
+    std::vector<std::thread> th;
+    for (size_t t = 1; t < n_threads; t++) th.emplace_back(worker, t);
+    worker(0);
+    for (auto &x : th) x.join();
+    for (cudaError_t ce : errs)
+        if (ce != cudaSuccess) throw CudaError{ce, "download_to_host", __LINE__};
+}
+
 static std::mutex g_mu;
 static std::vector<Engine> g_engines;
 // Extra engines (stream + workspaces) on the device of g_engines[0]: independent MSMs of one kgr_msm_batch call overlap on them.
@@ -1336,7 +1386,7 @@ int kgr_ntt(unsigned log_n, int op, const uint64_t *in, size_t n_in, uint64_t *o
         CK(cudaEventRecord(e.ev[EV_H2D], e.st));
         ntt_enqueue(e, d, e.ntt_buf[0].p, op);
         CK(cudaEventRecord(e.ev[EV_ACC], e.st));
-        CK(cudaMemcpyAsync(out, e.ntt_buf[0].p, n * 32, cudaMemcpyDeviceToHost, e.st));
+        download_to_host(e, out, e.ntt_buf[0].p, n * 32, e.st);
         CK(cudaEventRecord(e.ev[EV_END], e.st));
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e.st));
@@ -1395,7 +1445,7 @@ int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const ui
         e.launches++;
         ntt_enqueue(e, d, e.ntt_buf[0].p, 3);                                                             // coset_idft, prover.rs:47
         CK(cudaEventRecord(e.ev[EV_ACC], e.st));
-        CK(cudaMemcpyAsync(out, e.ntt_buf[0].p, n * 32, cudaMemcpyDeviceToHost, e.st));
+        download_to_host(e, out, e.ntt_buf[0].p, n * 32, e.st);
         CK(cudaEventRecord(e.ev[EV_END], e.st));
         CK(cudaGetLastError());
         CK(cudaStreamSynchronize(e.st));
@@ -1544,7 +1594,7 @@ int kgr_r1cs_mul(kgr_r1cs_t *s, int which, const uint64_t *z, uint64_t *out) {
         LaunchR1cs::spmv(e.st, s->field, (uint32_t)s->m, s->csr(which), s->z1.p, s->t.p);
         e.launches++;
         CK(cudaGetLastError());
-        if (s->m) CK(cudaMemcpyAsync(out, s->t.p, s->m * 32, cudaMemcpyDeviceToHost, e.st));
+        download_to_host(e, out, s->t.p, s->m * 32, e.st);
         CK(cudaStreamSynchronize(e.st));
         return KGR_OK;
     });
@@ -1571,7 +1621,7 @@ int kgr_nova_cross_term(kgr_r1cs_t *s, const uint64_t *z1, const uint64_t *z2, u
         e.launches++;
         CK(cudaGetLastError());
         CK(cudaEventRecord(e.aux_ev[2], e.st));
-        if (t_out && s->m) CK(cudaMemcpyAsync(t_out, s->t.p, s->m * 32, cudaMemcpyDeviceToHost, e.st));
+        if (t_out) download_to_host(e, t_out, s->t.p, s->m * 32, e.st);
         CK(cudaStreamSynchronize(e.st));
         cudaEventElapsedTime(&s->ms[0], e.aux_ev[0], e.aux_ev[1]);
         cudaEventElapsedTime(&s->ms[1], e.aux_ev[1], e.aux_ev[2]);
@@ -1616,7 +1666,7 @@ int kgr_vec_fold(int field, const uint64_t *a, const uint64_t *b, const uint64_t
         LaunchR1cs::vec_fold(e.st, field, (uint32_t)n, (const uint32_t *)e.ntt_buf[0].p, (const uint32_t *)e.ntt_buf[1].p, r8, (uint32_t *)e.ntt_buf[0].p);
         e.launches++;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(out, e.ntt_buf[0].p, n * 32, cudaMemcpyDeviceToHost, e.st));
+        download_to_host(e, out, e.ntt_buf[0].p, n * 32, e.st);
         CK(cudaStreamSynchronize(e.st));
         return KGR_OK;
     });

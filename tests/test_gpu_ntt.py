@@ -69,3 +69,20 @@ def test_h_coefficients_match_reference_pipeline(k, log_n, m):
     got = f.h_coefficients(a, b, c)
     assert got.shape[0] == n_exp and (got == exp[:n_exp]).all()
     assert n_exp <= (1 << log_n) - 1
+
+
+def test_large_transform_through_staged_host_copies():
+    """2^19 elements = 16 MiB each way from ordinary numpy memory: the upload and the download go through the pinned staging ring
+    (upload_from_host / download_to_host); result bit-exact with the restated reference FFT, ragged input included."""
+    import kogarashi_b200 as k
+    from kogarashi_b200.fft import Fft
+    k.init()
+    kk = 19
+    n = 1 << kk
+    vals = A.random_field(A.FIELD_FR, n - 12345, seed=bytes(range(21, 37)))
+    f = Fft(kk)
+    got = f.dft(vals)
+    exp, _ = A.fft(kk, "dft", vals)
+    assert got.shape == exp.shape and (got == exp).all()
+    back = f.idft(got)                       # idft strips trailing zeros (poly.rs:61-63): the ragged input comes back at its own length
+    assert back.shape[0] == vals.shape[0] and (back == vals).all()
