@@ -314,15 +314,23 @@ def main():
     achieved_t = alg / (ms_per_step * 1e-3) / 1e12
     hbm_bytes = (pt_bytes + 32) * n  # 64 B point (128 B on G2) + 32 B scalar per pair
     # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture of this workload (profiles/ncu_traffic.json)
-    traffic = None
+    traffic, pipe_util = None, None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.curve}/{args.logn}", {}).get("dram_bytes_per_launch")
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(f"{args.curve}/{args.logn}", {})
+        traffic, pipe_util = ncu.get("dram_bytes_per_launch"), ncu.get("fmaheavy_pipe_active_frac")
     except Exception:
         pass
+    # work this implementation actually issues (SURVEY §8d "executed-work fraction"): n*W mixed additions in XYZZ (8M + 2S = 10 products; 28 over Fq2)
+    # and about 2*W*B general additions in the bucket reduction (12M + 2S = 14; 40 over Fq2), 264 IMAD per 254-bit product
+    g2 = args.curve == "bn254_g2"
+    exec_imads = (n * shape["W"] * (28 if g2 else 10) + 2 * shape["W"] * shape["B"] * (40 if g2 else 14)) * 264
     roofline = {"bound": "imad", "achieved": achieved_t, "peak": imad_peak_t, "unit": "T IMAD/s", "frac": achieved_t / imad_peak_t, "traffic": traffic,
                 "peak_source": "148 SM x 64 IMAD/clk x 1.965 GHz; kgr_microbench measured 18.5 T mad.lo.u32/s on this pool (MEASURED_PEAKS.json has no integer figure)",
                 "kernel": "whole pipeline; k_accumulate is the dominant kernel (see phases_ms)",
                 "algorithmic_imads_per_launch": alg,
+                "executed": {"imads_per_launch": exec_imads, "achieved": exec_imads / (ms_per_step * 1e-3) / 1e12, "frac": exec_imads / (ms_per_step * 1e-3) / 1e12 / imad_peak_t,
+                             "note": "additions this implementation issues (signed digits, its own window size, XYZZ formulas) x products per addition x 264"},
+                "ncu_fmaheavy_pipe_active_frac": pipe_util,
                 # the dominant kernel on its own: the n*W bucket additions of the reference's inner loop (msm.rs:25-33) over k_accumulate's
                 # live CUDA-event duration (phases_ms.accumulate); the 2*(2^c - 1)*W running-sum additions belong to the reduce kernels
                 "dominant_kernel": (lambda adds: {"name": "k_accumulate", "ms": phases.get("accumulate"), "algorithmic_imads": adds,
