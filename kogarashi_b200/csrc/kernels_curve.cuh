@@ -127,23 +127,10 @@ template <class C> __global__ void __launch_bounds__(TPB_TREE) k_tree_sum(const 
 // total) plus plain sums of the upper halves (B adds) replace the serial running sums; every level is one add deep.
 // Level l (m = B >> l) reads Y^(l-1) (the buckets for l = 1) and writes Y^(l) at offset B - 2m of the window's row in F.
 template <class C>
-__global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *in, uint32_t in_off, XyzzPt<C> *out, uint32_t out_off, uint32_t B, uint32_t m,
-                                                  uint32_t n_windows, const uint32_t *bucket_offsets) {
-    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *buckets, XyzzPt<C> *F, uint32_t B, uint32_t l, uint32_t n_windows, const uint32_t *bucket_offsets) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x, m = B >> l;
     if (t >= n_windows * m) return;
-    uint32_t w = t / m, i = t % m;
-    size_t e = (size_t)w * B + in_off + i;
-    bool lo_ok = true, hi_ok = true;
-    if (bucket_offsets) {  // level 1: empty buckets were never written, they show as equal offsets
-        lo_ok = bucket_offsets[e] != bucket_offsets[e + 1];
-        hi_ok = bucket_offsets[e + m] != bucket_offsets[e + m + 1];
-    }
-    XyzzPt<C> a = lo_ok ? in[e] : xyzz_identity<C>();
-    if (hi_ok) {
-        XyzzPt<C> b = in[e + m];
-        xyzz_add(a, b);
-    }
-    store_xyzz(&out[(size_t)w * B + out_off + i], a);
+    body_fold<C>(t / m, t % m, l, B, buckets, F, bucket_offsets);
 }
 // Fold levels l_first .. nb of one window in one CTA (m = B >> l <= TPB_TAIL there): the deep levels are one add each and purely
 // latency-bound, so they are not worth a launch apiece.  Same reads and writes as k_fold; a level's output is the next level's input,
@@ -152,16 +139,8 @@ constexpr int TPB_TAIL = 256;
 constexpr uint32_t VSUM_ELEMS = 8;
 template <class C> __global__ void __launch_bounds__(TPB_TAIL) k_fold_tail(XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t l_first) {
     const uint32_t w = blockIdx.x, i = threadIdx.x;
-    XyzzPt<C> *row = F + (size_t)w * B;
-    for (uint32_t l = l_first; l <= nb; l++) {
-        uint32_t m = B >> l;
-        uint32_t in_off = B - (B >> (l - 2)), out_off = B - (B >> (l - 1));  // l_first >= 2: the input is always a fold level in F
-        if (i < m) {
-            XyzzPt<C> a = row[in_off + i];
-            XyzzPt<C> b = row[in_off + i + m];
-            xyzz_add(a, b);
-            store_xyzz(&row[out_off + i], a);
-        }
+    for (uint32_t l = l_first; l <= nb; l++) {  // l_first >= 2: the input is always a fold level in F
+        if (i < (B >> l)) body_fold<C>(w, i, l, B, nullptr, F, nullptr);
         __syncthreads();
     }
 }
@@ -173,13 +152,12 @@ __global__ void __launch_bounds__(TPB_TREE) k_vsum1(const XyzzPt<C> *buckets, co
     const uint32_t chunk = blockIdx.x, l = blockIdx.y + l_first, w = blockIdx.z;
     const uint32_t m = B >> l;
     if (chunk * VSUM_ELEMS * TPB_TREE >= m) return;  // uniform per CTA
-    const XyzzPt<C> *src = (l == 1) ? buckets + (size_t)w * B + m : F + (size_t)w * B + (B - (B >> (l - 2))) + m;
-    const uint32_t *off = (l == 1 && bucket_offsets) ? bucket_offsets + (size_t)w * B + m : nullptr;
     XyzzPt<C> acc = xyzz_identity<C>();
 #pragma unroll 1
     for (uint32_t k = 0; k < VSUM_ELEMS; k++) {
         uint32_t i = chunk * VSUM_ELEMS * TPB_TREE + k * TPB_TREE + threadIdx.x;
-        if (i < m && (!off || off[i] != off[i + 1])) xyzz_add(acc, src[i]);
+        XyzzPt<C> x;
+        if (i < m && fold_upper_elem<C>(w, i, l, B, buckets, F, bucket_offsets, x)) xyzz_add(acc, x);
     }
     acc = block_tree_sum<C>(acc, sm);
     if (threadIdx.x == 0) store_xyzz(&partial[((size_t)w * nb + (l - 1)) * chunks_max + chunk], acc);
@@ -200,13 +178,7 @@ template <class C> __global__ void __launch_bounds__(TPB_TREE) k_vsum2(const Xyz
 template <class C> __global__ void __launch_bounds__(TPB_TREE) k_fold_combine(const XyzzPt<C> *F, const XyzzPt<C> *V, uint32_t B, uint32_t nb, XyzzPt<C> *out) {
     __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     const uint32_t w = blockIdx.x, t = threadIdx.x;
-    XyzzPt<C> acc = xyzz_identity<C>();
-    if (t < nb) {
-        acc = V[(size_t)w * nb + t];
-        for (uint32_t d = 0; d < t; d++) acc = xyzz_dbl(acc);
-    } else if (t == nb) {
-        acc = F[(size_t)w * B + (B - 2)];  // Y^(nb): the single element of the last fold level = T0
-    }
+    XyzzPt<C> acc = (t <= nb) ? fold_combine_term<C>(w, t, B, nb, F, V) : xyzz_identity<C>();
     acc = block_tree_sum<C>(acc, sm);
     if (t == 0) store_xyzz(&out[w], acc);
 }

@@ -99,10 +99,7 @@ int Launch<C>::fold_reduce(cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_for
     for (; l <= nb; l++) {
         uint32_t m = B >> l;
         if (l >= 2 && m <= (uint32_t)TPB_TAIL) break;  // the rest in one kernel
-        const X *in = (l == 1) ? buckets : F;
-        uint32_t in_off = (l == 1) ? 0 : B - (B >> (l - 2));
-        uint32_t out_off = B - (B >> (l - 1));
-        k_fold<C><<<cdiv((size_t)n_windows * m, TPB_RED), TPB_RED, 0, st>>>(in, in_off, F, out_off, B, m, n_windows, l == 1 ? bucket_offsets : nullptr);
+        k_fold<C><<<cdiv((size_t)n_windows * m, TPB_RED), TPB_RED, 0, st>>>(buckets, F, B, l, n_windows, bucket_offsets);
         launches++;
         if (l + 1 == l_early && l_early < nb) {
             cudaEventRecord(ev_fork, st);

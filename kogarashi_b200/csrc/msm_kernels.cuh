@@ -796,6 +796,51 @@ KGR_HD void body_weight(uint32_t tid, uint32_t n_windows, uint32_t cnt, uint32_t
     store_xyzz(&out[tid], acc);
 }
 
+// ---- fold reduce: index arithmetic shared by the kernels (kernels_curve.cuh) and the host emulation (tests/host_emu.cpp) --------------------
+// Row of one window in F: level l (m = B >> l elements) lives at offset B - 2m = B - (B >> (l - 1)); level 0 is the bucket array itself.
+KGR_HD uint32_t fold_level_offset(uint32_t B, uint32_t l) { return B - (B >> (l - 1)); }
+// One element of fold level l: Y^(l)[i] = Y^(l-1)[i] + Y^(l-1)[i + m].  Level 1 reads the buckets and skips the ones the accumulate kernel never
+// wrote (equal offsets).
+template <class C>
+KGR_HD void body_fold(uint32_t w, uint32_t i, uint32_t l, uint32_t B, const XyzzPt<C> *buckets, XyzzPt<C> *F, const uint32_t *bucket_offsets) {
+    const uint32_t m = B >> l;
+    const XyzzPt<C> *in = (l == 1) ? buckets + (size_t)w * B : F + (size_t)w * B + fold_level_offset(B, l - 1);
+    bool lo_ok = true, hi_ok = true;
+    if (l == 1 && bucket_offsets) {
+        const uint32_t *off = bucket_offsets + (size_t)w * B;
+        lo_ok = off[i] != off[i + 1];
+        hi_ok = off[i + m] != off[i + m + 1];
+    }
+    XyzzPt<C> a = lo_ok ? in[i] : xyzz_identity<C>();
+    if (hi_ok) {
+        XyzzPt<C> b = in[i + m];
+        xyzz_add(a, b);
+    }
+    store_xyzz(&F[(size_t)w * B + fold_level_offset(B, l) + i], a);
+}
+// Element i of the upper half that level l folds away (its plain sum is V_{nb - l}); false if it is an empty bucket.
+template <class C>
+KGR_HD bool fold_upper_elem(uint32_t w, uint32_t i, uint32_t l, uint32_t B, const XyzzPt<C> *buckets, const XyzzPt<C> *F, const uint32_t *bucket_offsets, XyzzPt<C> &out) {
+    const uint32_t m = B >> l;
+    if (l == 1) {
+        if (bucket_offsets) {
+            const uint32_t *off = bucket_offsets + (size_t)w * B + m;
+            if (off[i] == off[i + 1]) return false;
+        }
+        out = buckets[(size_t)w * B + m + i];
+    } else {
+        out = F[(size_t)w * B + fold_level_offset(B, l - 1) + m + i];
+    }
+    return true;
+}
+// Term t of the window sum T0 + sum_b 2^b V_b: t < nb -> 2^t V_t, t == nb -> T0 = the single element of the last fold level.
+template <class C> KGR_HD XyzzPt<C> fold_combine_term(uint32_t w, uint32_t t, uint32_t B, uint32_t nb, const XyzzPt<C> *F, const XyzzPt<C> *V) {
+    if (t == nb) return F[(size_t)w * B + (B - 2)];
+    XyzzPt<C> acc = V[(size_t)w * nb + t];
+    for (uint32_t d = 0; d < t; d++) acc = xyzz_dbl(acc);
+    return acc;
+}
+
 // Horner over the per-window sums (msm.rs:41,45-47 in one pass), then XYZZ -> (X : Y : Z).
 template <class C> KGR_HD void body_final(const MsmShape &sh, const XyzzPt<C> *win_a, uint32_t *out24) {
     XyzzPt<C> r = win_a[sh.W - 1];

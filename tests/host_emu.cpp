@@ -153,6 +153,30 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         }
         bucket_acc[worklist[i]] = tot;
     }
+    std::vector<XyzzPt<C>> win(nwin);
+    const bool fold_reduce = ((seed >> 4) & 1) != 0 && sh.B >= 4;  // the default reduction of the GPU path (k_fold / k_fold_tail / k_vsum* / k_fold_combine)
+    if (fold_reduce) {
+        const uint32_t B = sh.B, nb = c - 1;
+        std::vector<XyzzPt<C>> F((size_t)nwin * B), V((size_t)nwin * nb);
+        memset(F.data(), 0x5A, F.size() * sizeof(XyzzPt<C>));
+        for (uint32_t l = 1; l <= nb; l++)
+            for (uint32_t w = 0; w < nwin; w++)
+                for (uint32_t i = 0; i < (B >> l); i++) body_fold<C>(w, i, l, B, bucket_acc.data(), F.data(), offsets.data());
+        for (uint32_t l = 1; l <= nb; l++)
+            for (uint32_t w = 0; w < nwin; w++) {
+                XyzzPt<C> acc = xyzz_identity<C>(), x;
+                for (uint32_t i = 0; i < (B >> l); i++)
+                    if (fold_upper_elem<C>(w, i, l, B, bucket_acc.data(), F.data(), offsets.data(), x)) xyzz_add(acc, x);
+                V[(size_t)w * nb + (nb - l)] = acc;
+            }
+        for (uint32_t w = 0; w < nwin; w++) {
+            win[w] = xyzz_identity<C>();
+            for (uint32_t t = 0; t <= nb; t++) {
+                XyzzPt<C> term = fold_combine_term<C>(w, t, B, nb, F.data(), V.data());
+                xyzz_add(win[w], term);
+            }
+        }
+    } else {
     uint32_t cnt = sh.B, m_log2 = 0, klog = 0;
     while ((1u << klog) < K) klog++;
     uint32_t cnt1 = (sh.B + K - 1) / K;
@@ -167,7 +191,6 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         cnt = cnt_out; m_log2 += klog; pp ^= 1;
         if (cnt <= rs_stop) break;
     }
-    std::vector<XyzzPt<C>> win(nwin);
     if (cnt > 1) {  // k_weight + k_tree_sum
         std::vector<XyzzPt<C>> v((size_t)nwin * cnt);
         for (uint32_t t = 0; t < nwin * cnt; t++) body_weight<C>(t, nwin, cnt, m_log2, in_s, in_a, v.data());
@@ -178,6 +201,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     } else {
         for (uint32_t w = 0; w < nwin; w++) win[w] = in_a[w];
     }
+    }
     uint32_t out24[48];
     MsmShape shf = sh;
     shf.W = nwin;  // collapsed: a single window sum, no doublings left
@@ -186,7 +210,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memcpy(&got.x, out24, EB); memcpy(&got.y, out24 + EB / 4, EB); memcpy(&got.z, out24 + 2 * (EB / 4), EB);
     OAffine got_aff = Cv::to_affine(got);
     bool ok = Cv::eq(got_aff, exp_aff) && (got_aff.inf || (got_aff.x == exp_aff.x && got_aff.y == exp_aff.y));
-    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_rounds=%u split=%d\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_rounds, (int)affine_split);
+    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_rounds=%u split=%d fold=%d\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_rounds, (int)affine_split, (int)fold_reduce);
     return ok ? 0 : 1;
 }
 

@@ -25,6 +25,7 @@ def host_emu():
 
 
 # curve n c L K mode seed   (mode: 0 uniform, 1 skewed zeros/ones/r-1, 2 duplicates + opposites + identity bases, 3 canonical scalars)
+# seed bits select variants: bit 0 window-major fill, bits 1-2 batched-affine levels, bit 3 per-phase affine kernels, bit 4 fold reduce
 EMU_CASES = [
     (0, 1, 4, 16, 16, 0, 1), (0, 2, 1, 16, 2, 0, 2), (0, 3, 3, 16, 4, 0, 3), (0, 37, 5, 8, 4, 0, 4), (0, 300, 8, 16, 16, 0, 5),
     (0, 300, 8, 16, 16, 1, 6), (0, 300, 7, 5, 8, 2, 7), (1, 257, 9, 32, 16, 0, 8), (1, 200, 6, 16, 2, 2, 9), (0, 129, 1, 16, 16, 0, 10),
@@ -36,6 +37,9 @@ EMU_CASES = [
     # curve 2: BN254 G2 (Fq2 coordinates) through the same bodies
     (2, 1, 4, 16, 16, 0, 32), (2, 150, 7, 16, 4, 0, 33), (2, 200, 6, 5, 8, 2, 34), (2, 180, 8, 8, 16, 1, 35, 16), (2, 100, 5, 4, 4, 12, 36, 8),
     (2, 120, 9, 32, 2, 3, 48),
+    # seed bit 4: the fold reduce (default GPU reduction) through the bodies shared with k_fold / k_fold_tail / k_vsum1 / k_fold_combine
+    (0, 300, 8, 16, 16, 0, 16), (0, 300, 7, 5, 8, 2, 17), (1, 257, 9, 32, 16, 1, 48), (2, 150, 7, 16, 4, 0, 49), (0, 200, 7, 16, 16, 10, 51, 4096),
+    (1, 64, 3, 16, 16, 1, 16), (0, 500, 11, 64, 16, 3, 18), (1, 90, 10, 8, 2, 13, 52, 4096),
 ]
 
 
