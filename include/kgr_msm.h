@@ -147,6 +147,13 @@ int kgr_r1cs_last_timing(const kgr_r1cs_t *shape, float ms[3]);
 /* RelaxedR1csWitness::fold (witness.rs:67-68): out[i] = a[i] + b[i] * r over `field`; host buffers, n x 4 uint64 Montgomery. */
 int kgr_vec_fold(int field, const uint64_t *a, const uint64_t *b, const uint64_t r[4], size_t n, uint64_t *out);
 
+/* groth16/src/prover.rs:36-65 as one call (row N1): the H coefficients are computed on the device (as kgr_groth16_h), fed to the h query
+ * `msm(params.h, q)` without leaving the device, and the other queries of the prover (`jobs`: l, a, b_g1, b_g2, blinding sums ...) overlap with that
+ * on separate lanes like kgr_msm_batch.  h must be a BN254 G1 vector; h_out: its projective result [12].  q_out (2^log_n x 4, host) and q_len
+ * (length after stripping trailing zeros) are optional.  Same results as kgr_groth16_h + kgr_msm + kgr_msm_batch. */
+int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, kgr_bases_t *h, uint64_t *h_out, uint64_t *q_out,
+                     size_t *q_len, const kgr_msm_job_t *jobs, size_t n_jobs);
+
 /* Tuning knobs: "window_bits" (0 = auto), "chunk" (entries per accumulate thread, 0 = auto),
  * "reduce_fanin" (power of two), "running_sum_stop" (elements per window below which the reduce
  * switches from running sums to the parallel weighting pass), "final_on_device" (1: Horner over

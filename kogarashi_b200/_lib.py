@@ -18,7 +18,7 @@ EXPORTS = [
     "kgr_proj_add", "kgr_set_param", "kgr_last_timing", "kgr_test_field_op", "kgr_test_point_op",
     "kgr_fixed_base_mul", "kgr_bases_generate", "kgr_microbench", "kgr_bases_download", "kgr_event_record",
     "kgr_event_elapsed_ms", "kgr_launch_count", "kgr_bases_precompute", "kgr_ntt", "kgr_ntt_device", "kgr_groth16_h",
-    "kgr_msm_batch", "kgr_r1cs_register", "kgr_r1cs_free", "kgr_r1cs_mul", "kgr_nova_cross_term", "kgr_r1cs_last_timing", "kgr_vec_fold",
+    "kgr_msm_batch", "kgr_groth16_msms", "kgr_r1cs_register", "kgr_r1cs_free", "kgr_r1cs_mul", "kgr_nova_cross_term", "kgr_r1cs_last_timing", "kgr_vec_fold",
 ]
 
 
@@ -78,6 +78,7 @@ def lib():
     u32p = ctypes.POINTER(ctypes.c_uint32)
     L.kgr_r1cs_register.argtypes = [ci, sz, sz, ctypes.POINTER(u32p), ctypes.POINTER(u32p), ctypes.POINTER(u64p), ctypes.POINTER(vp)]
     L.kgr_msm_batch.argtypes = [vp, sz]
+    L.kgr_groth16_msms.argtypes = [ctypes.c_uint, u64p, u64p, u64p, sz, vp, u64p, u64p, ctypes.POINTER(sz), vp, sz]
     L.kgr_r1cs_free.argtypes = [vp]
     L.kgr_r1cs_mul.argtypes = [vp, ci, u64p, u64p]
     L.kgr_nova_cross_term.argtypes = [vp, u64p, u64p, u64p, vp, u64p]

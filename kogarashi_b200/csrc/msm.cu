@@ -1023,6 +1023,27 @@ static void upload_padded(Engine &e, void *dbuf, const uint64_t *src, size_t n_i
     if (m < n) CK(cudaMemsetAsync((uint8_t *)dbuf + m * 32, 0, (n - m) * 32, e.st));
 }
 
+// prover.rs:36-47 enqueued on e.st: uploads a, b, c (m evaluations each, zero padded), leaves the 2^k coefficients of H in e.ntt_buf[0] (device).
+static void enqueue_groth16_h(Engine &e, NttDomain &d, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m) {
+    const size_t n = (size_t)1 << d.k;
+    const uint64_t *src[3] = {a, b, c};
+    for (int i = 0; i < 3; i++) {
+        e.ntt_buf[i].ensure(n * 32);
+        upload_padded(e, e.ntt_buf[i].p, src[i], m, n);
+    }
+    CK(cudaEventRecord(e.ev[EV_H2D], e.st));
+    for (int i = 0; i < 3; i++) {
+        // idft then coset_dft (prover.rs:36-41); the 1/n and coset scalings are one elementwise pass
+        e.launches += LaunchNtt::transform(e.st, e.ntt_buf[i].p, d.inv_tw.p, d.k);
+        LaunchNtt::scale(e.st, e.ntt_buf[i].p, d.cosets.p, &d.n_inv, (uint32_t)n);
+        e.launches += 1 + LaunchNtt::transform(e.st, e.ntt_buf[i].p, d.tw.p, d.k);
+    }
+    LaunchNtt::h_pointwise(e.st, e.ntt_buf[0].p, e.ntt_buf[1].p, e.ntt_buf[2].p, &d.z_inv, (uint32_t)n);  // prover.rs:43-46
+    e.launches++;
+    ntt_enqueue(e, d, e.ntt_buf[0].p, 3);                                                             // coset_idft, prover.rs:47
+}
+
+
 static int guarded(const std::function<int()> &f) {
     try {
         return f();
@@ -1428,22 +1449,8 @@ int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const ui
         CK(cudaSetDevice(e.dev));
         NttDomain &d = ntt_domain(e, log_n);
         const size_t n = (size_t)1 << log_n;
-        const uint64_t *src[3] = {a, b, c};
         CK(cudaEventRecord(e.ev[EV_START], e.st));
-        for (int i = 0; i < 3; i++) {
-            e.ntt_buf[i].ensure(n * 32);
-            upload_padded(e, e.ntt_buf[i].p, src[i], m, n);
-        }
-        CK(cudaEventRecord(e.ev[EV_H2D], e.st));
-        for (int i = 0; i < 3; i++) {
-            // idft then coset_dft (prover.rs:36-41); the 1/n and coset scalings are one elementwise pass
-            e.launches += LaunchNtt::transform(e.st, e.ntt_buf[i].p, d.inv_tw.p, d.k);
-            LaunchNtt::scale(e.st, e.ntt_buf[i].p, d.cosets.p, &d.n_inv, (uint32_t)n);
-            e.launches += 1 + LaunchNtt::transform(e.st, e.ntt_buf[i].p, d.tw.p, d.k);
-        }
-        LaunchNtt::h_pointwise(e.st, e.ntt_buf[0].p, e.ntt_buf[1].p, e.ntt_buf[2].p, &d.z_inv, (uint32_t)n);  // prover.rs:43-46
-        e.launches++;
-        ntt_enqueue(e, d, e.ntt_buf[0].p, 3);                                                             // coset_idft, prover.rs:47
+        enqueue_groth16_h(e, d, a, b, c, m);
         CK(cudaEventRecord(e.ev[EV_ACC], e.st));
         download_to_host(e, out, e.ntt_buf[0].p, n * 32, e.st);
         CK(cudaEventRecord(e.ev[EV_END], e.st));
@@ -1454,6 +1461,106 @@ int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const ui
         cudaEventElapsedTime(&e.last_ms[7], e.ev[EV_START], e.ev[EV_H2D]);
         cudaEventElapsedTime(&e.last_ms[4], e.ev[EV_H2D], e.ev[EV_ACC]);
         if (n_out) *n_out = stripped_len(out, n);
+        return KGR_OK;
+    });
+}
+
+int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, kgr_bases_t *h, uint64_t *h_out, uint64_t *q_out,
+                     size_t *q_len, const kgr_msm_job_t *jobs, size_t n_jobs) {
+    if (log_n < 1 || log_n > 28 || !a || !b || !c || !h || !h_out || (!jobs && n_jobs)) return fail(KGR_E_ARG, "bad argument");
+    const size_t n = (size_t)1 << log_n;
+    bool fused;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+        fused = g_engines.size() == 1 && h->curve == KGR_CURVE_BN254_G1 && h->shards.size() == 1 && n_jobs < MAX_LANES;
+        for (size_t j = 0; j < n_jobs && fused; j++)
+            if (!jobs[j].bases || jobs[j].bases->shards.size() != 1) fused = false;
+    }
+    if (!fused) {  // several devices: the same steps one after the other
+        std::vector<uint64_t> q(n * 4);
+        size_t len = 0;
+        int rc = kgr_groth16_h(log_n, a, b, c, m, q.data(), &len);
+        if (rc) return rc;
+        if (q_out) std::memcpy(q_out, q.data(), n * 32);
+        if (q_len) *q_len = len;
+        rc = kgr_msm(h, 0, q.data(), KGR_SCALARS_MONTGOMERY, std::min(len, h->n), h_out);
+        if (rc) return rc;
+        return kgr_msm_batch(jobs, n_jobs);
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (size_t j = 0; j < n_jobs; j++) {
+        const kgr_msm_job_t &jb = jobs[j];
+        if (!jb.out || (!jb.scalars && jb.n)) return fail(KGR_E_ARG, "null pointer");
+        if (jb.base_off > jb.bases->n || jb.n > jb.bases->n - jb.base_off) return fail(KGR_E_ARG, "range exceeds the registered vector");
+        if (jb.scalar_fmt != KGR_SCALARS_MONTGOMERY && jb.scalar_fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
+        if (jb.bases->curve < KGR_CURVE_BN254_G1 || jb.bases->curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
+    }
+    return guarded([&]() -> int {
+        const size_t n_lanes = std::min(n_jobs + 1, MAX_LANES);
+        ensure_lanes(0, n_lanes);
+        std::atomic<size_t> next(0);
+        std::vector<CudaError> errs(n_lanes, CudaError{cudaSuccess, "", 0});
+        std::vector<int> rcs(n_lanes, KGR_OK);
+        // lane 0: H on the device, then the h query with q as device-resident scalars (no D2H / H2D of q on the critical path)
+        auto h_worker = [&]() {
+            try {
+                Engine &e = g_engines[0];
+                CK(cudaSetDevice(e.dev));
+                NttDomain &d = ntt_domain(e, log_n);
+                CK(cudaEventRecord(e.ev[EV_START], e.st));
+                enqueue_groth16_h(e, d, a, b, c, m);
+                const Shard &sh = h->shards[0];
+                size_t nh = std::min(n, h->n);  // zip(q, h): coefficients beyond the degree are zero, so the unstripped q gives the same sum
+                if (nh == 0) {
+                    CK(cudaStreamSynchronize(e.st));
+                    combine_partials<Bn254G1>(std::vector<Partial>(), h_out);
+                } else {
+                    const uint32_t *d_q = reinterpret_cast<const uint32_t *>(e.ntt_buf[0].p);
+                    if (sh.d_table) enqueue_msm<Bn254G1>(e, (const AffinePt<Bn254G1> *)sh.d_table, d_q, 1, (uint32_t)nh, sh.table_c, (uint32_t)sh.count, 0);
+                    else enqueue_msm<Bn254G1>(e, (const AffinePt<Bn254G1> *)sh.d_pts, d_q, 1, (uint32_t)nh);
+                    lane_finish<Bn254G1>(e, h_out);
+                }
+                if (q_out) {
+                    download_to_host(e, q_out, e.ntt_buf[0].p, n * 32, e.st);
+                    if (q_len) *q_len = stripped_len(q_out, n);
+                }
+            } catch (CudaError &ce) {
+                errs[0] = ce;
+            }
+        };
+        auto worker = [&](size_t li) {
+            try {
+                for (;;) {
+                    size_t j = next.fetch_add(1);
+                    if (j >= n_jobs) break;
+                    const kgr_msm_job_t &jb = jobs[j];
+                    rcs[li] = [&]() -> int {
+                        if (jb.n == 0) {
+#define CALL(C) combine_partials<C>(std::vector<Partial>(), jb.out)
+                            DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+                            return KGR_OK;
+                        }
+#define CALL(C) lane_start<C>(lane_of(0, li), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n); lane_finish<C>(lane_of(0, li), jb.out)
+                        DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+                        return KGR_OK;
+                    }();
+                    if (rcs[li]) break;
+                }
+            } catch (CudaError &ce) {
+                errs[li] = ce;
+            }
+        };
+        std::vector<std::thread> th;
+        for (size_t li = 1; li < n_lanes; li++) th.emplace_back(worker, li);
+        h_worker();
+        for (auto &t : th) t.join();
+        for (auto &ce : errs)
+            if (ce.e != cudaSuccess) throw ce;
+        for (int rc : rcs)
+            if (rc) return rc;
         return KGR_OK;
     });
 }

@@ -14,7 +14,7 @@ of its slice layout, :58-62).  The blinding terms are a five-point MSM, so no cu
 import numpy as np
 
 from .fft import Fft
-from .msm import BN254_G1, BN254_G2, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Bases, msm_batch, msm_curve_addition, proj_add, to_affine
+from .msm import BN254_G1, BN254_G2, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Bases, groth16_msms, msm_batch, msm_curve_addition, proj_add, to_affine
 
 FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001  # bn254/src/fr.rs:11-16
 
@@ -68,10 +68,12 @@ class Groth16G1Prover:
         return self._assemble_g1(msm_batch(jobs), r, s)
 
     def prove_from_evaluations(self, log_n, a_evals, b_evals, c_evals, inputs, aux, r, s):
-        """The whole G1 side of create_proof from the R1CS evaluations (prover.rs:33): device NTTs for H, then the MSMs.
-        All scalars are Montgomery arrays (the reference's in-memory form)."""
-        q = Fft(log_n).h_coefficients(a_evals, b_evals, c_evals)
-        return self.prove_g1(q, inputs, aux, r, s) + (q,)
+        """The whole G1 side of create_proof from the R1CS evaluations (prover.rs:33): one kgr_groth16_msms call — H on the device feeding the h
+        query directly, the other queries overlapped with it.  All scalars are Montgomery arrays (the reference's in-memory form)."""
+        _, jobs = self._g1_jobs(np.zeros((0, 4), dtype=np.uint64), inputs, aux, r, SCALARS_MONTGOMERY)
+        del jobs[2]                                                   # the h query is the fused part of the call
+        q_pt, q, res = groth16_msms(log_n, a_evals, b_evals, c_evals, self.h, jobs)
+        return self._assemble_g1([res[0], res[1], q_pt, res[2], res[3]], r, s) + (q,)
 
     def commitments(self, q, inputs, aux, r, s):
         """Same as prove_g1 for scalars given as Python integers."""
@@ -105,8 +107,13 @@ class Groth16Prover(Groth16G1Prover):
         return g_a, to_affine(BN254_G2, proj_add(BN254_G2, res[6], res[0])), g_c
 
     def prove_from_evaluations(self, log_n, a_evals, b_evals, c_evals, inputs, aux, r, s):
-        q = Fft(log_n).h_coefficients(a_evals, b_evals, c_evals)
-        return self.prove(q, inputs, aux, r, s) + (q,)
+        """create_proof after witness generation (prover.rs:33-98) as one kgr_groth16_msms call + the dependent blinding sum."""
+        z, jobs = self._g1_jobs(np.zeros((0, 4), dtype=np.uint64), inputs, aux, r, SCALARS_MONTGOMERY)
+        del jobs[2]
+        jobs = [(self.b_g2, z, 0, SCALARS_MONTGOMERY)] + jobs + [(self.vk_g2_bases, _canonical([s, 1]), 0, SCALARS_CANONICAL)]
+        q_pt, q, res = groth16_msms(log_n, a_evals, b_evals, c_evals, self.h, jobs)
+        g_a, g_c = self._assemble_g1([res[1], res[2], q_pt, res[3], res[4]], r, s)
+        return g_a, to_affine(BN254_G2, proj_add(BN254_G2, res[5], res[0])), g_c, q
 
     def proof(self, q, inputs, aux, r, s):
         """Scalars as Python integers."""

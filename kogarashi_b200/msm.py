@@ -125,7 +125,13 @@ def msm_batch(jobs, scalar_fmt=SCALARS_MONTGOMERY):
     """kgr_msm_batch: jobs = [(Bases, coeffs[, base_off[, scalar_fmt]]), ...] -> list of projective results.  Independent MSMs
     on registered vectors (the prover's h, l, a, b_g1, b_g2 queries, prover.rs:51-65) overlap on separate lanes of the device."""
     _lib.ensure_init()
-    arr = (_Job * len(jobs))()
+    arr, keep, outs = _job_array(jobs, scalar_fmt)
+    _lib.check(_lib.lib().kgr_msm_batch(ctypes.cast(arr, ctypes.c_void_p), len(jobs)))
+    return outs
+
+
+def _job_array(jobs, scalar_fmt):
+    arr = (_Job * max(len(jobs), 1))()
     keep, outs = [], []
     for i, job in enumerate(jobs):
         bases, coeffs = job[0], _c(job[1]).reshape(-1, 4)
@@ -135,8 +141,22 @@ def msm_batch(jobs, scalar_fmt=SCALARS_MONTGOMERY):
         keep.append(coeffs)
         outs.append(out)
         arr[i] = _Job(bases._h.value if hasattr(bases._h, "value") else bases._h, off, _u64(coeffs), fmt, min(coeffs.shape[0], bases.n - off), _u64(out))
-    _lib.check(_lib.lib().kgr_msm_batch(ctypes.cast(arr, ctypes.c_void_p), len(jobs)))
-    return outs
+    return arr, keep, outs
+
+
+def groth16_msms(log_n, a_evals, b_evals, c_evals, h_bases, jobs, scalar_fmt=SCALARS_MONTGOMERY, want_q=True):
+    """kgr_groth16_msms: prover.rs:36-65 in one call.  H is computed on the device and goes into msm(h_bases, q) without leaving it; `jobs` (as in
+    msm_batch) overlap on other lanes.  -> (h_point (12,), q (stripped, (len, 4)) or None, [job results])."""
+    _lib.ensure_init()
+    a, b, c = (_c(x).reshape(-1, 4) for x in (a_evals, b_evals, c_evals))
+    assert a.shape == b.shape == c.shape
+    arr, keep, outs = _job_array(jobs, scalar_fmt)
+    h_out = np.zeros(12, dtype=np.uint64)
+    q = np.zeros((1 << log_n, 4), dtype=np.uint64) if want_q else None
+    q_len = ctypes.c_size_t()
+    _lib.check(_lib.lib().kgr_groth16_msms(log_n, _u64(a), _u64(b), _u64(c), a.shape[0], h_bases._h, _u64(h_out), _u64(q) if want_q else None,
+                                           ctypes.byref(q_len), ctypes.cast(arr, ctypes.c_void_p), len(jobs)))
+    return h_out, (q[: q_len.value] if want_q else None), outs
 
 
 def msm_device(bases, d_scalars_ptr, n, scalar_fmt=SCALARS_MONTGOMERY, base_off=0):

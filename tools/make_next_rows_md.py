@@ -42,9 +42,9 @@ for x in pr:
 md.append("""
 All eight MSMs of prover.rs:51-65 and the seven FFTs run on the device (`kogarashi_b200.groth16.Groth16Prover`); the whole 259-byte proof of the
 reference's example circuit is byte-identical to the all-CPU computation (tests/test_groth16.py).  The five queries (pairs fused) and the two independent
-blinding sums are one `kgr_msm_batch` call whose jobs overlap on separate lanes of the device (history of the 2^16 row: 10.3 ms with one MSM after
-the other, 7.4 ms with the batch call, 5.6-5.8 ms with one host thread per lane; `tools/probe_prover.py`: H 0.94 ms, batch 3.9 ms against 7.4 ms for the
-same jobs one by one, dependent blinding MSM + host 0.34 ms).  Still excluded on both sides: witness generation (R1CS evaluation), so this is prove
+blinding sums overlap on separate lanes of the device, and the H polynomial is computed on the device and goes into the h query without leaving it
+(`kgr_groth16_msms`; history of the 2^16 row: 10.3 ms with one MSM after the other, 7.4 ms with a batch call, 5.6-5.8 ms with one host thread per
+lane, 4.6-4.9 ms with H fused into the call; `tools/probe_prover.py`).  Still excluded on both sides: witness generation (R1CS evaluation), so this is prove
 latency after synthesis.  The literal 4-constraint example is covered for byte identity only; its 3-point MSMs cannot be accelerated (SURVEY H7).
 """)
 md.append("## N4 — Nova `compute_cross_term` + `ck.commit(&t)` + witness fold (nova/src/prover.rs:33-47), Fq / Grumpkin, chained x^3 + x + 5 circuit\n")

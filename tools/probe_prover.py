@@ -35,4 +35,6 @@ t_seq, _ = T(lambda: [k.msm_batch([j]) for j in jobs])
 t_asm, _ = T(lambda: prover._assemble_g1(res[1:6], r, s))
 t_all, _ = T(lambda: prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s))
 each = [T(lambda j=j: k.msm_batch([j]))[0] for j in jobs]
+t_old, _ = T(lambda: (lambda q2: prover.prove(q2, xs, ws, r, s))(f.h_coefficients(a_ev, b_ev, c_ev)))
+print(f"2^{logm}: separate H + batch {t_old:.2f} ms | fused call (prove_from_evaluations) {t_all:.2f} ms")
 print(f"2^{logm}: h_coefficients {t_h:.2f} ms | batch of {len(jobs)} {t_batch:.2f} ms (one by one {t_seq:.2f}: {[round(x, 2) for x in each]}) | assemble (1 small MSM + host) {t_asm:.2f} | whole {t_all:.2f}")
