@@ -92,3 +92,31 @@ def test_pieces_on_every_device():
     finally:
         k.set_param("oneshot_split", 0)
         k.init()
+
+
+def test_groth16_msms_on_several_devices():
+    """kgr_groth16_msms with several devices selected takes the plain sequence (H, h query, batch): same results as the fused single-device call."""
+    ng = _ngpu()
+    if ng < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import kogarashi_b200 as k
+    from kogarashi_b200.fft import Fft
+    kk, m = 10, 1000
+    ev = [A.random_field(A.FIELD_FR, m, seed=bytes(range(i, i + 16))) for i in (1, 2, 3)]
+    hp = A.random_points(A.BN254_G1, (1 << kk) - 1, seed=bytes(range(5, 21)))
+    zp = A.random_points(A.BN254_G1, 300, seed=bytes(range(6, 22)))
+    z = A.random_field(A.FIELD_FR, 300, seed=bytes(range(7, 23)))
+    results = []
+    for devs in ([0], list(range(min(ng, 8)))):
+        k.init(devs)
+        h, zb = k.Bases(A.BN254_G1, hp), k.Bases(A.BN254_G1, zp)
+        q_pt, q, res = k.groth16_msms(kk, *ev, h, [(zb, z)])
+        q_ref = Fft(kk).h_coefficients(*ev)
+        assert q.shape == q_ref.shape and (q == q_ref).all()
+        assert same_affine(k.to_affine(A.BN254_G1, q_pt), k.to_affine(A.BN254_G1, k.msm_curve_addition(h, q_ref)))
+        results.append((k.to_affine(A.BN254_G1, q_pt), k.to_affine(A.BN254_G1, res[0])))
+        h.free()
+        zb.free()
+    k.init()
+    assert same_affine(results[0][0], results[1][0]) and same_affine(results[0][1], results[1][1])
+    assert same_affine(results[0][1], A.to_affine(A.BN254_G1, A.msm(A.BN254_G1, zp, z)))
