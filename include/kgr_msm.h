@@ -1,4 +1,5 @@
-/* kgr_msm.h — C ABI of the B200-native MSM engine for Kogarashi's BN254 G1 and Grumpkin curves.
+/* kgr_msm.h — C ABI of the B200-native MSM engine for Kogarashi's BN254 G1 and Grumpkin curves, and of the rows built around it
+ * (BN254 G2 MSM, Fr NTT + Groth16 H polynomial, Nova folding vector work).
  *
  * The reference has no FFI for this path: the boundary is two Rust functions,
  *   groth16/src/msm.rs:6        fn msm_curve_addition<C: BNAffine>(bases: &[C], coeffs: &[C::Scalar]) -> C::Extended
