@@ -1253,14 +1253,13 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
         auto lane = [&](size_t i) -> Engine & { return lane_of(0, i); };
         // one host thread per lane: it takes the next job, enqueues it on its lane (uploads + ~25 launches), waits and finishes it on the
         // host (Horner over the window sums), so neither the enqueue work nor the host finish of one job delays another lane
-        std::atomic<size_t> next(0);
         std::vector<CudaError> errs(n_lanes, CudaError{cudaSuccess, "", 0});
         std::vector<int> rcs(n_lanes, KGR_OK);
         auto worker = [&](size_t li) {
             try {
-                for (;;) {
-                    size_t j = next.fetch_add(1);
-                    if (j >= n_jobs) break;
+                // static assignment (job j on lane j mod lanes): a lane sees the same jobs in every call of a repeated batch, so its grow-only
+                // workspaces settle after the first call instead of being re-allocated whenever a bigger job lands on it
+                for (size_t j = li; j < n_jobs; j += n_lanes) {
                     const kgr_msm_job_t &jb = jobs[j];
                     rcs[li] = [&]() -> int {
                         if (jb.n == 0) {  // empty sum: the identity (msm.rs:45-47 folds nothing)
@@ -1499,7 +1498,6 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
     return guarded([&]() -> int {
         const size_t n_lanes = std::min(n_jobs + 1, MAX_LANES);
         ensure_lanes(0, n_lanes);
-        std::atomic<size_t> next(0);
         std::vector<CudaError> errs(n_lanes, CudaError{cudaSuccess, "", 0});
         std::vector<int> rcs(n_lanes, KGR_OK);
         // lane 0: H on the device, then the h query with q as device-resident scalars (no D2H / H2D of q on the critical path)
@@ -1531,9 +1529,7 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
         };
         auto worker = [&](size_t li) {
             try {
-                for (;;) {
-                    size_t j = next.fetch_add(1);
-                    if (j >= n_jobs) break;
+                for (size_t j = li - 1; j < n_jobs; j += n_lanes - 1) {  // static assignment, lanes 1 .. n_lanes - 1 (lane 0 runs H and the h query)
                     const kgr_msm_job_t &jb = jobs[j];
                     rcs[li] = [&]() -> int {
                         if (jb.n == 0) {
