@@ -185,16 +185,19 @@ def run_groth16(args, rank):
     out = []
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
-        rows.bench_groth16(args.logm, out)     # a fresh process measures ~25 % slower whatever the number of warm-up proofs (first prover instance
-        rows.bench_groth16(args.logm, out)     # after start-up); the steady state a long-running prover sees is the second instance
+        # Measured twice.  In an otherwise idle process the call is ~20-25 % slower however many warm-up proofs precede it: the per-lane host
+        # threads wake up on sleeping cores.  The second pass runs right after the CPU baseline of the first kept all host cores busy, which is
+        # the state of a prover process that has just generated its witness; both figures are reported.
+        rows.bench_groth16(args.logm, out)
+        rows.bench_groth16(args.logm, out)
     rec, first = out[1], out[0]
     cpu_ms = rec["cpu_baseline"]["total_seconds"] * 1e3
     ours = args.impl != "reference"
     value = rec["gpu_wall_ms"]["normal"] if ours else cpu_ms
-    line = {"metric": "groth16_prove_latency", "value": value, "unit": "ms", "n_gpus": 1, "steps": 5, "warmup": 25, "ms_per_step": value, "higher_is_better": False,
+    line = {"metric": "groth16_prove_latency", "value": value, "unit": "ms", "n_gpus": 1, "steps": 5, "warmup": 5, "ms_per_step": value, "higher_is_better": False,
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 limbs (Montgomery Fq/Fr/Fq2)" if ours else "u64 limbs (Montgomery)", "data": "synthetic",
             "config": {"workload": f"Groth16 create_proof after witness generation, chained x^3 + x + 5 circuit, {rec['constraints']} constraints (2^{rec['log_n']} domain)",
-                       "timing": "wall clock around Groth16Prover.prove_from_evaluations, best of 5 after 25 warm-up proofs; CRS registered on the GPU"},
+                       "timing": "wall clock around Groth16Prover.prove_from_evaluations, best of 5 after 5 warm-up proofs; CRS registered on the GPU"},
             "e2e": {"value": value, "unit": "ms", "h2d_bytes_per_step": (3 * rec["constraints"] + 4 * rec["constraints"]) * 32 if ours else 0,
                     "d2h_bytes_per_step": (1 << rec["log_n"]) * 32 if ours else 0},
             "cpu_baseline": {"value": cpu_ms, "unit": "ms", "cores": rec["cpu_baseline"]["cores"], "kind": "port",
@@ -203,7 +206,7 @@ def run_groth16(args, rank):
     if ours:
         line["gpu_launches"] = int(k.launch_count(0))
         line["precomputed_crs_tables_ms"] = rec["gpu_wall_ms"]["precomputed"]
-        line["first_prover_instance_ms"] = first["gpu_wall_ms"]["normal"]
+        line["idle_host_ms"] = first["gpu_wall_ms"]["normal"]   # first pass: host cores idle before the call
     else:
         line["impl"] = "reference"
     print(json.dumps(line), flush=True)

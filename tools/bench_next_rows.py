@@ -82,7 +82,7 @@ def bench_groth16(logm, out):
     res = {}
     for pre in (False, True):
         prover = Groth16Prover(vk[0], vk[1], vk[2], *crs[0], *crs[1], *crs[2], *crs[3], vk2[0], vk2[1], *crs_g2, precompute=pre)
-        for _ in range(25):  # warm-up: lanes, NTT tables, workspaces, and enough load for the SM clock to settle (a fresh process starts ~25 % slower)
+        for _ in range(5):   # warm-up: lanes, NTT tables, workspaces
             prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)
         wall = min(_wall(lambda: prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)) for _ in range(5))
         Ap, Bp, Cp, q = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, xs, ws, r, s)
