@@ -185,9 +185,9 @@ def run_groth16(args, rank):
     out = []
     import contextlib, io
     with contextlib.redirect_stdout(io.StringIO()):
-        # Measured twice.  In an otherwise idle process the call is ~20-25 % slower however many warm-up proofs precede it: the per-lane host
-        # threads wake up on sleeping cores.  The second pass runs right after the CPU baseline of the first kept all host cores busy, which is
-        # the state of a prover process that has just generated its witness; both figures are reported.
+        # Measured twice.  In a process that has not run any multi-threaded CPU work yet the call is ~25 % slower however many warm-up proofs
+        # precede it (the per-lane host threads run on cores at idle clocks; tools/probe_prover_host.py).  The second pass runs after the CPU
+        # baseline of the first has used all host cores, which is the state of a prover process that has generated a witness; both figures are reported.
         rows.bench_groth16(args.logm, out)
         rows.bench_groth16(args.logm, out)
     rec, first = out[1], out[0]
@@ -206,7 +206,7 @@ def run_groth16(args, rank):
     if ours:
         line["gpu_launches"] = int(k.launch_count(0))
         line["precomputed_crs_tables_ms"] = rec["gpu_wall_ms"]["precomputed"]
-        line["idle_host_ms"] = first["gpu_wall_ms"]["normal"]   # first pass: host cores idle before the call
+        line["idle_host_ms"] = first["gpu_wall_ms"]["normal"]   # first pass: no multi-threaded CPU work in this process before it
     else:
         line["impl"] = "reference"
     print(json.dumps(line), flush=True)

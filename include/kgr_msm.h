@@ -163,7 +163,8 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
  * 1 window-major fill from stored digits), "reduce_mode" (1 fold reduce, 0 running sums), "affine_rounds" (0: XYZZ bucket
  * accumulation; r > 0: the first r levels of every bucket sum are a pairwise tree of batched affine additions; experimental, see profiles/r01_affine.md), "affine_split" (with affine_rounds > 0:
  * 1 one kernel per phase, 0 one fused kernel), "oneshot_split" (pieces a large single-device kgr_msm_oneshot call is cut into so that uploads
- * overlap the pipeline; 0 (default) = automatic: pieces of at least 2^19 pairs, at most 4; 1 = off). */
+ * overlap the pipeline; 0 (default) = automatic: pieces of at least 2^19 pairs, at most 4; 1 = off), "lane_threads" (kgr_groth16_msms: 1 (default) one
+ * host thread per lane, 0 everything enqueued from the calling thread). */
 int kgr_set_param(const char *name, long value);
 
 /* Per-phase time (ms) of the last MSM on device slot `dev`, CUDA events on the engine's stream:

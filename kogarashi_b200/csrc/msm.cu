@@ -55,7 +55,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0, affine_split = 1, oneshot_split = 0;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0, affine_split = 1, oneshot_split = 0, lane_threads = 1;
 };
 static Params g_params;
 
@@ -1129,6 +1129,7 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "sort_mode") g_params.sort_mode = value;
     else if (s == "reduce_mode") g_params.reduce_mode = value;
     else if (s == "affine_split") g_params.affine_split = value;
+    else if (s == "lane_threads") g_params.lane_threads = value ? 1 : 0;
     else if (s == "oneshot_split") g_params.oneshot_split = std::min<long>(std::max<long>(value, 0), (long)MAX_LANES);
     else if (s == "affine_rounds") g_params.affine_rounds = std::min<long>(std::max<long>(value, 0), 6);
     else return fail(KGR_E_ARG, "unknown parameter");
@@ -1501,28 +1502,64 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
         std::vector<CudaError> errs(n_lanes, CudaError{cudaSuccess, "", 0});
         std::vector<int> rcs(n_lanes, KGR_OK);
         // lane 0: H on the device, then the h query with q as device-resident scalars (no D2H / H2D of q on the critical path)
+        const size_t nh = std::min(n, h->n);  // zip(q, h): coefficients beyond the degree are zero, so the unstripped q gives the same sum
+        auto h_start = [&]() {
+            Engine &e = g_engines[0];
+            CK(cudaSetDevice(e.dev));
+            NttDomain &d = ntt_domain(e, log_n);
+            CK(cudaEventRecord(e.ev[EV_START], e.st));
+            enqueue_groth16_h(e, d, a, b, c, m);
+            const Shard &sh = h->shards[0];
+            if (nh) {
+                const uint32_t *d_q = reinterpret_cast<const uint32_t *>(e.ntt_buf[0].p);
+                if (sh.d_table) enqueue_msm<Bn254G1>(e, (const AffinePt<Bn254G1> *)sh.d_table, d_q, 1, (uint32_t)nh, sh.table_c, (uint32_t)sh.count, 0);
+                else enqueue_msm<Bn254G1>(e, (const AffinePt<Bn254G1> *)sh.d_pts, d_q, 1, (uint32_t)nh);
+            }
+        };
+        auto h_finish = [&]() {
+            Engine &e = g_engines[0];
+            if (nh) {
+                lane_finish<Bn254G1>(e, h_out);
+            } else {
+                CK(cudaSetDevice(e.dev));
+                CK(cudaStreamSynchronize(e.st));
+                combine_partials<Bn254G1>(std::vector<Partial>(), h_out);
+            }
+            if (q_out) {
+                download_to_host(e, q_out, e.ntt_buf[0].p, n * 32, e.st);
+                if (q_len) *q_len = stripped_len(q_out, n);
+            }
+        };
+        if (!g_params.lane_threads) {
+            // one host thread: enqueue everything (lane 0 first), then collect in order.  Slower than a thread per lane when the host cores are awake,
+            // less sensitive to sleeping cores (profiles/r01_next_rows.md)
+            h_start();
+            for (size_t j = 0; j < n_jobs; j++) {
+                const kgr_msm_job_t &jb = jobs[j];
+                if (jb.n == 0) continue;
+#define CALL(C) lane_start<C>(lane_of(0, 1 + j), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n)
+                DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+            }
+            h_finish();
+            for (size_t j = 0; j < n_jobs; j++) {
+                const kgr_msm_job_t &jb = jobs[j];
+                if (jb.n == 0) {
+#define CALL(C) combine_partials<C>(std::vector<Partial>(), jb.out)
+                    DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+                    continue;
+                }
+#define CALL(C) lane_finish<C>(lane_of(0, 1 + j), jb.out)
+                DISPATCH(jb.bases->curve, CALL);
+#undef CALL
+            }
+            return KGR_OK;
+        }
         auto h_worker = [&]() {
             try {
-                Engine &e = g_engines[0];
-                CK(cudaSetDevice(e.dev));
-                NttDomain &d = ntt_domain(e, log_n);
-                CK(cudaEventRecord(e.ev[EV_START], e.st));
-                enqueue_groth16_h(e, d, a, b, c, m);
-                const Shard &sh = h->shards[0];
-                size_t nh = std::min(n, h->n);  // zip(q, h): coefficients beyond the degree are zero, so the unstripped q gives the same sum
-                if (nh == 0) {
-                    CK(cudaStreamSynchronize(e.st));
-                    combine_partials<Bn254G1>(std::vector<Partial>(), h_out);
-                } else {
-                    const uint32_t *d_q = reinterpret_cast<const uint32_t *>(e.ntt_buf[0].p);
-                    if (sh.d_table) enqueue_msm<Bn254G1>(e, (const AffinePt<Bn254G1> *)sh.d_table, d_q, 1, (uint32_t)nh, sh.table_c, (uint32_t)sh.count, 0);
-                    else enqueue_msm<Bn254G1>(e, (const AffinePt<Bn254G1> *)sh.d_pts, d_q, 1, (uint32_t)nh);
-                    lane_finish<Bn254G1>(e, h_out);
-                }
-                if (q_out) {
-                    download_to_host(e, q_out, e.ntt_buf[0].p, n * 32, e.st);
-                    if (q_len) *q_len = stripped_len(q_out, n);
-                }
+                h_start();
+                h_finish();
             } catch (CudaError &ce) {
                 errs[0] = ce;
             }

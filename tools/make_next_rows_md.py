@@ -44,7 +44,9 @@ All eight MSMs of prover.rs:51-65 and the seven FFTs run on the device (`kogaras
 reference's example circuit is byte-identical to the all-CPU computation (tests/test_groth16.py).  The five queries (pairs fused) and the two independent
 blinding sums overlap on separate lanes of the device, and the H polynomial is computed on the device and goes into the h query without leaving it
 (`kgr_groth16_msms`; history of the 2^16 row: 10.3 ms with one MSM after the other, 7.4 ms with a batch call, 5.6-5.8 ms with one host thread per
-lane, 4.6-4.9 ms with H fused into the call; `tools/probe_prover.py`).  Still excluded on both sides: witness generation (R1CS evaluation), so this is prove
+lane, 4.5-4.9 ms with H fused into the call; `tools/probe_prover.py`).  Host side (`tools/probe_prover_host.py`, 2^16): a thread per lane 4.5 ms, everything
+enqueued from the calling thread (`lane_threads = 0`) 5.1-5.2 ms; in a process that has not yet run any multi-threaded CPU work the threaded call measures
+5.9 ms however many proofs precede it (host clocks), once it has, 4.5 ms even after a second of idling — a prover that builds its witness first is in that state.  Still excluded on both sides: witness generation (R1CS evaluation), so this is prove
 latency after synthesis.  The literal 4-constraint example is covered for byte identity only; its 3-point MSMs cannot be accelerated (SURVEY H7).
 """)
 md.append("## N4 — Nova `compute_cross_term` + `ck.commit(&t)` + witness fold (nova/src/prover.rs:33-47), Fq / Grumpkin, chained x^3 + x + 5 circuit\n")
