@@ -199,4 +199,13 @@ def test_scaled_prover_on_gpu(steps, precompute):
     assert enc(A) == G.encode_g1(G.G1.mul(G.G1.g, a_exp))
     assert enc(C) == G.encode_g1(G.G1.mul(G.G1.g, c_exp))
     assert _enc(Bp) == G.encode_g2(G.g2_mul(G.G2_GEN, b_exp))
+    # the same call with every lane driven from the calling thread, and the unfused sequence (H, then one batch): same proof
+    k.set_param("lane_threads", 0)
+    try:
+        A0, B0, C0, q0 = prover.prove_from_evaluations(E["k"], a_ev, b_ev, c_ev, mont(cs.x), mont(cs.w), r, s)
+    finally:
+        k.set_param("lane_threads", 1)
+    assert (A0 == A).all() and (B0 == Bp).all() and (C0 == C).all() and (q0 == q).all()
+    A1, B1, C1 = prover.prove(q, mont(cs.x), mont(cs.w), r, s)
+    assert (A1 == A).all() and (B1 == Bp).all() and (C1 == C).all()
     prover.free()
