@@ -19,6 +19,19 @@ from .msm import BN254_G1, BN254_G2, SCALARS_CANONICAL, SCALARS_MONTGOMERY, Base
 FR = 0x30644E72E131A029B85045B68181585D2833E84879B9709143E1F593F0000001  # bn254/src/fr.rs:11-16
 
 
+class ProverSubVersionCrsAttack(ValueError):
+    """groth16/src/error.rs:3 — `create_proof` refuses a CRS whose delta_g1 or delta_g2 is the identity (prover.rs:67-69)."""
+
+
+def _vk_points(points, inf, words):
+    """vk elements as a (k, words) array + (k,) infinity flags.  The reference encodes the identity as (0, R, is_infinity = true)
+    (zkstd/src/macros/curve/weierstrass/group.rs:106-110); (0, 0) — the device's own identity encoding — is accepted as well."""
+    pts = np.stack([np.ascontiguousarray(p, dtype=np.uint64).reshape(words) for p in points])
+    flags = np.zeros(len(points), dtype=np.uint8) if inf is None else np.ascontiguousarray(inf, dtype=np.uint8).reshape(len(points)).copy()
+    flags |= (~pts.any(axis=1)).astype(np.uint8)
+    return pts, flags
+
+
 def _canonical(vals):
     out = np.zeros((len(vals), 4), dtype=np.uint64)
     for i, v in enumerate(vals):
@@ -32,11 +45,14 @@ class Groth16G1Prover:
     """Points are (n, 8) uint64 Montgomery arrays with (n,) uint8 infinity flags (CRS entries may be the identity,
     groth16/src/zksnark.rs:62-66,177-185)."""
 
-    def __init__(self, delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, precompute=False):
-        pt = lambda p: np.ascontiguousarray(p, dtype=np.uint64).reshape(1, 8)
-        self.vk = np.concatenate([pt(delta_g1), pt(alpha_g1), pt(beta_g1)])
+    def __init__(self, delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, precompute=False, vk_inf=None):
+        """vk_inf: optional is_infinity flags of (delta_g1, alpha_g1, beta_g1).  An identity delta_g1 raises ProverSubVersionCrsAttack
+        before anything is uploaded — the reference returns that error from create_proof (prover.rs:67-69)."""
+        self.vk, self.vk_inf = _vk_points([delta_g1, alpha_g1, beta_g1], vk_inf, 8)
+        if self.vk_inf[0]:
+            raise ProverSubVersionCrsAttack("vk.delta_g1 is the identity")
         self.a, self.b_g1, self.h, self.l = (Bases(BN254_G1, p, f) for p, f in ((a, a_inf), (b_g1, b_g1_inf), (h, h_inf), (l, l_inf)))
-        self.vk_bases = Bases(BN254_G1, self.vk)
+        self.vk_bases = Bases(BN254_G1, self.vk, self.vk_inf)
         if precompute:
             for b in (self.a, self.b_g1, self.h, self.l):
                 b.precompute(0)
@@ -56,7 +72,7 @@ class Groth16G1Prover:
         g_a = proj_add(BN254_G1, blind_a, a_answer)
         aa, ba = to_affine(BN254_G1, a_answer), to_affine(BN254_G1, b1_answer)
         pts = np.stack([aa[:8], ba[:8], delta, alpha, beta])
-        inf = np.array([aa[8], ba[8], 0, 0, 0], dtype=np.uint8)
+        inf = np.array([aa[8], ba[8], self.vk_inf[0], self.vk_inf[1], self.vk_inf[2]], dtype=np.uint8)
         blind_c = msm_curve_addition(pts, _canonical([s, r, r * s, s, r]), curve=BN254_G1, inf=inf, scalar_fmt=SCALARS_CANONICAL)
         g_c = proj_add(BN254_G1, proj_add(BN254_G1, blind_c, q_pt), l_pt)
         return to_affine(BN254_G1, g_a), to_affine(BN254_G1, g_c)
@@ -87,12 +103,15 @@ class Groth16G1Prover:
 class Groth16Prover(Groth16G1Prover):
     """All three proof elements.  G2 points are (n, 16) uint64 = x.c0 x.c1 y.c0 y.c1 Montgomery (bn254/src/g2.rs:15-21)."""
 
-    def __init__(self, delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, delta_g2, beta_g2, b_g2, b_g2_inf, precompute=False):
-        super().__init__(delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, precompute=precompute)
-        pt = lambda p: np.ascontiguousarray(p, dtype=np.uint64).reshape(1, 16)
-        self.vk_g2 = np.concatenate([pt(delta_g2), pt(beta_g2)])
+    def __init__(self, delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, delta_g2, beta_g2, b_g2, b_g2_inf, precompute=False,
+                 vk_inf=None, vk_g2_inf=None):
+        """vk_g2_inf: optional is_infinity flags of (delta_g2, beta_g2); an identity delta_g2 raises ProverSubVersionCrsAttack (prover.rs:67-69)."""
+        self.vk_g2, self.vk_g2_inf = _vk_points([delta_g2, beta_g2], vk_g2_inf, 16)
+        if self.vk_g2_inf[0]:
+            raise ProverSubVersionCrsAttack("vk.delta_g2 is the identity")
+        super().__init__(delta_g1, alpha_g1, beta_g1, a, a_inf, b_g1, b_g1_inf, h, h_inf, l, l_inf, precompute=precompute, vk_inf=vk_inf)
         self.b_g2 = Bases(BN254_G2, b_g2, b_g2_inf)
-        self.vk_g2_bases = Bases(BN254_G2, self.vk_g2)
+        self.vk_g2_bases = Bases(BN254_G2, self.vk_g2, self.vk_g2_inf)
         if precompute:
             self.b_g2.precompute(0)
 
