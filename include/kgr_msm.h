@@ -159,8 +159,8 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
  * "reduce_fanin" (power of two), "running_sum_stop" (elements per window below which the reduce
  * switches from running sums to the parallel weighting pass), "final_on_device" (1: Horner over
  * windows in a one-thread kernel and one point per GPU in the D2H copy; 0 (default): the W window
- * sums come back in one D2H copy and the host applies the doublings), "sort_mode" (-1 auto, 0 per-scalar fill,
- * 1 window-major fill from stored digits), "reduce_mode" (1 fold reduce, 0 running sums), "affine_rounds" (0: XYZZ bucket
+ * sums come back in one D2H copy and the host applies the doublings), "sort_mode" (-1 auto, 0 counting sort with a per-scalar fill,
+ * 1 counting sort with a window-major fill from stored digits, 2 two block-local radix partitions: the default from 2^21 entries on), "reduce_mode" (1 fold reduce, 0 running sums), "affine_rounds" (0: XYZZ bucket
  * accumulation; r > 0: the first r levels of every bucket sum are a pairwise tree of batched affine additions; experimental, see profiles/r01_affine.md), "affine_split" (with affine_rounds > 0:
  * 1 one kernel per phase, 0 one fused kernel), "oneshot_split" (pieces a large single-device kgr_msm_oneshot call is cut into so that uploads
  * overlap the pipeline; 0 (default) = automatic: pieces of at least 2^19 pairs, at most 4; 1 = off), "lane_threads" (kgr_groth16_msms: 1 (default) one
@@ -197,6 +197,10 @@ int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy)
  * Scalars are derived on the device from a 64-bit seed (splitmix64 -> 8 words -> from_u512 like
  * zkstd/src/arithmetic/limbs/bits_256/represent.rs:18-28,80-103).  If k_out != NULL it receives the n scalars (Montgomery). */
 int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, uint64_t *k_out);
+/* The same stream from global index `first` on: point i of the result is point first + i of kgr_bases_generate(curve, seed, ...), so
+ * processes that each hold one shard of a large synthetic vector (bench.py under torchrun) together hold the vector a single process would
+ * generate.  Benchmark / test inputs only: the discrete logarithms are public. */
+int kgr_bases_generate_at(int curve, uint64_t seed, uint64_t first, size_t n, kgr_bases_t **out, uint64_t *k_out);
 /* Integer-pipe microbenchmark on device slot 0: fills results[0..7] with giga-ops/s of
  * [0] IMAD (mad.lo.u32), [1] IMAD.HI, [2] IMAD.WIDE.U32, [3] IMAD.WIDE.U32.X carry chains,
  * [4] IADD3, [5] field multiplications (Fq), [6] XYZZ mixed adds, [7] SM clock MHz seen. */

@@ -18,7 +18,7 @@ EXPORTS = [
     "kgr_proj_add", "kgr_set_param", "kgr_last_timing", "kgr_test_field_op", "kgr_test_point_op",
     "kgr_fixed_base_mul", "kgr_bases_generate", "kgr_microbench", "kgr_bases_download", "kgr_event_record",
     "kgr_event_elapsed_ms", "kgr_launch_count", "kgr_bases_precompute", "kgr_ntt", "kgr_ntt_device", "kgr_groth16_h",
-    "kgr_msm_batch", "kgr_groth16_msms", "kgr_r1cs_register", "kgr_r1cs_free", "kgr_r1cs_mul", "kgr_nova_cross_term", "kgr_r1cs_last_timing", "kgr_vec_fold",
+    "kgr_bases_generate_at", "kgr_msm_batch", "kgr_groth16_msms", "kgr_r1cs_register", "kgr_r1cs_free", "kgr_r1cs_mul", "kgr_nova_cross_term", "kgr_r1cs_last_timing", "kgr_vec_fold",
 ]
 
 
@@ -70,6 +70,7 @@ def lib():
     L.kgr_test_point_op.argtypes = [ci, ci, u64p, u8p, u64p, u8p, sz, u64p]
     L.kgr_fixed_base_mul.argtypes = [ci, u64p, sz, u64p]
     L.kgr_bases_generate.argtypes = [ci, ctypes.c_uint64, sz, ctypes.POINTER(vp), u64p]
+    L.kgr_bases_generate_at.argtypes = [ci, ctypes.c_uint64, ctypes.c_uint64, sz, ctypes.POINTER(vp), u64p]
     L.kgr_microbench.argtypes = [ctypes.POINTER(ctypes.c_double)]
     L.kgr_bases_download.argtypes = [vp, sz, sz, u64p]
     L.kgr_event_record.argtypes = [ci, ci]

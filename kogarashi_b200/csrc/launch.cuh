@@ -55,6 +55,25 @@ template <class C> struct Launch {
     static void fixed_base(cudaStream_t st, const S *k, const A *table, uint32_t n, A *out);
 };
 
+// Bucket sort by two block-local radix partitions (kernels_sort.cu): bucket index = (coarse bin << F) | fine bits.
+struct SortPlan {
+    uint32_t n, c, W;
+    uint32_t nseg;            // independent bucket sets: W, or 1 when all windows share the buckets (precomputed window table)
+    uint32_t nbins, F;        // coarse bins per segment, fine bits per bin (<= 8)
+    uint32_t T;               // digits per partition tile
+    uint32_t cap;             // elements of one bin that k_sort_buckets places in shared memory
+    uint32_t pstride, poff;   // entry payload = w * pstride + poff + i  (MsmShape)
+};
+struct LaunchSort {
+    // false: this shape is left to the counting sort (k_count / k_fill)
+    static bool plan(const MsmShape &sh, SortPlan &pl);
+    static size_t coarse_words(const SortPlan &pl);  // words of coarse_counts / coarse_off / cursor
+    // scalar_field: 0 Fq, 1 Fr.  digits / part_pay / entries: n * W words, part_fine: n * W bytes, offsets: G + 1 words.  Returns the launches.
+    static int run(cudaStream_t st, int scalar_field, int sm_count, const SortPlan &pl, const uint32_t *scalars, int is_mont, uint32_t *digits,
+                   uint32_t *coarse_counts, uint32_t *coarse_off, uint32_t *cursor, uint32_t *part_pay, uint8_t *part_fine, uint32_t *entries, uint32_t *offsets,
+                   cudaEvent_t ev_digits, cudaEvent_t ev_scan);
+};
+
 struct LaunchUtil {
     // field: 0 Fq, 1 Fr (test hook for the PTX carry chains)
     static void field_op(cudaStream_t st, int field, int op, const void *a, const void *b, void *out, uint32_t n);

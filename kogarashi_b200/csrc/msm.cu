@@ -28,6 +28,7 @@
 #include <mutex>
 #include <string>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/kgr_msm.h"
@@ -101,6 +102,8 @@ struct Engine {
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
+    DevBuf<uint32_t> coarse_counts, coarse_off, coarse_cursor, part_pay;  // radix-partition sort (kernels_sort.cu)
+    DevBuf<uint8_t> part_fine;
     DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v, aff_nodes, aff_suffix, aff_inv;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
@@ -146,6 +149,7 @@ struct Engine {
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
         counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
+        coarse_counts.release(); coarse_off.release(); coarse_cursor.release(); part_pay.release(); part_fine.release();
         bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release(); aff_nodes.release(); aff_suffix.release(); aff_inv.release();
         for (auto &t : fixed_table) t.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
@@ -396,18 +400,38 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
 
     CK(cudaEventRecord(e.ev[EV_H2D], e.st));
     typedef Launch<C> K;
-    // sort_mode 1: window-major fill from stored digits (scatter region per window stays in L2); 0: one thread per scalar
-    // recodes again and scatters into all windows; -1 (auto): window-major once the entry array outgrows the L2
-    const bool window_major = g_params.sort_mode == 1 || (g_params.sort_mode < 0 && (uint64_t)Mmax * 4 > (96ull << 20));
-    if (window_major) e.digits.ensure((size_t)Mmax + 1);
-    K::count(e.st, sh, d_scalars, is_mont, e.counts.p, window_major ? e.digits.p : nullptr);
-    CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
-    LaunchUtil::exclusive_scan(e.st, e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p);
-    e.launches += LaunchUtil::scan_launches((uint32_t)G1);
-    CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
-    if (window_major) K::fill_window(e.st, sh, e.digits.p, e.counts.p, e.offsets.p, e.entries.p);
-    else K::fill(e.st, sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
-    CK(cudaEventRecord(e.ev[EV_FILL], e.st));
+    // sort_mode 2: two block-local radix partitions (kernels_sort.cu); 1: counting sort with a window-major fill from stored digits (scatter
+    // region per window stays in L2); 0: counting sort, one thread per scalar recodes again and scatters into all windows;
+    // -1 (auto): radix partitions from 2^21 entries on (below, the second pass costs more than the atomics it saves: 2^16 points 0.91 vs 0.85 ms,
+    // 2^18 points 1.44 vs 1.48 ms, profiles/r02_sort.md)
+    SortPlan pl;
+    const bool radix = (g_params.sort_mode == 2 || (g_params.sort_mode < 0 && Mmax >= (1u << 21))) && LaunchSort::plan(sh, pl);
+    if (radix) {
+        const size_t cw = LaunchSort::coarse_words(pl);
+        if (e.coarse_counts.cap < cw) {
+            e.coarse_counts.ensure(cw);
+            CK(cudaMemsetAsync(e.coarse_counts.p, 0, e.coarse_counts.cap * sizeof(uint32_t), e.st));  // k_sort_scan leaves it zero again
+        }
+        e.coarse_off.ensure(cw);
+        e.coarse_cursor.ensure(cw);
+        e.digits.ensure((size_t)Mmax + 1);
+        e.part_pay.ensure((size_t)Mmax + 1);
+        e.part_fine.ensure((size_t)Mmax + 16);
+        e.launches += LaunchSort::run(e.st, std::is_same<typename C::Scalar, FqP>::value ? 0 : 1, e.sm_count, pl, d_scalars, is_mont, e.digits.p, e.coarse_counts.p,
+                                      e.coarse_off.p, e.coarse_cursor.p, e.part_pay.p, e.part_fine.p, e.entries.p, e.offsets.p, e.ev[EV_COUNT], e.ev[EV_SCAN]) - 2;
+        CK(cudaEventRecord(e.ev[EV_FILL], e.st));
+    } else {
+        const bool window_major = g_params.sort_mode == 1 || (g_params.sort_mode < 0 && (uint64_t)Mmax * 4 > (96ull << 20));
+        if (window_major) e.digits.ensure((size_t)Mmax + 1);
+        K::count(e.st, sh, d_scalars, is_mont, e.counts.p, window_major ? e.digits.p : nullptr);
+        CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
+        LaunchUtil::exclusive_scan(e.st, e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p);
+        e.launches += LaunchUtil::scan_launches((uint32_t)G1);
+        CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
+        if (window_major) K::fill_window(e.st, sh, e.digits.p, e.counts.p, e.offsets.p, e.entries.p);
+        else K::fill(e.st, sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
+        CK(cudaEventRecord(e.ev[EV_FILL], e.st));
+    }
     if (e.wait_pts) {
         CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
         e.wait_pts = false;
@@ -918,7 +942,7 @@ template <class C> static const AffinePt<C> *fixed_table(Engine &e) {
     return (const AffinePt<C> *)buf.p;
 }
 
-template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed, uint64_t *k_out) {
+template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed, uint64_t first, uint64_t *k_out) {
     typedef Fp<typename C::Scalar> S;
     CK(cudaSetDevice(e.dev));
     CK(cudaMalloc(&s.d_pts, std::max<size_t>(s.count, 1) * sizeof(AffinePt<C>)));
@@ -926,7 +950,7 @@ template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed
     S *dk = nullptr;
     CK(cudaMalloc(&dk, s.count * sizeof(S)));
     uint32_t n = (uint32_t)s.count;
-    Launch<C>::gen_scalars(e.st, seed, (uint64_t)s.first, n, dk);
+    Launch<C>::gen_scalars(e.st, seed, first + (uint64_t)s.first, n, dk);
     Launch<C>::fixed_base(e.st, dk, fixed_table<C>(e), n, (AffinePt<C> *)s.d_pts);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(e.st));
@@ -1650,7 +1674,9 @@ int kgr_fixed_base_mul(int curve, const uint64_t *k, size_t n, uint64_t *out_xy)
     });
 }
 
-int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, uint64_t *k_out) {
+int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, uint64_t *k_out) { return kgr_bases_generate_at(curve, seed, 0, n, out, k_out); }
+
+int kgr_bases_generate_at(int curve, uint64_t seed, uint64_t first, size_t n, kgr_bases_t **out, uint64_t *k_out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     if (!out) return fail(KGR_E_ARG, "null pointer");
@@ -1661,7 +1687,7 @@ int kgr_bases_generate(int curve, uint64_t seed, size_t n, kgr_bases_t **out, ui
         b->curve = curve;
         b->n = n;
         make_shards(b->shards, n);
-#define CALL(C) for (auto &s : b->shards) generate_shard<C>(g_engines[s.eng], s, seed, k_out)
+#define CALL(C) for (auto &s : b->shards) generate_shard<C>(g_engines[s.eng], s, seed, first, k_out)
         DISPATCH(curve, CALL);
 #undef CALL
         *out = b;

@@ -47,6 +47,13 @@ KGR_HD uint32_t window_raw(const uint32_t s[8], uint32_t bit, uint32_t c) {
     return (uint32_t)(v >> sh) & ((1u << c) - 1u);
 }
 
+// if (x >= p) x -= p, five times: any 256-bit input lands in [0, p) (2^256 < 6p for both moduli).  The reference never holds
+// an unreduced field element; a caller that passes one (canonical bytes >= the modulus, or limbs that are not fully reduced) gets
+// the scalar modulo the modulus instead of a digit string that silently lost its top bits.
+template <class P> KGR_HD void reduce_range(Fp<P> &s) {
+    for (int k = 0; k < 5; k++) fp_final_sub<P>(s.v);
+}
+
 // Load scalar i as canonical limbs.  Montgomery inputs (the reference's in-memory form, fr.rs:71)
 // are reduced exactly like to_raw_bytes does (zkstd/src/macros/field.rs:102-104 -> fr.rs:74-84).
 template <class C> KGR_HD void load_scalar(const uint32_t *scalars, uint32_t i, int is_mont, uint32_t out[8]) {
@@ -59,6 +66,7 @@ template <class C> KGR_HD void load_scalar(const uint32_t *scalars, uint32_t i, 
 #else
     for (int k = 0; k < 8; k++) s.v[k] = scalars[8 * (size_t)i + k];
 #endif
+    reduce_range(s);
     if (is_mont) s = fp_from_mont(s);
     for (int k = 0; k < 8; k++) out[k] = s.v[k];
 }

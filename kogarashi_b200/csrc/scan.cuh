@@ -43,7 +43,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t *t
 }
 
 // in/out may alias.  len need not be a multiple of anything; in/out must be 16-byte aligned.
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t *in, uint32_t *out, uint32_t len, uint32_t *tile_sums) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t *in, uint32_t *out, uint32_t len, uint32_t *tile_sums) {
     __shared__ uint32_t smem[33];
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t v[SCAN_ITEMS];
@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const uint32_t *in,
 }
 
 // single CTA: exclusive scan of tile_sums[0..n) in place
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t *tile_sums, uint32_t n) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t *tile_sums, uint32_t n) {
     __shared__ uint32_t smem[33];
     uint32_t carry = 0;
     for (uint32_t base = 0; base < n; base += SCAN_THREADS) {
@@ -83,7 +83,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint32_t *tile_sums,
     }
 }
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *out, uint32_t len, const uint32_t *tile_sums) {
+static __global__ void __launch_bounds__(SCAN_THREADS) k_scan_add(uint32_t *out, uint32_t len, const uint32_t *tile_sums) {
     uint32_t add = tile_sums[blockIdx.x];
     uint32_t base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     if (base + SCAN_ITEMS <= len) {

@@ -56,12 +56,14 @@ class Bases:
         self._h = h
 
     @classmethod
-    def generate(cls, curve, n, seed=1, return_scalars=False):
-        """n points k_i*G computed on the device from a seed (large synthetic benchmarks/tests)."""
+    def generate(cls, curve, n, seed, return_scalars=False, first=0):
+        """n points k_i*G computed on the device from a seed — SYNTHETIC BENCHMARK / TEST INPUTS ONLY: the k_i come from a public 64-bit
+        splitmix64 stream, so every discrete logarithm is known and a commitment key built this way is not binding.  `first`: global index
+        of point 0 (a shard of a larger vector)."""
         _lib.ensure_init()
         h = ctypes.c_void_p()
         ks = np.zeros((n, 4), dtype=np.uint64) if return_scalars else None
-        _lib.check(_lib.lib().kgr_bases_generate(curve, seed, n, ctypes.byref(h), _u64(ks) if ks is not None else None))
+        _lib.check(_lib.lib().kgr_bases_generate_at(curve, seed, first, n, ctypes.byref(h), _u64(ks) if ks is not None else None))
         b = cls(curve, _handle=h, _n=n)
         return (b, ks) if return_scalars else b
 

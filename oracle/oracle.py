@@ -56,6 +56,9 @@ def lib():
         L.zko_generator.argtypes = [ctypes.c_int, u64p]
         L.zko_random_field.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, u64p]
         L.zko_random_points.argtypes = [ctypes.c_int, u8p, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
+        L.zko_bench_scalars.argtypes = [ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_size_t, u64p]
+        L.zko_fixed_base.argtypes = [ctypes.c_int, u64p, ctypes.c_size_t, ctypes.c_int, u64p]
+        L.zko_field_dot.argtypes = [ctypes.c_int, u64p, u64p, ctypes.c_size_t, ctypes.c_int, u64p]
         L.zko_xorshift_u64.argtypes = [u8p, ctypes.c_size_t, u64p]
         L.zko_fft.argtypes = [ctypes.c_size_t, ctypes.c_int, u64p, ctypes.c_size_t, u64p, ctypes.POINTER(ctypes.c_size_t)]
         L.zko_groth16_h.argtypes = [ctypes.c_size_t, u64p, u64p, u64p, ctypes.c_size_t, u64p, ctypes.POINTER(ctypes.c_size_t)]
@@ -164,6 +167,31 @@ def random_points(curve, n, seed=DEFAULT_SEED, threads=None, return_scalars=Fals
     s = _seed(seed)
     assert lib().zko_random_points(curve, _u8(s), n, threads or os.cpu_count() or 1, _u64(xy), _u64(ks)) == 0
     return (xy, ks) if return_scalars else xy
+
+
+def bench_scalars(curve, seed, first, n):
+    """Bench input support (not reference code): k_i = from_u512(splitmix64 stream of (seed, first + i)) in the curve's scalar field, the
+    stream kgr_bases_generate_at uses on the device."""
+    out = np.zeros((n, 4), dtype=np.uint64)
+    assert lib().zko_bench_scalars(curve, seed, first, n, _u64(out)) == 0
+    return out
+
+
+def fixed_base(curve, k, threads=None):
+    """Bench input support: k_i * G as affine points (identity -> (0, 0), the device encoding) via a byte-window table and add_mixed."""
+    k = _c(k).reshape(-1, 4)
+    xy = np.zeros((k.shape[0], 2 * coord_limbs(curve)), dtype=np.uint64)
+    assert lib().zko_fixed_base(curve, _u64(k), k.shape[0], threads or os.cpu_count() or 1, _u64(xy)) == 0
+    return xy
+
+
+def field_dot(field_id, a, b, threads=None):
+    """sum a_i * b_i (Montgomery in / out): with bases k_i * G an MSM must equal (sum k_i s_i) * G."""
+    a, b = _c(a).reshape(-1, 4), _c(b).reshape(-1, 4)
+    assert a.shape == b.shape
+    out = np.zeros(4, dtype=np.uint64)
+    assert lib().zko_field_dot(field_id, _u64(a), _u64(b), a.shape[0], threads or os.cpu_count() or 1, _u64(out)) == 0
+    return out
 
 
 def xorshift_u64(n, seed=DEFAULT_SEED):

@@ -3,6 +3,7 @@
 // through ctypes.  Buffer formats are the same as include/kgr_msm.h so a test can hand the same
 // arrays to both sides.
 #include "zkstd_oracle.hpp"
+#include <mutex>
 #include <thread>
 #include <atomic>
 #include <algorithm>
@@ -175,6 +176,106 @@ template <class C> void random_points(const uint8_t seed[16], size_t n, uint64_t
     for (auto &t : pool) t.join();
 }
 
+
+// ---- bench / test input support (NOT part of the reference restatement) ------------------------------------------------------------
+// The synthetic inputs of bench.py are P_i = k_i * G with k_i = from_u512(8 words splitmix64(seed ^ splitmix64(8 i + j))): the stream the
+// device generator (kgr_bases_generate_at) uses, restated here so that the CPU arm can build the SAME vectors without a GPU.
+static inline uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ULL;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+    return x ^ (x >> 31);
+}
+template <class F> void bench_scalars(uint64_t seed, uint64_t first, size_t n, uint64_t *out) {
+    for (size_t i = 0; i < n; i++) {
+        uint64_t w[8];
+        for (int j = 0; j < 8; j++) w[j] = splitmix64(seed ^ splitmix64((first + i) * 8 + j));
+        st4(out + 4 * i, Field<F>::from_u512(w));
+    }
+}
+// k_i * G for many k_i (Montgomery scalars): byte-window table d * 2^(8 j) * G, at most 32 mixed additions per point with the reference's
+// own formulas (add_mixed, weierstrass.rs:63-97) and to_affine.  Same group elements as scalar_point(G, k_i), hence the same affine limbs.
+template <class C> void fixed_base_batch(const uint64_t *k, size_t n, int threads, uint64_t *xy) {
+    typedef Curve<C> Cv;
+    typedef Field<typename C::Scalar> Fs;
+    constexpr size_t N = PtIo<C>::N;
+    static std::vector<typename Cv::Affine> table;  // [32][255]
+    static std::mutex mu;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (table.empty()) {
+            table.resize(32 * 255);
+            typename Cv::Proj base = Cv::to_extended(Cv::generator());
+            for (int j = 0; j < 32; j++) {
+                typename Cv::Proj acc = base;
+                for (int d = 1; d <= 255; d++) {
+                    table[j * 255 + d - 1] = Cv::to_affine(acc);
+                    acc = Cv::add_proj(acc, base);
+                }
+                for (int b = 0; b < 8; b++) base = Cv::double_proj(base);
+            }
+        }
+    }
+    std::atomic<size_t> next(0);
+    auto worker = [&]() {
+        for (;;) {
+            size_t i0 = next.fetch_add(256);
+            if (i0 >= n) break;
+            const size_t i1 = std::min(n, i0 + 256), m = i1 - i0;
+            typename Cv::Proj acc[256];
+            typename Cv::El pre[256];
+            typename Cv::El run = Cv::Fb::one();
+            for (size_t t = 0; t < m; t++) {
+                Limbs c = Fs::montgomery_reduce(ld4(k + 4 * (i0 + t)));
+                acc[t] = Cv::proj_identity();
+                for (int j = 0; j < 32; j++) {
+                    unsigned d = (unsigned)(c[j / 8] >> (8 * (j % 8))) & 0xff;
+                    if (d) acc[t] = Cv::add_mixed(table[j * 255 + d - 1], acc[t]);
+                }
+                pre[t] = run;  // product of the non-zero z before t
+                if (!Cv::is_identity(acc[t])) run = Cv::Fb::mul(run, acc[t].z);
+            }
+            // one inversion per block (Montgomery's trick); x / z and y / z are the unique affine coordinates, as to_affine returns them
+            typename Cv::El inv;
+            Cv::Fb::invert(run, inv);
+            for (size_t t = m; t-- > 0;) {
+                typename Cv::El x = Cv::Fb::zero(), y = Cv::Fb::zero();  // identity (k_i = 0): the device generator's encoding (0, 0)
+                if (!Cv::is_identity(acc[t])) {
+                    typename Cv::El zi = Cv::Fb::mul(inv, pre[t]);
+                    inv = Cv::Fb::mul(inv, acc[t].z);
+                    x = Cv::Fb::mul(acc[t].x, zi);
+                    y = Cv::Fb::mul(acc[t].y, zi);
+                }
+                Io<typename Cv::El>::st(xy + 2 * N * (i0 + t), x);
+                Io<typename Cv::El>::st(xy + 2 * N * (i0 + t) + N, y);
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < std::max(1, threads); t++) pool.emplace_back(worker);
+    worker();
+    for (auto &t : pool) t.join();
+}
+// sum a_i * b_i in the field (Montgomery in and out): the discrete log of an MSM whose bases are k_i * G
+template <class F> void field_dot(const uint64_t *a, const uint64_t *b, size_t n, int threads, uint64_t *out) {
+    typedef Field<F> Fd;
+    int T = std::max(1, threads);
+    std::vector<Limbs> part(T, Limbs{0, 0, 0, 0});
+    auto worker = [&](int t) {
+        size_t lo = n * t / T, hi = n * (t + 1) / T;
+        Limbs acc{0, 0, 0, 0};
+        for (size_t i = lo; i < hi; i++) acc = Fd::add(acc, Fd::mul(ld4(a + 4 * i), ld4(b + 4 * i)));
+        part[t] = acc;
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; t++) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto &t : pool) t.join();
+    Limbs acc{0, 0, 0, 0};
+    for (auto &p : part) acc = Fd::add(acc, p);
+    st4(out, acc);
+}
+
 }  // namespace
 
 // BODY is instantiated with C = the curve's parameter struct
@@ -274,6 +375,22 @@ int zko_random_field(int field_id, const uint8_t seed[16], size_t n, uint64_t *o
 // n random points G * k_i (k_i from the sampler above); optionally returns the k_i (Montgomery).
 int zko_random_points(int curve, const uint8_t seed[16], size_t n, int threads, uint64_t *xy, uint64_t *scalars_out) {
     DISPATCH_CURVE(curve, random_points<C>(seed, n, xy, scalars_out, threads));
+    return 0;
+}
+
+// bench input support (see above): scalars of the curve's scalar field, fixed-base points, dot product in field 0 Fq / 1 Fr
+int zko_bench_scalars(int curve, uint64_t seed, uint64_t first, size_t n, uint64_t *out) {
+    DISPATCH_CURVE(curve, bench_scalars<typename C::Scalar>(seed, first, n, out));
+    return 0;
+}
+int zko_fixed_base(int curve, const uint64_t *k, size_t n, int threads, uint64_t *xy) {
+    DISPATCH_CURVE(curve, fixed_base_batch<C>(k, n, threads, xy));
+    return 0;
+}
+int zko_field_dot(int field_id, const uint64_t *a, const uint64_t *b, size_t n, int threads, uint64_t *out) {
+    if (field_id == 0) field_dot<FqParams>(a, b, n, threads, out);
+    else if (field_id == 1) field_dot<FrParams>(a, b, n, threads, out);
+    else return -1;
     return 0;
 }
 

@@ -126,7 +126,7 @@ def test_msm_golden_under_forced_shapes(k, golden, c, chunk):
 
 
 @pytest.mark.parametrize("param,value", [("final_on_device", 1), ("running_sum_stop", 1), ("running_sum_stop", 1 << 20), ("reduce_fanin", 4), ("sort_mode", 0),
-                                         ("sort_mode", 1), ("reduce_mode", 0), ("reduce_mode", 1), ("affine_rounds", 1), ("affine_rounds", 2), ("affine_rounds", 4)])
+                                         ("sort_mode", 1), ("sort_mode", 2), ("reduce_mode", 0), ("reduce_mode", 1), ("affine_rounds", 1), ("affine_rounds", 2), ("affine_rounds", 4)])
 def test_msm_golden_under_reduce_variants(k, golden, param, value):
     """Device-side Horner, pure running-sum reduction, pure weighting-pass reduction, small fan-in: same element."""
     defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1, "reduce_mode": 1, "affine_rounds": 0}
@@ -354,7 +354,7 @@ def test_random_shapes_vs_oracle(k, seed):
         for h in range(cl, 2 * cl, 4):
             pts[i, h:h + 4] = A.field_op(bf, "neg", pts[i, h:h + 4])
     m = n if seed % 4 else max(1, n - 3)                                # fewer scalars than bases
-    params = {"window_bits": int(rng.integers(0, 15)), "chunk": int(rng.choice([0, 1, 2, 5, 16, 64])), "sort_mode": int(rng.integers(-1, 2)),
+    params = {"window_bits": int(rng.integers(0, 15)), "chunk": int(rng.choice([0, 1, 2, 5, 16, 64])), "sort_mode": int(rng.integers(-1, 3)),
               "reduce_mode": int(rng.integers(0, 2)), "final_on_device": int(rng.integers(0, 2))}
     defaults = {"window_bits": 0, "chunk": 0, "sort_mode": -1, "reduce_mode": 1, "final_on_device": 0}
     exp = A.to_affine(curve, A.msm(curve, pts, sc[:m], inf=inf))
@@ -370,3 +370,75 @@ def test_random_shapes_vs_oracle(k, seed):
     finally:
         for name, v in defaults.items():
             k.set_param(name, v)
+
+
+@pytest.mark.parametrize("c", [2, 3, 7, 9, 12, 14, 16, 18])
+def test_radix_partition_sort_forced_window_sizes(k, golden, c):
+    """sort_mode = 2 (two block-local radix partitions, kernels_sort.cu) for every split of the bucket index into coarse bins and fine bits:
+    the goldens with duplicates / opposite points / identity bases / r-1 scalars, both scalar formats, and the window-table mode."""
+    k.set_param("sort_mode", 2)
+    k.set_param("window_bits", c)
+    try:
+        for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96", "gr_identity_bases_40", "g1_cancel_32", "g1_rm1_scalars", "gr_uniform_100"):
+            curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
+            pts, sc, inf, aff = (golden[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve, inf=inf)), aff), (name, c)
+            can = np.stack([A.field_op(A.SCALAR_FIELD[curve], "mont_reduce", x) for x in sc])
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, can, curve=curve, inf=inf, scalar_fmt=k.SCALARS_CANONICAL)), aff), (name, c)
+            if c <= 12:
+                bases = k.Bases(curve, pts, inf).precompute(c)
+                assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc)), aff), (name, c, "table")
+                bases.free()
+    finally:
+        k.set_param("sort_mode", -1)
+        k.set_param("window_bits", 0)
+
+
+@pytest.mark.parametrize("curve,logn", [(A.BN254_G1, 16), (A.GRUMPKIN, 14)])
+def test_radix_partition_sort_vs_oracle(k, curve, logn):
+    """Seeded inputs with hot buckets (half the scalars zero, a quarter equal) through sort_mode 2 against the restated reference algorithm:
+    bins that overflow the shared-memory buffer take the direct-placement path."""
+    n = 1 << logn
+    rng = np.random.default_rng(99 + logn)
+    pool = A.random_points(curve, 2048, seed=bytes(range(9, 25)))
+    pts = pool[rng.integers(0, pool.shape[0], size=n)]
+    fid = A.SCALAR_FIELD[curve]
+    sc = A.random_field(fid, n, seed=bytes(range(40, 56)))
+    kind = rng.integers(0, 4, size=n)
+    sc[kind == 0] = 0
+    sc[kind == 1] = sc[0]
+    exp = A.to_affine(curve, A.msm(curve, pts, sc))
+    k.set_param("sort_mode", 2)
+    try:
+        for c in (0, 8, 15):
+            k.set_param("window_bits", c)
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp), c
+    finally:
+        k.set_param("sort_mode", -1)
+        k.set_param("window_bits", 0)
+
+
+@pytest.mark.parametrize("sort_mode", [0, 1, 2])
+def test_unreduced_scalars_are_read_modulo_the_modulus(k, sort_mode):
+    """Canonical scalars >= r (which to_raw_bytes never produces) and Montgomery limbs that are not fully reduced give the MSM of the
+    scalars mod r — not a digit string that silently lost its top bits."""
+    curve, n = A.BN254_G1, 64
+    rng = np.random.default_rng(5)
+    pts = A.random_points(curve, n, seed=bytes(range(16)))
+    raw = rng.integers(0, 1 << 63, size=(n, 4), dtype=np.uint64) * np.uint64(2) + rng.integers(0, 2, size=(n, 4), dtype=np.uint64)
+    raw[0] = np.uint64(0xFFFFFFFFFFFFFFFF)                           # 2^256 - 1
+    raw[1] = B.int_to_limbs(B.FR)                                    # exactly r -> 0
+    raw[2] = B.int_to_limbs(B.FR + 5)
+    vals = [B.limbs_to_int(x) % B.FR for x in raw]
+    k.set_param("sort_mode", sort_mode)
+    try:
+        # canonical: value = raw mod r
+        red = np.array([B.int_to_limbs(B.to_mont(v, B.FR)) for v in vals], dtype=np.uint64)
+        exp = A.to_affine(curve, A.msm(curve, pts, red))
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, raw, curve=curve, scalar_fmt=k.SCALARS_CANONICAL)), exp)
+        # Montgomery: value = raw * R^-1 mod r
+        red_m = np.array([B.int_to_limbs(v) for v in vals], dtype=np.uint64)   # limbs of (raw mod r) are a valid Montgomery residue of the same class
+        exp_m = A.to_affine(curve, A.msm(curve, pts, red_m))
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, raw, curve=curve)), exp_m)
+    finally:
+        k.set_param("sort_mode", -1)
