@@ -17,6 +17,7 @@
 #pragma once
 #include <cstdint>
 #include <cstring>
+#include <thread>
 #include <vector>
 #include <array>
 
@@ -600,16 +601,31 @@ struct FrFft {
             right[i] = F::sub(right[i], t2);
         }
     }
-    // fft.rs:166-192
-    static void classic(Limbs *c, size_t m, size_t chunk, const std::vector<Limbs> &tw) {
+    // fft.rs:166-192.  The reference runs the two halves under rayon::join (:180-183, feature "std") and the butterfly of each level
+    // serially (:195-218); `fork` levels of the recursion get their own std::thread here (2^fork >= host threads), the same task tree.
+    static int &fork_levels() {
+        static int v = [] {
+            unsigned hw = std::thread::hardware_concurrency(), d = 0;
+            while ((1u << d) < (hw ? hw : 1u)) d++;
+            return (int)d;
+        }();
+        return v;
+    }
+    static void classic(Limbs *c, size_t m, size_t chunk, const std::vector<Limbs> &tw, int fork = fork_levels()) {
         if (m == 2) {
             Limbs t = c[1];
             c[1] = c[0];
             c[0] = F::add(c[0], t);
             c[1] = F::sub(c[1], t);
         } else {
-            classic(c, m / 2, chunk * 2, tw);
-            classic(c + m / 2, m / 2, chunk * 2, tw);
+            if (fork > 0 && m >= 1024) {
+                std::thread left([&] { classic(c, m / 2, chunk * 2, tw, fork - 1); });
+                classic(c + m / 2, m / 2, chunk * 2, tw, fork - 1);
+                left.join();
+            } else {
+                classic(c, m / 2, chunk * 2, tw, 0);
+                classic(c + m / 2, m / 2, chunk * 2, tw, 0);
+            }
             butterfly(c, c + m / 2, m / 2, chunk, tw);
         }
     }

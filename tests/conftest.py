@@ -41,3 +41,18 @@ def same_affine(a, b):
     if int(a[-1]) or int(b[-1]):
         return bool(int(a[-1]) and int(b[-1]))
     return bool((a[:-1] == b[:-1]).all())
+
+
+def alt_bn128_kat():
+    """tests/golden/alt_bn128_kat.json as Montgomery limb arrays: external known-answer vectors (EIP-196 / go-ethereum precompile tests)."""
+    import json
+
+    from oracle import pyref as B
+    raw = json.load(open(os.path.join(ROOT, "tests", "golden", "alt_bn128_kat.json")))
+
+    def pt(xy):  # canonical hex -> (8,) uint64 x || y Montgomery limbs over Fq
+        return np.array([w for v in xy for w in B.int_to_limbs(B.to_mont(int(v, 16), B.FQ))], dtype=np.uint64)
+
+    adds = [(c["name"], pt(c["a"]), pt(c["b"]), pt(c["sum"])) for c in raw["add"]]
+    muls = [(c["name"], pt(c["p"]), int(c["k"], 16), pt(c["product"])) for c in raw["mul"]]
+    return raw, adds, muls

@@ -63,3 +63,56 @@ def test_shard_range_covers_everything():
             for first, count in spans:
                 assert first == pos or count == 0
                 pos += count
+
+
+def test_bench_scalars_do_not_depend_on_the_sharding():
+    """bench.py draws the scalar vector in global blocks: any shard of it is the same numbers (strong scaling needs ONE vector for every N)."""
+    import bench
+    whole = bench.scalars_range(0, 3 * bench.SC_BLOCK + 17)
+    for first, n in ((0, 5), (bench.SC_BLOCK - 3, 10), (bench.SC_BLOCK, bench.SC_BLOCK), (2 * bench.SC_BLOCK + 9, bench.SC_BLOCK + 8)):
+        assert (bench.scalars_range(first, n) == whole[first:first + n]).all()
+    assert (whole[:, 3] < np.uint64(bench.FR_TOP)).all()
+
+
+def _strong_worker(rank, world, port, n, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    from kogarashi_b200 import sharding
+    from oracle import pyref as B
+    curve = A.BN254_G1
+    first, count = sharding.shard_range(n, world, rank)
+    ks = A.bench_scalars(curve, bench.BASE_SEED, first, count)     # the stream kgr_bases_generate_at(first) uses on the device
+    pts = A.fixed_base(curve, ks, threads=2)
+    sc = bench.scalars_range(first, count)
+    partial = A.msm(curve, pts, sc, threads=2)                      # stands in for the rank's GPU MSM
+    dot = bench.dot_of_shard(curve, ks, sc)
+    parts = sharding.gather_partials(partial)
+    dots = sharding.gather_partials(dot)
+    if rank == 0:
+        import kogarashi_b200 as k
+        total = k.to_affine(curve, sharding.combine_partials(curve, parts))
+        acc = sum(B.limbs_to_int(d) for d in dots) % B.FR
+        exp = bench.expected_from_dot(curve, np.array(B.int_to_limbs(acc), dtype=np.uint64))
+        # the same vector in one piece
+        ks_all = A.bench_scalars(curve, bench.BASE_SEED, 0, n)
+        one = A.to_affine(curve, A.msm(curve, A.fixed_base(curve, ks_all, threads=2), bench.scalars_range(0, n), threads=2))
+        q.put((total, exp, one))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_strong_scaling_checksum():
+    """The N > 1 leg of bench.py on CPU: shards of ONE seeded vector, partial points gathered and summed, and the all-gathered
+    sum k_i s_i giving the same point — which is also the unsharded MSM."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_strong_worker, args=(r, 2, port, 515, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    total, exp, one = q.get(timeout=300)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert same_affine(total, exp) and same_affine(total, one)

@@ -109,7 +109,7 @@ def bench_groth16(logm, out):
            "constraints": cs.m, "log_n": E["k"], "gpu_wall_ms": res, "checked_against_discrete_logs": bool(ok),
            "h_bit_exact_with_oracle": bool(q.shape[0] == n_ref and (q == q_ref[:n_ref]).all()),
            "cpu_baseline": {"fft_seconds": fft_s, "msm_seconds": msm_s, "total_seconds": fft_s + msm_s, "cores": cores, "kind": "port",
-                            "note": "restated reference FFT (single thread) + the eight reference-algorithm MSMs on all cores"},
+                            "note": "restated reference FFTs (recursion halves forked like rayon::join, fft.rs:180-183) + the eight reference-algorithm MSMs on all cores"},
            "speedup_vs_cpu_baseline": {m: (fft_s + msm_s) * 1e3 / v for m, v in res.items()}, "setup_python_s": setup_s}
     out.append(rec)
     print(json.dumps(rec), flush=True)
