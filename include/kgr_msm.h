@@ -19,7 +19,11 @@
  *                           fields of G1Projective / grumpkin::Projective (g1.rs:119); identity =
  *                           (0, R, 0) as in zkstd/src/macros/curve/weierstrass/group.rs:106-110.
  *                           Any representative of the correct group element may be returned;
- *                           compare after to_affine (macros/curve/weierstrass.rs:57-66).
+ *                           compare after to_affine (macros/curve/weierstrass.rs:57-66).  The
+ *                           representative is NOT stable from run to run: the order of the entries inside
+ *                           a bucket depends on the order in which thread blocks claim their ranges, and a
+ *                           different summation order gives a different (X : Y : Z) of the same point.
+ *                           The normalised affine point is bit-identical every time.
  *
  * Every function returns 0 on success or a negative KGR_E_* code; kgr_last_error() gives the
  * text for the calling thread.  No C++ exception crosses this boundary.  There is no CPU
@@ -145,8 +149,36 @@ int kgr_r1cs_mul(kgr_r1cs_t *shape, int which, const uint64_t *z, uint64_t *out)
 int kgr_nova_cross_term(kgr_r1cs_t *shape, const uint64_t *z1, const uint64_t *z2, uint64_t *t_out, kgr_bases_t *ck, uint64_t *commit_out);
 /* ms[0] H2D of z1 and z2, ms[1] cross-term kernel, ms[2] commitment MSM (device events + host finish) of the last kgr_nova_cross_term. */
 int kgr_r1cs_last_timing(const kgr_r1cs_t *shape, float ms[3]);
-/* RelaxedR1csWitness::fold (witness.rs:67-68): out[i] = a[i] + b[i] * r over `field`; host buffers, n x 4 uint64 Montgomery. */
+/* RelaxedR1csWitness::fold (witness.rs:67-68): out[i] = a[i] + b[i] * r over `field`; host buffers, n x 4 uint64 Montgomery
+ * (kgr_vec_fold_device below keeps all three vectors on the GPU). */
 int kgr_vec_fold(int field, const uint64_t *a, const uint64_t *b, const uint64_t r[4], size_t n, uint64_t *out);
+
+/* ---- device-resident vectors (Nova: z = (u, x, w), E and T stay on the GPU between folding steps) ----------------------------------
+ * nova/src/relaxed_r1cs/witness.rs:20-21,56-71 and nova/src/ivc.rs:160-205: every IVC step commits the new witness, computes and commits the
+ * cross term and folds (w, e) — with host buffers each of those vectors crosses PCIe in both directions per step.  A kgr_vec_t is a vector
+ * of field elements (field 0 = Fq, 1 = Fr; Montgomery, n x 4 uint64) on the first device of kgr_init. */
+typedef struct kgr_vec kgr_vec_t;
+int kgr_vec_upload(int field, const uint64_t *host, size_t n, kgr_vec_t **out);   /* host == NULL: n zero elements */
+int kgr_vec_download(const kgr_vec_t *v, size_t off, size_t n, uint64_t *host);
+int kgr_vec_free(kgr_vec_t *v);
+size_t kgr_vec_len(const kgr_vec_t *v);
+/* Overwrite elements [off, off + n) from host memory (the step's public inputs / fresh witness entering a resident z). */
+int kgr_vec_write(kgr_vec_t *v, size_t off, const uint64_t *host, size_t n);
+/* RelaxedR1csWitness::fold on the device: out[i] = a[i] + b[i] * r for i < n = len(out); out may be a or b.  (witness.rs:67-68) */
+int kgr_vec_fold_device(const kgr_vec_t *a, const kgr_vec_t *b, const uint64_t r[4], kgr_vec_t *out);
+/* sum_{i<n} scalars[sc_off + i] * bases[base_off + i] with the scalars taken from a resident vector (their field must be the curve's scalar
+ * field; bases on the first device only): the commitment `ck.commit(&w)` of a witness that never left the GPU (w = z[1 + l ..]). */
+int kgr_msm_vec(kgr_bases_t *bases, size_t base_off, const kgr_vec_t *scalars, size_t sc_off, size_t n, uint64_t *out /* [12] */);
+/* PedersenCommitment::commit of the elements [sc_off, sc_off + n) of a resident vector: out = x[4] y[4] is_infinity. */
+int kgr_pedersen_commit_vec(kgr_bases_t *ck, const kgr_vec_t *m, size_t sc_off, size_t n, uint64_t *out /* [9] */);
+/* kgr_nova_cross_term with z1, z2 resident (n_z elements each) and T left in the resident vector t (m elements; NULL: internal buffer).
+ * With ck != NULL also commit(T).  No host <-> device traffic except the 72-byte commitment. */
+int kgr_nova_cross_term_device(kgr_r1cs_t *shape, const kgr_vec_t *z1, const kgr_vec_t *z2, kgr_vec_t *t, kgr_bases_t *ck, uint64_t *commit_out);
+
+/* Page-locked host memory for callers that marshal into a reusable arena instead of a fresh pageable buffer per call (a Rust Vec is
+ * pageable: the library then stages it through its own pinned ring, one extra copy).  cudaHostAlloc / cudaFreeHost underneath. */
+int kgr_host_alloc(size_t bytes, void **out);
+int kgr_host_free(void *p);
 
 /* groth16/src/prover.rs:36-65 as one call (row N1): the H coefficients are computed on the device (as kgr_groth16_h), fed to the h query
  * `msm(params.h, q)` without leaving the device, and the other queries of the prover (`jobs`: l, a, b_g1, b_g2, blinding sums ...) overlap with that
@@ -165,6 +197,8 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
  * 1 one kernel per phase, 0 one fused kernel), "oneshot_split" (pieces a large single-device kgr_msm_oneshot call is cut into so that uploads
  * overlap the pipeline; 0 (default) = automatic: pieces of at least 2^19 pairs, at most 4; 1 = off), "lane_threads" (kgr_groth16_msms: 1 (default) one
  * host thread per lane, 0 everything enqueued from the calling thread). */
+/* The tuning state belongs to the CALLING THREAD: kgr_set_param changes the values used by MSMs this thread issues afterwards (the
+ * library's own worker threads inherit the caller's snapshot) and never those of a call in flight on another thread. */
 int kgr_set_param(const char *name, long value);
 
 /* Per-phase time (ms) of the last MSM on device slot `dev`, CUDA events on the engine's stream:

@@ -8,3 +8,4 @@ from .msm import (BN254_G1, BN254_G2, GRUMPKIN, SCALARS_CANONICAL, SCALARS_MONTG
                   microbench, groth16_msms, msm_batch, msm_curve_addition, msm_device, proj_add, set_param, to_affine)
 from .fft import Fft  # noqa: F401
 from .pedersen import PedersenCommitment  # noqa: F401
+from .groth16 import ProverSubVersionCrsAttack  # noqa: F401

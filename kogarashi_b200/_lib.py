@@ -18,7 +18,8 @@ EXPORTS = [
     "kgr_proj_add", "kgr_set_param", "kgr_last_timing", "kgr_test_field_op", "kgr_test_point_op",
     "kgr_fixed_base_mul", "kgr_bases_generate", "kgr_microbench", "kgr_bases_download", "kgr_event_record",
     "kgr_event_elapsed_ms", "kgr_launch_count", "kgr_bases_precompute", "kgr_ntt", "kgr_ntt_device", "kgr_groth16_h",
-    "kgr_bases_generate_at", "kgr_msm_batch", "kgr_groth16_msms", "kgr_r1cs_register", "kgr_r1cs_free", "kgr_r1cs_mul", "kgr_nova_cross_term", "kgr_r1cs_last_timing", "kgr_vec_fold",
+    "kgr_bases_generate_at", "kgr_vec_upload", "kgr_vec_download", "kgr_vec_free", "kgr_vec_len", "kgr_vec_write", "kgr_vec_fold_device", "kgr_msm_vec",
+    "kgr_pedersen_commit_vec", "kgr_nova_cross_term_device", "kgr_host_alloc", "kgr_host_free", "kgr_msm_batch", "kgr_groth16_msms", "kgr_r1cs_register", "kgr_r1cs_free", "kgr_r1cs_mul", "kgr_nova_cross_term", "kgr_r1cs_last_timing", "kgr_vec_fold",
 ]
 
 
@@ -85,6 +86,18 @@ def lib():
     L.kgr_nova_cross_term.argtypes = [vp, u64p, u64p, u64p, vp, u64p]
     L.kgr_r1cs_last_timing.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
     L.kgr_vec_fold.argtypes = [ci, u64p, u64p, u64p, sz, u64p]
+    L.kgr_vec_upload.argtypes = [ci, u64p, sz, ctypes.POINTER(vp)]
+    L.kgr_vec_download.argtypes = [vp, sz, sz, u64p]
+    L.kgr_vec_free.argtypes = [vp]
+    L.kgr_vec_len.argtypes = [vp]
+    L.kgr_vec_len.restype = sz
+    L.kgr_vec_write.argtypes = [vp, sz, u64p, sz]
+    L.kgr_vec_fold_device.argtypes = [vp, vp, u64p, vp]
+    L.kgr_msm_vec.argtypes = [vp, sz, vp, sz, sz, u64p]
+    L.kgr_pedersen_commit_vec.argtypes = [vp, vp, sz, sz, u64p]
+    L.kgr_nova_cross_term_device.argtypes = [vp, vp, vp, vp, vp, u64p]
+    L.kgr_host_alloc.argtypes = [sz, ctypes.POINTER(vp)]
+    L.kgr_host_free.argtypes = [vp]
     _lib = L
     return L
 

@@ -58,7 +58,10 @@ struct CudaError {
 struct Params {
     long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0, affine_split = 1, oneshot_split = 0, lane_threads = 1;
 };
-static Params g_params;
+// Tuning state is per calling thread (kgr_set_param changes the calling thread's copy only): an entry point snapshots it once and hands the
+// snapshot to every engine it drives (Engine::params), so a kgr_set_param on one thread never changes an MSM in flight on another, and the
+// library's own worker threads (lanes, devices) see the caller's values.
+static thread_local Params t_params;
 
 template <class T> struct DevBuf {
     T *p = nullptr;
@@ -92,6 +95,7 @@ struct NttDomain {
 enum { EV_START, EV_H2D, EV_COUNT, EV_SCAN, EV_FILL, EV_ACC, EV_FIXUP, EV_END, EV_N };
 
 struct Engine {
+    Params params;  // snapshot of the caller's tuning state for the MSM being enqueued
     int dev = -1;
     int sm_count = 0;
     cudaStream_t st = nullptr;
@@ -167,6 +171,8 @@ struct Engine {
         if (st_copy) cudaStreamDestroy(st_copy);
         if (ev_pts) cudaEventDestroy(ev_pts);
         if (ev_sc) cudaEventDestroy(ev_sc);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
         dev = -1;
     }
 };
@@ -267,6 +273,7 @@ static void download_to_host(Engine &e, void *dst, const void *src, size_t bytes
 
 static std::mutex g_mu;
 static std::vector<Engine> g_engines;
+static uint64_t g_generation = 0;  // bumped by every kgr_init
 // Extra engines (stream + workspaces) on the device of g_engines[0]: independent MSMs of one kgr_msm_batch call overlap on them.
 static std::vector<std::vector<std::unique_ptr<Engine>>> g_lanes;  // [engine index][lane - 1]; lane 0 of a device is g_engines[index] itself
 static constexpr size_t MAX_LANES = 8;
@@ -289,8 +296,8 @@ static Engine &lane_of(size_t eng, size_t i) { return i == 0 ? g_engines[eng] : 
 //   accumulate 0.174 per entry; counting sort 0.0155 per entry growing with the histogram size G
 //   (random L2 atomics + sector-granular scatter); reduce 0.4 ms fixed + 0.7 per bucket;
 //   a thin top window (few leading scalar bits) concentrates n / 2^t entries in 2^t buckets.
-static uint32_t choose_window_bits(uint32_t n) {
-    if (g_params.window_bits > 0) return (uint32_t)std::min<long>(std::max<long>(g_params.window_bits, 1), 24);
+static uint32_t choose_window_bits(uint32_t n, const Params &P) {
+    if (P.window_bits > 0) return (uint32_t)std::min<long>(std::max<long>(P.window_bits, 1), 24);
     double best = 1e300;
     // c >= 9: with fewer than 256 buckets per window the bucket reduction falls back to serial running sums, which is never faster
     // from 2^8 points on (sweeps in profiles/r01_phase_sweep.md); a handful of points (the prover's blinding sums) is cheapest with tiny windows
@@ -332,27 +339,27 @@ static uint32_t choose_window_bits_collapsed(uint32_t n, double mul_weight) {
 }
 
 // table_c == 0: normal mode.  Otherwise the bases pointer is a precomputed table built for window size table_c.
-static MsmShape make_shape(uint32_t n, int blocks_per_sm, int sm_count, uint32_t table_c = 0, uint32_t table_stride = 0, uint32_t table_off = 0) {
+static MsmShape make_shape(const Params &P, uint32_t n, int blocks_per_sm, int sm_count, uint32_t table_c = 0, uint32_t table_stride = 0, uint32_t table_off = 0) {
     MsmShape sh;
     sh.n = n;
-    sh.c = table_c ? table_c : choose_window_bits(n);
+    sh.c = table_c ? table_c : choose_window_bits(n, P);
     sh.W = (255 + sh.c - 1) / sh.c;
     sh.B = 1u << (sh.c - 1);
     sh.G = table_c ? sh.B : sh.W * sh.B;
     sh.gstride = table_c ? 0 : sh.B;
     sh.pstride = table_c ? table_stride : 0;
     sh.poff = table_c ? table_off : 0;
-    sh.K = (uint32_t)g_params.reduce_fanin;
+    sh.K = (uint32_t)P.reduce_fanin;
     uint64_t M = (uint64_t)n * sh.W;
-    if (g_params.chunk > 0) {
-        sh.L = (uint32_t)g_params.chunk;
+    if (P.chunk > 0) {
+        sh.L = (uint32_t)P.chunk;
     } else {
         // pick the chunk length that minimises (waves x (L + per-chunk overhead)) for this GPU
         uint64_t concurrent = (uint64_t)std::max(1, blocks_per_sm) * TPB_ACC * std::max(1, sm_count);
         double best = 1e300;
         uint32_t bestL = 32;
         // batched-affine accumulate: every thread shares one inversion per tree level among its ~L/2 pairs, so long chunks pay
-        for (uint32_t L = (g_params.affine_rounds > 0 ? 160 : 16); L <= 256; L += 4) {
+        for (uint32_t L = (P.affine_rounds > 0 ? 160 : 16); L <= 256; L += 4) {
             uint64_t chunks = (M + L - 1) / L;
             uint64_t waves = (chunks + concurrent - 1) / concurrent;
             double cost = (double)waves * (L + 2.0);
@@ -368,8 +375,9 @@ template <class C>
 static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d_scalars, int is_mont, uint32_t n, uint32_t table_c = 0,
                         uint32_t table_stride = 0, uint32_t table_off = 0) {
     typedef XyzzPt<C> X;
-    const bool affine = g_params.affine_rounds > 0 && C::ID != Bn254G2::ID;  // the experimental batched-affine path is built for 8-word coordinates only
-    MsmShape sh = make_shape(n, affine ? e.aff_blocks_per_sm[C::ID] : e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
+    const Params &P = e.params;
+    const bool affine = P.affine_rounds > 0 && C::ID != Bn254G2::ID;  // the experimental batched-affine path is built for 8-word coordinates only
+    MsmShape sh = make_shape(P, n, affine ? e.aff_blocks_per_sm[C::ID] : e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
     const uint32_t nwin = table_c ? 1u : sh.W;  // independent bucket sets to reduce
     uint64_t M64 = (uint64_t)n * sh.W;
     if (M64 >= (1ull << 32) - 1) throw CudaError{cudaErrorInvalidValue, "n * windows exceeds 2^32 entries", __LINE__};
@@ -405,7 +413,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     // -1 (auto): radix partitions from 2^21 entries on (below, the second pass costs more than the atomics it saves: 2^16 points 0.91 vs 0.85 ms,
     // 2^18 points 1.44 vs 1.48 ms, profiles/r02_sort.md)
     SortPlan pl;
-    const bool radix = (g_params.sort_mode == 2 || (g_params.sort_mode < 0 && Mmax >= (1u << 21))) && LaunchSort::plan(sh, pl);
+    const bool radix = (P.sort_mode == 2 || (P.sort_mode < 0 && Mmax >= (1u << 21))) && LaunchSort::plan(sh, pl);
     if (radix) {
         const size_t cw = LaunchSort::coarse_words(pl);
         if (e.coarse_counts.cap < cw) {
@@ -421,7 +429,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
                                       e.coarse_off.p, e.coarse_cursor.p, e.part_pay.p, e.part_fine.p, e.entries.p, e.offsets.p, e.ev[EV_COUNT], e.ev[EV_SCAN]) - 2;
         CK(cudaEventRecord(e.ev[EV_FILL], e.st));
     } else {
-        const bool window_major = g_params.sort_mode == 1 || (g_params.sort_mode < 0 && (uint64_t)Mmax * 4 > (96ull << 20));
+        const bool window_major = P.sort_mode == 1 || (P.sort_mode < 0 && (uint64_t)Mmax * 4 > (96ull << 20));
         if (window_major) e.digits.ensure((size_t)Mmax + 1);
         K::count(e.st, sh, d_scalars, is_mont, e.counts.p, window_major ? e.digits.p : nullptr);
         CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
@@ -440,12 +448,12 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     if (affine && sh.L <= AFF_MAX_L) {
         e.aff_nodes.ensure((size_t)chunks * sh.L * sizeof(AffinePt<C>));
         e.aff_suffix.ensure((size_t)chunks * ((sh.L + 1) / 2) * 32);
-        if (g_params.affine_split) {
+        if (P.affine_split) {
             e.aff_inv.ensure((size_t)chunks * 32);
-            e.launches += K::accumulate_affine_split(e.st, sh, chunks, (uint32_t)g_params.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p,
+            e.launches += K::accumulate_affine_split(e.st, sh, chunks, (uint32_t)P.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p,
                                                      (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p, e.aff_inv.p) - 1;
         } else {
-            K::accumulate_affine(e.st, sh, chunks, (uint32_t)g_params.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
+            K::accumulate_affine(e.st, sh, chunks, (uint32_t)P.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
                                  (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p);
         }
     }
@@ -461,7 +469,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     // (kernels_curve.cuh).  reduce_mode 0: running-sum levels (fan-in K) while many elements per window remain, then one
     // parallel weighting pass and block-level tree sums.
     const X *win = nullptr;
-    if (g_params.reduce_mode == 1 && sh.B >= 256) {
+    if (P.reduce_mode == 1 && sh.B >= 256) {
         uint32_t nb = sh.c - 1, chunks_max = K::fold_chunks_max(sh.B);
         e.fold_f.ensure((size_t)nwin * sh.B * sizeof(X));
         e.fold_partial.ensure((size_t)nwin * nb * chunks_max * sizeof(X));
@@ -484,7 +492,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
             cnt = cnt_out;
             m_log2 += klog;
             pp ^= 1;
-        } while (cnt > (uint32_t)g_params.running_sum_stop);
+        } while (cnt > (uint32_t)P.running_sum_stop);
         win = in_a;  // [nwin] once cnt == 1
         if (cnt > 1) {
             X *v = (X *)e.lvl_s[pp].p;
@@ -504,7 +512,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
             win = tin;
         }
     }
-    if (g_params.final_on_device && !table_c) {
+    if (P.final_on_device && !table_c) {
         K::final_horner(e.st, sh, win, (X *)e.result.p);
         e.launches++;
         CK(cudaMemcpyAsync(e.h_result, e.result.p, sizeof(X), cudaMemcpyDeviceToHost, e.st));
@@ -541,6 +549,7 @@ static void collect_timing(Engine &e) {
 
 struct Shard {
     int eng = 0;
+    int dev = -1;  // CUDA device of d_pts / d_table (valid after a later kgr_init re-numbered the engines)
     size_t first = 0, count = 0;
     void *d_pts = nullptr;
     void *d_table = nullptr;  // kgr_bases_precompute: W * count affine points, table[w * count + i] = 2^(c*w) * P_i
@@ -551,7 +560,16 @@ struct Shard {
 struct kgr_bases {
     int curve = 0;
     size_t n = 0;
+    uint64_t generation = 0;  // kgr_init that created it: a handle from an earlier kgr_init is refused by every call but kgr_bases_free
     std::vector<kgr::Shard> shards;
+    ~kgr_bases() {  // device memory goes with the handle, also when registration fails half way
+        for (auto &s : shards) {
+            if (s.dev < 0) continue;
+            cudaSetDevice(s.dev);
+            if (s.d_pts) cudaFree(s.d_pts);
+            if (s.d_table) cudaFree(s.d_table);
+        }
+    }
 };
 
 // An R1CS shape (A, B, C in CSR) resident on the first device (nova/src/relaxed_r1cs.rs R1csShape).
@@ -563,10 +581,19 @@ struct kgr_r1cs {
     kgr::Csr csr(int i) const { return kgr::Csr{row_ptr[i].p, cols[i].p, coeffs[i].p}; }
 };
 
+// A vector of field elements resident on the first device (nova: z, E, T between folding steps).
+struct kgr_vec {
+    int field = 0;
+    size_t n = 0;
+    uint64_t generation = 0;
+    kgr::DevBuf<uint32_t> d;
+};
+
 namespace kgr {
 
 template <class C> static void upload_shard(Engine &e, Shard &s, const uint64_t *xy, const uint8_t *inf) {
     CK(cudaSetDevice(e.dev));
+    s.dev = e.dev;
     CK(cudaMalloc(&s.d_pts, std::max<size_t>(s.count, 1) * sizeof(AffinePt<C>)));
     if (s.count == 0) return;
     upload_from_host(e, s.d_pts, xy + (sizeof(AffinePt<C>) / 8) * s.first, s.count * sizeof(AffinePt<C>), e.st);
@@ -639,6 +666,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         cudaEvent_t after = nullptr;  // pieces of one call: this piece's uploads start when the previous piece's are on the device
         size_t eng = 0;               // index of the device's engine (pieces of one device form a group)
     };
+    const Params P = t_params;  // the calling thread's tuning state, handed to every engine this call drives
     std::vector<Job> jobs;
     for (auto &s : shards) {
         size_t lo = std::max(off, s.first), hi = std::min(off + n, s.first + s.count);
@@ -660,7 +688,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
     if (!on_device) {
         std::vector<Job> cut;
         for (const Job &whole : jobs) {
-            size_t k = g_params.oneshot_split > 0 ? (size_t)g_params.oneshot_split
+            size_t k = P.oneshot_split > 0 ? (size_t)P.oneshot_split
                                                   : std::max<size_t>(1, std::min<size_t>(4, whole.count >> (hp ? 19 : 21)));  // scalars only: a third of the traffic, larger pieces
             if (k > 1) {
                 ensure_lanes(whole.eng, k);
@@ -691,6 +719,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         try {
             Job &jb = jobs[j];
             Engine &e = *jb.e;
+            e.params = P;
             CK(cudaSetDevice(e.dev));
             if (jb.after) CK(cudaStreamWaitEvent(e.st, jb.after, 0));
             CK(cudaEventRecord(e.ev[EV_START], e.st));
@@ -798,7 +827,8 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
 }
 
 // ---- kgr_msm_batch: one single-shard MSM per lane, started without waiting and finished later --------------------------
-template <class C> static void lane_start(Engine &e, const Shard &s, size_t off, const uint64_t *scalars, int fmt, size_t n) {
+template <class C> static void lane_start(Engine &e, const Params &P, const Shard &s, size_t off, const uint64_t *scalars, int fmt, size_t n) {
+    e.params = P;
     CK(cudaSetDevice(e.dev));
     CK(cudaEventRecord(e.ev[EV_START], e.st));
     e.scalars.ensure(std::max<size_t>(n, 1) * 8);
@@ -945,6 +975,7 @@ template <class C> static const AffinePt<C> *fixed_table(Engine &e) {
 template <class C> static void generate_shard(Engine &e, Shard &s, uint64_t seed, uint64_t first, uint64_t *k_out) {
     typedef Fp<typename C::Scalar> S;
     CK(cudaSetDevice(e.dev));
+    s.dev = e.dev;
     CK(cudaMalloc(&s.d_pts, std::max<size_t>(s.count, 1) * sizeof(AffinePt<C>)));
     if (!s.count) return;
     S *dk = nullptr;
@@ -1126,6 +1157,7 @@ int kgr_init(const int *devices, int n_devices) {
         }
         g_engines.resize(devs.size());
         for (size_t i = 0; i < devs.size(); i++) g_engines[i].init(devs[i]);
+        g_generation++;
         return KGR_OK;
     });
 }
@@ -1141,21 +1173,20 @@ int kgr_shutdown(void) {
 int kgr_device_count(void) { return (int)g_engines.size(); }
 
 int kgr_set_param(const char *name, long value) {
-    std::lock_guard<std::mutex> lk(g_mu);
     std::string s(name ? name : "");
-    if (s == "window_bits") g_params.window_bits = value;
-    else if (s == "chunk") g_params.chunk = value;
+    if (s == "window_bits") t_params.window_bits = value;
+    else if (s == "chunk") t_params.chunk = value;
     else if (s == "reduce_fanin") {
         if (value < 2 || (value & (value - 1))) return fail(KGR_E_ARG, "reduce_fanin must be a power of two >= 2");
-        g_params.reduce_fanin = value;
-    } else if (s == "final_on_device") g_params.final_on_device = value;
-    else if (s == "running_sum_stop") g_params.running_sum_stop = std::max<long>(1, value);
-    else if (s == "sort_mode") g_params.sort_mode = value;
-    else if (s == "reduce_mode") g_params.reduce_mode = value;
-    else if (s == "affine_split") g_params.affine_split = value;
-    else if (s == "lane_threads") g_params.lane_threads = value ? 1 : 0;
-    else if (s == "oneshot_split") g_params.oneshot_split = std::min<long>(std::max<long>(value, 0), (long)MAX_LANES);
-    else if (s == "affine_rounds") g_params.affine_rounds = std::min<long>(std::max<long>(value, 0), 6);
+        t_params.reduce_fanin = value;
+    } else if (s == "final_on_device") t_params.final_on_device = value;
+    else if (s == "running_sum_stop") t_params.running_sum_stop = std::max<long>(1, value);
+    else if (s == "sort_mode") t_params.sort_mode = value;
+    else if (s == "reduce_mode") t_params.reduce_mode = value;
+    else if (s == "affine_split") t_params.affine_split = value;
+    else if (s == "lane_threads") t_params.lane_threads = value ? 1 : 0;
+    else if (s == "oneshot_split") t_params.oneshot_split = std::min<long>(std::max<long>(value, 0), (long)MAX_LANES);
+    else if (s == "affine_rounds") t_params.affine_rounds = std::min<long>(std::max<long>(value, 0), 6);
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
 }
@@ -1167,14 +1198,15 @@ int kgr_bases_register(int curve, const uint64_t *xy, const uint8_t *inf, size_t
     if (curve < KGR_CURVE_BN254_G1 || curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
     if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 bases per vector");
     return guarded([&]() -> int {
-        kgr_bases *b = new kgr_bases;
+        std::unique_ptr<kgr_bases> b(new kgr_bases);  // frees the shards uploaded so far if a later one throws
         b->curve = curve;
         b->n = n;
+        b->generation = g_generation;
         make_shards(b->shards, n);
 #define CALL(C) for (auto &s : b->shards) upload_shard<C>(g_engines[s.eng], s, xy, inf)
         DISPATCH(curve, CALL);
 #undef CALL
-        *out = b;
+        *out = b.release();
         return KGR_OK;
     });
 }
@@ -1182,13 +1214,7 @@ int kgr_bases_register(int curve, const uint64_t *xy, const uint8_t *inf, size_t
 int kgr_bases_free(kgr_bases_t *b) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!b) return KGR_OK;
-    for (auto &s : b->shards)
-        if (s.d_pts && s.eng < (int)g_engines.size()) {
-            cudaSetDevice(g_engines[s.eng].dev);
-            cudaFree(s.d_pts);
-            if (s.d_table) cudaFree(s.d_table);
-        }
-    delete b;
+    delete b;  // ~kgr_bases frees the shards on the devices they were allocated on, whatever kgr_init has done since
     return KGR_OK;
 }
 
@@ -1198,6 +1224,7 @@ int kgr_bases_precompute(kgr_bases_t *b, int window_bits) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     if (!b) return fail(KGR_E_ARG, "null pointer");
+    if (b->generation != g_generation) return fail(KGR_E_ARG, "base handle was created before the last kgr_init");
     if (window_bits < 0 || window_bits > 24) return fail(KGR_E_ARG, "window_bits out of range");
     return guarded([&]() -> int {
         for (auto &s : b->shards) {
@@ -1225,6 +1252,7 @@ int kgr_bases_precompute(kgr_bases_t *b, int window_bits) {
 static int msm_common(kgr_bases_t *b, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t *out) {
     if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
     if (!b || !out || (!scalars && n)) return fail(KGR_E_ARG, "null pointer");
+    if (b->generation != g_generation) return fail(KGR_E_ARG, "base handle was created before the last kgr_init");
     if (off > b->n || n > b->n - off) return fail(KGR_E_ARG, "range exceeds the registered vector");
     if (fmt != KGR_SCALARS_MONTGOMERY && fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
     return guarded([&]() -> int {
@@ -1271,7 +1299,9 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
         if (jb.base_off > jb.bases->n || jb.n > jb.bases->n - jb.base_off) return fail(KGR_E_ARG, "range exceeds the registered vector");
         if (jb.scalar_fmt != KGR_SCALARS_MONTGOMERY && jb.scalar_fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
         if (jb.bases->curve < KGR_CURVE_BN254_G1 || jb.bases->curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
+        if (jb.bases->generation != g_generation) return fail(KGR_E_ARG, "base handle was created before the last kgr_init");
     }
+    const Params P = t_params;
     return guarded([&]() -> int {
         size_t n_lanes = std::min(n_jobs, MAX_LANES);
         ensure_lanes(0, n_lanes);
@@ -1280,6 +1310,7 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
         // host (Horner over the window sums), so neither the enqueue work nor the host finish of one job delays another lane
         std::vector<CudaError> errs(n_lanes, CudaError{cudaSuccess, "", 0});
         std::vector<int> rcs(n_lanes, KGR_OK);
+        std::vector<std::string> msgs(n_lanes);  // kgr_last_error is per thread: a worker's text is carried back to the caller
         auto worker = [&](size_t li) {
             try {
                 // static assignment (job j on lane j mod lanes): a lane sees the same jobs in every call of a repeated batch, so its grow-only
@@ -1293,12 +1324,15 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
 #undef CALL
                             return KGR_OK;
                         }
-#define CALL(C) lane_start<C>(lane(li), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n); lane_finish<C>(lane(li), jb.out)
+#define CALL(C) lane_start<C>(lane(li), P, jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n); lane_finish<C>(lane(li), jb.out)
                         DISPATCH(jb.bases->curve, CALL);
 #undef CALL
                         return KGR_OK;
                     }();
-                    if (rcs[li]) break;
+                    if (rcs[li]) {
+                        msgs[li] = g_err;
+                        break;
+                    }
                 }
             } catch (CudaError &ce) {
                 errs[li] = ce;
@@ -1310,8 +1344,8 @@ int kgr_msm_batch(const kgr_msm_job_t *jobs, size_t n_jobs) {
         for (auto &t : th) t.join();
         for (auto &ce : errs)
             if (ce.e != cudaSuccess) throw ce;
-        for (int rc : rcs)
-            if (rc) return rc;
+        for (size_t li = 0; li < n_lanes; li++)
+            if (rcs[li]) return fail(rcs[li], msgs[li]);
         return KGR_OK;
     });
 }
@@ -1338,6 +1372,7 @@ int kgr_msm_oneshot(int curve, const uint64_t *xy, const uint8_t *inf, size_t n_
 int kgr_bases_download(const kgr_bases_t *b, size_t off, size_t n, uint64_t *xy_out) {
     std::lock_guard<std::mutex> lk(g_mu);
     if (!b || (!xy_out && n)) return fail(KGR_E_ARG, "null pointer");
+    if (b->generation != g_generation) return fail(KGR_E_ARG, "base handle was created before the last kgr_init");
     if (off > b->n || n > b->n - off) return fail(KGR_E_ARG, "range exceeds the registered vector");
     return guarded([&]() -> int {
         for (auto &s : b->shards) {
@@ -1492,6 +1527,7 @@ int kgr_groth16_h(unsigned log_n, const uint64_t *a, const uint64_t *b, const ui
 int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const uint64_t *c, size_t m, kgr_bases_t *h, uint64_t *h_out, uint64_t *q_out,
                      size_t *q_len, const kgr_msm_job_t *jobs, size_t n_jobs) {
     if (log_n < 1 || log_n > 28 || !a || !b || !c || !h || !h_out || (!jobs && n_jobs)) return fail(KGR_E_ARG, "bad argument");
+    if (h->curve != KGR_CURVE_BN254_G1) return fail(KGR_E_ARG, "the h query must be a BN254 G1 vector (its scalars are the Fr coefficients of H, its result 12 words)");
     const size_t n = (size_t)1 << log_n;
     bool fused;
     {
@@ -1519,16 +1555,21 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
         if (jb.base_off > jb.bases->n || jb.n > jb.bases->n - jb.base_off) return fail(KGR_E_ARG, "range exceeds the registered vector");
         if (jb.scalar_fmt != KGR_SCALARS_MONTGOMERY && jb.scalar_fmt != KGR_SCALARS_CANONICAL) return fail(KGR_E_ARG, "unknown scalar format");
         if (jb.bases->curve < KGR_CURVE_BN254_G1 || jb.bases->curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
+        if (jb.bases->generation != g_generation) return fail(KGR_E_ARG, "base handle was created before the last kgr_init");
     }
+    if (h->generation != g_generation) return fail(KGR_E_ARG, "base handle was created before the last kgr_init");
+    const Params P = t_params;
     return guarded([&]() -> int {
         const size_t n_lanes = std::min(n_jobs + 1, MAX_LANES);
         ensure_lanes(0, n_lanes);
         std::vector<CudaError> errs(n_lanes, CudaError{cudaSuccess, "", 0});
         std::vector<int> rcs(n_lanes, KGR_OK);
+        std::vector<std::string> msgs(n_lanes);
         // lane 0: H on the device, then the h query with q as device-resident scalars (no D2H / H2D of q on the critical path)
         const size_t nh = std::min(n, h->n);  // zip(q, h): coefficients beyond the degree are zero, so the unstripped q gives the same sum
         auto h_start = [&]() {
             Engine &e = g_engines[0];
+            e.params = P;
             CK(cudaSetDevice(e.dev));
             NttDomain &d = ntt_domain(e, log_n);
             CK(cudaEventRecord(e.ev[EV_START], e.st));
@@ -1554,14 +1595,14 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
                 if (q_len) *q_len = stripped_len(q_out, n);
             }
         };
-        if (!g_params.lane_threads) {
+        if (!P.lane_threads) {
             // one host thread: enqueue everything (lane 0 first), then collect in order.  Slower than a thread per lane when the host cores are awake,
             // less sensitive to sleeping cores (profiles/r01_next_rows.md)
             h_start();
             for (size_t j = 0; j < n_jobs; j++) {
                 const kgr_msm_job_t &jb = jobs[j];
                 if (jb.n == 0) continue;
-#define CALL(C) lane_start<C>(lane_of(0, 1 + j), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n)
+#define CALL(C) lane_start<C>(lane_of(0, 1 + j), P, jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n)
                 DISPATCH(jb.bases->curve, CALL);
 #undef CALL
             }
@@ -1599,12 +1640,15 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
 #undef CALL
                             return KGR_OK;
                         }
-#define CALL(C) lane_start<C>(lane_of(0, li), jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n); lane_finish<C>(lane_of(0, li), jb.out)
+#define CALL(C) lane_start<C>(lane_of(0, li), P, jb.bases->shards[0], jb.base_off, jb.scalars, jb.scalar_fmt, jb.n); lane_finish<C>(lane_of(0, li), jb.out)
                         DISPATCH(jb.bases->curve, CALL);
 #undef CALL
                         return KGR_OK;
                     }();
-                    if (rcs[li]) break;
+                    if (rcs[li]) {
+                        msgs[li] = g_err;
+                        break;
+                    }
                 }
             } catch (CudaError &ce) {
                 errs[li] = ce;
@@ -1616,8 +1660,8 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
         for (auto &t : th) t.join();
         for (auto &ce : errs)
             if (ce.e != cudaSuccess) throw ce;
-        for (int rc : rcs)
-            if (rc) return rc;
+        for (size_t li = 0; li < n_lanes; li++)
+            if (rcs[li]) return fail(rcs[li], msgs[li]);
         return KGR_OK;
     });
 }
@@ -1683,14 +1727,15 @@ int kgr_bases_generate_at(int curve, uint64_t seed, uint64_t first, size_t n, kg
     if (curve < KGR_CURVE_BN254_G1 || curve > KGR_CURVE_BN254_G2) return fail(KGR_E_ARG, "unknown curve id");
     if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 bases per vector");
     return guarded([&]() -> int {
-        kgr_bases *b = new kgr_bases;
+        std::unique_ptr<kgr_bases> b(new kgr_bases);
         b->curve = curve;
         b->n = n;
+        b->generation = g_generation;
         make_shards(b->shards, n);
 #define CALL(C) for (auto &s : b->shards) generate_shard<C>(g_engines[s.eng], s, seed, first, k_out)
         DISPATCH(curve, CALL);
 #undef CALL
-        *out = b;
+        *out = b.release();
         return KGR_OK;
     });
 }
@@ -1836,6 +1881,178 @@ int kgr_vec_fold(int field, const uint64_t *a, const uint64_t *b, const uint64_t
         CK(cudaStreamSynchronize(e.st));
         return KGR_OK;
     });
+}
+
+// ---- device-resident vectors (Nova residency) ------------------------------------------------------------------------------------------------
+static int vec_check(const kgr_vec *v) {
+    if (!v) return fail(KGR_E_ARG, "null vector");
+    if (v->generation != g_generation) return fail(KGR_E_ARG, "vector handle was created before the last kgr_init");
+    return KGR_OK;
+}
+
+int kgr_vec_upload(int field, const uint64_t *host, size_t n, kgr_vec_t **out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if ((field != 0 && field != 1) || !out) return fail(KGR_E_ARG, "bad argument");
+    if (n >= (1ull << 31)) return fail(KGR_E_TOO_LARGE, "at most 2^31 - 1 elements");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        std::unique_ptr<kgr_vec> v(new kgr_vec);
+        v->field = field;
+        v->n = n;
+        v->generation = g_generation;
+        v->d.ensure(std::max<size_t>(n, 1) * 8);
+        if (host) upload_from_host(e, v->d.p, host, n * 32, e.st);
+        else CK(cudaMemsetAsync(v->d.p, 0, std::max<size_t>(n, 1) * 32, e.st));
+        CK(cudaStreamSynchronize(e.st));
+        *out = v.release();
+        return KGR_OK;
+    });
+}
+
+int kgr_vec_free(kgr_vec_t *v) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!v) return KGR_OK;
+    if (!g_engines.empty()) cudaSetDevice(g_engines[0].dev);
+    v->d.release();
+    delete v;
+    return KGR_OK;
+}
+
+size_t kgr_vec_len(const kgr_vec_t *v) { return v ? v->n : 0; }
+
+int kgr_vec_download(const kgr_vec_t *v, size_t off, size_t n, uint64_t *host) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (int rc = vec_check(v)) return rc;
+    if (off > v->n || n > v->n - off || (!host && n)) return fail(KGR_E_ARG, "range exceeds the vector");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        download_to_host(e, host, v->d.p + 8 * off, n * 32, e.st);
+        return KGR_OK;
+    });
+}
+
+int kgr_vec_write(kgr_vec_t *v, size_t off, const uint64_t *host, size_t n) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (int rc = vec_check(v)) return rc;
+    if (off > v->n || n > v->n - off || (!host && n)) return fail(KGR_E_ARG, "range exceeds the vector");
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        upload_from_host(e, v->d.p + 8 * off, host, n * 32, e.st);
+        CK(cudaStreamSynchronize(e.st));
+        return KGR_OK;
+    });
+}
+
+int kgr_vec_fold_device(const kgr_vec_t *a, const kgr_vec_t *b, const uint64_t r[4], kgr_vec_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (int rc = vec_check(a)) return rc;
+    if (int rc = vec_check(b)) return rc;
+    if (int rc = vec_check(out)) return rc;
+    if (!r) return fail(KGR_E_ARG, "null pointer");
+    if (a->field != b->field || a->field != out->field) return fail(KGR_E_ARG, "vectors of different fields");
+    if (a->n < out->n || b->n < out->n) return fail(KGR_E_ARG, "inputs shorter than the output vector");
+    if (!out->n) return KGR_OK;
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        uint32_t r8[8];
+        std::memcpy(r8, r, 32);
+        LaunchR1cs::vec_fold(e.st, out->field, (uint32_t)out->n, a->d.p, b->d.p, r8, out->d.p);
+        e.launches++;
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(e.st));
+        return KGR_OK;
+    });
+}
+
+int kgr_msm_vec(kgr_bases_t *b, size_t base_off, const kgr_vec_t *scalars, size_t sc_off, size_t n, uint64_t *out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (int rc = vec_check(scalars)) return rc;
+    if (!b) return fail(KGR_E_ARG, "null pointer");
+    if (sc_off > scalars->n || n > scalars->n - sc_off) return fail(KGR_E_ARG, "range exceeds the scalar vector");
+    if ((b->curve == KGR_CURVE_GRUMPKIN ? 0 : 1) != scalars->field) return fail(KGR_E_ARG, "the vector's field is not the scalar field of the curve");
+    if (b->shards.size() != 1 || b->shards[0].eng != 0) return fail(KGR_E_ARG, "the bases must live on the first device only");
+    return msm_common(b, base_off, reinterpret_cast<const uint64_t *>(scalars->d.p + 8 * sc_off), true, KGR_SCALARS_MONTGOMERY, n, out);
+}
+
+int kgr_pedersen_commit_vec(kgr_bases_t *ck, const kgr_vec_t *m, size_t sc_off, size_t n, uint64_t *out) {
+    if (!ck || !m) return fail(KGR_E_ARG, "null pointer");
+    uint64_t proj[24];
+    size_t pairs = std::min(n, ck->n);  // m.iter().zip(self.g.iter()), nova/src/pedersen.rs:16-17
+    int rc = kgr_msm_vec(ck, 0, m, sc_off, pairs, proj);
+    if (rc) return rc;
+    return kgr_to_affine(ck->curve, proj, out);
+}
+
+int kgr_nova_cross_term_device(kgr_r1cs_t *s, const kgr_vec_t *z1, const kgr_vec_t *z2, kgr_vec_t *t, kgr_bases_t *ck, uint64_t *commit_out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+    if (!s || (ck && !commit_out)) return fail(KGR_E_ARG, "bad argument");
+    if (int rc = vec_check(z1)) return rc;
+    if (int rc = vec_check(z2)) return rc;
+    if (t)
+        if (int rc = vec_check(t)) return rc;
+    if (z1->field != s->field || z2->field != s->field || (t && t->field != s->field)) return fail(KGR_E_ARG, "vector field does not match the R1CS field");
+    if (z1->n < s->n_z || z2->n < s->n_z || (t && t->n < s->m)) return fail(KGR_E_ARG, "vector shorter than the shape needs");
+    if (ck) {
+        int scalar_field = ck->curve == KGR_CURVE_GRUMPKIN ? 0 : 1;
+        if (scalar_field != s->field) return fail(KGR_E_ARG, "commitment key curve does not match the R1CS field");
+        if (ck->shards.size() != 1 || ck->shards[0].eng != 0) return fail(KGR_E_ARG, "the commitment key must live on the first device only");
+        if (ck->generation != g_generation) return fail(KGR_E_ARG, "base handle was created before the last kgr_init");
+    }
+    return guarded([&]() -> int {
+        Engine &e = g_engines[0];
+        CK(cudaSetDevice(e.dev));
+        uint32_t *d_t = t ? t->d.p : s->t.p;
+        CK(cudaEventRecord(e.aux_ev[1], e.st));
+        LaunchR1cs::cross_term(e.st, s->field, (uint32_t)s->m, s->csr(0), s->csr(1), s->csr(2), z1->d.p, z2->d.p, d_t);
+        e.launches++;
+        CK(cudaGetLastError());
+        CK(cudaEventRecord(e.aux_ev[2], e.st));
+        s->ms[0] = 0;
+        s->ms[2] = 0;
+        if (ck) {
+            uint64_t proj[24];
+            size_t pairs = std::min(s->m, ck->n);
+#define CALL(C) run_msm<C>(ck->shards, 0, reinterpret_cast<const uint64_t *>(d_t), true, KGR_SCALARS_MONTGOMERY, pairs, proj, nullptr)
+            DISPATCH(ck->curve, CALL);
+#undef CALL
+            s->ms[2] = e.last_ms[0];
+#define CALL(C) proj_to_affine_host<C>(proj, commit_out)
+            DISPATCH(ck->curve, CALL);
+#undef CALL
+        } else {
+            CK(cudaStreamSynchronize(e.st));
+        }
+        cudaEventElapsedTime(&s->ms[1], e.aux_ev[1], e.aux_ev[2]);
+        return KGR_OK;
+    });
+}
+
+int kgr_host_alloc(size_t bytes, void **out) {
+    if (!out) return fail(KGR_E_ARG, "null pointer");
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        if (g_engines.empty()) return fail(KGR_E_NOT_INIT, "kgr_init has not been called");
+        cudaSetDevice(g_engines[0].dev);
+    }
+    return guarded([&]() -> int {
+        CK(cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable));
+        return KGR_OK;
+    });
+}
+
+int kgr_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+    return KGR_OK;
 }
 
 int kgr_microbench(double r[8]) {

@@ -86,3 +86,69 @@ def vec_fold(field, a, b, r):
     out = np.zeros_like(a)
     _lib.check(_lib.lib().kgr_vec_fold(field, _u64(a), _u64(b), _u64(r), a.shape[0], _u64(out)))
     return out
+
+
+class DeviceVec:
+    """A vector of field elements that stays on the GPU between folding steps (kgr_vec_t): nova's z = (u, x, w), E, T.
+    `RelaxedR1csWitness { w, e }` (nova/src/relaxed_r1cs/witness.rs:20-21) with both members resident is two of these."""
+
+    def __init__(self, field, values=None, n=None):
+        _lib.ensure_init()
+        self.field = field
+        h = ctypes.c_void_p()
+        if values is not None:
+            v = _c(values).reshape(-1, 4)
+            self.n = v.shape[0]
+            _lib.check(_lib.lib().kgr_vec_upload(field, _u64(v), self.n, ctypes.byref(h)))
+        else:
+            self.n = int(n)
+            _lib.check(_lib.lib().kgr_vec_upload(field, None, self.n, ctypes.byref(h)))
+        self._h = h
+
+    def __len__(self):
+        return self.n
+
+    def download(self, off=0, n=None):
+        n = self.n - off if n is None else n
+        out = np.zeros((n, 4), dtype=np.uint64)
+        _lib.check(_lib.lib().kgr_vec_download(self._h, off, n, _u64(out)))
+        return out
+
+    def write(self, off, values):
+        v = _c(values).reshape(-1, 4)
+        _lib.check(_lib.lib().kgr_vec_write(self._h, off, _u64(v), v.shape[0]))
+
+    def fold(self, other, r, out=None):
+        """self + other * r element-wise on the device (witness.rs:67-68); out defaults to self (in place) and is returned."""
+        out = out or self
+        r = _c(r).reshape(4)
+        _lib.check(_lib.lib().kgr_vec_fold_device(self._h, other._h, _u64(r), out._h))
+        return out
+
+    def commit(self, ck, off=0, n=None):
+        """PedersenCommitment::commit of elements [off, off + n) without leaving the device -> (9,) x, y, is_infinity."""
+        bases = getattr(ck, "g", ck)
+        n = self.n - off if n is None else n
+        out = np.zeros(9, dtype=np.uint64)
+        _lib.check(_lib.lib().kgr_pedersen_commit_vec(bases._h, self._h, off, n, _u64(out)))
+        return out
+
+    def free(self):
+        if getattr(self, "_h", None):
+            _lib.lib().kgr_vec_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def cross_term_device(shape, z1, z2, t=None, ck=None):
+    """compute_cross_term with z1, z2 (DeviceVec) resident; T stays in `t` (DeviceVec) — -> commit (9,) when a key is given."""
+    bases = getattr(ck, "g", ck)
+    commit = np.zeros(9, dtype=np.uint64) if bases is not None else None
+    _lib.check(_lib.lib().kgr_nova_cross_term_device(shape._h, z1._h, z2._h, t._h if t is not None else None, bases._h if bases is not None else None,
+                                                     _u64(commit) if commit is not None else None))
+    return commit

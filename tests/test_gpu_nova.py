@@ -112,3 +112,62 @@ def test_register_rejects_malformed_csr(k):
     bad_ptr = (np.array([0, 2, 1], dtype=np.uint32), good[1], good[2])
     with pytest.raises(AssertionError):
         nova.R1csShape(A.FIELD_FR, 2, 2, bad_ptr, good, good)
+
+
+@pytest.mark.parametrize("curve", [A.GRUMPKIN, A.BN254_G1])
+def test_resident_folding_step(k, curve):
+    """One NIFS step with z1, z2, E, T resident on the GPU (witness.rs:20-21,56-71; prover.rs:33-35; ivc.rs:160-205): the witness commitment
+    from z[1 + l ..], the cross term and its commitment, and both folds never cross PCIe — every value equals the host-buffer path / the
+    oracle, and the folded (z, E) still satisfies the relaxed relation."""
+    from kogarashi_b200 import nova
+    fid = A.SCALAR_FIELD[curve]
+    p = B.FQ if fid == A.FIELD_FQ else B.FR
+    m, n_z, mats, z1_int = chain_r1cs(700, 3, p)
+    z2_int = chain_r1cs(700, 5, p)[3]
+    z1, z2 = mont(z1_int, p), mont(z2_int, p)
+    l = 3                                                              # z = (u, x0, out | w)
+    shape = nova.R1csShape(fid, m, n_z, *mats)
+    ck = k.PedersenCommitment(curve, A.random_points(curve, max(m, n_z), seed=bytes(range(5, 21))))
+    d_z1, d_z2 = nova.DeviceVec(fid, z1), nova.DeviceVec(fid, z2)
+    d_e, d_t = nova.DeviceVec(fid, n=m), nova.DeviceVec(fid, n=m)
+    assert len(d_z1) == n_z and (d_z1.download() == z1).all() and (d_e.download() == 0).all()
+    # commit(W) of the incoming witness straight from the resident z (R1csWitness::commit, relaxed_r1cs.rs:36)
+    assert same_affine(d_z2.commit(ck, off=l), ck.commit(z2[l:]))
+    assert same_affine(d_z2.commit(ck, off=l, n=100), ck.commit(z2[l:l + 100]))
+    # T and commit(T)
+    commit_t = nova.cross_term_device(shape, d_z1, d_z2, t=d_t, ck=ck)
+    t_ref = A.cross_term(fid, m, *mats, z1, z2)
+    assert (d_t.download() == t_ref).all()
+    assert same_affine(commit_t, ck.commit(t_ref))
+    assert nova.cross_term_device(shape, d_z1, d_z2, t=d_t) is None     # without a key: T only
+    # folds in place: z <- z1 + r z2, E <- E + r T
+    r = 0x1F2E3D4C5B6A79880123456789ABCDEF % p
+    rm = mont([r], p)[0]
+    d_z1.fold(d_z2, rm)
+    d_e.fold(d_t, rm)
+    assert (d_z1.download() == A.vec_fold(fid, z1, z2, rm)).all()
+    assert (d_e.download() == A.vec_fold(fid, np.zeros_like(t_ref), t_ref, rm)).all()
+    assert relaxed_sat(shape.prod, m, mats, ints(d_z1.download(), p), ints(d_e.download(), p), p)
+    # a second step on the folded state, with the fresh instance written into the resident z2
+    z3 = mont(chain_r1cs(700, 7, p)[3], p)
+    d_z2.write(0, z3)
+    zf, ef = d_z1.download(), d_e.download()
+    commit_t2 = nova.cross_term_device(shape, d_z1, d_z2, t=d_t, ck=ck)
+    t2_ref = A.cross_term(fid, m, *mats, zf, z3)
+    assert same_affine(commit_t2, ck.commit(t2_ref))
+    d_z1.fold(d_z2, rm)
+    d_e.fold(d_t, rm)
+    assert relaxed_sat(shape.prod, m, mats, ints(d_z1.download(), p), ints(d_e.download(), p), p)
+    # errors: wrong field, short vector, range
+    other = nova.DeviceVec(1 - fid, n=n_z)
+    with pytest.raises(k.KgrError):
+        nova.cross_term_device(shape, d_z1, other)
+    with pytest.raises(k.KgrError):
+        d_z1.fold(other, rm)
+    with pytest.raises(k.KgrError):
+        nova.cross_term_device(shape, d_z1, nova.DeviceVec(fid, n=n_z - 1))
+    with pytest.raises(k.KgrError):
+        d_z1.download(n_z - 1, 2)
+    for v in (d_z1, d_z2, d_e, d_t, other):
+        v.free()
+    shape.free()

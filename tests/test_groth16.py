@@ -209,3 +209,43 @@ def test_scaled_prover_on_gpu(steps, precompute):
     A1, B1, C1 = prover.prove(q, mont(cs.x), mont(cs.w), r, s)
     assert (A1 == A).all() and (B1 == Bp).all() and (C1 == C).all()
     prover.free()
+
+
+@pytest.mark.gpu
+def test_prover_refuses_identity_delta(fixture):
+    """prover.rs:67-69: `if vk.delta_g1.is_identity() || vk.delta_g2.is_identity() { return Err(Error::ProverSubVersionCrsAttack) }` —
+    in the reference's encoding (0, R, is_infinity = true), with the flag passed through vk_inf / vk_g2_inf, and as all-zero coordinates."""
+    import kogarashi_b200 as k
+    from kogarashi_b200.groth16 import Groth16G1Prover, Groth16Prover, ProverSubVersionCrsAttack
+    k.init()
+    P, trap, uvw, proof, internals = fixture
+    vk = P["vk"]
+    one = lambda p: _pts([p])[0][0]
+    one2 = lambda p: _pts_g2([p])[0][0]
+    g1_args = (*_pts(P["a"]), *_pts(P["b_g1"]), *_pts(P["h"]), *_pts(P["l"]))
+    ident_g1 = np.zeros(8, dtype=np.uint64)
+    ident_g1[4:] = B.int_to_limbs(B.to_mont(1, B.FQ))                     # (0, R): the reference's affine identity coordinates
+    with pytest.raises(ProverSubVersionCrsAttack):
+        Groth16G1Prover(ident_g1, one(vk["alpha_g1"]), one(vk["beta_g1"]), *g1_args, vk_inf=[1, 0, 0])
+    with pytest.raises(ProverSubVersionCrsAttack):
+        Groth16G1Prover(np.zeros(8, dtype=np.uint64), one(vk["alpha_g1"]), one(vk["beta_g1"]), *g1_args)
+    ident_g2 = np.zeros(16, dtype=np.uint64)
+    ident_g2[8:12] = B.int_to_limbs(B.to_mont(1, B.FQ))
+    with pytest.raises(ProverSubVersionCrsAttack):
+        Groth16Prover(one(vk["delta_g1"]), one(vk["alpha_g1"]), one(vk["beta_g1"]), *g1_args, ident_g2, one2(vk["beta_g2"]), *_pts_g2(P["b_g2"]), vk_g2_inf=[1, 0])
+    # an identity alpha / beta is legal for the prover: the flag reaches the device and the proof equals the one computed without that term
+    prover = Groth16G1Prover(one(vk["delta_g1"]), ident_g1, one(vk["beta_g1"]), *g1_args, vk_inf=[0, 1, 0])
+    a_pt, _ = prover.commitments(internals["q"], internals["inputs"], internals["aux"], internals["r"], internals["s"])
+    ref = Groth16G1Prover(one(vk["delta_g1"]), one(vk["alpha_g1"]), one(vk["beta_g1"]), *g1_args)
+    a_ref, _ = ref.commitments(internals["q"], internals["inputs"], internals["aux"], internals["r"], internals["s"])
+    minus_alpha = np.concatenate([one(vk["alpha_g1"])[:4], A_field_neg(one(vk["alpha_g1"])[4:])])
+    exp = k.to_affine(k.BN254_G1, k.msm_curve_addition(np.stack([a_ref[:8], minus_alpha]), np.array([[1, 0, 0, 0], [1, 0, 0, 0]], dtype=np.uint64),
+                                                       curve=k.BN254_G1, scalar_fmt=k.SCALARS_CANONICAL))
+    assert (a_pt == exp).all()
+    prover.free()
+    ref.free()
+
+
+def A_field_neg(y):
+    from oracle import oracle as A_
+    return A_.field_op(A_.FIELD_FQ, "neg", np.asarray(y, dtype=np.uint64))
