@@ -473,3 +473,12 @@ def test_gpu_matches_alt_bn128_kat(k):
         sc = np.array([B.int_to_limbs(B.to_mont(v, B.FR)) for v in parts], dtype=np.uint64)
         assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc)), exp), name
         bases.free()
+
+
+def test_gpu_matches_reference_binary_vectors(k):
+    """The CUDA path against vectors printed by the Rust reference itself (skipped until tests/golden/msm_vectors_ref.npz exists)."""
+    from test_oracle import _ref_vectors
+    z, names = _ref_vectors()
+    for name in names:
+        got = k.msm_curve_addition(z[name + "_pts"], z[name + "_sc"], curve=A.BN254_G1, inf=z[name + "_inf"])
+        assert same_affine(k.to_affine(A.BN254_G1, got), z[name + "_aff"]), name

@@ -197,3 +197,21 @@ def test_oracle_matches_alt_bn128_kat():
         km = L(B.int_to_limbs(B.to_mont(k % B.FR, B.FR)))
         assert same_affine(A.to_affine(curve, A.scalar_point(curve, np.concatenate([p, one]), km)), exp), name
         assert same_affine(A.to_affine(curve, A.msm(curve, p.reshape(1, 8), km.reshape(1, 4))), exp), name
+
+
+def _ref_vectors():
+    import os
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "msm_vectors_ref.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/msm_vectors_ref.npz absent: it is produced by the Rust reference (oracle/_ref/README.md); no rustc/cargo in this image")
+    z = np.load(path)
+    return z, sorted({k[: -len("_aff")] for k in z.files if k.endswith("_aff")})
+
+
+def test_oracle_matches_reference_binary_vectors():
+    """Vectors printed by the reference's own msm_curve_addition (tests/golden/gen_from_reference.rs): the pin that turns parity from
+    'partial' into 'pinned'.  Skipped until a maintainer with cargo produces the file."""
+    z, names = _ref_vectors()
+    for name in names:
+        got = A.to_affine(A.BN254_G1, A.msm(A.BN254_G1, z[name + "_pts"], z[name + "_sc"], inf=z[name + "_inf"]))
+        assert same_affine(got, z[name + "_aff"]), name
