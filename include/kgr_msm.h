@@ -192,9 +192,9 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
  * switches from running sums to the parallel weighting pass), "final_on_device" (1: Horner over
  * windows in a one-thread kernel and one point per GPU in the D2H copy; 0 (default): the W window
  * sums come back in one D2H copy and the host applies the doublings), "sort_mode" (-1 auto, 0 counting sort with a per-scalar fill,
- * 1 counting sort with a window-major fill from stored digits, 2 two block-local radix partitions: the default from 2^21 entries on), "reduce_mode" (1 fold reduce, 0 running sums), "affine_rounds" (0: XYZZ bucket
- * accumulation; r > 0: the first r levels of every bucket sum are a pairwise tree of batched affine additions; experimental, see profiles/r01_affine.md), "affine_split" (with affine_rounds > 0:
- * 1 one kernel per phase, 0 one fused kernel), "oneshot_split" (pieces a large single-device kgr_msm_oneshot call is cut into so that uploads
+ * 1 counting sort with a window-major fill from stored digits, 2 two block-local radix partitions: the default from 2^21 entries on), "reduce_mode" (1 fold reduce, 0 running sums), "affine_levels" (levels of pairwise batched-affine
+ * sums inside every bucket before the XYZZ accumulation, affine_kernels.cuh: -1 (default) automatic from the entry count, 0 none, 1..5; 8-word curves only),
+ * "oneshot_split" (pieces a large single-device kgr_msm_oneshot call is cut into so that uploads
  * overlap the pipeline; 0 (default) = automatic: pieces of at least 2^19 pairs, at most 4; 1 = off), "lane_threads" (kgr_groth16_msms: 1 (default) one
  * host thread per lane, 0 everything enqueued from the calling thread). */
 /* The tuning state belongs to the CALLING THREAD: kgr_set_param changes the values used by MSMs this thread issues afterwards (the

@@ -33,28 +33,6 @@ __global__ void __launch_bounds__(TPB_ACC, acc_min_blocks<C>()) k_accumulate(Msm
     body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
 template <class C>
-__global__ void __launch_bounds__(TPB_ACC) k_accumulate_affine(MsmShape sh, uint32_t rounds, const AffinePt<C> *bases, const uint32_t *offsets,
-                                                               const uint32_t *entries, XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail,
-                                                               uint32_t *tail_bucket, AffinePt<C> *scratch_nodes, typename C::Elem *scratch_suffix) {
-    body_accumulate_affine<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, rounds, bases, offsets, entries, bucket_acc, head, tail, tail_bucket, scratch_nodes,
-                              scratch_suffix);
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_ACC) k_affine_phase1(MsmShape sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                                                           const AffinePt<C> *nodes, typename C::Elem *suffix, typename C::Elem *inv) {
-    body_affine_phase1<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, bases, offsets, entries, nodes, suffix, inv);
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_ACC) k_affine_phase2(MsmShape sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                                                           AffinePt<C> *nodes, const typename C::Elem *suffix, const typename C::Elem *inv) {
-    body_affine_phase2<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, bases, offsets, entries, nodes, suffix, inv);
-}
-template <class C>
-__global__ void __launch_bounds__(TPB_ACC, acc_min_blocks<C>()) k_affine_tail(MsmShape sh, uint32_t r, const uint32_t *offsets, const AffinePt<C> *nodes, XyzzPt<C> *bucket_acc,
-                                                            XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
-    body_affine_tail<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, r, offsets, nodes, bucket_acc, head, tail, tail_bucket);
-}
-template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
                                                    const XyzzPt<C> *tail, const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
     body_fixup<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);

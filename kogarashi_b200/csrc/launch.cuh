@@ -25,13 +25,12 @@ template <class C> struct Launch {
     static void fill(cudaStream_t st, const MsmShape &sh, const uint32_t *scalars, int is_mont, uint32_t *counts, const uint32_t *offsets, uint32_t *entries);
     static void accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks, const A *bases, const uint32_t *offsets, const uint32_t *entries, X *bucket_acc,
                            X *head, X *tail, uint32_t *tail_bucket);
-    static int accumulate_affine_blocks_per_sm();
-    static void accumulate_affine(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
-                                  const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix);
-    // one kernel per phase (2 * rounds + 1 launches); inv: one field element per chunk
-    static int accumulate_affine_split(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
-                                       const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix,
-                                       void *scratch_inv);
+    // Batched-affine tree levels (affine_kernels.cuh): level i reads off[i] / node array i (level 0: entries over bases) and writes off[i + 1] /
+    // nodes[i & 1]; cnt: G + 1 words of scratch.  Returns the number of launches.  out_max[i]: host-side bound of the nodes of level i + 1.
+    // pre: 8 words per node of the largest level, tot: 8 words per thread (affine_scratch_words gives both sizes for out_max[0])
+    static int affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const A *bases, const uint32_t *entries, uint32_t *const off[], A *const nodes[2],
+                             const uint32_t out_max[], uint32_t *cnt, uint32_t *tile_sums, uint32_t *pre, uint32_t *tot);
+    static void affine_scratch_words(uint32_t out_max0, size_t &pre_words, size_t &tot_words);
     static void fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
                       const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len);
     static void reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a,

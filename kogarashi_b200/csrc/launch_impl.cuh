@@ -1,13 +1,17 @@
 // launch_impl.cuh — definitions of Launch<C>; include once per curve and instantiate explicitly.
 // KGR_PART selects which member groups a translation unit defines (an explicit instantiation of the class instantiates only the
 // members defined at that point), so a curve whose kernels compile slowly (G2) can be spread over several TUs:
-// 1 scalar side + accumulate + fixup, 2 experimental batched-affine accumulate, 4 running-sum reduce, 8 fold reduce, 16 utilities.
+// 1 scalar side + accumulate + fixup, 2 batched-affine tree levels, 4 running-sum reduce, 8 fold reduce, 16 utilities.
 #pragma once
 #ifndef KGR_PART
 #define KGR_PART 31
 #endif
 #include "kernels_curve.cuh"
 #include "launch.cuh"
+#if KGR_PART & 2
+#include "affine_kernels.cuh"
+#include "scan.cuh"
+#endif
 
 namespace kgr {
 
@@ -37,28 +41,27 @@ void Launch<C>::accumulate(cudaStream_t st, const MsmShape &sh, uint32_t chunks,
 }
 #endif
 #if KGR_PART & 2
-template <class C> int Launch<C>::accumulate_affine_blocks_per_sm() {
-    int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_accumulate_affine<C>, TPB_ACC, 0);
-    return nb;
+static inline uint32_t affine_threads(uint32_t out_max) { return cdiv(cdiv(out_max, AFF_K), AFF_TPB) * AFF_TPB; }
+template <class C> void Launch<C>::affine_scratch_words(uint32_t out_max0, size_t &pre_words, size_t &tot_words) {
+    const size_t NT = affine_threads(out_max0), EW = El<typename C::Elem>::WORDS;
+    pre_words = NT * AFF_K * EW;
+    tot_words = NT * EW;
 }
 template <class C>
-void Launch<C>::accumulate_affine(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
-                                  const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix) {
-    k_accumulate_affine<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, rounds, bases, offsets, entries, bucket_acc, head, tail, tail_bucket,
-                                                                      (A *)scratch_nodes, (typename C::Elem *)scratch_suffix);
-}
-template <class C>
-int Launch<C>::accumulate_affine_split(cudaStream_t st, const MsmShape &sh, uint32_t chunks, uint32_t rounds, const A *bases, const uint32_t *offsets,
-                                       const uint32_t *entries, X *bucket_acc, X *head, X *tail, uint32_t *tail_bucket, void *scratch_nodes, void *scratch_suffix,
-                                       void *scratch_inv) {
-    typedef typename C::Elem F;
-    for (uint32_t r = 0; r < rounds; r++) {
-        k_affine_phase1<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, r, bases, offsets, entries, (const A *)scratch_nodes, (F *)scratch_suffix, (F *)scratch_inv);
-        k_affine_phase2<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, r, bases, offsets, entries, (A *)scratch_nodes, (const F *)scratch_suffix, (const F *)scratch_inv);
+int Launch<C>::affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const A *bases, const uint32_t *entries, uint32_t *const off[], A *const nodes[2],
+                             const uint32_t out_max[], uint32_t *cnt, uint32_t *tile_sums, uint32_t *pre, uint32_t *tot) {
+    int launches = 0;
+    for (uint32_t l = 0; l < levels; l++) {
+        k_affine_counts<<<cdiv((size_t)G + 1, 256), 256, 0, st>>>(off[l], G, cnt);
+        exclusive_scan_u32(cnt, off[l + 1], G + 1, tile_sums, st);
+        AffLevelIn<C> in{l == 0 ? bases : nodes[(l - 1) & 1], l == 0 ? entries : nullptr};
+        const uint32_t NT = affine_threads(out_max[l]);
+        k_affine_den<C><<<NT / AFF_TPB, AFF_TPB, 0, st>>>(in, off[l], off[l + 1], G, NT, pre, tot);
+        k_batch_inv<typename C::Elem><<<cdiv(NT, AFF_TPB * INV_K), AFF_TPB, 0, st>>>(tot, NT, NT);
+        k_affine_add<C><<<NT / AFF_TPB, AFF_TPB, 0, st>>>(in, off[l], off[l + 1], G, NT, pre, tot, nodes[l & 1]);
+        launches += 4 + (scan_num_tiles(G + 1) > 1 ? 3 : 1);
     }
-    k_affine_tail<C><<<cdiv(chunks, TPB_ACC), TPB_ACC, 0, st>>>(sh, rounds, offsets, (const A *)scratch_nodes, bucket_acc, head, tail, tail_bucket);
-    return 2 * (int)rounds + 1;
+    return launches;
 }
 #endif
 #if KGR_PART & 1

@@ -56,7 +56,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_rounds = 0, affine_split = 1, oneshot_split = 0, lane_threads = 1;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_levels = -1, oneshot_split = 0, lane_threads = 1;
 };
 // Tuning state is per calling thread (kgr_set_param changes the calling thread's copy only): an entry point snapshots it once and hands the
 // snapshot to every engine it drives (Engine::params), so a kgr_set_param on one thread never changes an MSM in flight on another, and the
@@ -107,8 +107,10 @@ struct Engine {
     cudaEvent_t ev[EV_N] = {};
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
     DevBuf<uint32_t> coarse_counts, coarse_off, coarse_cursor, part_pay;  // radix-partition sort (kernels_sort.cu)
+    DevBuf<uint32_t> lvl_off[5], lvl_cnt, lvl_pre, lvl_tot;                                // batched-affine levels (affine_kernels.cuh): offsets per level
+    DevBuf<uint8_t> lvl_nodes[2];                                          // ... and their node arrays (ping-pong)
     DevBuf<uint8_t> part_fine;
-    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v, aff_nodes, aff_suffix, aff_inv;  // raw bytes, cast per curve
+    DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
     uint32_t result_c = 0;                                                // window bits to apply between them (0: already combined)
@@ -117,7 +119,7 @@ struct Engine {
     size_t counts_zeroed = 0;  // counts[0..counts_zeroed) are known to be zero
     float last_ms[9] = {};
     uint32_t last_shape[6] = {};
-    int acc_blocks_per_sm[3] = {0, 0, 0}, aff_blocks_per_sm[3] = {0, 0, 0};
+    int acc_blocks_per_sm[3] = {0, 0, 0};
     uint64_t launches = 0;            // kernels of this library launched on this engine since init
     cudaEvent_t user_ev[4] = {};      // kgr_event_record / kgr_event_elapsed_ms
     cudaEvent_t aux_ev[3] = {};       // phase marks of the R1CS calls (kgr_r1cs_last_timing)
@@ -144,8 +146,6 @@ struct Engine {
         CK(cudaMallocHost(&h_result, 256 * 64 * sizeof(uint32_t)));  // up to 255 window sums of the widest XYZZ point (G2)
         acc_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_blocks_per_sm();
         acc_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_blocks_per_sm();
-        aff_blocks_per_sm[0] = Launch<Bn254G1>::accumulate_affine_blocks_per_sm();
-        aff_blocks_per_sm[1] = Launch<GrumpkinC>::accumulate_affine_blocks_per_sm();
         acc_blocks_per_sm[2] = Launch<Bn254G2>::accumulate_blocks_per_sm();
     }
     void destroy() {
@@ -154,7 +154,9 @@ struct Engine {
         cudaStreamSynchronize(st);
         counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
         coarse_counts.release(); coarse_off.release(); coarse_cursor.release(); part_pay.release(); part_fine.release();
-        bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release(); aff_nodes.release(); aff_suffix.release(); aff_inv.release();
+        for (auto &b : lvl_off) b.release();
+        lvl_cnt.release(); lvl_pre.release(); lvl_tot.release(); lvl_nodes[0].release(); lvl_nodes[1].release();
+        bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release();
         for (auto &t : fixed_table) t.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
@@ -339,7 +341,8 @@ static uint32_t choose_window_bits_collapsed(uint32_t n, double mul_weight) {
 }
 
 // table_c == 0: normal mode.  Otherwise the bases pointer is a precomputed table built for window size table_c.
-static MsmShape make_shape(const Params &P, uint32_t n, int blocks_per_sm, int sm_count, uint32_t table_c = 0, uint32_t table_stride = 0, uint32_t table_off = 0) {
+static MsmShape make_shape(const Params &P, uint32_t n, int blocks_per_sm, int sm_count, uint32_t table_c = 0, uint32_t table_stride = 0, uint32_t table_off = 0,
+                           uint64_t entries_override = 0) {
     MsmShape sh;
     sh.n = n;
     sh.c = table_c ? table_c : choose_window_bits(n, P);
@@ -350,7 +353,7 @@ static MsmShape make_shape(const Params &P, uint32_t n, int blocks_per_sm, int s
     sh.pstride = table_c ? table_stride : 0;
     sh.poff = table_c ? table_off : 0;
     sh.K = (uint32_t)P.reduce_fanin;
-    uint64_t M = (uint64_t)n * sh.W;
+    uint64_t M = entries_override ? entries_override : (uint64_t)n * sh.W;
     if (P.chunk > 0) {
         sh.L = (uint32_t)P.chunk;
     } else {
@@ -358,8 +361,7 @@ static MsmShape make_shape(const Params &P, uint32_t n, int blocks_per_sm, int s
         uint64_t concurrent = (uint64_t)std::max(1, blocks_per_sm) * TPB_ACC * std::max(1, sm_count);
         double best = 1e300;
         uint32_t bestL = 32;
-        // batched-affine accumulate: every thread shares one inversion per tree level among its ~L/2 pairs, so long chunks pay
-        for (uint32_t L = (P.affine_rounds > 0 ? 160 : 16); L <= 256; L += 4) {
+        for (uint32_t L = 16; L <= 256; L += 4) {
             uint64_t chunks = (M + L - 1) / L;
             uint64_t waves = (chunks + concurrent - 1) / concurrent;
             double cost = (double)waves * (L + 2.0);
@@ -376,13 +378,12 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
                         uint32_t table_stride = 0, uint32_t table_off = 0) {
     typedef XyzzPt<C> X;
     const Params &P = e.params;
-    const bool affine = P.affine_rounds > 0 && C::ID != Bn254G2::ID;  // the experimental batched-affine path is built for 8-word coordinates only
-    MsmShape sh = make_shape(P, n, affine ? e.aff_blocks_per_sm[C::ID] : e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
+    MsmShape sh = make_shape(P, n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
     const uint32_t nwin = table_c ? 1u : sh.W;  // independent bucket sets to reduce
     uint64_t M64 = (uint64_t)n * sh.W;
     if (M64 >= (1ull << 32) - 1) throw CudaError{cudaErrorInvalidValue, "n * windows exceeds 2^32 entries", __LINE__};
     uint32_t Mmax = (uint32_t)M64;
-    uint32_t chunks = (Mmax + sh.L - 1) / sh.L;
+    uint32_t chunks = (Mmax + sh.L - 1) / sh.L;  // re-derived below when batched-affine levels shorten the list
     uint32_t cnt1 = (sh.B + sh.K - 1) / sh.K;
 
     size_t G1 = (size_t)sh.G + 1;
@@ -444,25 +445,55 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
         e.wait_pts = false;
     }
+    // affine_levels r > 0 (8-word coordinates only): r levels of pairwise batched-affine sums inside every bucket (affine_kernels.cuh) leave
+    // ceil(len / 2^r) affine nodes per bucket; the XYZZ kernel then sums those instead of the base points.  -1 (auto), from the sweeps in
+    // profiles/r02_affine.md: none below 1.2e7 entries or 32 entries per bucket (the three extra kernels per level cost more than they save:
+    // 2^18 points 1.44 vs 1.43 ms), 2 up to 4e7 entries (2^20: 3.48 vs 3.82 ms), then 3, and 4 from 128 entries per bucket on (2^24: 39.3 vs 42.9 ms)
+    const uint32_t *off_final = e.offsets.p;
+    bool levels_ran = false;
     if constexpr (C::ID != Bn254G2::ID) {
-    if (affine && sh.L <= AFF_MAX_L) {
-        e.aff_nodes.ensure((size_t)chunks * sh.L * sizeof(AffinePt<C>));
-        e.aff_suffix.ensure((size_t)chunks * ((sh.L + 1) / 2) * 32);
-        if (P.affine_split) {
-            e.aff_inv.ensure((size_t)chunks * 32);
-            e.launches += K::accumulate_affine_split(e.st, sh, chunks, (uint32_t)P.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p,
-                                                     (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p, e.aff_inv.p) - 1;
-        } else {
-            K::accumulate_affine(e.st, sh, chunks, (uint32_t)P.affine_rounds, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p,
-                                 (X *)e.tail.p, e.tail_bucket.p, e.aff_nodes.p, e.aff_suffix.p);
+        uint32_t levels = (uint32_t)std::max<long>(P.affine_levels, 0);
+        if (P.affine_levels < 0) {
+            const double per_bucket = (double)Mmax / (double)sh.G;
+            levels = (Mmax < 12000000u || per_bucket < 32.0) ? 0u : Mmax < 40000000u ? 2u : per_bucket >= 128.0 ? 4u : 3u;
+        }
+        if (levels > 0 && Mmax >= 2) {
+            uint32_t out_max[5], m_in = Mmax;
+            for (uint32_t l = 0; l < levels; l++) {
+                out_max[l] = (uint32_t)(((uint64_t)m_in + std::min<uint64_t>(sh.G, m_in) + 1) / 2);  // sum of ceil(len / 2) over the non-empty buckets
+                m_in = out_max[l];
+            }
+            uint32_t *off[6] = {e.offsets.p};
+            for (uint32_t l = 0; l < levels; l++) {
+                e.lvl_off[l].ensure(G1 + 4);
+                off[l + 1] = e.lvl_off[l].p;
+            }
+            e.lvl_cnt.ensure(G1 + 4);
+            e.lvl_nodes[0].ensure((size_t)out_max[0] * sizeof(AffinePt<C>));
+            if (levels > 1) e.lvl_nodes[1].ensure((size_t)out_max[1] * sizeof(AffinePt<C>));
+            AffinePt<C> *nodes[2] = {(AffinePt<C> *)e.lvl_nodes[0].p, (AffinePt<C> *)e.lvl_nodes[1].p};
+            size_t pre_words, tot_words;
+            K::affine_scratch_words(out_max[0], pre_words, tot_words);
+            e.lvl_pre.ensure(pre_words);
+            e.lvl_tot.ensure(tot_words);
+            e.launches += K::affine_levels(e.st, levels, sh.G, d_bases, e.entries.p, off, nodes, out_max, e.lvl_cnt.p, e.tile_sums.p, e.lvl_pre.p, e.lvl_tot.p);
+            // the XYZZ kernel sums what is left: chunk length re-chosen for the shorter list
+            MsmShape sh2 = make_shape(P, n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off, out_max[levels - 1]);
+            sh.L = sh2.L;
+            chunks = (out_max[levels - 1] + sh.L - 1) / sh.L;
+            e.head.ensure((size_t)chunks * sizeof(X));
+            e.tail.ensure((size_t)chunks * sizeof(X));
+            e.tail_bucket.ensure((size_t)chunks + 1);
+            off_final = off[levels];
+            K::accumulate(e.st, sh, chunks, nodes[(levels - 1) & 1], off_final, nullptr, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
+            levels_ran = true;
         }
     }
-    }
-    if (!(affine && sh.L <= AFF_MAX_L))
+    if (!levels_ran)
         K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
     CK(cudaEventRecord(e.ev[EV_ACC], e.st));
     CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
-    K::fixup(e.st, sh, chunks, e.sm_count, e.offsets.p, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1,
+    K::fixup(e.st, sh, chunks, e.sm_count, off_final, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1,
              e.worklist.p);
     CK(cudaEventRecord(e.ev[EV_FIXUP], e.st));
     // Reduce.  reduce_mode 1 (default, B >= 256): fold reduce — parallel halving folds + plain sums of the upper halves
@@ -474,7 +505,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         e.fold_f.ensure((size_t)nwin * sh.B * sizeof(X));
         e.fold_partial.ensure((size_t)nwin * nb * chunks_max * sizeof(X));
         e.fold_v.ensure((size_t)nwin * nb * sizeof(X));
-        e.launches += K::fold_reduce(e.st, e.st_copy, e.ev_fork, e.ev_join, nwin, sh.B, (const X *)e.bucket_acc.p, e.offsets.p, (X *)e.fold_f.p, (X *)e.fold_partial.p, (X *)e.fold_v.p,
+        e.launches += K::fold_reduce(e.st, e.st_copy, e.ev_fork, e.ev_join, nwin, sh.B, (const X *)e.bucket_acc.p, off_final, (X *)e.fold_f.p, (X *)e.fold_partial.p, (X *)e.fold_v.p,
                                      (X *)e.lvl_a[0].p);
         win = (const X *)e.lvl_a[0].p;
     } else {
@@ -485,7 +516,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         do {
             uint32_t cnt_out = (cnt + sh.K - 1) / sh.K;
             X *os = (X *)e.lvl_s[pp].p, *oa = (X *)e.lvl_a[pp].p;
-            K::reduce(e.st, nwin, cnt, sh.K, m_log2, in_s, in_a, os, oa, in_a ? nullptr : e.offsets.p);
+            K::reduce(e.st, nwin, cnt, sh.K, m_log2, in_s, in_a, os, oa, in_a ? nullptr : off_final);
             e.launches++;
             in_s = os;
             in_a = oa;
@@ -1183,10 +1214,9 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "running_sum_stop") t_params.running_sum_stop = std::max<long>(1, value);
     else if (s == "sort_mode") t_params.sort_mode = value;
     else if (s == "reduce_mode") t_params.reduce_mode = value;
-    else if (s == "affine_split") t_params.affine_split = value;
     else if (s == "lane_threads") t_params.lane_threads = value ? 1 : 0;
     else if (s == "oneshot_split") t_params.oneshot_split = std::min<long>(std::max<long>(value, 0), (long)MAX_LANES);
-    else if (s == "affine_rounds") t_params.affine_rounds = std::min<long>(std::max<long>(value, 0), 6);
+    else if (s == "affine_levels") t_params.affine_levels = std::min<long>(std::max<long>(value, -1), 5);
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
 }

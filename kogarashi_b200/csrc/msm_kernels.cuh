@@ -292,14 +292,15 @@ KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *b
     uint32_t g = bucket_of_position(offsets, sh.G, s);
     uint32_t g_end = offsets[g + 1];
     XyzzPt<C> acc = xyzz_identity<C>();
-    uint32_t ent = entries[s];
+    // entries == nullptr: the "bases" are the nodes left by the batched-affine levels (affine_kernels.cuh), one per position, no sign
+    uint32_t ent = entries ? entries[s] : s;
     AffinePt<C> pt = load_affine(bases, ent & 0x7fffffffu);
     for (uint32_t pos = s; pos < e; pos++) {
         // prefetch the next entry's point while this one is being added
         uint32_t ent_next = 0;
         AffinePt<C> pt_next = pt;
         if (pos + 1 < e) {
-            ent_next = entries[pos + 1];
+            ent_next = entries ? entries[pos + 1] : pos + 1;
             pt_next = load_affine(bases, ent_next & 0x7fffffffu);
         }
         if (pos >= g_end) {
@@ -318,30 +319,12 @@ KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *b
     tail_bucket[t] = flush_segment(t, g, s, e, offsets, acc, bucket_acc, head, tail);
 }
 
-// ---- batched-affine accumulate (experimental, kgr_set_param("affine_rounds", r)) ------------------------------
-// Same chunking and the same outputs as body_accumulate, but the first `rounds` levels of every bucket's sum are
-// done as a pairwise tree in affine coordinates: all pairs of a level (about L/2, L/4, ... per thread) share ONE
-// modular inversion (Montgomery's trick: suffix products backwards, recovery forwards), so an addition costs
-// 1 (product) + 2 (recovery) + 3 (lambda, lambda^2, y3) = 6 field multiplications plus its share of the inversion
-// (safegcd, ~80 multiplications' worth, modinv.cuh) instead of the 10 of the XYZZ mixed add.  What is left of each
-// bucket segment after `rounds` levels is summed with XYZZ mixed adds and flushed exactly like before.
-// Level-0 nodes are read straight from the base array (x only for the denominators, then the full point); later
-// levels live in a per-thread slice of global scratch.  All special cases keep the group law exact: identity
-// operands, equal points (tangent, denominator 2y), opposite points (result identity).
-// Measured (profiles/r01_affine.md): the multiplier work drops by 25 % but the loops become chains of dependent
-// gathers (long_scoreboard), so on B200 it is not faster than the XYZZ kernel yet: off by default.
-constexpr uint32_t AFF_MAX_L = 256;
-
+// ---- helpers of the batched-affine tree levels (affine_kernels.cuh) -------------------------------------------------------------------------
 // x coordinate only (32 bytes): all the chord denominators of phase 1 need
 template <class C> KGR_HD typename C::Elem load_x(const AffinePt<C> *p) {
     typename C::Elem x;
     el_load(x, &p->x);
     return x;
-}
-template <class C> KGR_HD AffinePt<C> load_node0(const AffinePt<C> *bases, uint32_t ent) {
-    AffinePt<C> p = load_affine(bases, ent & 0x7fffffffu);
-    p.y = fp_cneg(p.y, (ent >> 31) != 0);
-    return p;
 }
 // case of the pair (a, b) and its denominator: 0 chord (xb - xa), 1 tangent (2 ya), 2 result a, 3 result b, 4 result identity
 template <class C> KGR_HD int pair_case(const AffinePt<C> &a, const AffinePt<C> &b, typename C::Elem &den) {
@@ -380,322 +363,6 @@ template <class C> KGR_HD AffinePt<C> pair_sum(int code, const AffinePt<C> &a, c
     r.x = fp_sub(fp_sub(fp_sqr(lam), a.x), b.x);
     r.y = fp_sub(fp_mul(lam, fp_sub(a.x, r.x)), a.y);
     return r;
-}
-
-template <class C>
-KGR_HD void body_accumulate_affine(uint32_t t, const MsmShape &sh, uint32_t rounds, const AffinePt<C> *bases, const uint32_t *offsets,
-                                   const uint32_t *entries, XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket,
-                                   AffinePt<C> *scratch_nodes, typename C::Elem *scratch_suffix) {
-    typedef typename C::Elem E;
-    uint32_t M = offsets[sh.G];
-    uint64_t s64 = (uint64_t)t * sh.L;
-    if (s64 >= M) return;
-    const uint32_t s = (uint32_t)s64;
-    const uint32_t e = (M - s > sh.L) ? s + sh.L : M;
-    // segments of this chunk: bucket id and node count
-    uint32_t seg_g[AFF_MAX_L];
-    uint16_t seg_len[AFF_MAX_L];
-    uint32_t nseg = 0, n_pairs = 0;
-    {
-        uint32_t g = bucket_of_position(offsets, sh.G, s), pos = s;
-        while (pos < e) {
-            uint32_t g_end = offsets[g + 1];
-            if (g_end <= pos) {
-                g++;
-                continue;
-            }
-            uint32_t len = (g_end < e ? g_end : e) - pos;
-            seg_g[nseg] = g;
-            seg_len[nseg] = (uint16_t)len;
-            n_pairs += len >> 1;
-            nseg++;
-            pos += len;
-            g++;
-        }
-    }
-    // Per-thread scratch lives in global memory, one contiguous slice per thread (L nodes, L/2 suffix products): the node
-    // indices differ from lane to lane, which would turn interleaved local memory into 4-byte scattered accesses, while a
-    // thread-major slice gives every lane whole 32-byte sectors (worst case, all segments odd, a level keeps all its nodes).
-    AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    E *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
-    uint32_t n_nodes = e - s;
-    bool in_R = false;  // nodes still are the gathered base points until the first level has run
-    for (uint32_t round = 0; round < rounds && n_pairs > 0; round++) {
-        // Both phases are FLAT loops over "steps" (a pair, or the odd last node of a segment): every lane runs about
-        // n_nodes / 2 steps whatever its bucket boundaries are, so the warp stays converged.
-        // phase 1, backwards: suffix[i] = product of the denominators of the pairs after i
-        E run = El<E>::one();
-        {
-            uint32_t pos = n_nodes, pidx = n_pairs, j = nseg, rem = 0;
-            while (pos > 0) {
-                if (rem == 0) rem = seg_len[--j];
-                if (rem & 1) {  // odd node at the end of the segment: no pair
-                    rem--;
-                    pos--;
-                    continue;
-                }
-                pos -= 2;
-                rem -= 2;
-                // the chord denominator needs the two x coordinates only; the full points are fetched in the rare other cases
-                uint32_t ea = 0, eb = 0;
-                const AffinePt<C> *pa, *pb;
-                if (!in_R) {
-                    ea = entries[s + pos];
-                    eb = entries[s + pos + 1];
-                    pa = bases + (ea & 0x7fffffffu);
-                    pb = bases + (eb & 0x7fffffffu);
-                } else {
-                    pa = R + pos;
-                    pb = R + pos + 1;
-                }
-                E xa = load_x(pa), xb = load_x(pb);
-                E den = fp_sub(xb, xa);
-                if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {  // equal x, or x = 0 (maybe the identity encoding (0, 0))
-                    AffinePt<C> a = in_R ? *pa : load_node0(bases, ea), b = in_R ? *pb : load_node0(bases, eb);
-                    (void)pair_case(a, b, den);
-                }
-                pidx--;
-                suffix[pidx] = run;
-                run = fp_mul(run, den);
-            }
-        }
-        E pre = fp_inv_fast(run);  // 1 / (product of all denominators)
-        // phase 2, forwards: 1/den_i = pre * suffix[i]; pre *= den_i.  Output index <= input index, so writing R in place is safe.
-        {
-            uint32_t pos = 0, out = 0, pidx = 0, j = 0, rem = 0, new_pairs = 0, seg_out = 0;
-            while (pos < n_nodes) {
-                if (rem == 0) {
-                    rem = seg_len[j];
-                    seg_out = 0;
-                }
-                if (rem >= 2) {
-                    AffinePt<C> a, b;
-                    if (!in_R) {
-                        a = load_node0(bases, entries[s + pos]);
-                        b = load_node0(bases, entries[s + pos + 1]);
-                    } else {
-                        a = R[pos];
-                        b = R[pos + 1];
-                    }
-                    E den;
-                    int code = pair_case(a, b, den);
-                    E den_inv = fp_mul(pre, suffix[pidx]);
-                    pre = fp_mul(pre, den);
-                    pidx++;
-                    R[out] = pair_sum(code, a, b, den_inv);
-                    pos += 2;
-                    rem -= 2;
-                } else {
-                    R[out] = in_R ? R[pos] : load_node0(bases, entries[s + pos]);
-                    pos += 1;
-                    rem -= 1;
-                }
-                out++;
-                seg_out++;
-                if (rem == 0) {
-                    seg_len[j] = (uint16_t)seg_out;
-                    new_pairs += seg_out >> 1;
-                    j++;
-                }
-            }
-            n_nodes = out;
-            n_pairs = new_pairs;
-        }
-        in_R = true;
-    }
-    // remaining nodes of every segment: XYZZ mixed adds in one flat loop over the nodes, flushing at segment ends
-    {
-        uint32_t tail_g = NO_DIGIT, j = 0, rem = nseg ? seg_len[0] : 0;
-        XyzzPt<C> acc = xyzz_identity<C>();
-        for (uint32_t pos = 0; pos < n_nodes; pos++) {
-            AffinePt<C> p = in_R ? R[pos] : load_node0(bases, entries[s + pos]);
-            xyzz_madd(acc, p);
-            if (--rem == 0) {
-                uint32_t r = flush_segment(t, seg_g[j], s, e, offsets, acc, bucket_acc, head, tail);
-                if (r != NO_DIGIT) tail_g = r;
-                acc = xyzz_identity<C>();
-                j++;
-                rem = (j < nseg) ? seg_len[j] : 0;
-            }
-        }
-        tail_bucket[t] = tail_g;
-    }
-}
-
-// ---- batched-affine accumulate, split into one kernel per phase (affine_split = 1) -----------------------------------
-// The fused body above needs ~120 registers for its XYZZ tail, so only 4 warps per sub-partition hide the dependent
-// gathers of the affine phases.  Here each phase is its own small body (launched at high occupancy); the segment
-// structure is re-derived from offsets[] on the fly: a segment with len0 level-0 nodes has (len0 + 2^r - 1) >> r nodes
-// at level r, so nothing but the nodes, the suffix products and one inverse per thread lives in global scratch.
-struct ChunkSpan {
-    uint32_t s, e, g_first;
-    bool valid;
-};
-KGR_HD ChunkSpan chunk_span(uint32_t t, const MsmShape &sh, const uint32_t *offsets) {
-    ChunkSpan c;
-    uint32_t M = offsets[sh.G];
-    uint64_t s64 = (uint64_t)t * sh.L;
-    c.valid = s64 < M;
-    c.s = (uint32_t)s64;
-    c.e = c.valid ? ((M - c.s > sh.L) ? c.s + sh.L : M) : c.s;
-    c.g_first = c.valid ? bucket_of_position(offsets, sh.G, c.s) : 0;
-    return c;
-}
-KGR_HD uint32_t level_len(uint32_t len0, uint32_t r) { return (len0 + (1u << r) - 1u) >> r; }
-
-// phase 1 of level r (backwards): suffix products, then the inverse of the product of all denominators -> inv_out[t]
-template <class C>
-KGR_HD void body_affine_phase1(uint32_t t, const MsmShape &sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                               const AffinePt<C> *scratch_nodes, typename C::Elem *scratch_suffix, typename C::Elem *inv_out) {
-    typedef typename C::Elem E;
-    ChunkSpan c = chunk_span(t, sh, offsets);
-    if (!c.valid) return;
-    const AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    E *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
-    // totals at this level
-    uint32_t n_nodes = 0, n_pairs = 0, g_last = c.g_first;
-    for (uint32_t g = c.g_first, pos = c.s; pos < c.e; g++) {
-        uint32_t g_end = offsets[g + 1];
-        if (g_end <= pos) continue;
-        uint32_t len = level_len((g_end < c.e ? g_end : c.e) - pos, r);
-        n_nodes += len;
-        n_pairs += len >> 1;
-        pos = g_end < c.e ? g_end : c.e;
-        g_last = g;
-    }
-    E run = El<E>::one();
-    uint32_t pos = n_nodes, pidx = n_pairs, rem = 0, g = g_last + 1, hi0 = c.e;
-    while (pos > 0) {
-        if (rem == 0) {  // previous non-empty bucket (backwards)
-            uint32_t lo;
-            do {
-                g--;
-                lo = offsets[g] > c.s ? offsets[g] : c.s;
-            } while (lo >= hi0);
-            rem = level_len(hi0 - lo, r);
-            hi0 = lo;
-        }
-        if (rem & 1) {
-            rem--;
-            pos--;
-            continue;
-        }
-        pos -= 2;
-        rem -= 2;
-        uint32_t ea = 0, eb = 0;
-        const AffinePt<C> *pa, *pb;
-        if (r == 0) {
-            ea = entries[c.s + pos];
-            eb = entries[c.s + pos + 1];
-            pa = bases + (ea & 0x7fffffffu);
-            pb = bases + (eb & 0x7fffffffu);
-        } else {
-            pa = R + pos;
-            pb = R + pos + 1;
-        }
-        E xa = load_x(pa), xb = load_x(pb);
-        E den = fp_sub(xb, xa);
-        if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {
-            AffinePt<C> a = r ? *pa : load_node0(bases, ea), b = r ? *pb : load_node0(bases, eb);
-            (void)pair_case(a, b, den);
-        }
-        pidx--;
-        suffix[pidx] = run;
-        run = fp_mul(run, den);
-    }
-    inv_out[t] = fp_inv_fast(run);
-}
-
-// phase 2 of level r (forwards): recover the inverses, write the level r+1 nodes in place
-template <class C>
-KGR_HD void body_affine_phase2(uint32_t t, const MsmShape &sh, uint32_t r, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
-                               AffinePt<C> *scratch_nodes, const typename C::Elem *scratch_suffix, const typename C::Elem *inv_in) {
-    typedef typename C::Elem E;
-    ChunkSpan c = chunk_span(t, sh, offsets);
-    if (!c.valid) return;
-    AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    const E *suffix = scratch_suffix + (size_t)t * ((sh.L + 1) / 2);
-    E pre = inv_in[t];
-    uint32_t pos = 0, out = 0, pidx = 0, rem = 0, g = c.g_first, lo0 = c.s;
-    bool more = true;
-    while (more) {
-        if (rem == 0) {  // next non-empty bucket
-            uint32_t hi;
-            for (;;) {
-                hi = offsets[g + 1] < c.e ? offsets[g + 1] : c.e;
-                if (hi > lo0) break;
-                g++;
-            }
-            rem = level_len(hi - lo0, r);
-            lo0 = hi;
-            g++;
-        }
-        if (rem >= 2) {
-            AffinePt<C> a, b;
-            if (r == 0) {
-                a = load_node0(bases, entries[c.s + pos]);
-                b = load_node0(bases, entries[c.s + pos + 1]);
-            } else {
-                a = R[pos];
-                b = R[pos + 1];
-            }
-            E den;
-            int code = pair_case(a, b, den);
-            E den_inv = fp_mul(pre, suffix[pidx]);
-            pre = fp_mul(pre, den);
-            pidx++;
-            R[out] = pair_sum(code, a, b, den_inv);
-            pos += 2;
-            rem -= 2;
-        } else {
-            R[out] = r ? R[pos] : load_node0(bases, entries[c.s + pos]);
-            pos += 1;
-            rem -= 1;
-        }
-        out++;
-        more = !(rem == 0 && lo0 >= c.e);
-    }
-}
-
-// XYZZ tail: the level-`r` nodes of every segment are summed with mixed adds and flushed like body_accumulate does
-template <class C>
-KGR_HD void body_affine_tail(uint32_t t, const MsmShape &sh, uint32_t r, const uint32_t *offsets, const AffinePt<C> *scratch_nodes, XyzzPt<C> *bucket_acc,
-                             XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
-    ChunkSpan c = chunk_span(t, sh, offsets);
-    if (!c.valid) return;
-    const AffinePt<C> *R = scratch_nodes + (size_t)t * sh.L;
-    // flat loop over the nodes (the warp stays converged), flushing at segment ends
-    uint32_t tail_g = NO_DIGIT, g = c.g_first, lo0 = c.s, rem = 0, n_nodes = 0;
-    for (uint32_t gg = c.g_first, pos0 = c.s; pos0 < c.e; gg++) {
-        uint32_t g_end = offsets[gg + 1];
-        if (g_end <= pos0) continue;
-        uint32_t hi = g_end < c.e ? g_end : c.e;
-        n_nodes += level_len(hi - pos0, r);
-        pos0 = hi;
-    }
-    XyzzPt<C> acc = xyzz_identity<C>();
-    uint32_t cur_g = g;
-    for (uint32_t pos = 0; pos < n_nodes; pos++) {
-        if (rem == 0) {
-            uint32_t hi;
-            for (;;) {
-                hi = offsets[g + 1] < c.e ? offsets[g + 1] : c.e;
-                if (hi > lo0) break;
-                g++;
-            }
-            rem = level_len(hi - lo0, r);
-            lo0 = hi;
-            cur_g = g;
-            g++;
-        }
-        xyzz_madd(acc, R[pos]);
-        if (--rem == 0) {
-            uint32_t f = flush_segment(t, cur_g, c.s, c.e, offsets, acc, bucket_acc, head, tail);
-            if (f != NO_DIGIT) tail_g = f;
-            acc = xyzz_identity<C>();
-        }
-    }
-    tail_bucket[t] = tail_g;
 }
 
 // One thread per chunk: a chunk whose last segment continues into the following chunks owns that bucket

@@ -123,32 +123,56 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memset(head.data(), 0xCD, head.size() * sizeof(XyzzPt<C>));
     memset(tail.data(), 0xEF, tail.size() * sizeof(XyzzPt<C>));
     std::vector<uint32_t> tail_bucket(chunks, 0x12345678u);
-    std::vector<AffinePt<C>> aff_nodes((size_t)chunks * L);
-    std::vector<typename C::Elem> aff_suffix((size_t)chunks * ((L + 1) / 2));
-    const uint32_t affine_rounds = (seed >> 1) % 4;  // 0: XYZZ accumulate; 1..3: batched-affine tree levels first
-    const bool affine_split = ((seed >> 3) & 1) != 0;  // one body per phase, structure re-derived from offsets
-    if (affine_rounds && affine_split) {
-        std::vector<typename C::Elem> aff_inv(chunks);
-        for (uint32_t r = 0; r < affine_rounds; r++) {
-            for (uint32_t t = 0; t < chunks; t++) body_affine_phase1<C>(t, sh, r, acc_bases, offsets.data(), entries.data(), aff_nodes.data(), aff_suffix.data(), aff_inv.data());
-            for (uint32_t t = 0; t < chunks; t++) body_affine_phase2<C>(t, sh, r, acc_bases, offsets.data(), entries.data(), aff_nodes.data(), aff_suffix.data(), aff_inv.data());
+    // seed bits 1-2: batched-affine tree levels in front of the XYZZ accumulation (affine_kernels.cuh).  The level structure — pairs by
+    // position inside every bucket, the odd last node copied, off_{l+1} = scan of ceil(len / 2) — and the pair_case / pair_sum helpers are the
+    // device code; the inverse of each denominator is computed directly here (the kernels share one inversion between many denominators by
+    // Montgomery's trick, which yields the same field element).  G2 has no affine levels on the device.
+    const uint32_t affine_levels = C::ID == 2 ? 0 : (seed >> 1) % 4;
+    std::vector<uint32_t> off_cur(offsets.begin(), offsets.begin() + sh.G + 1);
+    std::vector<AffinePt<C>> nodes;
+    if constexpr (C::ID != 2) {
+        for (uint32_t l = 0; l < affine_levels; l++) {
+            std::vector<uint32_t> off_next(sh.G + 1, 0);
+            for (uint32_t g = 0; g < sh.G; g++) off_next[g + 1] = off_next[g] + ((off_cur[g + 1] - off_cur[g] + 1) >> 1);
+            std::vector<AffinePt<C>> next(off_next[sh.G]);
+            auto load = [&](uint32_t pos) {
+                if (l > 0) return nodes[pos];
+                uint32_t ent = entries[pos];
+                AffinePt<C> pt = acc_bases[ent & 0x7fffffffu];
+                pt.y = fp_cneg(pt.y, (ent >> 31) != 0);
+                return pt;
+            };
+            for (uint32_t g = 0; g < sh.G; g++)
+                for (uint32_t q = off_next[g]; q < off_next[g + 1]; q++) {
+                    uint32_t p0 = off_cur[g] + 2 * (q - off_next[g]);
+                    AffinePt<C> a = load(p0), r = a;
+                    if (p0 + 1 < off_cur[g + 1]) {
+                        AffinePt<C> b = load(p0 + 1);
+                        typename C::Elem den;
+                        int code = pair_case(a, b, den);
+                        r = pair_sum(code, a, b, fp_inv(den));
+                    }
+                    next[q] = r;
+                }
+            nodes.swap(next);
+            off_cur.swap(off_next);
         }
-        for (uint32_t t = 0; t < chunks; t++) body_affine_tail<C>(t, sh, affine_rounds, offsets.data(), aff_nodes.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
-    } else
+    }
+    const uint32_t *acc_off = affine_levels ? off_cur.data() : offsets.data();
     for (uint32_t t = 0; t < chunks; t++) {
-        if (affine_rounds && L <= AFF_MAX_L)
-            body_accumulate_affine<C>(t, sh, affine_rounds, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data(), aff_nodes.data(), aff_suffix.data());
+        if (affine_levels)
+            body_accumulate<C>(t, sh, nodes.data(), acc_off, (const uint32_t *)nullptr, bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
         else
             body_accumulate<C>(t, sh, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
     }
     std::vector<uint32_t> worklist(sh.G + 1);
     uint32_t wl_len = 0;
-    for (uint32_t t = 0; t < chunks; t++) body_fixup<C>(t, sh, offsets.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data(), worklist.data(), &wl_len);
+    for (uint32_t t = 0; t < chunks; t++) body_fixup<C>(t, sh, acc_off, bucket_acc.data(), head.data(), tail.data(), tail_bucket.data(), worklist.data(), &wl_len);
     for (uint32_t i = 0; i < wl_len; i++) {  // k_fixup_long: lanes cooperate, then a tree sum
         const uint32_t lanes = 5;
         XyzzPt<C> tot = xyzz_identity<C>();
         for (uint32_t lane = 0; lane < lanes; lane++) {
-            XyzzPt<C> part = fixup_long_partial<C>(worklist[i], lane, lanes, sh, offsets.data(), head.data(), tail.data());
+            XyzzPt<C> part = fixup_long_partial<C>(worklist[i], lane, lanes, sh, acc_off, head.data(), tail.data());
             xyzz_add(tot, part);
         }
         bucket_acc[worklist[i]] = tot;
@@ -161,12 +185,12 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         memset(F.data(), 0x5A, F.size() * sizeof(XyzzPt<C>));
         for (uint32_t l = 1; l <= nb; l++)
             for (uint32_t w = 0; w < nwin; w++)
-                for (uint32_t i = 0; i < (B >> l); i++) body_fold<C>(w, i, l, B, bucket_acc.data(), F.data(), offsets.data());
+                for (uint32_t i = 0; i < (B >> l); i++) body_fold<C>(w, i, l, B, bucket_acc.data(), F.data(), acc_off);
         for (uint32_t l = 1; l <= nb; l++)
             for (uint32_t w = 0; w < nwin; w++) {
                 XyzzPt<C> acc = xyzz_identity<C>(), x;
                 for (uint32_t i = 0; i < (B >> l); i++)
-                    if (fold_upper_elem<C>(w, i, l, B, bucket_acc.data(), F.data(), offsets.data(), x)) xyzz_add(acc, x);
+                    if (fold_upper_elem<C>(w, i, l, B, bucket_acc.data(), F.data(), acc_off, x)) xyzz_add(acc, x);
                 V[(size_t)w * nb + (nb - l)] = acc;
             }
         for (uint32_t w = 0; w < nwin; w++) {
@@ -186,7 +210,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     int pp = 0;
     for (;;) {
         uint32_t cnt_out = (cnt + K - 1) / K;
-        for (uint32_t t = 0; t < nwin * cnt_out; t++) body_reduce<C>(t, nwin, cnt, K, m_log2, in_s, in_a, ls[pp].data(), la[pp].data(), in_a ? nullptr : offsets.data());
+        for (uint32_t t = 0; t < nwin * cnt_out; t++) body_reduce<C>(t, nwin, cnt, K, m_log2, in_s, in_a, ls[pp].data(), la[pp].data(), in_a ? nullptr : acc_off);
         in_s = ls[pp].data(); in_a = la[pp].data();
         cnt = cnt_out; m_log2 += klog; pp ^= 1;
         if (cnt <= rs_stop) break;
@@ -210,7 +234,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     memcpy(&got.x, out24, EB); memcpy(&got.y, out24 + EB / 4, EB); memcpy(&got.z, out24 + 2 * (EB / 4), EB);
     OAffine got_aff = Cv::to_affine(got);
     bool ok = Cv::eq(got_aff, exp_aff) && (got_aff.inf || (got_aff.x == exp_aff.x && got_aff.y == exp_aff.y));
-    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_rounds=%u split=%d fold=%d\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_rounds, (int)affine_split, (int)fold_reduce);
+    printf("%s curve=%d n=%u c=%u W=%u L=%u K=%u mode=%d M=%u inf=%d affine_levels=%u fold=%d\n", ok ? "OK" : "FAIL", C::ID, n, c, sh.W, L, K, mode, M, (int)got_aff.inf, affine_levels, (int)fold_reduce);
     return ok ? 0 : 1;
 }
 

@@ -126,10 +126,10 @@ def test_msm_golden_under_forced_shapes(k, golden, c, chunk):
 
 
 @pytest.mark.parametrize("param,value", [("final_on_device", 1), ("running_sum_stop", 1), ("running_sum_stop", 1 << 20), ("reduce_fanin", 4), ("sort_mode", 0),
-                                         ("sort_mode", 1), ("sort_mode", 2), ("reduce_mode", 0), ("reduce_mode", 1), ("affine_rounds", 1), ("affine_rounds", 2), ("affine_rounds", 4)])
+                                         ("sort_mode", 1), ("sort_mode", 2), ("reduce_mode", 0), ("reduce_mode", 1), ("affine_levels", 1), ("affine_levels", 2), ("affine_levels", 4)])
 def test_msm_golden_under_reduce_variants(k, golden, param, value):
     """Device-side Horner, pure running-sum reduction, pure weighting-pass reduction, small fan-in: same element."""
-    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1, "reduce_mode": 1, "affine_rounds": 0}
+    defaults = {"final_on_device": 0, "running_sum_stop": 4096, "reduce_fanin": 16, "sort_mode": -1, "reduce_mode": 1, "affine_levels": -1}
     k.set_param(param, value)
     try:
         for cbits in (0, 10):  # c = 10: 512 buckets per window, enough for the fold reduce to engage
@@ -355,8 +355,8 @@ def test_random_shapes_vs_oracle(k, seed):
             pts[i, h:h + 4] = A.field_op(bf, "neg", pts[i, h:h + 4])
     m = n if seed % 4 else max(1, n - 3)                                # fewer scalars than bases
     params = {"window_bits": int(rng.integers(0, 15)), "chunk": int(rng.choice([0, 1, 2, 5, 16, 64])), "sort_mode": int(rng.integers(-1, 3)),
-              "reduce_mode": int(rng.integers(0, 2)), "final_on_device": int(rng.integers(0, 2))}
-    defaults = {"window_bits": 0, "chunk": 0, "sort_mode": -1, "reduce_mode": 1, "final_on_device": 0}
+              "reduce_mode": int(rng.integers(0, 2)), "final_on_device": int(rng.integers(0, 2)), "affine_levels": int(rng.integers(-1, 5))}
+    defaults = {"window_bits": 0, "chunk": 0, "sort_mode": -1, "reduce_mode": 1, "final_on_device": 0, "affine_levels": -1}
     exp = A.to_affine(curve, A.msm(curve, pts, sc[:m], inf=inf))
     try:
         for name, v in params.items():
@@ -482,3 +482,54 @@ def test_gpu_matches_reference_binary_vectors(k):
     for name in names:
         got = k.msm_curve_addition(z[name + "_pts"], z[name + "_sc"], curve=A.BN254_G1, inf=z[name + "_inf"])
         assert same_affine(k.to_affine(A.BN254_G1, got), z[name + "_aff"]), name
+
+
+@pytest.mark.parametrize("levels", [1, 2, 3, 5])
+def test_batched_affine_levels_special_cases(k, golden, levels):
+    """affine_levels = r (affine_kernels.cuh): pairs inside a bucket that are equal (tangent), opposite (identity), identities themselves, odd
+    bucket lengths, empty buckets, a single bucket with everything in it — every golden, small windows so that buckets are long."""
+    k.set_param("affine_levels", levels)
+    try:
+        for c in (2, 5, 0):
+            k.set_param("window_bits", c)
+            for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96", "gr_identity_bases_40", "g1_cancel_32", "g1_rm1_scalars", "gr_uniform_100", "gr_cancel_32"):
+                curve = A.BN254_G1 if name.startswith("g1_") else A.GRUMPKIN
+                pts, sc, inf, aff = (golden[name + s] for s in ("_pts", "_sc", "_inf", "_aff"))
+                assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve, inf=inf)), aff), (name, levels, c)
+        # all scalars equal: one bucket per window holds every point (the same point 300 times: every pair is a doubling)
+        curve = A.BN254_G1
+        p = A.random_points(curve, 1, seed=bytes(range(16)))
+        pts = np.tile(p, (300, 1))
+        sc = np.tile(A.random_field(A.FIELD_FR, 1, seed=bytes(range(1, 17))), (300, 1))
+        exp = A.to_affine(curve, A.msm(curve, pts, sc))
+        for c in (3, 9):
+            k.set_param("window_bits", c)
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp), (levels, c)
+        bases = k.Bases(curve, pts).precompute(4)
+        assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc)), exp)
+        bases.free()
+    finally:
+        k.set_param("affine_levels", -1)
+        k.set_param("window_bits", 0)
+
+
+@pytest.mark.parametrize("curve,logn", [(A.BN254_G1, 16), (A.GRUMPKIN, 15)])
+def test_batched_affine_levels_vs_oracle(k, curve, logn):
+    """Seeded inputs with repeated bases and hot buckets through 1..4 affine levels against the restated reference algorithm."""
+    n = 1 << logn
+    rng = np.random.default_rng(7 + logn)
+    pool = A.random_points(curve, 512, seed=bytes(range(11, 27)))          # few distinct bases: equal / opposite pairs inside buckets are common
+    pts = pool[rng.integers(0, pool.shape[0], size=n)]
+    fid = A.SCALAR_FIELD[curve]
+    sc = A.random_field(fid, n, seed=bytes(range(60, 76)))
+    kind = rng.integers(0, 4, size=n)
+    sc[kind == 0] = sc[1]
+    exp = A.to_affine(curve, A.msm(curve, pts, sc))
+    try:
+        for levels, c in ((1, 0), (2, 8), (3, 10), (4, 6)):
+            k.set_param("affine_levels", levels)
+            k.set_param("window_bits", c)
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp), (levels, c)
+    finally:
+        k.set_param("affine_levels", -1)
+        k.set_param("window_bits", 0)

@@ -25,7 +25,7 @@ def host_emu():
 
 
 # curve n c L K mode seed   (mode: 0 uniform, 1 skewed zeros/ones/r-1, 2 duplicates + opposites + identity bases, 3 canonical scalars)
-# seed bits select variants: bit 0 window-major fill, bits 1-2 batched-affine levels, bit 3 per-phase affine kernels, bit 4 fold reduce
+# seed bits select variants: bit 0 window-major fill, bits 1-2 batched-affine tree levels in front of the XYZZ accumulation, bit 4 fold reduce
 EMU_CASES = [
     (0, 1, 4, 16, 16, 0, 1), (0, 2, 1, 16, 2, 0, 2), (0, 3, 3, 16, 4, 0, 3), (0, 37, 5, 8, 4, 0, 4), (0, 300, 8, 16, 16, 0, 5),
     (0, 300, 8, 16, 16, 1, 6), (0, 300, 7, 5, 8, 2, 7), (1, 257, 9, 32, 16, 0, 8), (1, 200, 6, 16, 2, 2, 9), (0, 129, 1, 16, 16, 0, 10),
