@@ -31,4 +31,4 @@ def test_header_compiles_as_c_and_program_fails_loudly_without_a_device(demo):
 @pytest.mark.gpu
 def test_c_program_msm_identities(demo):
     out = subprocess.run([demo], capture_output=True, text=True, timeout=300)
-    assert out.returncode == 0 and out.stdout.count(": yes") == 2, out.stdout + out.stderr
+    assert out.returncode == 0 and out.stdout.count(": yes") == 3, out.stdout + out.stderr
