@@ -81,6 +81,10 @@ __global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint
     }
 }
 template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_bucket_merge(uint32_t G, const uint32_t *piece_offsets, const XyzzPt<C> *piece_acc, XyzzPt<C> *bucket_acc) {
+    body_bucket_merge<C>(blockIdx.x * blockDim.x + threadIdx.x, G, piece_offsets, piece_acc, bucket_acc);
+}
+template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_reduce(uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const XyzzPt<C> *in_s,
                                                     const XyzzPt<C> *in_a, XyzzPt<C> *out_s, XyzzPt<C> *out_a, const uint32_t *bucket_offsets) {
     body_reduce<C>(blockIdx.x * blockDim.x + threadIdx.x, n_windows, cnt_in, K, m_log2, in_s, in_a, out_s, out_a, bucket_offsets);

@@ -73,6 +73,11 @@ void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int 
     k_fixup_long<C><<<blocks, TPB_TREE, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
 }
 #endif
+#if KGR_PART & 1
+template <class C> void Launch<C>::bucket_merge(cudaStream_t st, uint32_t G, const uint32_t *piece_offsets, const X *piece_acc, X *bucket_acc) {
+    k_bucket_merge<C><<<cdiv(G, TPB_RED), TPB_RED, 0, st>>>(G, piece_offsets, piece_acc, bucket_acc);
+}
+#endif
 #if KGR_PART & 4
 template <class C>
 void Launch<C>::reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a,

@@ -105,11 +105,16 @@ struct Engine {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;  // fold reduce: the big upper-half sums run on st_copy beside the deep fold levels
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
+    cudaEvent_t ev_piece_sc[16] = {}, ev_piece_pts[16] = {};  // piece k's scalars / points are on the device (recorded on st_copy)
+    cudaEvent_t pev[16][6] = {};      // per-piece phase marks of a streamed call (enqueue_msm)
+    size_t n_pev = 0;
+    uint32_t n_pieces = 1;            // pieces of the last MSM enqueued on this engine
     DevBuf<uint32_t> counts, offsets, tile_sums, entries, scalars, worklist, tail_bucket, digits;
     DevBuf<uint32_t> coarse_counts, coarse_off, coarse_cursor, part_pay;  // radix-partition sort (kernels_sort.cu)
     DevBuf<uint32_t> lvl_off[5], lvl_cnt, lvl_pre, lvl_tot;                                // batched-affine levels (affine_kernels.cuh): offsets per level
     DevBuf<uint8_t> lvl_nodes[2];                                          // ... and their node arrays (ping-pong)
     DevBuf<uint8_t> part_fine;
+    DevBuf<uint8_t> piece_acc;  // bucket sums of one piece of a streamed call (enqueue_msm)
     DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
@@ -156,6 +161,7 @@ struct Engine {
         coarse_counts.release(); coarse_off.release(); coarse_cursor.release(); part_pay.release(); part_fine.release();
         for (auto &b : lvl_off) b.release();
         lvl_cnt.release(); lvl_pre.release(); lvl_tot.release(); lvl_nodes[0].release(); lvl_nodes[1].release();
+        piece_acc.release();
         bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release();
         for (auto &t : fixed_table) t.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
@@ -164,6 +170,11 @@ struct Engine {
         h_stage = nullptr;
         for (auto &e : stage_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
         for (auto &e : ev) if (e) cudaEventDestroy(e);
+        for (size_t k = 0; k < n_pev; k++)
+            for (auto &pe : pev[k]) if (pe) cudaEventDestroy(pe);
+        n_pev = 0;
+        for (auto &x : ev_piece_sc) if (x) { cudaEventDestroy(x); x = nullptr; }
+        for (auto &x : ev_piece_pts) if (x) { cudaEventDestroy(x); x = nullptr; }
         for (auto &e : user_ev) if (e) cudaEventDestroy(e);
         for (auto &e : aux_ev) if (e) cudaEventDestroy(e);
         oneshot_pts.release(); oneshot_inf.release();
@@ -372,18 +383,41 @@ static MsmShape make_shape(const Params &P, uint32_t n, int blocks_per_sm, int s
     return sh;
 }
 
+// One piece of a host-buffer call that is streamed over PCIe: pairs [first, first + count) of the call, usable once ev_sc (its scalars are on
+// the device) and ev_pts (its points are; nullptr for registered bases) have fired.
+struct StreamPiece {
+    size_t first, count;
+    cudaEvent_t ev_sc, ev_pts;
+    // number of pieces whose events have been RECORDED (a wait on an event that was never recorded is a no-op, so the waits of piece k must
+    // not be enqueued before that); nullptr: all of them were recorded before enqueue_msm was called
+    const std::atomic<size_t> *recorded;
+};
+enum { PE_BEGIN, PE_COUNT, PE_SCAN, PE_FILL, PE_ACC, PE_FIXUP, PE_N };
+constexpr size_t MAX_PIECES = 16;
+
 // Enqueue one MSM over n pairs on engine e.  d_scalars: device pointer (n x 8 words).
+// pieces (optional, more than one): the call's inputs arrive piece by piece.  Every piece is sorted and accumulated as soon as it is on the
+// device, with the window size of the whole call, its bucket sums are added to one shared, zero-initialised bucket set (k_bucket_merge), and
+// ONE bucket reduction closes the call.  (Round 1 ran the pieces as independent MSMs on separate lanes: each paid its own reduction and the smaller window size
+// of a smaller MSM, 2 x 1.9 ms for the two halves of a 2^20-point call against 3.5 ms for the whole, profiles/r02_e2e.md.)
 template <class C>
 static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d_scalars, int is_mont, uint32_t n, uint32_t table_c = 0,
-                        uint32_t table_stride = 0, uint32_t table_off = 0) {
+                        uint32_t table_stride = 0, uint32_t table_off = 0, const std::vector<StreamPiece> *pieces = nullptr) {
     typedef XyzzPt<C> X;
+    typedef Launch<C> K;
     const Params &P = e.params;
+    const bool streamed = pieces && pieces->size() > 1;
+    if (streamed && pieces->size() > MAX_PIECES) throw CudaError{cudaErrorInvalidValue, "too many pieces", __LINE__};
+    uint32_t n_piece_max = n;
+    if (streamed) {
+        n_piece_max = 0;
+        for (auto &pc : *pieces) n_piece_max = std::max<uint32_t>(n_piece_max, (uint32_t)pc.count);
+    }
     MsmShape sh = make_shape(P, n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off);
     const uint32_t nwin = table_c ? 1u : sh.W;  // independent bucket sets to reduce
-    uint64_t M64 = (uint64_t)n * sh.W;
+    uint64_t M64 = (uint64_t)n_piece_max * sh.W;
     if (M64 >= (1ull << 32) - 1) throw CudaError{cudaErrorInvalidValue, "n * windows exceeds 2^32 entries", __LINE__};
-    uint32_t Mmax = (uint32_t)M64;
-    uint32_t chunks = (Mmax + sh.L - 1) / sh.L;  // re-derived below when batched-affine levels shorten the list
+    const uint32_t Mmax = (uint32_t)M64;  // entries of the largest piece
     uint32_t cnt1 = (sh.B + sh.K - 1) / sh.K;
 
     size_t G1 = (size_t)sh.G + 1;
@@ -393,109 +427,150 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
     e.tile_sums.ensure(LaunchUtil::scan_tiles((uint32_t)G1) + 1);
     e.entries.ensure((size_t)Mmax + 1);
     e.bucket_acc.ensure((size_t)sh.G * sizeof(X));
-    e.head.ensure((size_t)chunks * sizeof(X));
-    e.tail.ensure((size_t)chunks * sizeof(X));
     for (int i = 0; i < 2; i++) {
         e.lvl_s[i].ensure((size_t)nwin * cnt1 * sizeof(X));
         e.lvl_a[i].ensure((size_t)nwin * cnt1 * sizeof(X));
     }
     e.result.ensure(sizeof(X));
     e.worklist.ensure((size_t)sh.G + 2);
-    e.tail_bucket.ensure((size_t)chunks + 1);
     if (e.counts_zeroed < G1) {
         CK(cudaMemsetAsync(e.counts.p, 0, e.counts.cap * sizeof(uint32_t), e.st));
         e.counts_zeroed = e.counts.cap;
     }
+    X *piece_dst = (X *)e.bucket_acc.p;  // where a piece's bucket sums go: the call's bucket set itself unless the call is streamed
+    if (streamed) {
+        CK(cudaMemsetAsync(e.bucket_acc.p, 0, (size_t)sh.G * sizeof(X), e.st));  // all-zero words: XYZZ identity (zz = 0)
+        e.piece_acc.ensure((size_t)sh.G * sizeof(X));
+        piece_dst = (X *)e.piece_acc.p;
+        for (size_t k = e.n_pev; k < pieces->size(); k++) {
+            for (auto &ev : e.pev[k]) CK(cudaEventCreate(&ev));
+            e.n_pev = k + 1;
+        }
+    }
+    e.n_pieces = streamed ? (uint32_t)pieces->size() : 1;
 
-    CK(cudaEventRecord(e.ev[EV_H2D], e.st));
-    typedef Launch<C> K;
-    // sort_mode 2: two block-local radix partitions (kernels_sort.cu); 1: counting sort with a window-major fill from stored digits (scatter
-    // region per window stays in L2); 0: counting sort, one thread per scalar recodes again and scatters into all windows;
-    // -1 (auto): radix partitions from 2^21 entries on (below, the second pass costs more than the atomics it saves: 2^16 points 0.91 vs 0.85 ms,
-    // 2^18 points 1.44 vs 1.48 ms, profiles/r02_sort.md)
-    SortPlan pl;
-    const bool radix = (P.sort_mode == 2 || (P.sort_mode < 0 && Mmax >= (1u << 21))) && LaunchSort::plan(sh, pl);
-    if (radix) {
-        const size_t cw = LaunchSort::coarse_words(pl);
-        if (e.coarse_counts.cap < cw) {
-            e.coarse_counts.ensure(cw);
-            CK(cudaMemsetAsync(e.coarse_counts.p, 0, e.coarse_counts.cap * sizeof(uint32_t), e.st));  // k_sort_scan leaves it zero again
-        }
-        e.coarse_off.ensure(cw);
-        e.coarse_cursor.ensure(cw);
-        e.digits.ensure((size_t)Mmax + 1);
-        e.part_pay.ensure((size_t)Mmax + 1);
-        e.part_fine.ensure((size_t)Mmax + 16);
-        e.launches += LaunchSort::run(e.st, std::is_same<typename C::Scalar, FqP>::value ? 0 : 1, e.sm_count, pl, d_scalars, is_mont, e.digits.p, e.coarse_counts.p,
-                                      e.coarse_off.p, e.coarse_cursor.p, e.part_pay.p, e.part_fine.p, e.entries.p, e.offsets.p, e.ev[EV_COUNT], e.ev[EV_SCAN]) - 2;
-        CK(cudaEventRecord(e.ev[EV_FILL], e.st));
-    } else {
-        const bool window_major = P.sort_mode == 1 || (P.sort_mode < 0 && (uint64_t)Mmax * 4 > (96ull << 20));
-        if (window_major) e.digits.ensure((size_t)Mmax + 1);
-        K::count(e.st, sh, d_scalars, is_mont, e.counts.p, window_major ? e.digits.p : nullptr);
-        CK(cudaEventRecord(e.ev[EV_COUNT], e.st));
-        LaunchUtil::exclusive_scan(e.st, e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p);
-        e.launches += LaunchUtil::scan_launches((uint32_t)G1);
-        CK(cudaEventRecord(e.ev[EV_SCAN], e.st));
-        if (window_major) K::fill_window(e.st, sh, e.digits.p, e.counts.p, e.offsets.p, e.entries.p);
-        else K::fill(e.st, sh, d_scalars, is_mont, e.counts.p, e.offsets.p, e.entries.p);
-        CK(cudaEventRecord(e.ev[EV_FILL], e.st));
-    }
-    if (e.wait_pts) {
-        CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
-        e.wait_pts = false;
-    }
-    // affine_levels r > 0 (8-word coordinates only): r levels of pairwise batched-affine sums inside every bucket (affine_kernels.cuh) leave
-    // ceil(len / 2^r) affine nodes per bucket; the XYZZ kernel then sums those instead of the base points.  -1 (auto), from the sweeps in
-    // profiles/r02_affine.md: none below 1.2e7 entries or 32 entries per bucket (the three extra kernels per level cost more than they save:
-    // 2^18 points 1.44 vs 1.43 ms), 2 up to 4e7 entries (2^20: 3.48 vs 3.82 ms), then 3, and 4 from 128 entries per bucket on (2^24: 39.3 vs 42.9 ms)
     const uint32_t *off_final = e.offsets.p;
-    bool levels_ran = false;
-    if constexpr (C::ID != Bn254G2::ID) {
-        uint32_t levels = (uint32_t)std::max<long>(P.affine_levels, 0);
-        if (P.affine_levels < 0) {
-            const double per_bucket = (double)Mmax / (double)sh.G;
-            levels = (Mmax < 12000000u || per_bucket < 32.0) ? 0u : Mmax < 40000000u ? 2u : per_bucket >= 128.0 ? 4u : 3u;
-        }
-        if (levels > 0 && Mmax >= 2) {
-            uint32_t out_max[5], m_in = Mmax;
-            for (uint32_t l = 0; l < levels; l++) {
-                out_max[l] = (uint32_t)(((uint64_t)m_in + std::min<uint64_t>(sh.G, m_in) + 1) / 2);  // sum of ceil(len / 2) over the non-empty buckets
-                m_in = out_max[l];
+    // ---- one piece: sort, (batched-affine levels,) accumulate, fix-up ------------------------------------------------------------------------------
+    auto run_piece = [&](const AffinePt<C> *bases_k, const uint32_t *scalars_k, uint32_t n_k, uint32_t poff_k, cudaEvent_t ev_sc, cudaEvent_t ev_pts, cudaEvent_t *pe) {
+        MsmShape shp = make_shape(P, n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, poff_k, (uint64_t)n_k * sh.W);
+        shp.n = n_k;
+        const uint32_t Mk = n_k * sh.W;
+        uint32_t chunks = (Mk + shp.L - 1) / shp.L;  // re-derived below when batched-affine levels shorten the list
+        e.head.ensure((size_t)chunks * sizeof(X));
+        e.tail.ensure((size_t)chunks * sizeof(X));
+        e.tail_bucket.ensure((size_t)chunks + 1);
+        if (ev_sc) CK(cudaStreamWaitEvent(e.st, ev_sc, 0));
+        CK(cudaEventRecord(pe[PE_BEGIN], e.st));
+        // sort_mode 2: two block-local radix partitions (kernels_sort.cu); 1: counting sort with a window-major fill from stored digits (scatter
+        // region per window stays in L2); 0: counting sort, one thread per scalar recodes again and scatters into all windows;
+        // -1 (auto): radix partitions from 2^21 entries on (below, the second pass costs more than the atomics it saves: 2^16 points 0.91 vs 0.85 ms,
+        // 2^18 points 1.44 vs 1.48 ms, profiles/r02_sort.md)
+        SortPlan pl;
+        const bool radix = (P.sort_mode == 2 || (P.sort_mode < 0 && Mk >= (1u << 21))) && LaunchSort::plan(shp, pl);
+        if (radix) {
+            const size_t cw = LaunchSort::coarse_words(pl);
+            if (e.coarse_counts.cap < cw) {
+                e.coarse_counts.ensure(cw);
+                CK(cudaMemsetAsync(e.coarse_counts.p, 0, e.coarse_counts.cap * sizeof(uint32_t), e.st));  // k_sort_scan leaves it zero again
             }
-            uint32_t *off[6] = {e.offsets.p};
-            for (uint32_t l = 0; l < levels; l++) {
-                e.lvl_off[l].ensure(G1 + 4);
-                off[l + 1] = e.lvl_off[l].p;
-            }
-            e.lvl_cnt.ensure(G1 + 4);
-            e.lvl_nodes[0].ensure((size_t)out_max[0] * sizeof(AffinePt<C>));
-            if (levels > 1) e.lvl_nodes[1].ensure((size_t)out_max[1] * sizeof(AffinePt<C>));
-            AffinePt<C> *nodes[2] = {(AffinePt<C> *)e.lvl_nodes[0].p, (AffinePt<C> *)e.lvl_nodes[1].p};
-            size_t pre_words, tot_words;
-            K::affine_scratch_words(out_max[0], pre_words, tot_words);
-            e.lvl_pre.ensure(pre_words);
-            e.lvl_tot.ensure(tot_words);
-            e.launches += K::affine_levels(e.st, levels, sh.G, d_bases, e.entries.p, off, nodes, out_max, e.lvl_cnt.p, e.tile_sums.p, e.lvl_pre.p, e.lvl_tot.p);
-            // the XYZZ kernel sums what is left: chunk length re-chosen for the shorter list
-            MsmShape sh2 = make_shape(P, n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, table_off, out_max[levels - 1]);
-            sh.L = sh2.L;
-            chunks = (out_max[levels - 1] + sh.L - 1) / sh.L;
-            e.head.ensure((size_t)chunks * sizeof(X));
-            e.tail.ensure((size_t)chunks * sizeof(X));
-            e.tail_bucket.ensure((size_t)chunks + 1);
-            off_final = off[levels];
-            K::accumulate(e.st, sh, chunks, nodes[(levels - 1) & 1], off_final, nullptr, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
-            levels_ran = true;
+            e.coarse_off.ensure(cw);
+            e.coarse_cursor.ensure(cw);
+            e.digits.ensure((size_t)Mmax + 1);
+            e.part_pay.ensure((size_t)Mmax + 1);
+            e.part_fine.ensure((size_t)Mmax + 16);
+            e.launches += LaunchSort::run(e.st, std::is_same<typename C::Scalar, FqP>::value ? 0 : 1, e.sm_count, pl, scalars_k, is_mont, e.digits.p, e.coarse_counts.p,
+                                          e.coarse_off.p, e.coarse_cursor.p, e.part_pay.p, e.part_fine.p, e.entries.p, e.offsets.p, pe[PE_COUNT], pe[PE_SCAN]);
+            CK(cudaEventRecord(pe[PE_FILL], e.st));
+        } else {
+            const bool window_major = P.sort_mode == 1 || (P.sort_mode < 0 && (uint64_t)Mk * 4 > (96ull << 20));
+            if (window_major) e.digits.ensure((size_t)Mmax + 1);
+            K::count(e.st, shp, scalars_k, is_mont, e.counts.p, window_major ? e.digits.p : nullptr);
+            CK(cudaEventRecord(pe[PE_COUNT], e.st));
+            LaunchUtil::exclusive_scan(e.st, e.counts.p, e.offsets.p, (uint32_t)G1, e.tile_sums.p);
+            e.launches += 2 + LaunchUtil::scan_launches((uint32_t)G1);
+            CK(cudaEventRecord(pe[PE_SCAN], e.st));
+            if (window_major) K::fill_window(e.st, shp, e.digits.p, e.counts.p, e.offsets.p, e.entries.p);
+            else K::fill(e.st, shp, scalars_k, is_mont, e.counts.p, e.offsets.p, e.entries.p);
+            CK(cudaEventRecord(pe[PE_FILL], e.st));
         }
+        if (ev_pts) CK(cudaStreamWaitEvent(e.st, ev_pts, 0));
+        if (e.wait_pts) {
+            CK(cudaStreamWaitEvent(e.st, e.ev_pts, 0));
+            e.wait_pts = false;
+        }
+        // affine_levels r > 0 (8-word coordinates only): r levels of pairwise batched-affine sums inside every bucket (affine_kernels.cuh) leave
+        // ceil(len / 2^r) affine nodes per bucket; the XYZZ kernel then sums those instead of the base points.  -1 (auto), from the sweeps in
+        // profiles/r02_affine.md: none below 1.2e7 entries or 32 entries per bucket (the three extra kernels per level cost more than they save:
+        // 2^18 points 1.44 vs 1.43 ms), 2 up to 4e7 entries (2^20: 3.48 vs 3.82 ms), then 3, and 4 from 128 entries per bucket on (2^24: 39.3 vs 42.9 ms)
+        const uint32_t *off_k = e.offsets.p;
+        bool levels_ran = false;
+        if constexpr (C::ID != Bn254G2::ID) {
+            uint32_t levels = (uint32_t)std::max<long>(P.affine_levels, 0);
+            if (P.affine_levels < 0) {
+                const double per_bucket = (double)Mk / (double)sh.G;
+                levels = (Mk < 12000000u || per_bucket < 32.0) ? 0u : Mk < 40000000u ? 2u : per_bucket >= 128.0 ? 4u : 3u;
+            }
+            if (levels > 0 && Mk >= 2) {
+                uint32_t out_max[5], m_in = Mk;
+                for (uint32_t l = 0; l < levels; l++) {
+                    out_max[l] = (uint32_t)(((uint64_t)m_in + std::min<uint64_t>(sh.G, m_in) + 1) / 2);  // sum of ceil(len / 2) over the non-empty buckets
+                    m_in = out_max[l];
+                }
+                uint32_t *off[6] = {e.offsets.p};
+                for (uint32_t l = 0; l < levels; l++) {
+                    e.lvl_off[l].ensure(G1 + 4);
+                    off[l + 1] = e.lvl_off[l].p;
+                }
+                e.lvl_cnt.ensure(G1 + 4);
+                e.lvl_nodes[0].ensure((size_t)out_max[0] * sizeof(AffinePt<C>));
+                if (levels > 1) e.lvl_nodes[1].ensure((size_t)out_max[1] * sizeof(AffinePt<C>));
+                AffinePt<C> *nodes[2] = {(AffinePt<C> *)e.lvl_nodes[0].p, (AffinePt<C> *)e.lvl_nodes[1].p};
+                size_t pre_words, tot_words;
+                K::affine_scratch_words(out_max[0], pre_words, tot_words);
+                e.lvl_pre.ensure(pre_words);
+                e.lvl_tot.ensure(tot_words);
+                e.launches += K::affine_levels(e.st, levels, sh.G, bases_k, e.entries.p, off, nodes, out_max, e.lvl_cnt.p, e.tile_sums.p, e.lvl_pre.p, e.lvl_tot.p);
+                // the XYZZ kernel sums what is left: chunk length re-chosen for the shorter list
+                MsmShape sh2 = make_shape(P, n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, poff_k, out_max[levels - 1]);
+                shp.L = sh2.L;
+                chunks = (out_max[levels - 1] + shp.L - 1) / shp.L;
+                e.head.ensure((size_t)chunks * sizeof(X));
+                e.tail.ensure((size_t)chunks * sizeof(X));
+                e.tail_bucket.ensure((size_t)chunks + 1);
+                off_k = off[levels];
+                K::accumulate(e.st, shp, chunks, nodes[(levels - 1) & 1], off_k, nullptr, piece_dst, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
+                levels_ran = true;
+            }
+        }
+        if (!levels_ran)
+            K::accumulate(e.st, shp, chunks, bases_k, e.offsets.p, e.entries.p, piece_dst, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
+        CK(cudaEventRecord(pe[PE_ACC], e.st));
+        CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
+        K::fixup(e.st, shp, chunks, e.sm_count, off_k, piece_dst, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1, e.worklist.p);
+        if (streamed) {
+            K::bucket_merge(e.st, sh.G, off_k, piece_dst, (X *)e.bucket_acc.p);
+            e.launches++;
+        }
+        CK(cudaEventRecord(pe[PE_FIXUP], e.st));
+        e.launches += 4;  // accumulate, fixup, fixup_long (+ memset)
+        off_final = off_k;
+        sh.L = shp.L;
+    };
+    if (streamed) {
+        for (size_t k = 0; k < pieces->size(); k++) {
+            const StreamPiece &pc = (*pieces)[k];
+            if (pc.recorded)
+                while (pc.recorded->load(std::memory_order_acquire) <= k) std::this_thread::yield();  // the uploader thread is still staging this piece
+            // window table: same base pointer, shifted column; plain vector: shifted pointer
+            run_piece(table_c ? d_bases : d_bases + pc.first, d_scalars + 8 * pc.first, (uint32_t)pc.count, table_c ? table_off + (uint32_t)pc.first : 0u, pc.ev_sc,
+                      pc.ev_pts, e.pev[k]);
+        }
+        off_final = nullptr;  // every bucket is defined (zero-initialised): the reduction reads them all
+    } else {
+        cudaEvent_t pe[PE_N] = {e.ev[EV_H2D], e.ev[EV_COUNT], e.ev[EV_SCAN], e.ev[EV_FILL], e.ev[EV_ACC], e.ev[EV_FIXUP]};
+        const bool one = pieces && pieces->size() == 1;  // a host-buffer call small enough for one upload: still wait for it
+        run_piece(d_bases, d_scalars, n, table_off, one ? (*pieces)[0].ev_sc : nullptr, one ? (*pieces)[0].ev_pts : nullptr, pe);
     }
-    if (!levels_ran)
-        K::accumulate(e.st, sh, chunks, d_bases, e.offsets.p, e.entries.p, (X *)e.bucket_acc.p, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
-    CK(cudaEventRecord(e.ev[EV_ACC], e.st));
-    CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
-    K::fixup(e.st, sh, chunks, e.sm_count, off_final, (X *)e.bucket_acc.p, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1,
-             e.worklist.p);
-    CK(cudaEventRecord(e.ev[EV_FIXUP], e.st));
     // Reduce.  reduce_mode 1 (default, B >= 256): fold reduce — parallel halving folds + plain sums of the upper halves
     // (kernels_curve.cuh).  reduce_mode 0: running-sum levels (fan-in K) while many elements per window remain, then one
     // parallel weighting pass and block-level tree sums.
@@ -556,7 +631,6 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         e.n_result = nwin;
         e.result_c = sh.c;
     }
-    e.launches += 6;  // count, fill, accumulate, fixup, fixup_long (+ memset)
     CK(cudaEventRecord(e.ev[EV_END], e.st));
     CK(cudaGetLastError());
     e.last_shape[0] = sh.c; e.last_shape[1] = sh.W; e.last_shape[2] = sh.B; e.last_shape[3] = sh.L; e.last_shape[4] = sh.K; e.last_shape[5] = n;
@@ -568,6 +642,27 @@ static void collect_timing(Engine &e) {
         cudaEventElapsedTime(&ms, e.ev[a], e.ev[b]);
         return ms;
     };
+    if (e.n_pieces > 1) {  // streamed call: phases summed over the pieces; the waits for the uploads count as h2d
+        auto pel = [&](size_t k, int a, int b) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e.pev[k][a], e.pev[k][b]);
+            return ms;
+        };
+        for (int q = 1; q <= 7; q++) e.last_ms[q] = 0;
+        e.last_ms[0] = el(EV_START, EV_END);
+        float busy = 0;
+        for (size_t k = 0; k < e.n_pieces; k++) {
+            e.last_ms[1] += pel(k, PE_BEGIN, PE_COUNT);
+            e.last_ms[2] += pel(k, PE_COUNT, PE_SCAN);
+            e.last_ms[3] += pel(k, PE_SCAN, PE_FILL);
+            e.last_ms[4] += pel(k, PE_FILL, PE_ACC);   // includes the wait for the piece's points
+            e.last_ms[5] += pel(k, PE_ACC, PE_FIXUP);
+            busy += pel(k, PE_BEGIN, PE_FIXUP);
+        }
+        cudaEventElapsedTime(&e.last_ms[6], e.pev[e.n_pieces - 1][PE_FIXUP], e.ev[EV_END]);
+        e.last_ms[7] = e.last_ms[0] - busy - e.last_ms[6];
+        return;
+    }
     e.last_ms[0] = el(EV_START, EV_END);
     e.last_ms[7] = el(EV_START, EV_H2D);
     e.last_ms[1] = el(EV_H2D, EV_COUNT);
@@ -683,9 +778,18 @@ struct HostPts {
     const uint8_t *inf;
 };
 
+static bool is_pageable(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) == cudaSuccess) return at.type == cudaMemoryTypeUnregistered;
+    cudaGetLastError();
+    return true;
+}
+
 // Run an MSM over [off, off+n) of a sharded base vector.  scalars: host pointer unless on_device.
-// hp != nullptr: the bases themselves come from host memory for this call only (kgr_msm_oneshot);
-// each GPU uploads its shard into a cached buffer on its own stream before the pipeline.
+// hp != nullptr: the bases themselves come from host memory for this call only (kgr_msm_oneshot).
+// A host-buffer call is bound by PCIe upload + pipeline in sequence (the bucket accumulation of a point needs the point).  MSM is linear, so
+// every device's share is cut into pieces that are uploaded back to back on the copy stream while the pieces already on the device are sorted
+// and accumulated INTO one shared bucket set (enqueue_msm, StreamPiece); one bucket reduction closes the call.
 template <class C>
 static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scalars, bool on_device, int fmt, size_t n, uint64_t *out,
                     const HostPts *hp) {
@@ -694,8 +798,6 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
         const AffinePt<C> *pts;
         size_t pt_first, sc_first, count;
         uint32_t table_c, table_stride, table_off;
-        cudaEvent_t after = nullptr;  // pieces of one call: this piece's uploads start when the previous piece's are on the device
-        size_t eng = 0;               // index of the device's engine (pieces of one device form a group)
     };
     const Params P = t_params;  // the calling thread's tuning state, handed to every engine this call drives
     std::vector<Job> jobs;
@@ -706,146 +808,107 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             jobs.push_back(Job{&g_engines[s.eng], (const AffinePt<C> *)s.d_table, lo, lo - off, hi - lo, s.table_c, (uint32_t)s.count, (uint32_t)(lo - s.first)});
         else
             jobs.push_back(Job{&g_engines[s.eng], hp ? nullptr : (const AffinePt<C> *)s.d_pts + (lo - s.first), lo, lo - off, hi - lo, 0, 0, 0});
-        jobs.back().eng = (size_t)s.eng;
     }
     if (on_device && jobs.size() > 1) throw CudaError{cudaErrorInvalidValue, "device-resident scalars need a single-device range", __LINE__};
-    // kgr_msm_oneshot on one device: the call is bound by PCIe upload + pipeline in sequence (the bucket accumulation needs every base).
-    // MSM is linear, so a large call is cut into pieces that run as independent MSMs on separate lanes: piece k + 1 uploads while piece k
-    // accumulates, and the latency-bound reduction of one piece hides under the accumulation of the next.  Uploads are chained with events so
-    // that the pieces do not share the link.
-    bool pieces = false;
-    // pieces of >= 2^19 pairs, at most 4 (measured: 2^20 5.50 -> 4.96 ms with 2, 2^24 69.3 -> 53.3 ms with 4; below 2^19 a cut only adds fixed costs);
-    // with several devices every device's shard is cut the same way on that device's own lanes
-    if (!on_device) {
-        std::vector<Job> cut;
-        for (const Job &whole : jobs) {
-            size_t k = P.oneshot_split > 0 ? (size_t)P.oneshot_split
-                                                  : std::max<size_t>(1, std::min<size_t>(4, whole.count >> (hp ? 19 : 21)));  // scalars only: a third of the traffic, larger pieces
-            if (k > 1) {
-                ensure_lanes(whole.eng, k);
-                pieces = true;
-            }
-            size_t per = (whole.count + k - 1) / k, first_of_group = cut.size();
-            for (size_t i = 0; i < k; i++) {
-                size_t lo = std::min(whole.count, i * per), hi = std::min(whole.count, (i + 1) * per);
-                if (lo >= hi) continue;
-                Job jb = whole;
-                jb.e = &lane_of(whole.eng, i);
-                jb.pt_first = whole.pt_first + lo;
-                jb.sc_first = whole.sc_first + lo;
-                jb.count = hi - lo;
-                if (!hp) {
-                    if (whole.table_c) jb.table_off = whole.table_off + (uint32_t)lo;   // window table: same base pointer, shifted column
-                    else jb.pts = whole.pts + lo;
-                }
-                jb.after = cut.size() == first_of_group ? nullptr : (hp ? cut.back().e->ev_pts : cut.back().e->ev_sc);
-                cut.push_back(jb);
-            }
-        }
-        if (pieces) jobs.swap(cut);
-    }
     int is_mont = (fmt == KGR_SCALARS_MONTGOMERY);
     std::vector<CudaError> errs(jobs.size(), CudaError{cudaSuccess, "", 0});
-    auto launch = [&](size_t j, bool wait) {
+    auto launch = [&](size_t j) {
         try {
             Job &jb = jobs[j];
             Engine &e = *jb.e;
             e.params = P;
             CK(cudaSetDevice(e.dev));
-            if (jb.after) CK(cudaStreamWaitEvent(e.st, jb.after, 0));
             CK(cudaEventRecord(e.ev[EV_START], e.st));
-            auto dbg_t0 = std::chrono::steady_clock::now();
-            auto dbg = [&](const char *what) {
-                if (getenv("KGR_DEBUG")) fprintf(stderr, "[kgr] %s at %.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - dbg_t0).count());
-            };
-            const uint32_t *d_sc;
             if (on_device) {
-                d_sc = reinterpret_cast<const uint32_t *>(scalars) + 8 * jb.sc_first;
+                enqueue_msm<C>(e, jb.pts, reinterpret_cast<const uint32_t *>(scalars) + 8 * jb.sc_first, is_mont, (uint32_t)jb.count, jb.table_c, jb.table_stride, jb.table_off);
             } else {
-                e.scalars.ensure(jb.count * 8);
-                upload_from_host(e, e.scalars.p, scalars + 4 * jb.sc_first, jb.count * 32, e.st);
-                CK(cudaEventRecord(e.ev_sc, e.st));
-                d_sc = e.scalars.p;
-                dbg("scalars memcpyAsync returned");
-            }
-            if (hp) {
-                // bases of this call: uploaded on the copy stream while count/scan/fill (which only need the
-                // scalars) run on the main stream; the accumulate kernel waits for ev_pts
-                // (the scalars go first on the link: the copy stream waits for them, otherwise the two uploads
-                // share the PCIe bandwidth and the scalar-only kernels start late)
-                e.oneshot_pts.ensure(jb.count * sizeof(AffinePt<C>));
-                CK(cudaStreamWaitEvent(e.st_copy, e.ev_sc, 0));
-                upload_from_host(e, e.oneshot_pts.p, hp->xy + (sizeof(AffinePt<C>) / 8) * jb.pt_first, jb.count * sizeof(AffinePt<C>), e.st_copy);
-                if (hp->inf) {
-                    e.oneshot_inf.ensure(jb.count);
-                    CK(cudaMemcpyAsync(e.oneshot_inf.p, hp->inf + jb.pt_first, jb.count, cudaMemcpyHostToDevice, e.st_copy));
-                    Launch<C>::fold_inf(e.st_copy, (AffinePt<C> *)e.oneshot_pts.p, e.oneshot_inf.p, (uint32_t)jb.count);
-                    e.launches++;
+                // pieces: "oneshot_split" or automatic — points + scalars: pieces of >= 2^19 pairs, at most 4 (2^20: 4.92 ms with 2 pieces against
+                // 5.29 with one, 2^24: 49.0 ms with 4 against 65.9); scalars only (a third of the traffic): pieces of >= 2^21 pairs, at most 4
+                // (2^24: 44.4 ms against 49.0) — profiles/r02_e2e.md.  More pieces cost more than they hide: each pays its sort's fixed part,
+                // shorter buckets for the batched-affine levels and a merge pass over all buckets.
+                size_t k = P.oneshot_split > 0 ? (size_t)P.oneshot_split : std::max<size_t>(1, std::min<size_t>(4, jb.count >> (hp ? 19 : 21)));
+                k = std::min<size_t>(std::min<size_t>(k, MAX_PIECES), std::max<size_t>(jb.count, 1));
+                const size_t per = (jb.count + k - 1) / k;
+                e.scalars.ensure(std::max<size_t>(jb.count, 1) * 8);
+                if (hp) {
+                    e.oneshot_pts.ensure(std::max<size_t>(jb.count, 1) * sizeof(AffinePt<C>));
+                    if (hp->inf) e.oneshot_inf.ensure(std::max<size_t>(jb.count, 1));
+                    jb.pts = (const AffinePt<C> *)e.oneshot_pts.p;
                 }
-                CK(cudaEventRecord(e.ev_pts, e.st_copy));
-                dbg("points memcpyAsync returned");
-                e.wait_pts = true;
-                jb.pts = (const AffinePt<C> *)e.oneshot_pts.p;
+                std::vector<StreamPiece> pieces;
+                for (size_t i = 0; i < k; i++) {
+                    size_t lo = std::min(jb.count, i * per), hi = std::min(jb.count, (i + 1) * per);
+                    if (lo >= hi && i > 0) break;
+                    if (!e.ev_piece_sc[i]) {
+                        CK(cudaEventCreateWithFlags(&e.ev_piece_sc[i], cudaEventDisableTiming));
+                        CK(cudaEventCreateWithFlags(&e.ev_piece_pts[i], cudaEventDisableTiming));
+                    }
+                    pieces.push_back(StreamPiece{lo, hi - lo, e.ev_piece_sc[i], hp ? e.ev_piece_pts[i] : nullptr, nullptr});
+                }
+                std::atomic<size_t> recorded(0);
+                CudaError up_err{cudaSuccess, "", 0};
+                // uploads, piece after piece on the copy stream (scalars first: the sort only needs them); the copy stream starts after
+                // everything enqueued on the main stream so far (the previous call's kernels may still read the buffers)
+                auto upload_all = [&]() {
+                    try {
+                        CK(cudaSetDevice(e.dev));
+                        CK(cudaStreamWaitEvent(e.st_copy, e.ev[EV_START], 0));
+                        for (size_t i = 0; i < pieces.size(); i++) {
+                            const StreamPiece &pc = pieces[i];
+                            upload_from_host(e, e.scalars.p + 8 * pc.first, scalars + 4 * (jb.sc_first + pc.first), pc.count * 32, e.st_copy);
+                            CK(cudaEventRecord(pc.ev_sc, e.st_copy));
+                            if (hp) {
+                                AffinePt<C> *dst = (AffinePt<C> *)e.oneshot_pts.p + pc.first;
+                                upload_from_host(e, dst, hp->xy + (sizeof(AffinePt<C>) / 8) * (jb.pt_first + pc.first), pc.count * sizeof(AffinePt<C>), e.st_copy);
+                                if (hp->inf) {
+                                    CK(cudaMemcpyAsync(e.oneshot_inf.p + pc.first, hp->inf + jb.pt_first + pc.first, pc.count, cudaMemcpyHostToDevice, e.st_copy));
+                                    Launch<C>::fold_inf(e.st_copy, dst, e.oneshot_inf.p + pc.first, (uint32_t)pc.count);
+                                    e.launches++;
+                                }
+                                CK(cudaEventRecord(pc.ev_pts, e.st_copy));
+                            }
+                            recorded.store(i + 1, std::memory_order_release);
+                        }
+                    } catch (CudaError &ce) {
+                        up_err = ce;
+                        recorded.store(pieces.size(), std::memory_order_release);  // never leave the enqueueing thread waiting
+                    }
+                };
+                // Pinned sources: the copies are enqueued at once, from this thread.  Pageable sources are staged through pinned slots by host
+                // threads (upload_from_host), which takes as long as the transfer itself: a second thread does that while this one enqueues the
+                // pieces that are already on their way.
+                const bool threaded = pieces.size() > 1 && (is_pageable(scalars) || (hp && is_pageable(hp->xy)));
+                std::thread uploader;
+                if (threaded) {
+                    for (auto &pc : pieces) pc.recorded = &recorded;
+                    uploader = std::thread(upload_all);
+                } else {
+                    upload_all();
+                }
+                try {
+                    enqueue_msm<C>(e, jb.pts, e.scalars.p, is_mont, (uint32_t)jb.count, jb.table_c, jb.table_stride, jb.table_off, &pieces);
+                } catch (...) {
+                    if (uploader.joinable()) uploader.join();
+                    throw;
+                }
+                if (uploader.joinable()) uploader.join();
+                if (up_err.e != cudaSuccess) throw up_err;
             }
-            enqueue_msm<C>(e, jb.pts, d_sc, is_mont, (uint32_t)jb.count, jb.table_c, jb.table_stride, jb.table_off);
-            dbg("pipeline enqueued");
-            if (!wait) return;
             CK(cudaStreamSynchronize(e.st));
-            dbg("stream synchronized");
             collect_timing(e);
         } catch (CudaError &ce) {
             errs[j] = ce;
         }
     };
-    if (pieces) {
-        // per device one thread enqueues that device's pieces in order (the upload chain needs every event recorded before the next piece waits
-        // on it), then waits for them
-        auto run_group = [&](size_t eng) {
-            for (size_t j = 0; j < jobs.size(); j++)
-                if (jobs[j].eng == eng) launch(j, false);
-            for (size_t j = 0; j < jobs.size(); j++) {
-                if (jobs[j].eng != eng || errs[j].e != cudaSuccess) continue;
-                cudaSetDevice(jobs[j].e->dev);
-                if (cudaError_t ce = cudaStreamSynchronize(jobs[j].e->st); ce != cudaSuccess) errs[j] = CudaError{ce, "cudaStreamSynchronize", __LINE__};
-                else collect_timing(*jobs[j].e);
-            }
-        };
-        std::vector<size_t> groups;
-        for (auto &jb : jobs)
-            if (std::find(groups.begin(), groups.end(), jb.eng) == groups.end()) groups.push_back(jb.eng);
-        if (groups.size() == 1) {
-            run_group(groups[0]);
-        } else {
-            std::vector<std::thread> th;
-            for (size_t g : groups) th.emplace_back(run_group, g);
-            for (auto &t : th) t.join();
-        }
-    } else if (jobs.size() <= 1) {
-        for (size_t j = 0; j < jobs.size(); j++) launch(j, true);
+    if (jobs.size() <= 1) {
+        for (size_t j = 0; j < jobs.size(); j++) launch(j);
     } else {
         std::vector<std::thread> th;
-        for (size_t j = 0; j < jobs.size(); j++) th.emplace_back(launch, j, true);
+        for (size_t j = 0; j < jobs.size(); j++) th.emplace_back(launch, j);
         for (auto &t : th) t.join();
     }
     for (auto &ce : errs)
         if (ce.e != cudaSuccess) throw ce;
-    if (pieces) {
-        // kgr_last_timing of a call cut into pieces: per device, phases summed over its pieces, total = first start .. last end, n = the device's pairs
-        for (size_t j = 0; j < jobs.size(); j++) {
-            if (jobs[j].e != &g_engines[jobs[j].eng]) continue;  // lane 0 of a device carries the device's figures
-            Engine &e0 = *jobs[j].e;
-            size_t pairs = jobs[j].count, last = j;
-            for (size_t i = 0; i < jobs.size(); i++) {
-                if (i == j || jobs[i].eng != jobs[j].eng) continue;
-                for (int q = 1; q <= 7; q++) e0.last_ms[q] += jobs[i].e->last_ms[q];
-                pairs += jobs[i].count;
-                last = std::max(last, i);
-            }
-            cudaSetDevice(e0.dev);
-            cudaEventElapsedTime(&e0.last_ms[0], e0.ev[EV_START], jobs[last].e->ev[EV_END]);
-            e0.last_shape[5] = (uint32_t)pairs;
-        }
-    }
     std::vector<Partial> parts;
     for (auto &jb : jobs) parts.push_back(Partial{jb.e->h_result, jb.e->n_result, jb.e->result_c});
     auto t0 = std::chrono::steady_clock::now();

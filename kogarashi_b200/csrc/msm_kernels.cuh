@@ -388,6 +388,17 @@ KGR_HD void body_fixup(uint32_t t, const MsmShape &sh, const uint32_t *offsets, 
     store_xyzz(&bucket_acc[g], acc);
 }
 
+// A host-buffer call streamed in pieces (msm.cu: enqueue_msm, StreamPiece): every piece is accumulated into its own bucket array and then
+// added, bucket by bucket, to the call's zero-initialised bucket set (all-zero words are an XYZZ identity: zz = 0), so that ONE bucket
+// reduction serves the whole call.  One thread per bucket: every lane does the same general addition, unlike an addition at the moment a
+// bucket is flushed inside the accumulate loop, which diverges (measured: the accumulate kernel 2.3x slower, profiles/r02_e2e.md).
+template <class C> KGR_HD void body_bucket_merge(uint32_t g, uint32_t G, const uint32_t *piece_offsets, const XyzzPt<C> *piece_acc, XyzzPt<C> *bucket_acc) {
+    if (g >= G || piece_offsets[g] == piece_offsets[g + 1]) return;  // buckets the piece never wrote
+    XyzzPt<C> a = bucket_acc[g];
+    xyzz_add(a, piece_acc[g]);
+    store_xyzz(&bucket_acc[g], a);
+}
+
 // Partial sum of the pieces of hot bucket g owned by lane `lane` of `lanes` cooperating threads
 // (piece 0 is tail[t0], piece k >= 1 is head[t0 + k]); the caller tree-adds the lane results.
 template <class C>

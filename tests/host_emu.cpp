@@ -101,23 +101,41 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         for (uint32_t i = 0; i < n + 5; i++) body_precompute<C>(i, n + 5, sh.c, sh.W, n + 5, ext.data(), table.data());
     }
     const AffinePt<C> *acc_bases = collapsed ? table.data() : bases.data();
+    // seed bit 5: the call arrives in two pieces (msm.cu: StreamPiece): each piece is sorted and accumulated on its own, its bucket sums are
+    // merged into one shared, zero-initialised bucket set (body_bucket_merge), and one reduction over all buckets closes the call
+    const uint32_t n_pieces = ((seed >> 5) & 1) && n >= 2 ? 2 : 1;
+    const bool streamed = n_pieces > 1;
+    const uint32_t chunks_max = ((uint64_t)n * sh.W + L - 1) / L + 1;
+    std::vector<XyzzPt<C>> call_acc(sh.G), bucket_acc(sh.G), head(chunks_max), tail(chunks_max);
+    memset(call_acc.data(), 0, call_acc.size() * sizeof(XyzzPt<C>));  // the device zero-fills the call's buckets: all-zero words are an XYZZ identity
+    const uint32_t affine_levels = C::ID == 2 ? 0 : (seed >> 1) % 4;
+    uint32_t M = 0;
+    std::vector<uint32_t> offsets_last, off_cur_last;
+    const MsmShape sh_call = sh;
+    for (uint32_t piece = 0; piece < n_pieces; piece++) {
+    const uint32_t first = piece ? n / 2 : 0, n_k = n_pieces == 1 ? n : (piece ? n - n / 2 : n / 2);
+    MsmShape sh = sh_call;
+    sh.n = n_k;
+    if (collapsed) sh.poff = sh_call.poff + first;  // window table: same base pointer, shifted column
+    const uint32_t *scalars_k = scalars.data() + 8 * (size_t)first;
+    const AffinePt<C> *acc_bases_k = collapsed ? acc_bases : acc_bases + first;
     std::vector<uint32_t> counts(sh.G + 1, 0), offsets(sh.G + 2, 0);
     const bool window_major = (seed & 1) != 0;  // odd seeds exercise the window-major fill from stored digits
-    std::vector<uint32_t> digits((size_t)n * sh.W + 1, 0x77777777u);
-    for (uint32_t i = 0; i < n; i++) body_count<C>(i, sh, scalars.data(), is_mont, counts.data(), window_major ? digits.data() : nullptr);
+    std::vector<uint32_t> digits((size_t)n_k * sh.W + 1, 0x77777777u);
+    for (uint32_t i = 0; i < n_k; i++) body_count<C>(i, sh, scalars_k, is_mont, counts.data(), window_major ? digits.data() : nullptr);
     uint32_t run_sum = 0;
     for (uint32_t g = 0; g <= sh.G; g++) { offsets[g] = run_sum; run_sum += counts[g]; }
-    uint32_t M = offsets[sh.G];
-    std::vector<uint32_t> entries(M + 1, 0xdeadbeefu);
+    const uint32_t M_k = offsets[sh.G];
+    M += M_k;
+    std::vector<uint32_t> entries(M_k + 1, 0xdeadbeefu);
     if (window_major) {
         for (uint32_t w = 0; w < sh.W; w++)
-            for (uint32_t i = 0; i < n; i++) body_fill_window<C>(i, w, sh, digits.data(), counts.data(), offsets.data(), entries.data());
+            for (uint32_t i = 0; i < n_k; i++) body_fill_window<C>(i, w, sh, digits.data(), counts.data(), offsets.data(), entries.data());
     } else {
-        for (uint32_t i = 0; i < n; i++) body_fill<C>(i, sh, scalars.data(), is_mont, counts.data(), offsets.data(), entries.data());
+        for (uint32_t i = 0; i < n_k; i++) body_fill<C>(i, sh, scalars_k, is_mont, counts.data(), offsets.data(), entries.data());
     }
     for (uint32_t g = 0; g <= sh.G; g++) if (counts[g] != 0) { printf("FAIL counts not consumed at %u\n", g); return 1; }
-    uint32_t chunks = ((uint64_t)n * sh.W + L - 1) / L + 1;
-    std::vector<XyzzPt<C>> bucket_acc(sh.G), head(chunks), tail(chunks);
+    uint32_t chunks = ((uint64_t)n_k * sh.W + L - 1) / L + 1;
     // poison so that a missing write is noticed
     memset(bucket_acc.data(), 0xAB, bucket_acc.size() * sizeof(XyzzPt<C>));
     memset(head.data(), 0xCD, head.size() * sizeof(XyzzPt<C>));
@@ -127,7 +145,6 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     // position inside every bucket, the odd last node copied, off_{l+1} = scan of ceil(len / 2) — and the pair_case / pair_sum helpers are the
     // device code; the inverse of each denominator is computed directly here (the kernels share one inversion between many denominators by
     // Montgomery's trick, which yields the same field element).  G2 has no affine levels on the device.
-    const uint32_t affine_levels = C::ID == 2 ? 0 : (seed >> 1) % 4;
     std::vector<uint32_t> off_cur(offsets.begin(), offsets.begin() + sh.G + 1);
     std::vector<AffinePt<C>> nodes;
     if constexpr (C::ID != 2) {
@@ -138,7 +155,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
             auto load = [&](uint32_t pos) {
                 if (l > 0) return nodes[pos];
                 uint32_t ent = entries[pos];
-                AffinePt<C> pt = acc_bases[ent & 0x7fffffffu];
+                AffinePt<C> pt = acc_bases_k[ent & 0x7fffffffu];
                 pt.y = fp_cneg(pt.y, (ent >> 31) != 0);
                 return pt;
             };
@@ -163,7 +180,7 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         if (affine_levels)
             body_accumulate<C>(t, sh, nodes.data(), acc_off, (const uint32_t *)nullptr, bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
         else
-            body_accumulate<C>(t, sh, acc_bases, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
+            body_accumulate<C>(t, sh, acc_bases_k, offsets.data(), entries.data(), bucket_acc.data(), head.data(), tail.data(), tail_bucket.data());
     }
     std::vector<uint32_t> worklist(sh.G + 1);
     uint32_t wl_len = 0;
@@ -177,6 +194,14 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
         }
         bucket_acc[worklist[i]] = tot;
     }
+    if (streamed)
+        for (uint32_t g = 0; g < sh.G; g++) body_bucket_merge<C>(g, sh.G, acc_off, bucket_acc.data(), call_acc.data());
+    offsets_last = offsets;
+    off_cur_last = off_cur;
+    }  // pieces
+    if (streamed) bucket_acc = call_acc;
+    // the reduction: a streamed call reads every bucket (they are all defined), otherwise the empty ones are recognised from the offsets
+    const uint32_t *acc_off = streamed ? nullptr : (affine_levels ? off_cur_last.data() : offsets_last.data());
     std::vector<XyzzPt<C>> win(nwin);
     const bool fold_reduce = ((seed >> 4) & 1) != 0 && sh.B >= 4;  // the default reduction of the GPU path (k_fold / k_fold_tail / k_vsum* / k_fold_combine)
     if (fold_reduce) {
