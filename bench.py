@@ -339,7 +339,7 @@ def measure_strong(k, torch, dist, sharding, curve_name, logn_total, world, rank
                "max_rank_device_ms": res["resident"]["max_rank_device_ms"],
                "e2e": {"value": n_total / res["host_scalars"]["wall_ms_per_step"] / 1e3, "unit": UNIT, "ms_per_step": res["host_scalars"]["wall_ms_per_step"],
                        "h2d_bytes_per_step": 32 * n_total, "d2h_bytes_per_step": world * max(1, min(4, count >> 21)) * W * 128,
-                       "h2d_gbs_per_gpu": 32 * count / (res["host_scalars"]["wall_ms_per_step"] * 1e-3) / 1e9,
+                       "h2d_gbs_per_gpu_averaged_over_the_step": 32 * count / (res["host_scalars"]["wall_ms_per_step"] * 1e-3) / 1e9,
                        "call": "kgr_msm per rank (bases registered, scalars uploaded from pinned host memory every step) + all_gather of the partial points + host sum"},
                "checksum_ok": bool((exp == aff[0]).all() and (exp == aff[1]).all()), "result_is_identity": bool(int(aff[0][-1])), "affine": aff[0],
                "clocks": clocks, "gpu_launches_per_step_per_rank": launches,
