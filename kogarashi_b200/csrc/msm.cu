@@ -500,15 +500,16 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         }
         // affine_levels r > 0 (8-word coordinates only): r levels of pairwise batched-affine sums inside every bucket (affine_kernels.cuh) leave
         // ceil(len / 2^r) affine nodes per bucket; the XYZZ kernel then sums those instead of the base points.  -1 (auto), from the sweeps in
-        // profiles/r02_affine.md: none below 1.2e7 entries or 32 entries per bucket (the three extra kernels per level cost more than they save:
-        // 2^18 points 1.44 vs 1.43 ms), 2 up to 4e7 entries (2^20: 3.48 vs 3.82 ms), then 3, and 4 from 128 entries per bucket on (2^24: 39.3 vs 42.9 ms)
+        // profiles/r02_affine.md and r02_e2e.md: none below 8e6 entries or 16 entries per bucket (the three extra kernels per level cost more than they
+        // save: 2^18 points 1.44 vs 1.43 ms), 1 up to 1.2e7 (a 2^19-point piece of a streamed 2^20 call: 4.77 vs 4.91 ms), 2 up to 4e7 entries
+        // (2^20: 3.48 vs 3.82 ms), then 3, and 4 from 128 entries per bucket on (2^24: 39.3 vs 42.9 ms)
         const uint32_t *off_k = e.offsets.p;
         bool levels_ran = false;
         if constexpr (C::ID != Bn254G2::ID) {
             uint32_t levels = (uint32_t)std::max<long>(P.affine_levels, 0);
             if (P.affine_levels < 0) {
                 const double per_bucket = (double)Mk / (double)sh.G;
-                levels = (Mk < 12000000u || per_bucket < 32.0) ? 0u : Mk < 40000000u ? 2u : per_bucket >= 128.0 ? 4u : 3u;
+                levels = (Mk < 8000000u || per_bucket < 16.0) ? 0u : Mk < 12000000u ? 1u : Mk < 40000000u ? 2u : per_bucket >= 128.0 ? 4u : 3u;
             }
             if (levels > 0 && Mk >= 2) {
                 uint32_t out_max[5], m_in = Mk;
@@ -822,11 +823,14 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             if (on_device) {
                 enqueue_msm<C>(e, jb.pts, reinterpret_cast<const uint32_t *>(scalars) + 8 * jb.sc_first, is_mont, (uint32_t)jb.count, jb.table_c, jb.table_stride, jb.table_off);
             } else {
-                // pieces: "oneshot_split" or automatic — points + scalars: pieces of >= 2^19 pairs, at most 4 (2^20: 4.92 ms with 2 pieces against
-                // 5.29 with one, 2^24: 49.0 ms with 4 against 65.9); scalars only (a third of the traffic): pieces of >= 2^21 pairs, at most 4
-                // (2^24: 44.4 ms against 49.0) — profiles/r02_e2e.md.  More pieces cost more than they hide: each pays its sort's fixed part,
-                // shorter buckets for the batched-affine levels and a merge pass over all buckets.
-                size_t k = P.oneshot_split > 0 ? (size_t)P.oneshot_split : std::max<size_t>(1, std::min<size_t>(4, jb.count >> (hp ? 19 : 21)));
+                // pieces: "oneshot_split" or automatic (profiles/r02_e2e.md) — points + scalars: 2 pieces from 2^20 pairs, 3 from 2^22, 4 from 2^24
+                // (2^20: 4.92 ms with 2 pieces against 5.29 with one; 2^22: 15.1 with 3 against 17.7; 2^24: 49.0 with 4 against 65.9); scalars only
+                // (a third of the traffic): 2 from 2^22, 3 from 2^24 (2^24: 44.7 ms against 49.0).  More pieces cost more than they hide: each pays
+                // its sort's fixed part, shorter buckets for the batched-affine levels and a merge pass over all buckets.
+                size_t lg = 0;
+                while (((size_t)2 << lg) <= jb.count) lg++;  // floor(log2(count))
+                size_t k_auto = lg >= (hp ? 20u : 22u) ? std::min<size_t>(4, (lg - (hp ? 16 : 18)) / 2) : 1;
+                size_t k = P.oneshot_split > 0 ? (size_t)P.oneshot_split : k_auto;
                 k = std::min<size_t>(std::min<size_t>(k, MAX_PIECES), std::max<size_t>(jb.count, 1));
                 const size_t per = (jb.count + k - 1) / k;
                 e.scalars.ensure(std::max<size_t>(jb.count, 1) * 8);
