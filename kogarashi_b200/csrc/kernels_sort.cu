@@ -152,7 +152,7 @@ __global__ void __launch_bounds__(SORT_TPB) k_sort_partition(SortPlan pl, const 
                 uint32_t c = cnt[b];
                 lstart[b] = ex;
                 gbase[b] = c ? atomicAdd(&cursor[seg * pl.nbins + b], c) : 0u;
-                cnt[b] = 0;  // becomes the running rank of the second pass
+                cnt[b] = ex;  // becomes the running staging position of the second pass (start + rank: no second lookup of lstart[])
                 ex += c;
             }
         }
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(SORT_TPB) k_sort_partition(SortPlan pl, const 
             for (int u = 0; u < 4; u++) {
                 if (wd[u] != NO_DIGIT) {
                     uint32_t b = wd[u] & 0x7fffffffu, bin = b >> pl.F;
-                    uint32_t pos = lstart[bin] + atomicAdd(&cnt[bin], 1u);
+                    uint32_t pos = atomicAdd(&cnt[bin], 1u);
                     stage_pay[pos] = (pay0 + k0 + u * SORT_TPB + threadIdx.x) | (wd[u] & 0x80000000u);
                     stage_fine[pos] = (uint8_t)(b & fmask);
                 }
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(SORT_TPB) k_sort_partition(SortPlan pl, const 
 __global__ void __launch_bounds__(SORT_TPB) k_sort_buckets(SortPlan pl, const uint32_t *coarse_off, const uint32_t *part_pay, const uint8_t *part_fine,
                                                           uint32_t *entries, uint32_t *offsets) {
     extern __shared__ uint32_t sorted[];
-    __shared__ uint32_t cnt[256], start[256], scan_sm[33];
+    __shared__ uint32_t cnt[256], scan_sm[33];
     const uint32_t nf = 1u << pl.F;
     for (uint32_t sb = blockIdx.x; sb < pl.nseg * pl.nbins; sb += gridDim.x) {
         const uint32_t base = coarse_off[sb], size = coarse_off[sb + 1] - base;
@@ -218,8 +218,7 @@ __global__ void __launch_bounds__(SORT_TPB) k_sort_buckets(SortPlan pl, const ui
             uint32_t v = threadIdx.x < nf ? cnt[threadIdx.x] : 0u, total;
             uint32_t ex = block_exclusive_scan(v, &total, scan_sm);
             if (threadIdx.x < nf) {
-                start[threadIdx.x] = ex;
-                cnt[threadIdx.x] = 0;
+                cnt[threadIdx.x] = ex;  // running position of the placement pass (bucket start + rank)
                 offsets[(size_t)seg * (pl.nbins << pl.F) + ((size_t)bin << pl.F) + threadIdx.x] = base + ex;
             }
         }
@@ -235,7 +234,7 @@ __global__ void __launch_bounds__(SORT_TPB) k_sort_buckets(SortPlan pl, const ui
                 }
 #pragma unroll
                 for (int u = 0; u < 8; u++)
-                    if (f[u] != 0xffffffffu) sorted[start[f[u]] + atomicAdd(&cnt[f[u]], 1u)] = py[u];
+                    if (f[u] != 0xffffffffu) sorted[atomicAdd(&cnt[f[u]], 1u)] = py[u];
             }
             __syncthreads();
             for (uint32_t k = threadIdx.x; k < size; k += SORT_TPB) entries[base + k] = sorted[k];
@@ -243,7 +242,7 @@ __global__ void __launch_bounds__(SORT_TPB) k_sort_buckets(SortPlan pl, const ui
             // a bin that outgrew the shared-memory buffer (skewed scalars, or the thin top window): same placement, written straight to global
             for (uint32_t k = threadIdx.x; k < size; k += SORT_TPB) {
                 uint32_t f = part_fine[base + k];
-                entries[base + start[f] + atomicAdd(&cnt[f], 1u)] = part_pay[base + k];
+                entries[base + atomicAdd(&cnt[f], 1u)] = part_pay[base + k];
             }
         }
         __syncthreads();

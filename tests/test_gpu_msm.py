@@ -533,3 +533,62 @@ def test_batched_affine_levels_vs_oracle(k, curve, logn):
     finally:
         k.set_param("affine_levels", -1)
         k.set_param("window_bits", 0)
+
+
+def test_handles_die_with_their_kgr_init_and_pinned_arena(k):
+    """ADVICE r1: a handle created before a second kgr_init is refused (its shards name engines that no longer exist) but can still be freed;
+    kgr_host_alloc gives page-locked memory that the calls read directly (what the Rust shim's PinnedArena marshals into)."""
+    import ctypes
+
+    from kogarashi_b200 import _lib
+    curve = A.BN254_G1
+    pts = A.random_points(curve, 64, seed=bytes(range(16)))
+    sc = A.random_field(A.FIELD_FR, 64, seed=bytes(range(1, 17)))
+    exp = A.to_affine(curve, A.msm(curve, pts, sc))
+    old = k.Bases(curve, pts)
+    assert same_affine(k.to_affine(curve, k.msm_curve_addition(old, sc)), exp)
+    k.init([0])                                            # re-numbers the engines: `old` belongs to the previous generation
+    with pytest.raises(k.KgrError, match="before the last kgr_init"):
+        k.msm_curve_addition(old, sc)
+    with pytest.raises(k.KgrError, match="before the last kgr_init"):
+        old.precompute(4)
+    old.free()                                             # its device memory is released on the device it was allocated on
+    fresh = k.Bases(curve, pts)
+    assert same_affine(k.to_affine(curve, k.msm_curve_addition(fresh, sc)), exp)
+    fresh.free()
+    # pinned arena
+    L = _lib.lib()
+    p_xy, p_sc = ctypes.c_void_p(), ctypes.c_void_p()
+    _lib.check(L.kgr_host_alloc(pts.nbytes, ctypes.byref(p_xy)))
+    _lib.check(L.kgr_host_alloc(sc.nbytes, ctypes.byref(p_sc)))
+    ctypes.memmove(p_xy, pts.ctypes.data, pts.nbytes)
+    ctypes.memmove(p_sc, sc.ctypes.data, sc.nbytes)
+    got = k.msm_oneshot_ptr(curve, p_xy.value, 64, p_sc.value, 64)
+    assert same_affine(k.to_affine(curve, got), exp)
+    _lib.check(L.kgr_host_free(p_xy))
+    _lib.check(L.kgr_host_free(p_sc))
+
+
+def test_set_param_is_per_thread(k):
+    """kgr_set_param changes the calling thread's tuning state only — a window size forced on another thread does not
+    reach an MSM issued from this one (the engine's last shape shows the automatic choice), and vice versa."""
+    import threading
+    curve = A.BN254_G1
+    pts = A.random_points(curve, 256, seed=bytes(range(16)))
+    sc = A.random_field(A.FIELD_FR, 256, seed=bytes(range(1, 17)))
+    exp = A.to_affine(curve, A.msm(curve, pts, sc))
+    k.msm_curve_addition(pts, sc, curve=curve)
+    auto_c = k.last_timing(0)[1]["c"]
+    seen = {}
+
+    def other():
+        k.set_param("window_bits", 3)
+        seen["aff"] = k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve))
+        seen["c"] = k.last_timing(0)[1]["c"]
+
+    t = threading.Thread(target=other)
+    t.start()
+    t.join()
+    assert seen["c"] == 3 and same_affine(seen["aff"], exp)
+    assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp)
+    assert k.last_timing(0)[1]["c"] == auto_c              # this thread never asked for c = 3
