@@ -17,8 +17,8 @@
 // (profiles/r02_affine.md).  Now a level is three kernels, each with every lane busy:
 //   k_affine_den   thread = AFF_K consecutive OUTPUT nodes: chord / tangent denominators front to back, prefix products to a coalesced
 //                  scratch array, the thread's total to tot[]
-//   k_batch_inv    tot[] inverted in place: each CTA shares ONE safegcd inversion between 1024 values (prefixes in shared memory, product
-//                  tree, inverses pushed back down) — 1 inversion per 16 K additions
+//   k_batch_inv    tot[] inverted in place: each CTA shares ONE safegcd inversion between 2048 values (per-thread prefixes, product
+//                  tree in shared memory, inverses pushed back down) — 1 inversion per 32 K additions
 //   k_affine_add   back to front: 1 / den_j = inv * prefix_j, lambda, x3, y3 (5 multiplications), output node stored
 // All inputs and outputs are whole 64-byte points at consecutive addresses per thread.
 #pragma once
@@ -28,7 +28,7 @@ namespace kgr {
 
 constexpr int AFF_TPB = 128;  // threads per CTA of the level kernels
 constexpr int AFF_K = 16;     // output nodes per thread
-constexpr int INV_K = 8;      // values per thread of k_batch_inv (one inversion per AFF_TPB * INV_K values)
+constexpr int INV_K = 16;     // values per thread of k_batch_inv (one inversion per AFF_TPB * INV_K values)
 
 // level-l nodes: the sorted entries over the base array (level 0) or an array of affine points (level >= 1)
 template <class C> struct AffLevelIn {
@@ -141,10 +141,12 @@ __global__ void __launch_bounds__(AFF_TPB, 4) k_affine_den(AffLevelIn<C> in, con
     }
 }
 
-// v[0 .. n) (word-major, stride NT) inverted in place; all values are non-zero.  One inversion per CTA.
-template <class E> __global__ void __launch_bounds__(AFF_TPB) k_batch_inv(uint32_t *v, uint32_t n, uint32_t NT) {
+// v[0 .. n) (word-major, stride NT) inverted in place; all values are non-zero.  One inversion per CTA (AFF_TPB * INV_K values).
+// The per-thread prefix products go to `pfx` (same layout as v) rather than to shared memory: the CTA then holds 8 KB of shared memory instead
+// of 40, so that enough CTAs are resident per SM to fill the ~100 dependent multiplications of the product tree and the single-thread
+// inversion with the other CTAs' prefix / back-substitution work (r02: 15.8 of 32 lanes active and 58 % multiplier utilisation before).
+template <class E> __global__ void __launch_bounds__(AFF_TPB) k_batch_inv(uint32_t *v, uint32_t n, uint32_t NT, uint32_t *pfx) {
     constexpr int EW = El<E>::WORDS;
-    __shared__ uint32_t s_pre[INV_K * EW * AFF_TPB];
     __shared__ uint32_t s_tree[EW * 2 * AFF_TPB];
     const int tid = threadIdx.x;
     const uint32_t base = blockIdx.x * (AFF_TPB * INV_K);
@@ -152,13 +154,15 @@ template <class E> __global__ void __launch_bounds__(AFF_TPB) k_batch_inv(uint32
 #pragma unroll 1
     for (int i = 0; i < INV_K; i++) {
         const uint32_t idx = base + i * AFF_TPB + tid;
-        E x = El<E>::one();
         if (idx < n) {
+            E x;
 #pragma unroll
-            for (int w = 0; w < EW; w++) El<E>::word(x, w) = v[(size_t)w * NT + idx];
+            for (int w = 0; w < EW; w++) {
+                El<E>::word(x, w) = v[(size_t)w * NT + idx];
+                pfx[(size_t)w * NT + idx] = El<E>::word(run, w);
+            }
+            run = fp_mul(run, x);
         }
-        sm_put_el(s_pre, INV_K * AFF_TPB, i * AFF_TPB + tid, run);
-        run = fp_mul(run, x);
     }
     sm_put_el(s_tree, 2 * AFF_TPB, AFF_TPB + tid, run);
     __syncthreads();
@@ -186,10 +190,13 @@ template <class E> __global__ void __launch_bounds__(AFF_TPB) k_batch_inv(uint32
     for (int i = INV_K; i-- > 0;) {
         const uint32_t idx = base + i * AFF_TPB + tid;
         if (idx < n) {
-            E x;
+            E x, pj;
 #pragma unroll
-            for (int w = 0; w < EW; w++) El<E>::word(x, w) = v[(size_t)w * NT + idx];
-            E xi = fp_mul(inv_run, sm_get_el<E>(s_pre, INV_K * AFF_TPB, i * AFF_TPB + tid));
+            for (int w = 0; w < EW; w++) {
+                El<E>::word(x, w) = v[(size_t)w * NT + idx];
+                El<E>::word(pj, w) = pfx[(size_t)w * NT + idx];
+            }
+            E xi = fp_mul(inv_run, pj);
             inv_run = fp_mul(inv_run, x);
 #pragma unroll
             for (int w = 0; w < EW; w++) v[(size_t)w * NT + idx] = El<E>::word(xi, w);

@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *buckets, Xyzz
 // latency-bound, so they are not worth a launch apiece.  Same reads and writes as k_fold; a level's output is the next level's input,
 // ordered by the CTA barrier.
 constexpr int TPB_TAIL = 256;
-constexpr uint32_t VSUM_ELEMS = 2;  // 2 serial additions + a 7-level tree per CTA (8: 15 dependent additions, +50 us on the critical path of the reduction)
+constexpr uint32_t VSUM_ELEMS = 8;  // 8 serial additions + a 7-level tree per CTA: one wave of CTAs at B = 2^14 (2: four times the CTAs and their trees, reduce 0.46 -> 0.55 ms at 2^20)
 template <class C> __global__ void __launch_bounds__(TPB_TAIL) k_fold_tail(XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t l_first) {
     const uint32_t w = blockIdx.x, i = threadIdx.x;
     for (uint32_t l = l_first; l <= nb; l++) {  // l_first >= 2: the input is always a fold level in F

@@ -45,7 +45,7 @@ static inline uint32_t affine_threads(uint32_t out_max) { return cdiv(cdiv(out_m
 template <class C> void Launch<C>::affine_scratch_words(uint32_t out_max0, size_t &pre_words, size_t &tot_words) {
     const size_t NT = affine_threads(out_max0), EW = El<typename C::Elem>::WORDS;
     pre_words = NT * AFF_K * EW;
-    tot_words = NT * EW;
+    tot_words = 2 * NT * EW;  // totals + the prefix products of k_batch_inv
 }
 template <class C>
 int Launch<C>::affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const A *bases, const uint32_t *entries, uint32_t *const off[], A *const nodes[2],
@@ -57,7 +57,7 @@ int Launch<C>::affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const
         AffLevelIn<C> in{l == 0 ? bases : nodes[(l - 1) & 1], l == 0 ? entries : nullptr};
         const uint32_t NT = affine_threads(out_max[l]);
         k_affine_den<C><<<NT / AFF_TPB, AFF_TPB, 0, st>>>(in, off[l], off[l + 1], G, NT, pre, tot);
-        k_batch_inv<typename C::Elem><<<cdiv(NT, AFF_TPB * INV_K), AFF_TPB, 0, st>>>(tot, NT, NT);
+        k_batch_inv<typename C::Elem><<<cdiv(NT, AFF_TPB * INV_K), AFF_TPB, 0, st>>>(tot, NT, NT, tot + (size_t)NT * El<typename C::Elem>::WORDS);
         k_affine_add<C><<<NT / AFF_TPB, AFF_TPB, 0, st>>>(in, off[l], off[l + 1], G, NT, pre, tot, nodes[l & 1]);
         launches += 4 + (scan_num_tiles(G + 1) > 1 ? 3 : 1);
     }

@@ -56,7 +56,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_levels = -1, oneshot_split = 0, lane_threads = 1;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_levels = -1, oneshot_split = 0, oneshot_growth = 0, lane_threads = 1;
 };
 // Tuning state is per calling thread (kgr_set_param changes the calling thread's copy only): an entry point snapshots it once and hands the
 // snapshot to every engine it drives (Engine::params), so a kgr_set_param on one thread never changes an MSM in flight on another, and the
@@ -823,16 +823,29 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
             if (on_device) {
                 enqueue_msm<C>(e, jb.pts, reinterpret_cast<const uint32_t *>(scalars) + 8 * jb.sc_first, is_mont, (uint32_t)jb.count, jb.table_c, jb.table_stride, jb.table_off);
             } else {
-                // pieces: "oneshot_split" or automatic (profiles/r02_e2e.md) — points + scalars: 2 pieces from 2^20 pairs, 3 from 2^22, 4 from 2^24
-                // (2^20: 4.92 ms with 2 pieces against 5.29 with one; 2^22: 15.1 with 3 against 17.7; 2^24: 49.0 with 4 against 65.9); scalars only
-                // (a third of the traffic): 2 from 2^22, 3 from 2^24 (2^24: 44.7 ms against 49.0).  More pieces cost more than they hide: each pays
-                // its sort's fixed part, shorter buckets for the batched-affine levels and a merge pass over all buckets.
+                // pieces: "oneshot_split" / "oneshot_growth" or automatic (tools/probe_e2e_growth.py, profiles/r02_e2e.md).  Nothing overlaps the FIRST
+                // piece's upload, so it is the smallest; piece i + 1 is `growth` times piece i, as long as its upload still ends before the
+                // pipeline is through with the pieces before it (points + scalars: 1.75 ms of PCIe against 2.35 ms of pipeline per 2^20 pairs, so
+                // growth <= 1.3 for long calls; scalars only: a third of the traffic, growth 3).  Each piece pays its sort's fixed part, shorter
+                // buckets for the batched-affine levels and a merge pass over all buckets (0.1 - 0.3 ms), which bounds their number:
+                // points + scalars 2^20: 2 pieces x 1.7 (4.63 ms; equal halves 4.88, one piece 5.25), 2^24: 5 x 1.3 (46.7; four equal pieces 49.0, one 66.0);
+                // scalars only 2^20: one piece (4.25), 2^24: 3 x 3.0 (42.4; equal 44.7, one 49.0).
                 size_t lg = 0;
                 while (((size_t)2 << lg) <= jb.count) lg++;  // floor(log2(count))
-                size_t k_auto = lg >= (hp ? 20u : 22u) ? std::min<size_t>(4, (lg - (hp ? 16 : 18)) / 2) : 1;
+                size_t k_auto = hp ? (lg < 20 ? 1 : lg < 22 ? 2 : lg == 22 ? 3 : lg == 23 ? 4 : 5) : (lg < 22 ? 1 : lg < 24 ? 2 : 3);
                 size_t k = P.oneshot_split > 0 ? (size_t)P.oneshot_split : k_auto;
                 k = std::min<size_t>(std::min<size_t>(k, MAX_PIECES), std::max<size_t>(jb.count, 1));
-                const size_t per = (jb.count + k - 1) / k;
+                const double growth = (P.oneshot_growth > 0 ? (double)P.oneshot_growth : !hp ? 300.0 : k <= 2 ? 170.0 : k == 3 ? 150.0 : 130.0) / 100.0;
+                std::vector<size_t> cut(k + 1, 0);
+                {
+                    double tot_w = 0, w = 1, acc_w = 0;
+                    for (size_t i = 0; i < k; i++, w *= growth) tot_w += w;
+                    w = 1;
+                    for (size_t i = 0; i < k; i++, w *= growth) {
+                        acc_w += w;
+                        cut[i + 1] = i + 1 == k ? jb.count : std::min<size_t>(jb.count, (size_t)((double)jb.count * (acc_w / tot_w)));
+                    }
+                }
                 e.scalars.ensure(std::max<size_t>(jb.count, 1) * 8);
                 if (hp) {
                     e.oneshot_pts.ensure(std::max<size_t>(jb.count, 1) * sizeof(AffinePt<C>));
@@ -841,8 +854,8 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 }
                 std::vector<StreamPiece> pieces;
                 for (size_t i = 0; i < k; i++) {
-                    size_t lo = std::min(jb.count, i * per), hi = std::min(jb.count, (i + 1) * per);
-                    if (lo >= hi && i > 0) break;
+                    size_t lo = cut[i], hi = cut[i + 1];
+                    if (lo >= hi && !(i + 1 == k && pieces.empty())) continue;  // an empty piece of a tiny call (the last one is kept if nothing else exists)
                     if (!e.ev_piece_sc[i]) {
                         CK(cudaEventCreateWithFlags(&e.ev_piece_sc[i], cudaEventDisableTiming));
                         CK(cudaEventCreateWithFlags(&e.ev_piece_pts[i], cudaEventDisableTiming));
@@ -1283,6 +1296,7 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "reduce_mode") t_params.reduce_mode = value;
     else if (s == "lane_threads") t_params.lane_threads = value ? 1 : 0;
     else if (s == "oneshot_split") t_params.oneshot_split = std::min<long>(std::max<long>(value, 0), (long)MAX_LANES);
+    else if (s == "oneshot_growth") t_params.oneshot_growth = std::min<long>(std::max<long>(value, 0), 1000);
     else if (s == "affine_levels") t_params.affine_levels = std::min<long>(std::max<long>(value, -1), 5);
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
