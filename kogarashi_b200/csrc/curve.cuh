@@ -160,6 +160,85 @@ template <class C> KGR_HD void xyzz_add(XyzzPt<C> &acc, const XyzzPt<C> &q) {
     acc.zzz = fp_mul(fp_mul(acc.zzz, q.zzz), ppp);
 }
 
+#if defined(__CUDACC__)
+// ---- quad-cooperative group law (device only) ----------------------------------------------------------------------------------------------
+// The tail of the bucket reduction (deep fold levels, tree sums, the per-bit doubling chains) is a chain of dependent point operations on a
+// handful of points: one lone warp needs ~6-8 us per general addition because its 14 field multiplications run one after the other.  Here the
+// FOUR lanes of a quad hold the same operands, each computes one of up to four independent products of a round and the results are exchanged
+// with shuffles: 4 rounds instead of 14 multiplications for an addition, 3 instead of 9 for a doubling.  Same formulas, same special cases and
+// the same field elements as xyzz_add / xyzz_dbl (add-2008-s, dbl-2008-s-1), so the result is identical in every word.
+// All four lanes of the quad must call with identical arguments; the result is returned in all four.
+template <class E> __device__ __forceinline__ E quad_get(const E &v, unsigned mask, int src_lane) {
+    E r;
+#pragma unroll
+    for (int w = 0; w < El<E>::WORDS; w++) El<E>::word(r, w) = __shfl_sync(mask, El<E>::word(v, w), src_lane);
+    return r;
+}
+template <class E> __device__ __forceinline__ E quad_sel(int role, const E &a, const E &b, const E &c, const E &d) {
+    E r;
+#pragma unroll
+    for (int w = 0; w < El<E>::WORDS; w++) {
+        uint32_t lo = role & 1 ? El<E>::word(b, w) : El<E>::word(a, w), hi = role & 1 ? El<E>::word(d, w) : El<E>::word(c, w);
+        El<E>::word(r, w) = role & 2 ? hi : lo;
+    }
+    return r;
+}
+template <class C> __device__ __forceinline__ XyzzPt<C> xyzz_dbl_quad(const XyzzPt<C> &p) {
+    typedef typename C::Elem E;
+    if (xyzz_is_identity(p)) return p;
+    const int lane = (int)(threadIdx.x & 31u), role = lane & 3, qb = lane & 28;
+    const unsigned mask = 0xFu << qb;
+    XyzzPt<C> r;
+    E u = fp_dbl(p.y);
+    // round 1: v = u^2 | xx = x^2
+    E m1 = fp_sqr(quad_sel(role, u, p.x, u, p.x));
+    E v = quad_get(m1, mask, qb), xx = quad_get(m1, mask, qb + 1);
+    E m = fp_add(fp_dbl(xx), xx);
+    // round 2: w = u v | s = x v | zz3 = v zz | mm = m^2
+    E m2 = fp_mul(quad_sel(role, u, p.x, v, m), quad_sel(role, v, v, p.zz, m));
+    E w = quad_get(m2, mask, qb), sv = quad_get(m2, mask, qb + 1), mm = quad_get(m2, mask, qb + 3);
+    r.zz = quad_get(m2, mask, qb + 2);
+    r.x = fp_sub(mm, fp_dbl(sv));
+    // round 3: m (s - x3) | w y | zzz3 = w zzz
+    E m3 = fp_mul(quad_sel(role, m, w, w, w), quad_sel(role, fp_sub(sv, r.x), p.y, p.zzz, p.zzz));
+    r.y = fp_sub(quad_get(m3, mask, qb), quad_get(m3, mask, qb + 1));
+    r.zzz = quad_get(m3, mask, qb + 2);
+    return r;
+}
+template <class C> __device__ __forceinline__ void xyzz_add_quad(XyzzPt<C> &acc, const XyzzPt<C> &q) {
+    typedef typename C::Elem E;
+    if (xyzz_is_identity(q)) return;
+    if (xyzz_is_identity(acc)) {
+        acc = q;
+        return;
+    }
+    const int lane = (int)(threadIdx.x & 31u), role = lane & 3, qb = lane & 28;
+    const unsigned mask = 0xFu << qb;
+    // round 1: u1 = x1 zz2 | u2 = x2 zz1 | s1 = y1 zzz2 | s2 = y2 zzz1
+    E m1 = fp_mul(quad_sel(role, acc.x, q.x, acc.y, q.y), quad_sel(role, q.zz, acc.zz, q.zzz, acc.zzz));
+    E u1 = quad_get(m1, mask, qb), u2 = quad_get(m1, mask, qb + 1), s1 = quad_get(m1, mask, qb + 2), s2 = quad_get(m1, mask, qb + 3);
+    E p = fp_sub(u2, u1);
+    E r = fp_sub(s2, s1);
+    if (fp_is_zero(p)) {  // the same for all four lanes
+        if (fp_is_zero(r)) acc = xyzz_dbl_quad(acc);
+        else acc = xyzz_identity<C>();
+        return;
+    }
+    // round 2: pp = p^2 | rr = r^2 | zz1 zz2 | zzz1 zzz2
+    E m2 = fp_mul(quad_sel(role, p, r, acc.zz, acc.zzz), quad_sel(role, p, r, q.zz, q.zzz));
+    E pp = quad_get(m2, mask, qb), rr = quad_get(m2, mask, qb + 1), zz12 = quad_get(m2, mask, qb + 2), zzz12 = quad_get(m2, mask, qb + 3);
+    // round 3: ppp = p pp | qq = u1 pp | zz3 = zz12 pp
+    E m3 = fp_mul(quad_sel(role, p, u1, zz12, zz12), pp);
+    E ppp = quad_get(m3, mask, qb), qq = quad_get(m3, mask, qb + 1);
+    acc.zz = quad_get(m3, mask, qb + 2);
+    acc.x = fp_sub(fp_sub(rr, ppp), fp_dbl(qq));
+    // round 4: r (qq - x3) | s1 ppp | zzz3 = zzz12 ppp
+    E m4 = fp_mul(quad_sel(role, r, s1, zzz12, zzz12), quad_sel(role, fp_sub(qq, acc.x), ppp, ppp, ppp));
+    acc.y = fp_sub(quad_get(m4, mask, qb), quad_get(m4, mask, qb + 1));
+    acc.zzz = quad_get(m4, mask, qb + 2);
+}
+#endif
+
 // XYZZ -> the reference's homogeneous projective (X : Y : Z), x = X/Z, y = Y/Z
 // (zkstd/src/macros/curve/weierstrass/group.rs:106-110 identity = (0, 1, 0)).
 template <class C> KGR_HD void xyzz_to_projective(const XyzzPt<C> &p, typename C::Elem out[3]) {

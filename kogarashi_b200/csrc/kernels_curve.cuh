@@ -51,12 +51,26 @@ template <class C> __device__ __forceinline__ XyzzPt<C> sm_get(const uint32_t *s
     for (int k = 0; k < xyzz_words<C>(); k++) w[k] = sm[k * TPB_TREE + t];
     return p;
 }
-// Sum of the TPB_TREE per-thread points of a CTA, returned in thread 0 (log2(TPB_TREE) add latencies).
+// Sum of the first 2 * s0 points of the shared-memory array (s0 a power of two <= TPB_TREE / 4), left in slot 0: level s adds slot qd + s to
+// slot qd with the four lanes of quad qd working on one addition (xyzz_add_quad), log2(2 s0) quad-addition latencies.  Every thread of the
+// CTA calls it (barriers inside); sm must be complete and visible (barrier before the call).
+template <class C> __device__ __forceinline__ void quad_tree_sum(uint32_t *sm, int s0) {
+    const int t = threadIdx.x, qd = t >> 2;
+    for (int s = s0; s > 0; s >>= 1) {
+        if (qd < s) {
+            XyzzPt<C> a = sm_get<C>(sm, qd), b = sm_get<C>(sm, qd + s);
+            xyzz_add_quad(a, b);
+            if ((t & 3) == 0) sm_put<C>(sm, qd, a);
+        }
+        __syncthreads();
+    }
+}
+// Sum of the TPB_TREE per-thread points of a CTA, returned in thread 0: one level with a thread per addition, then the quad tree.
 template <class C> __device__ __forceinline__ XyzzPt<C> block_tree_sum(XyzzPt<C> v, uint32_t *sm) {
     const int t = threadIdx.x;
     sm_put<C>(sm, t, v);
     __syncthreads();
-    for (int s = TPB_TREE / 2; s > 0; s >>= 1) {
+    for (int s = TPB_TREE / 2; s > TPB_TREE / 4; s >>= 1) {
         if (t < s) {
             XyzzPt<C> o = sm_get<C>(sm, t + s);
             xyzz_add(v, o);
@@ -64,7 +78,8 @@ template <class C> __device__ __forceinline__ XyzzPt<C> block_tree_sum(XyzzPt<C>
         }
         __syncthreads();
     }
-    return v;
+    quad_tree_sum<C>(sm, TPB_TREE / 4);
+    return sm_get<C>(sm, 0);
 }
 // One CTA per queued hot bucket (grid-stride over the worklist).
 template <class C>
@@ -119,25 +134,38 @@ __global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *buckets, Xyzz
 // ordered by the CTA barrier.
 constexpr int TPB_TAIL = 256;
 constexpr uint32_t VSUM_ELEMS = 8;  // 8 serial additions + a 7-level tree per CTA: one wave of CTAs at B = 2^14 (2: four times the CTAs and their trees, reduce 0.46 -> 0.55 ms at 2^20)
+constexpr uint32_t VSUM_ELEMS_LATE = 1;  // the levels summed after the folds (l > l_split) are on the critical path and small: one element per thread
+__host__ __device__ __forceinline__ uint32_t vsum_elems(uint32_t l, uint32_t l_split) { return l <= l_split ? VSUM_ELEMS : VSUM_ELEMS_LATE; }
 template <class C> __global__ void __launch_bounds__(TPB_TAIL) k_fold_tail(XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t l_first) {
     const uint32_t w = blockIdx.x, i = threadIdx.x;
     for (uint32_t l = l_first; l <= nb; l++) {  // l_first >= 2: the input is always a fold level in F
-        if (i < (B >> l)) body_fold<C>(w, i, l, B, nullptr, F, nullptr);
+        const uint32_t m = B >> l;
+        if (4 * m <= (uint32_t)TPB_TAIL) {  // few additions left: four lanes per addition
+            const uint32_t qd = i >> 2;
+            if (qd < m) {
+                const XyzzPt<C> *in = F + (size_t)w * B + fold_level_offset(B, l - 1);
+                XyzzPt<C> a = in[qd], b = in[qd + m];
+                xyzz_add_quad(a, b);
+                if ((i & 3) == 0) store_xyzz(&F[(size_t)w * B + fold_level_offset(B, l) + qd], a);
+            }
+        } else if (i < m) {
+            body_fold<C>(w, i, l, B, nullptr, F, nullptr);
+        }
         __syncthreads();
     }
 }
-// Partial sums of the upper halves: grid (chunk, level - l_first, window); a CTA sums up to 8 * TPB_TREE elements of one upper half.
+// Partial sums of the upper halves: grid (chunk, level - l_first, window); a CTA sums up to vsum_elems(l) * TPB_TREE elements of one upper half.
 template <class C>
 __global__ void __launch_bounds__(TPB_TREE) k_vsum1(const XyzzPt<C> *buckets, const XyzzPt<C> *F, uint32_t B, uint32_t nb, uint32_t chunks_max,
-                                                    const uint32_t *bucket_offsets, XyzzPt<C> *partial, uint32_t l_first) {
+                                                    const uint32_t *bucket_offsets, XyzzPt<C> *partial, uint32_t l_first, uint32_t l_split) {
     __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     const uint32_t chunk = blockIdx.x, l = blockIdx.y + l_first, w = blockIdx.z;
-    const uint32_t m = B >> l;
-    if (chunk * VSUM_ELEMS * TPB_TREE >= m) return;  // uniform per CTA
+    const uint32_t m = B >> l, elems = vsum_elems(l, l_split);
+    if (chunk * elems * TPB_TREE >= m) return;  // uniform per CTA
     XyzzPt<C> acc = xyzz_identity<C>();
 #pragma unroll 1
-    for (uint32_t k = 0; k < VSUM_ELEMS; k++) {
-        uint32_t i = chunk * VSUM_ELEMS * TPB_TREE + k * TPB_TREE + threadIdx.x;
+    for (uint32_t k = 0; k < elems; k++) {
+        uint32_t i = chunk * elems * TPB_TREE + k * TPB_TREE + threadIdx.x;
         XyzzPt<C> x;
         if (i < m && fold_upper_elem<C>(w, i, l, B, buckets, F, bucket_offsets, x)) xyzz_add(acc, x);
     }
@@ -145,24 +173,33 @@ __global__ void __launch_bounds__(TPB_TREE) k_vsum1(const XyzzPt<C> *buckets, co
     if (threadIdx.x == 0) store_xyzz(&partial[((size_t)w * nb + (l - 1)) * chunks_max + chunk], acc);
 }
 // grid (level - 1, window): V[w][bit] = sum of that level's partials, bit = nb - level
-template <class C> __global__ void __launch_bounds__(TPB_TREE) k_vsum2(const XyzzPt<C> *partial, uint32_t B, uint32_t nb, uint32_t chunks_max, XyzzPt<C> *V) {
+template <class C>
+__global__ void __launch_bounds__(TPB_TREE) k_vsum2(const XyzzPt<C> *partial, uint32_t B, uint32_t nb, uint32_t chunks_max, XyzzPt<C> *V, uint32_t l_split) {
     __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
     const uint32_t l = blockIdx.x + 1, w = blockIdx.y;
-    const uint32_t m = B >> l;
-    const uint32_t cnt = (m + VSUM_ELEMS * TPB_TREE - 1) / (VSUM_ELEMS * TPB_TREE);
+    const uint32_t m = B >> l, per = vsum_elems(l, l_split) * TPB_TREE;
+    const uint32_t cnt = (m + per - 1) / per;
     const XyzzPt<C> *src = partial + ((size_t)w * nb + (l - 1)) * chunks_max;
     XyzzPt<C> acc = xyzz_identity<C>();
     for (uint32_t i = threadIdx.x; i < cnt; i += TPB_TREE) xyzz_add(acc, src[i]);
     acc = block_tree_sum<C>(acc, sm);
     if (threadIdx.x == 0) store_xyzz(&V[(size_t)w * nb + (nb - l)], acc);
 }
-// grid (window): out[w] = T0 + sum_b 2^b V[w][b]; lane b doubles V_b b times, then a CTA tree sum.
+// grid (window): out[w] = T0 + sum_b 2^b V[w][b]; quad b doubles V_b b times (four lanes per doubling), then a quad tree sum over the nb + 1 terms.
 template <class C> __global__ void __launch_bounds__(TPB_TREE) k_fold_combine(const XyzzPt<C> *F, const XyzzPt<C> *V, uint32_t B, uint32_t nb, XyzzPt<C> *out) {
     __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
-    const uint32_t w = blockIdx.x, t = threadIdx.x;
-    XyzzPt<C> acc = (t <= nb) ? fold_combine_term<C>(w, t, B, nb, F, V) : xyzz_identity<C>();
-    acc = block_tree_sum<C>(acc, sm);
-    if (t == 0) store_xyzz(&out[w], acc);
+    static_assert(TPB_TREE / 4 >= 24, "one quad per term: nb + 1 <= 24");
+    const uint32_t w = blockIdx.x, t = threadIdx.x, qd = t >> 2;
+    XyzzPt<C> acc = xyzz_identity<C>();
+    if (qd == nb) acc = F[(size_t)w * B + (B - 2)];
+    else if (qd < nb) {
+        acc = V[(size_t)w * nb + qd];
+        for (uint32_t d = 0; d < qd; d++) acc = xyzz_dbl_quad(acc);
+    }
+    if ((t & 3) == 0) sm_put<C>(sm, qd, acc);
+    __syncthreads();
+    quad_tree_sum<C>(sm, TPB_TREE / 8);
+    if (t == 0) store_xyzz(&out[w], sm_get<C>(sm, 0));
 }
 // Horner over windows on the device (kept for kgr_set_param("final_on_device", 1)); one thread.
 template <class C> __global__ void k_final(MsmShape sh, const XyzzPt<C> *win_a, XyzzPt<C> *out) {
@@ -198,6 +235,34 @@ template <class C> __global__ void k_point_op(int op, const AffinePt<C> *a, cons
         xyzz_madd(t, b[i]);             // 3b  (non-unit zz)
         xyzz_add(acc, t);               // a + 3b
     }
+    typename C::Elem o[3];
+    xyzz_to_projective(acc, o);
+    constexpr int NW = El<typename C::Elem>::WORDS;
+    for (int k = 0; k < 3; k++)
+        for (int j = 0; j < NW; j++) out24[3 * NW * (size_t)i + NW * k + j] = El<typename C::Elem>::word(o[k], j);
+}
+
+// The quad-cooperative operations against the oracle (four threads per element): op 3: a + 3b with 3b = dbl_quad(b) + b, op 4: (a + b) + (b + a)
+// through the equal-points branch on two different representatives, op 5: (a + b) + (-(b + a)) -> identity.
+template <class C> __global__ void k_point_op_quad(int op, const AffinePt<C> *a, const AffinePt<C> *b, uint32_t *out24, uint32_t n) {
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+    if (i >= n) return;
+    XyzzPt<C> acc = xyzz_from_affine(a[i]);
+    if (op == 3) {
+        XyzzPt<C> t = xyzz_dbl_quad(xyzz_from_affine(b[i]));
+        xyzz_madd(t, b[i]);
+        xyzz_add_quad(acc, t);
+    } else {
+        xyzz_madd(acc, b[i]);  // a + b, zz = (xb - xa)^2
+        XyzzPt<C> v = xyzz_dbl(xyzz_from_affine(b[i]));
+        xyzz_madd(v, a[i]);    // 2b + a
+        AffinePt<C> nb_ = b[i];
+        nb_.y = fp_neg(nb_.y);
+        xyzz_madd(v, nb_);     // (2b + a) - b = b + a on another representative (identity operands fall through the special cases)
+        if (op == 5) v.y = fp_neg(v.y);
+        xyzz_add_quad(acc, v);
+    }
+    if ((threadIdx.x & 3) != 0) return;
     typename C::Elem o[3];
     xyzz_to_projective(acc, o);
     constexpr int NW = El<typename C::Elem>::WORDS;

@@ -93,7 +93,9 @@ template <class C> void Launch<C>::tree_sum(cudaStream_t st, uint32_t n_windows,
 }
 #endif
 #if KGR_PART & 8
-template <class C> uint32_t Launch<C>::fold_chunks_max(uint32_t B) { return ((B >> 1) + VSUM_ELEMS * TPB_TREE - 1) / (VSUM_ELEMS * TPB_TREE); }
+// columns of `partial` per (window, level): the early levels (<= l_split) are summed VSUM_ELEMS * TPB_TREE elements per CTA, the late ones
+// VSUM_ELEMS_LATE * TPB_TREE; level 1 (B / 2 elements) bounds both
+template <class C> uint32_t Launch<C>::fold_chunks_max(uint32_t B) { return ((B >> 1) + VSUM_ELEMS_LATE * TPB_TREE - 1) / (VSUM_ELEMS_LATE * TPB_TREE); }
 template <class C>
 int Launch<C>::fold_reduce(cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_fork, cudaEvent_t ev_join, uint32_t n_windows, uint32_t B, const X *buckets,
                            const uint32_t *bucket_offsets, X *F, X *partial, X *V, X *out) {
@@ -102,20 +104,21 @@ int Launch<C>::fold_reduce(cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_for
     int launches = 0;
     const uint32_t chunks_max = fold_chunks_max(B);
     const uint32_t l_early = 3;  // upper halves of levels 1..3 are summed on st2 as soon as fold level 2 exists
-    bool forked = false;
+    const bool fork = l_early < nb && (B >> 2) > (uint32_t)TPB_TAIL;  // fold level 2 gets its own launch
+    const uint32_t l_split = fork ? l_early : 0;
     uint32_t l = 1;
     for (; l <= nb; l++) {
         uint32_t m = B >> l;
         if (l >= 2 && m <= (uint32_t)TPB_TAIL) break;  // the rest in one kernel
         k_fold<C><<<cdiv((size_t)n_windows * m, TPB_RED), TPB_RED, 0, st>>>(buckets, F, B, l, n_windows, bucket_offsets);
         launches++;
-        if (l + 1 == l_early && l_early < nb) {
+        if (fork && l + 1 == l_early) {
             cudaEventRecord(ev_fork, st);
             cudaStreamWaitEvent(st2, ev_fork, 0);
-            k_vsum1<C><<<dim3(chunks_max, l_early, n_windows), TPB_TREE, 0, st2>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial, 1);
+            const uint32_t chunks = ((B >> 1) + VSUM_ELEMS * TPB_TREE - 1) / (VSUM_ELEMS * TPB_TREE);
+            k_vsum1<C><<<dim3(chunks, l_early, n_windows), TPB_TREE, 0, st2>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial, 1, l_split);
             cudaEventRecord(ev_join, st2);
             launches++;
-            forked = true;
         }
     }
     if (l <= nb) {
@@ -123,14 +126,14 @@ int Launch<C>::fold_reduce(cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_for
         launches++;
     }
     {
-        uint32_t first = forked ? l_early + 1 : 1;
+        uint32_t first = fork ? l_early + 1 : 1;
         uint32_t m = B >> first;
-        uint32_t chunks = (m + VSUM_ELEMS * TPB_TREE - 1) / (VSUM_ELEMS * TPB_TREE);
-        k_vsum1<C><<<dim3(chunks, nb - first + 1, n_windows), TPB_TREE, 0, st>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial, first);
+        uint32_t chunks = (m + VSUM_ELEMS_LATE * TPB_TREE - 1) / (VSUM_ELEMS_LATE * TPB_TREE);
+        k_vsum1<C><<<dim3(chunks, nb - first + 1, n_windows), TPB_TREE, 0, st>>>(buckets, F, B, nb, chunks_max, bucket_offsets, partial, first, l_split);
         launches++;
     }
-    if (forked) cudaStreamWaitEvent(st, ev_join, 0);
-    k_vsum2<C><<<dim3(nb, n_windows), TPB_TREE, 0, st>>>(partial, B, nb, chunks_max, V);
+    if (fork) cudaStreamWaitEvent(st, ev_join, 0);
+    k_vsum2<C><<<dim3(nb, n_windows), TPB_TREE, 0, st>>>(partial, B, nb, chunks_max, V, l_split);
     k_fold_combine<C><<<n_windows, TPB_TREE, 0, st>>>(F, V, B, nb, out);
     return launches + 2;
 }
@@ -144,7 +147,8 @@ template <class C> void Launch<C>::precompute(cudaStream_t st, uint32_t n, uint3
     k_precompute<C><<<cdiv(n, 128), 128, 0, st>>>(n, c, W, stride, pts, table);
 }
 template <class C> void Launch<C>::point_op(cudaStream_t st, int op, const A *a, const A *b, uint32_t *out24, uint32_t n) {
-    k_point_op<C><<<cdiv(n, 64), 64, 0, st>>>(op, a, b, out24, n);
+    if (op >= 3) k_point_op_quad<C><<<cdiv((size_t)n * 4, 64), 64, 0, st>>>(op, a, b, out24, n);
+    else k_point_op<C><<<cdiv(n, 64), 64, 0, st>>>(op, a, b, out24, n);
 }
 template <class C> void Launch<C>::gen_scalars(cudaStream_t st, uint64_t seed, uint64_t first, uint32_t n, S *out) {
     k_gen_scalars<C><<<cdiv(n, 256), 256, 0, st>>>(seed, first, n, out);

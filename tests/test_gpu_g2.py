@@ -68,6 +68,17 @@ def test_point_ops_bit_exact(k):
         # host-side helpers of the library agree with the oracle as well
         assert same_affine(k.to_affine(C2, got_add[i]), A.to_affine(C2, got_add[i])), i
         assert same_affine(k.to_affine(C2, k.proj_add(C2, pa, pb)), A.to_affine(C2, A.point_op(C2, 0, pa, pb))), i
+    # quad-cooperative addition / doubling (reduction tail): general case, equal-points and opposite-points branches, identity operands
+    got_q3 = M.test_point_op(C2, 3, a, b, a_inf, b_inf)
+    got_q4 = M.test_point_op(C2, 4, a, b, a_inf, b_inf)
+    got_q5 = M.test_point_op(C2, 5, a, b, a_inf, b_inf)
+    ident = A.to_affine(C2, _proj(a[0], 1))
+    for i in range(n):
+        pa, pb = _proj(a[i], a_inf[i]), _proj(b[i], b_inf[i])
+        b3 = A.point_op(C2, 0, A.point_op(C2, 1, pb), pb)
+        assert same_affine(A.to_affine(C2, got_q3[i]), A.to_affine(C2, A.point_op(C2, 0, pa, b3))), i
+        assert same_affine(A.to_affine(C2, got_q4[i]), A.to_affine(C2, A.point_op(C2, 1, A.point_op(C2, 0, pa, pb)))), i
+        assert same_affine(A.to_affine(C2, got_q5[i]), ident), i
 
 
 @pytest.mark.parametrize("name", golden_g2_case_names())

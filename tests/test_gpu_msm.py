@@ -95,6 +95,18 @@ def test_point_ops_bit_exact(k, curve):
         assert same_affine(A.to_affine(curve, got_dbl[i]), A.to_affine(curve, A.point_op(curve, 1, pa))), i
         b3 = A.point_op(curve, 0, A.point_op(curve, 1, pb), pb)
         assert same_affine(A.to_affine(curve, got_a3b[i]), A.to_affine(curve, A.point_op(curve, 0, pa, b3))), i
+    # the quad-cooperative addition / doubling of the reduction tail (curve.cuh: four lanes per point operation): general case on non-trivial
+    # representatives, the equal-points branch (two representatives of a + b), the opposite-points branch, identity operands
+    got_q3 = M.test_point_op(curve, 3, a, b, a_inf, b_inf)
+    got_q4 = M.test_point_op(curve, 4, a, b, a_inf, b_inf)
+    got_q5 = M.test_point_op(curve, 5, a, b, a_inf, b_inf)
+    ident = A.to_affine(curve, proj(a[0], 1))
+    for i in range(n):
+        pa, pb = proj(a[i], a_inf[i]), proj(b[i], b_inf[i])
+        b3 = A.point_op(curve, 0, A.point_op(curve, 1, pb), pb)
+        assert same_affine(A.to_affine(curve, got_q3[i]), A.to_affine(curve, A.point_op(curve, 0, pa, b3))), i
+        assert same_affine(A.to_affine(curve, got_q4[i]), A.to_affine(curve, A.point_op(curve, 1, A.point_op(curve, 0, pa, pb)))), i
+        assert same_affine(A.to_affine(curve, got_q5[i]), ident), i
 
 
 @pytest.mark.parametrize("name", golden_case_names())
