@@ -501,7 +501,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         // affine_levels r > 0 (8-word coordinates only): r levels of pairwise batched-affine sums inside every bucket (affine_kernels.cuh) leave
         // ceil(len / 2^r) affine nodes per bucket; the XYZZ kernel then sums those instead of the base points.  -1 (auto), from the sweeps in
         // profiles/r02_affine.md and r02_e2e.md: none below 8e6 entries or 16 entries per bucket (the three extra kernels per level cost more than they
-        // save: 2^18 points 1.44 vs 1.43 ms), 1 up to 1.2e7 (a 2^19-point piece of a streamed 2^20 call: 4.77 vs 4.91 ms), 2 up to 4e7 entries
+        // save: 2^18 points 1.44 vs 1.43 ms), 1 up to 1.2e7 (a 2^19-point piece of a streamed 2^20 call: 4.77 vs 4.91 ms), 2 up to 3e7 entries
         // (2^20: 3.48 vs 3.82 ms), then 3, and 4 from 128 entries per bucket on (2^24: 39.3 vs 42.9 ms)
         const uint32_t *off_k = e.offsets.p;
         bool levels_ran = false;
@@ -509,7 +509,7 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
             uint32_t levels = (uint32_t)std::max<long>(P.affine_levels, 0);
             if (P.affine_levels < 0) {
                 const double per_bucket = (double)Mk / (double)sh.G;
-                levels = (Mk < 8000000u || per_bucket < 16.0) ? 0u : Mk < 12000000u ? 1u : Mk < 40000000u ? 2u : per_bucket >= 128.0 ? 4u : 3u;
+                levels = (Mk < 8000000u || per_bucket < 16.0) ? 0u : Mk < 12000000u ? 1u : Mk < 30000000u ? 2u : per_bucket >= 128.0 ? 4u : 3u;
             }
             if (levels > 0 && Mk >= 2) {
                 uint32_t out_max[5], m_in = Mk;
