@@ -68,7 +68,9 @@ int Launch<C>::affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const
 template <class C>
 void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
                       const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
-    k_fixup<C><<<cdiv(chunks, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);
+    // four lanes per chunk, or per bucket when the chunks outnumber the buckets (kernels_curve.cuh)
+    if (chunks > sh.G) k_fixup_buckets<C><<<cdiv((size_t)sh.G * 4, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+    else k_fixup<C><<<cdiv((size_t)chunks * 4, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);
     unsigned blocks = sh.G < 4u * (unsigned)sm_count ? sh.G : 4u * (unsigned)sm_count;
     k_fixup_long<C><<<blocks, TPB_TREE, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
 }
