@@ -372,7 +372,12 @@ static MsmShape make_shape(const Params &P, uint32_t n, int blocks_per_sm, int s
         uint64_t concurrent = (uint64_t)std::max(1, blocks_per_sm) * TPB_ACC * std::max(1, sm_count);
         double best = 1e300;
         uint32_t bestL = 32;
-        for (uint32_t L = 16; L <= 256; L += 4) {
+        // short lists (one wave whatever L is): the chain of L dependent additions per thread is the latency of the kernel, and the quad fix-up sums
+        // the pieces of a cut bucket cheaply, so L goes down to 4 as long as a typical bucket is cut into <= ~4 pieces (more than
+        // FIXUP_INLINE_MAX pieces take the hot-bucket path): 2^10 points 0.38 -> 0.32 ms, 2^12 0.37 -> 0.34 ms
+        const uint64_t per_bucket = M / std::max<uint64_t>(1, sh.G);
+        const uint32_t L_lo = (uint32_t)std::min<uint64_t>(16, std::max<uint64_t>(4, (per_bucket / 4 + 3) & ~3ull));
+        for (uint32_t L = L_lo; L <= 256; L += 4) {
             uint64_t chunks = (M + L - 1) / L;
             uint64_t waves = (chunks + concurrent - 1) / concurrent;
             double cost = (double)waves * (L + 2.0);

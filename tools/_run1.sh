@@ -1,2 +1,1 @@
-timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-for a in "10" "12" "13" "14" "15" "16" "17" "18" "20" "14 curve=2" "16 curve=2"; do echo "== $a"; python tools/one_msm.py $a 2>&1 | tail -1 | cut -c1-330; done
+for n in 10 12 14 15 16; do for L in 4 8 12 16; do echo "== $n chunk=$L"; python tools/one_msm.py $n chunk=$L 2>&1 | tail -1 | cut -c1-250; done; done
