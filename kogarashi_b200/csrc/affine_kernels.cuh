@@ -103,7 +103,7 @@ struct AffWalk {
 
 // scratch layout: word w of (slot j, thread t) at ((j * EW + w) * NT + t): every warp access is 128 consecutive bytes
 template <class C>
-__global__ void __launch_bounds__(AFF_TPB, 6) k_affine_den(AffLevelIn<C> in, const uint32_t *off_in, const uint32_t *off_out, uint32_t G, uint32_t NT, uint32_t *pre,
+__global__ void __launch_bounds__(AFF_TPB, 4) k_affine_den(AffLevelIn<C> in, const uint32_t *off_in, const uint32_t *off_out, uint32_t G, uint32_t NT, uint32_t *pre,
                                                             uint32_t *tot) {
     typedef typename C::Elem E;
     constexpr int EW = El<E>::WORDS;
@@ -115,31 +115,15 @@ __global__ void __launch_bounds__(AFF_TPB, 6) k_affine_den(AffLevelIn<C> in, con
         const uint32_t q0 = (uint32_t)q0_64, nq = min((uint32_t)AFF_K, total - q0);
         AffWalk wk;
         wk.start(off_in, off_out, G, q0);
-        // the x coordinates of output j + 1 are requested before the product of output j is formed: at level 0 they are gathered by entry
-        // (two dependent loads), and one pair in flight per thread left the kernel latency-bound (36 % multiplier utilisation at 2^20)
-        E xa_n = El<E>::one(), xb_n = El<E>::one();
-        uint32_t p0_n = 0;
-        bool has_n = false;
-        auto fetch = [&](uint32_t j) {
+        for (uint32_t j = 0; j < nq; j++) {
             const uint32_t q = q0 + j;
             wk.forward(off_in, off_out, q);
-            p0_n = wk.in_lo + 2 * (q - wk.g_lo);
-            has_n = p0_n + 1 < wk.in_hi;
-            if (has_n) {
-                bool na, nb;
-                const AffinePt<C> *pa = in.addr(p0_n, na), *pb = in.addr(p0_n + 1, nb);
-                xa_n = load_x(pa);   // the chord denominator needs the x coordinates only
-                xb_n = load_x(pb);
-            }
-        };
-        fetch(0);
-        for (uint32_t j = 0; j < nq; j++) {
-            const E xa = xa_n, xb = xb_n;
-            const uint32_t p0 = p0_n;
-            const bool has = has_n;
-            if (j + 1 < nq) fetch(j + 1);
+            const uint32_t p0 = wk.in_lo + 2 * (q - wk.g_lo);
             E den = El<E>::one();
-            if (has) {
+            if (p0 + 1 < wk.in_hi) {
+                bool na, nb;
+                const AffinePt<C> *pa = in.addr(p0, na), *pb = in.addr(p0 + 1, nb);
+                E xa = load_x(pa), xb = load_x(pb);   // the chord denominator needs the x coordinates only
                 den = fp_sub(xb, xa);
                 if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {  // equal x, or x = 0 (maybe the identity encoding (0, 0))
                     AffinePt<C> a = in.load(p0), b = in.load(p0 + 1);

@@ -170,6 +170,18 @@ __global__ void __launch_bounds__(TPB_RED) k_fold(const XyzzPt<C> *buckets, Xyzz
     if (t >= n_windows * m) return;
     body_fold<C>(t / m, t % m, l, B, buckets, F, bucket_offsets);
 }
+// The same level with four lanes per addition (xyzz_add_quad), for the levels that no longer fill the GPU with a thread per addition: there a
+// launch lasts one addition of a lone warp (15 - 17 us per level at 2^20 points), a quad needs a third of it.  l >= 2 (the input is a fold level).
+template <class C>
+__global__ void __launch_bounds__(TPB_RED) k_fold_quad(XyzzPt<C> *F, uint32_t B, uint32_t l, uint32_t n_windows) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, t = tid >> 2, m = B >> l;
+    if (t >= n_windows * m) return;
+    const uint32_t w = t / m, i = t % m;
+    const XyzzPt<C> *in = F + (size_t)w * B + fold_level_offset(B, l - 1);
+    XyzzPt<C> a = in[i], b = in[i + m];
+    xyzz_add_quad(a, b);
+    if ((tid & 3) == 0) store_xyzz(&F[(size_t)w * B + fold_level_offset(B, l) + i], a);
+}
 // Fold levels l_first .. nb of one window in one CTA (m = B >> l <= TPB_TAIL there): the deep levels are one add each and purely
 // latency-bound, so they are not worth a launch apiece.  Same reads and writes as k_fold; a level's output is the next level's input,
 // ordered by the CTA barrier.

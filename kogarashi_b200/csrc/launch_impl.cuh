@@ -112,7 +112,9 @@ int Launch<C>::fold_reduce(cudaStream_t st, cudaStream_t st2, cudaEvent_t ev_for
     for (; l <= nb; l++) {
         uint32_t m = B >> l;
         if (l >= 2 && m <= (uint32_t)TPB_TAIL) break;  // the rest in one kernel
-        k_fold<C><<<cdiv((size_t)n_windows * m, TPB_RED), TPB_RED, 0, st>>>(buckets, F, B, l, n_windows, bucket_offsets);
+        // four lanes per addition once 4 x the additions fit the resident threads of the GPU (~75 K): 2^20 points, levels 4 and 5
+        if (l >= 2 && (size_t)n_windows * m <= 18000) k_fold_quad<C><<<cdiv((size_t)n_windows * m * 4, TPB_RED), TPB_RED, 0, st>>>(F, B, l, n_windows);
+        else k_fold<C><<<cdiv((size_t)n_windows * m, TPB_RED), TPB_RED, 0, st>>>(buckets, F, B, l, n_windows, bucket_offsets);
         launches++;
         if (fork && l + 1 == l_early) {
             cudaEventRecord(ev_fork, st);
