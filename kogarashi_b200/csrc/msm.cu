@@ -305,10 +305,15 @@ static void ensure_lanes(size_t eng, size_t k) {
 }
 static Engine &lane_of(size_t eng, size_t i) { return i == 0 ? g_engines[eng] : *g_lanes[eng][i - 1]; }
 
-// Cost model for the window size, fitted to the per-phase timings in profiles/r01_phase_sweep.md (ns):
+// Cost model for the window size (ns).  Small inputs (no batched-affine levels, counting sort), fitted to profiles/r01_phase_sweep.md:
 //   accumulate 0.174 per entry; counting sort 0.0155 per entry growing with the histogram size G
 //   (random L2 atomics + sector-granular scatter); reduce 0.4 ms fixed + 0.7 per bucket;
 //   a thin top window (few leading scalar bits) concentrates n / 2^t entries in 2^t buckets.
+// From 2^19 points on (batched-affine levels, radix-partition sort, quad reduction tail), refitted to profiles/r02_sweep_c_levels_quad_reduce.txt
+// and the 2^24 - 2^26 sweeps of r02: accumulate 0.139 + 0.35 / (entries per bucket) per entry (short buckets: fewer useful
+// affine levels, more flushes), sort 0.011 per entry, reduce 0.25 ms + 0.6 per bucket; the top window's digits fall into 2^(top_bits - 1 - F)
+// coarse bins of the sort, each placed by ONE CTA at ~0.7 ns per element (c = 19 at 2^25: + 24 ms), and beyond 4096 coarse bins the sort
+// falls back to the counting sort.  2^25 points: c = 20 (72.6 ms) instead of 17 (76.6); 2^24 stays at 17 (38.6 against 39.2).
 static uint32_t choose_window_bits(uint32_t n, const Params &P) {
     if (P.window_bits > 0) return (uint32_t)std::min<long>(std::max<long>(P.window_bits, 1), 24);
     double best = 1e300;
@@ -318,10 +323,20 @@ static uint32_t choose_window_bits(uint32_t n, const Params &P) {
     uint32_t best_c = c_min;
     for (uint32_t c = c_min; c <= 22; c++) {
         double W = std::ceil(255.0 / c), B = std::ldexp(1.0, (int)c - 1), G = W * B;
-        double lg = std::log2(G);
-        double sort_ns = 0.0155 + (lg > 19 ? 0.008 * (lg - 19) : 0.0);
-        double cost = (double)n * W * (0.174 + sort_ns) + 0.7 * G + (G > 64 ? 0.4e6 : 0.1e6);
         int top_bits = 255 - (int)c * ((int)W - 1);  // bits of the top window incl. the carry bit
+        double cost;
+        if (n >= (1u << 19)) {
+            const double per_bucket = (double)n / B;
+            cost = (double)n * W * (0.139 + 0.35 / per_bucket + 0.011) + 0.6 * G + 0.25e6;
+            const int F = std::min(8, (int)c - 1);
+            const double used_bins = top_bits - 1 > F ? std::ldexp(1.0, top_bits - 1 - F) : 1.0;
+            cost += 0.7 * (double)n / used_bins;
+            if (c >= 22) cost += 0.5 * (double)n * W;
+        } else {
+            double lg = std::log2(G);
+            double sort_ns = 0.0155 + (lg > 19 ? 0.008 * (lg - 19) : 0.0);
+            cost = (double)n * W * (0.174 + sort_ns) + 0.7 * G + (G > 64 ? 0.4e6 : 0.1e6);
+        }
         if (top_bits < (int)c) cost += 0.08e6;       // a thin top window fills few buckets: the hot-bucket fix-up path runs
         if (top_bits < 8 && top_bits < (int)c) cost += 0.08 * n * (8 - top_bits);
         if (cost < best) { best = cost; best_c = c; }
