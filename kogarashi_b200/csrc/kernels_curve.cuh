@@ -101,6 +101,7 @@ template <class C> __device__ __forceinline__ void quad_tree_sum(uint32_t *sm, i
         if (qd < s) {
             XyzzPt<C> a = sm_get<C>(sm, qd), b = sm_get<C>(sm, qd + s);
             xyzz_add_quad(a, b);
+            __syncwarp(0xFu << (t & 28));  // the quad's reads of slot qd are complete (its shuffles order them already; this names it)
             if ((t & 3) == 0) sm_put<C>(sm, qd, a);
         }
         __syncthreads();

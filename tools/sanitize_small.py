@@ -17,6 +17,16 @@ for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96", "gr_identity_b
     got = k.to_affine(curve, k.msm_curve_addition(b, z[name + "_sc"]))
     ok &= bool((got[:8] == z[name + "_aff"][:8]).all() or (got[8] and z[name + "_aff"][8]))
     b.free()
+# round 2 kernels, forced at a small size: radix-partition sort, batched-affine levels (3: odd and even levels, padding-free offsets), a host-buffer
+# call streamed in two pieces (per-piece buckets + merge); the quad-cooperative fix-up / reduction tail runs in every case of this script
+for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96"):
+    curve = 0 if name.startswith("g1_") else 1
+    for pname, v in (("sort_mode", 2), ("affine_levels", 3), ("oneshot_split", 2), ("chunk", 0)):
+        k.set_param(pname, v)
+    got = k.to_affine(curve, k.msm_curve_addition(z[name + "_pts"], z[name + "_sc"], curve=curve, inf=z[name + "_inf"]))
+    ok &= bool((got[:8] == z[name + "_aff"][:8]).all() or (got[8] and z[name + "_aff"][8]))
+    for pname, v in (("sort_mode", -1), ("affine_levels", -1), ("oneshot_split", 0)):
+        k.set_param(pname, v)
 z2 = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "g2_vectors.npz"))
 for name in ("g2_uniform_128", "g2_dup_neg_48", "g2_identity_bases_24", "g2_skewed_64", "g2_uniform_0"):
     for chunk in (0, 2):
