@@ -20,6 +20,7 @@
 #include <atomic>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -94,6 +95,60 @@ struct NttDomain {
 
 enum { EV_START, EV_H2D, EV_COUNT, EV_SCAN, EV_FILL, EV_ACC, EV_FIXUP, EV_END, EV_N };
 
+// Worker threads that stay alive between calls (the staging copies of upload_from_host / download_to_host).  Starting and joining seven
+// std::threads per buffer — each paying the CUDA runtime's per-thread initialisation at its first call — cost more than the copies they ran:
+// a 2^20-point oneshot call from pageable memory took 7.3 ms with 8 threads and 6.6 ms with 4 (pinned memory: 4.4 ms).
+struct StagePool {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> workers;
+    const std::function<void(size_t)> *job = nullptr;
+    size_t n_job = 0, next = 0, done = 0;
+    bool stop = false;
+    explicit StagePool(size_t n_workers) {
+        for (size_t i = 0; i < n_workers; i++) workers.emplace_back([this]() { loop(); });
+    }
+    ~StagePool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            stop = true;
+        }
+        cv_work.notify_all();
+        for (auto &t : workers) t.join();
+    }
+    void loop() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+            cv_work.wait(lk, [&]() { return stop || next < n_job; });
+            if (stop) return;
+            const size_t idx = next++;
+            const std::function<void(size_t)> *f = job;
+            lk.unlock();
+            (*f)(idx);
+            lk.lock();
+            if (++done == n_job) cv_done.notify_all();
+        }
+    }
+    // f(0) .. f(n - 1), f(0) on the calling thread; returns when all have finished
+    void run(size_t n, const std::function<void(size_t)> &f) {
+        if (n == 0) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = &f;
+            n_job = n;
+            next = 1;
+            done = 0;
+        }
+        if (n > 1) cv_work.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(mu);
+        if (++done < n_job) cv_done.wait(lk, [&]() { return done >= n_job; });
+        n_job = 0;
+        next = 0;
+        job = nullptr;
+    }
+};
+
 struct Engine {
     Params params;  // snapshot of the caller's tuning state for the MSM being enqueued
     int dev = -1;
@@ -120,6 +175,7 @@ struct Engine {
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
     uint32_t result_c = 0;                                                // window bits to apply between them (0: already combined)
     uint8_t *h_stage = nullptr;                                           // pinned ring for uploads from pageable memory (upload_from_host)
+    std::unique_ptr<StagePool> stage_pool;                                // its copy threads, started at first use
     cudaEvent_t stage_ev[16] = {};                                         // slot s may be refilled once its last copy has completed
     size_t counts_zeroed = 0;  // counts[0..counts_zeroed) are known to be zero
     float last_ms[9] = {};
@@ -166,6 +222,7 @@ struct Engine {
         for (auto &t : fixed_table) t.release();
         for (int i = 0; i < 2; i++) { lvl_s[i].release(); lvl_a[i].release(); }
         if (h_result) cudaFreeHost(h_result);
+        stage_pool.reset();
         if (h_stage) cudaFreeHost(h_stage);
         h_stage = nullptr;
         for (auto &e : stage_ev) if (e) { cudaEventDestroy(e); e = nullptr; }
@@ -195,6 +252,14 @@ struct Engine {
 // call: 11.4 ms against 5.0 ms from pinned buffers); here a few host threads copy 4-MiB chunks into a ring of pinned slots and enqueue the
 // slot copies themselves, so the link is fed at several times that rate.  Returns when every chunk has been enqueued.
 static constexpr size_t STAGE_CHUNK = 2u << 20, STAGE_SLOTS = 16, STAGE_THREADS = 8;
+static size_t stage_threads_now() {  // development knob (KGR_STAGE_THREADS): number of staging threads actually used, <= STAGE_THREADS
+    static const size_t v = [] {
+        const char *e = getenv("KGR_STAGE_THREADS");
+        long x = e ? atol(e) : (long)STAGE_THREADS;
+        return (size_t)std::min<long>(std::max<long>(x, 1), (long)STAGE_THREADS);
+    }();
+    return v;
+}
 static void upload_from_host(Engine &e, void *dst, const void *src, size_t bytes, cudaStream_t st) {
     if (!bytes) return;
     cudaPointerAttributes at;
@@ -210,7 +275,7 @@ static void upload_from_host(Engine &e, void *dst, const void *src, size_t bytes
         for (auto &ev : e.stage_ev) CK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     }
     const size_t n_chunks = (bytes + STAGE_CHUNK - 1) / STAGE_CHUNK;
-    const size_t n_threads = std::min(STAGE_THREADS, n_chunks);
+    const size_t n_threads = std::min(stage_threads_now(), n_chunks);
     std::vector<cudaError_t> errs(n_threads, cudaSuccess);
     auto worker = [&](size_t t) {
         cudaError_t ce = cudaSetDevice(e.dev);
@@ -226,10 +291,8 @@ static void upload_from_host(Engine &e, void *dst, const void *src, size_t bytes
         }
         errs[t] = ce;
     };
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < n_threads; t++) th.emplace_back(worker, t);
-    worker(0);
-    for (auto &x : th) x.join();
+    if (!e.stage_pool) e.stage_pool.reset(new StagePool(STAGE_THREADS - 1));
+    e.stage_pool->run(n_threads, worker);
     for (cudaError_t ce : errs)
         if (ce != cudaSuccess) throw CudaError{ce, "upload_from_host", __LINE__};
 }
@@ -276,10 +339,8 @@ static void download_to_host(Engine &e, void *dst, const void *src, size_t bytes
         }
         errs[t] = ce;
     };
-    std::vector<std::thread> th;
-    for (size_t t = 1; t < n_threads; t++) th.emplace_back(worker, t);
-    worker(0);
-    for (auto &x : th) x.join();
+    if (!e.stage_pool) e.stage_pool.reset(new StagePool(STAGE_THREADS - 1));
+    e.stage_pool->run(n_threads, worker);
     for (cudaError_t ce : errs)
         if (ce != cudaSuccess) throw CudaError{ce, "download_to_host", __LINE__};
 }
