@@ -32,6 +32,21 @@ __global__ void __launch_bounds__(TPB_ACC, acc_min_blocks<C>()) k_accumulate(Msm
                                                         XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
     body_accumulate<C>(blockIdx.x * blockDim.x + threadIdx.x, sh, bases, offsets, entries, bucket_acc, head, tail, tail_bucket);
 }
+// Hot buckets (cut into more than FIXUP_INLINE_MAX pieces: skewed scalars, a thin top window) are summed by k_fixup_long.  A bucket of P pieces
+// becomes S = ceil(P / FL_SLICE) <= FL_MAX_SLICES worklist records (bucket, slice | S << 8, index of its first record, -), one CTA each, so that a
+// bucket holding a large part of the input (Nova witnesses: half the scalars equal) is summed by many CTAs instead of by the 128 lanes of one
+// (2^20 points, all scalars 0 / 1: 8192 pieces, 64 dependent additions per lane before).  wl: 4 words per record.
+constexpr uint32_t FL_SLICE = 512, FL_MAX_SLICES = 64;
+KGR_D void push_hot_bucket(uint32_t g, uint32_t pieces, uint32_t *wl, uint32_t *wl_len) {
+    uint32_t S = (pieces + FL_SLICE - 1) / FL_SLICE;
+    if (S > FL_MAX_SLICES) S = FL_MAX_SLICES;
+    const uint32_t base = atomic_add_u32(wl_len, S);
+    for (uint32_t k = 0; k < S; k++) {
+        wl[4 * (size_t)(base + k)] = g;
+        wl[4 * (size_t)(base + k) + 1] = k | (S << 8);
+        wl[4 * (size_t)(base + k) + 2] = base;
+    }
+}
 // body_fixup with FOUR lanes per chunk (xyzz_add_quad): the up to FIXUP_INLINE_MAX dependent additions of a cut bucket are the longest chain
 // between the accumulation and the reduction (6 x ~7 us for a lone thread; 20 us each over Fq2).  Same reads, same sums, same result.
 template <class C>
@@ -43,8 +58,8 @@ __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *
     const uint32_t g = tail_bucket[t];
     if (g == NO_DIGIT) return;
     const uint32_t t1 = (offsets[g + 1] - 1) / sh.L;
-    if (t1 - t > FIXUP_INLINE_MAX && worklist) {
-        if ((tid & 3) == 0) worklist[atomic_add_u32(worklist_len, 1u)] = g;
+    if (t1 - t > FIXUP_INLINE_MAX) {
+        if ((tid & 3) == 0) push_hot_bucket(g, t1 - t + 1, worklist, worklist_len);
         return;
     }
     XyzzPt<C> acc = tail[t];
@@ -68,7 +83,7 @@ __global__ void __launch_bounds__(TPB_RED) k_fixup_buckets(MsmShape sh, const ui
     const uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L;
     if (t0 == t1) return;  // inside one chunk: the accumulate kernel wrote the bucket itself
     if (t1 - t0 > FIXUP_INLINE_MAX) {
-        if ((tid & 3) == 0) worklist[atomic_add_u32(worklist_len, 1u)] = g;
+        if ((tid & 3) == 0) push_hot_bucket(g, t1 - t0 + 1, worklist, worklist_len);
         return;
     }
     XyzzPt<C> acc = tail[t0];
@@ -123,17 +138,59 @@ template <class C> __device__ __forceinline__ XyzzPt<C> block_tree_sum(XyzzPt<C>
     quad_tree_sum<C>(sm, TPB_TREE / 4);
     return sm_get<C>(sm, 0);
 }
-// One CTA per queued hot bucket (grid-stride over the worklist).
+// One CTA per worklist record (grid-stride): the CTA sums its slice of the bucket's pieces (piece 0 is tail[t0], piece k >= 1 is head[t0 + k]);
+// the CTA that finishes a multi-slice bucket LAST (counter + __threadfence) adds the S slice sums.  counter[] is zero on entry and is left zero.
+template <class C> __device__ __forceinline__ XyzzPt<C> load_xyzz_cg(const XyzzPt<C> *p) {  // written by other CTAs of this launch: not through the read-only path
+    XyzzPt<C> r;
+    const uint4 *q = reinterpret_cast<const uint4 *>(p);
+    uint32_t *w = reinterpret_cast<uint32_t *>(&r);
+#pragma unroll
+    for (int k = 0; k < xyzz_words<C>() / 4; k++) {
+        uint4 a = __ldcg(q + k);
+        w[4 * k] = a.x; w[4 * k + 1] = a.y; w[4 * k + 2] = a.z; w[4 * k + 3] = a.w;
+    }
+    return r;
+}
 template <class C>
 __global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
-                                                         const XyzzPt<C> *tail, const uint32_t *worklist, const uint32_t *worklist_len) {
+                                                         const XyzzPt<C> *tail, const uint32_t *worklist, const uint32_t *worklist_len, XyzzPt<C> *partial,
+                                                         uint32_t *counter) {
     __shared__ uint32_t sm[xyzz_words<C>() * TPB_TREE];
-    uint32_t n = *worklist_len;
+    __shared__ uint32_t last_flag;
+    static_assert(FL_MAX_SLICES <= TPB_TREE, "one lane per slice sum");
+    const uint32_t n = *worklist_len;
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-        uint32_t g = worklist[i];
-        XyzzPt<C> v = fixup_long_partial<C>(g, threadIdx.x, TPB_TREE, sh, offsets, head, tail);
+        const uint32_t g = worklist[4 * (size_t)i], ss = worklist[4 * (size_t)i + 1], base = worklist[4 * (size_t)i + 2];
+        const uint32_t sl = ss & 0xffu, S = ss >> 8;
+        const uint32_t lo = offsets[g], hi = offsets[g + 1];
+        const uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L, P = t1 - t0 + 1;
+        const uint32_t per = (P + S - 1) / S, first = sl * per, last = min(P, first + per);
+        XyzzPt<C> v = xyzz_identity<C>();
+        for (uint32_t p = first + threadIdx.x; p < last; p += TPB_TREE) {
+            XyzzPt<C> x = p == 0 ? tail[t0] : head[t0 + p];
+            xyzz_add(v, x);
+        }
         v = block_tree_sum<C>(v, sm);
-        if (threadIdx.x == 0) store_xyzz(&bucket_acc[g], v);
+        if (S == 1) {
+            if (threadIdx.x == 0) store_xyzz(&bucket_acc[g], v);
+        } else {
+            if (threadIdx.x == 0) {
+                store_xyzz(&partial[i], v);
+                __threadfence();
+                last_flag = atomicAdd(&counter[base], 1u) == S - 1;
+            }
+            __syncthreads();
+            if (last_flag) {
+                __threadfence();
+                XyzzPt<C> q = threadIdx.x < S ? load_xyzz_cg<C>(&partial[base + threadIdx.x]) : xyzz_identity<C>();
+                __syncthreads();
+                q = block_tree_sum<C>(q, sm);
+                if (threadIdx.x == 0) {
+                    store_xyzz(&bucket_acc[g], q);
+                    counter[base] = 0;
+                }
+            }
+        }
         __syncthreads();
     }
 }

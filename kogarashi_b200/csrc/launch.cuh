@@ -31,8 +31,11 @@ template <class C> struct Launch {
     static int affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const A *bases, const uint32_t *entries, uint32_t *const off[], A *const nodes[2],
                              const uint32_t out_max[], uint32_t *cnt, uint32_t *tile_sums, uint32_t *pre, uint32_t *tot);
     static void affine_scratch_words(uint32_t out_max0, size_t &pre_words, size_t &tot_words);
+    // worklist: 4 words per record, fixup_records_max(chunks) records; partial: one XYZZ point per record; counter: one word per record, zero on
+    // entry and left zero
+    static size_t fixup_records_max(uint32_t chunks);
     static void fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
-                      const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len);
+                      const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len, X *partial, uint32_t *counter);
     static void bucket_merge(cudaStream_t st, uint32_t G, const uint32_t *piece_offsets, const X *piece_acc, X *bucket_acc);
     static void reduce(cudaStream_t st, uint32_t n_windows, uint32_t cnt_in, uint32_t K, uint32_t m_log2, const X *in_s, const X *in_a, X *out_s, X *out_a,
                        const uint32_t *bucket_offsets);

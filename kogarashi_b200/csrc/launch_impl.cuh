@@ -65,14 +65,17 @@ int Launch<C>::affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const
 }
 #endif
 #if KGR_PART & 1
+// worklist records of the hot buckets: a hot bucket owns at least FIXUP_INLINE_MAX chunks outright and adds one record per FL_SLICE pieces (bound with slack)
+template <class C> size_t Launch<C>::fixup_records_max(uint32_t chunks) { return (size_t)chunks / FIXUP_INLINE_MAX + (size_t)chunks / (FL_SLICE / 2) + 4; }
 template <class C>
 void Launch<C>::fixup(cudaStream_t st, const MsmShape &sh, uint32_t chunks, int sm_count, const uint32_t *offsets, X *bucket_acc, const X *head, const X *tail,
-                      const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
+                      const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len, X *partial, uint32_t *counter) {
     // four lanes per chunk, or per bucket when the chunks outnumber the buckets (kernels_curve.cuh)
     if (chunks > sh.G) k_fixup_buckets<C><<<cdiv((size_t)sh.G * 4, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
     else k_fixup<C><<<cdiv((size_t)chunks * 4, TPB_RED), TPB_RED, 0, st>>>(sh, offsets, bucket_acc, head, tail, tail_bucket, worklist, worklist_len);
     unsigned blocks = sh.G < 4u * (unsigned)sm_count ? sh.G : 4u * (unsigned)sm_count;
-    k_fixup_long<C><<<blocks, TPB_TREE, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len);
+    if (blocks < (unsigned)FL_MAX_SLICES) blocks = FL_MAX_SLICES;  // a single hot bucket still spreads over its slices
+    k_fixup_long<C><<<blocks, TPB_TREE, 0, st>>>(sh, offsets, bucket_acc, head, tail, worklist, worklist_len, partial, counter);
 }
 #endif
 #if KGR_PART & 1

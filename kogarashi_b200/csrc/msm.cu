@@ -170,6 +170,8 @@ struct Engine {
     DevBuf<uint8_t> lvl_nodes[2];                                          // ... and their node arrays (ping-pong)
     DevBuf<uint8_t> part_fine;
     DevBuf<uint8_t> piece_acc;  // bucket sums of one piece of a streamed call (enqueue_msm)
+    DevBuf<uint8_t> fix_partial;  // slice sums of the hot buckets (k_fixup_long)
+    DevBuf<uint32_t> fix_counter;  // ... and their arrival counters (zero between launches)
     DevBuf<uint8_t> bucket_acc, head, tail, lvl_s[2], lvl_a[2], result, fold_f, fold_partial, fold_v;  // raw bytes, cast per curve
     uint32_t *h_result = nullptr;                                         // pinned, 256 x 32 words (window sums)
     uint32_t n_result = 0;                                                // XYZZ points in h_result for the last MSM
@@ -213,7 +215,7 @@ struct Engine {
         if (dev < 0) return;
         cudaSetDevice(dev);
         cudaStreamSynchronize(st);
-        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release();
+        counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release(); fix_partial.release(); fix_counter.release();
         coarse_counts.release(); coarse_off.release(); coarse_cursor.release(); part_pay.release(); part_fine.release();
         for (auto &b : lvl_off) b.release();
         lvl_cnt.release(); lvl_pre.release(); lvl_tot.release(); lvl_nodes[0].release(); lvl_nodes[1].release();
@@ -513,7 +515,6 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         e.lvl_a[i].ensure((size_t)nwin * cnt1 * sizeof(X));
     }
     e.result.ensure(sizeof(X));
-    e.worklist.ensure((size_t)sh.G + 2);
     if (e.counts_zeroed < G1) {
         CK(cudaMemsetAsync(e.counts.p, 0, e.counts.cap * sizeof(uint32_t), e.st));
         e.counts_zeroed = e.counts.cap;
@@ -627,8 +628,18 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
         if (!levels_ran)
             K::accumulate(e.st, shp, chunks, bases_k, e.offsets.p, e.entries.p, piece_dst, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
         CK(cudaEventRecord(pe[PE_ACC], e.st));
+        {
+            const size_t rec = K::fixup_records_max(chunks);
+            e.worklist.ensure(4 * rec + 4);
+            e.fix_partial.ensure(rec * sizeof(X));
+            if (e.fix_counter.cap < rec) {
+                e.fix_counter.ensure(rec);
+                CK(cudaMemsetAsync(e.fix_counter.p, 0, e.fix_counter.cap * sizeof(uint32_t), e.st));  // k_fixup_long leaves it zero again
+            }
+        }
         CK(cudaMemsetAsync(e.worklist.p, 0, sizeof(uint32_t), e.st));
-        K::fixup(e.st, shp, chunks, e.sm_count, off_k, piece_dst, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 1, e.worklist.p);
+        K::fixup(e.st, shp, chunks, e.sm_count, off_k, piece_dst, (const X *)e.head.p, (const X *)e.tail.p, e.tail_bucket.p, e.worklist.p + 4, e.worklist.p,
+                 (X *)e.fix_partial.p, e.fix_counter.p);
         if (streamed) {
             K::bucket_merge(e.st, sh.G, off_k, piece_dst, (X *)e.bucket_acc.p);
             e.launches++;

@@ -340,6 +340,28 @@ def test_oneshot_pieces_same_element(k, curve):
     reg_inf.free()
 
 
+def test_geometric_pieces_tiny_and_lopsided(k):
+    """The pieces of a streamed host-buffer call grow geometrically ("oneshot_growth", percent): lopsided cuts, pieces of a single pair, cuts
+    that would be empty (skipped) — always the oracle's group element."""
+    curve = A.BN254_G1
+    try:
+        for n in (1, 2, 5, 64, 1000):
+            pts = A.random_points(curve, n, seed=bytes(range(3, 19)))
+            sc = A.random_field(A.FIELD_FR, n, seed=bytes(range(5, 21)))
+            exp = A.to_affine(curve, A.msm(curve, pts, sc))
+            bases = k.Bases(curve, pts)
+            for pieces in (2, 3, 5, 8):
+                for growth in (100, 170, 300, 1000):
+                    k.set_param("oneshot_split", pieces)
+                    k.set_param("oneshot_growth", growth)
+                    assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp), (n, pieces, growth)
+                    assert same_affine(k.to_affine(curve, k.msm_curve_addition(bases, sc)), exp), (n, pieces, growth, "registered")
+            bases.free()
+    finally:
+        k.set_param("oneshot_split", 0)
+        k.set_param("oneshot_growth", 0)
+
+
 @pytest.mark.parametrize("seed", range(16))
 def test_random_shapes_vs_oracle(k, seed):
     """Randomised configurations: curve, size, forced window / chunk, sort and reduce variants, scalar mix (zeros, ones, r - 1, uniform),
