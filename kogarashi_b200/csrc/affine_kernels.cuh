@@ -145,11 +145,15 @@ __global__ void __launch_bounds__(AFF_TPB, 4) k_affine_den(AffLevelIn<C> in, con
 // The per-thread prefix products go to `pfx` (same layout as v) rather than to shared memory: the CTA then holds 8 KB of shared memory instead
 // of 40, so that enough CTAs are resident per SM to fill the ~100 dependent multiplications of the product tree and the single-thread
 // inversion with the other CTAs' prefix / back-substitution work (r02: 15.8 of 32 lanes active and 58 % multiplier utilisation before).
-template <class E> __global__ void __launch_bounds__(AFF_TPB) k_batch_inv(uint32_t *v, uint32_t n, uint32_t NT, uint32_t *pfx) {
+template <class E> __global__ void __launch_bounds__(AFF_TPB) k_batch_inv(uint32_t *v, uint32_t n, uint32_t NT, uint32_t *pfx, const uint32_t *total_out) {
     constexpr int EW = El<E>::WORDS;
     __shared__ uint32_t s_tree[EW * 2 * AFF_TPB];
     const int tid = threadIdx.x;
     const uint32_t base = blockIdx.x * (AFF_TPB * INV_K);
+    // the grid is sized for the host's bound on the output nodes; only the threads of k_affine_den / k_affine_add that own nodes use their total
+    // (skewed scalars: a fraction of the bound — the other CTAs leave at once)
+    n = min(n, (*total_out + (uint32_t)AFF_K - 1) / (uint32_t)AFF_K);
+    if (base >= n) return;
     E run = El<E>::one();
 #pragma unroll 1
     for (int i = 0; i < INV_K; i++) {

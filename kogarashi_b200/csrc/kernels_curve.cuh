@@ -53,11 +53,11 @@ template <class C>
 __global__ void __launch_bounds__(TPB_RED) k_fixup(MsmShape sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
                                                    const XyzzPt<C> *tail, const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, t = tid >> 2;
-    const uint32_t M = offsets[sh.G];
-    if ((uint64_t)t * sh.L >= M) return;  // the same for the four lanes of a quad
+    const uint32_t M = offsets[sh.G], L = eff_chunk_len(sh, M);
+    if ((uint64_t)t * L >= M) return;  // the same for the four lanes of a quad
     const uint32_t g = tail_bucket[t];
     if (g == NO_DIGIT) return;
-    const uint32_t t1 = (offsets[g + 1] - 1) / sh.L;
+    const uint32_t t1 = (offsets[g + 1] - 1) / L;
     if (t1 - t > FIXUP_INLINE_MAX) {
         if ((tid & 3) == 0) push_hot_bucket(g, t1 - t + 1, worklist, worklist_len);
         return;
@@ -80,7 +80,8 @@ __global__ void __launch_bounds__(TPB_RED) k_fixup_buckets(MsmShape sh, const ui
     if (g >= sh.G) return;
     const uint32_t lo = offsets[g], hi = offsets[g + 1];
     if (lo == hi) return;
-    const uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L;
+    const uint32_t L = eff_chunk_len(sh, offsets[sh.G]);
+    const uint32_t t0 = lo / L, t1 = (hi - 1) / L;
     if (t0 == t1) return;  // inside one chunk: the accumulate kernel wrote the bucket itself
     if (t1 - t0 > FIXUP_INLINE_MAX) {
         if ((tid & 3) == 0) push_hot_bucket(g, t1 - t0 + 1, worklist, worklist_len);
@@ -163,7 +164,8 @@ __global__ void __launch_bounds__(TPB_TREE) k_fixup_long(MsmShape sh, const uint
         const uint32_t g = worklist[4 * (size_t)i], ss = worklist[4 * (size_t)i + 1], base = worklist[4 * (size_t)i + 2];
         const uint32_t sl = ss & 0xffu, S = ss >> 8;
         const uint32_t lo = offsets[g], hi = offsets[g + 1];
-        const uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L, P = t1 - t0 + 1;
+        const uint32_t L = eff_chunk_len(sh, offsets[sh.G]);
+        const uint32_t t0 = lo / L, t1 = (hi - 1) / L, P = t1 - t0 + 1;
         const uint32_t per = (P + S - 1) / S, first = sl * per, last = min(P, first + per);
         XyzzPt<C> v = xyzz_identity<C>();
         for (uint32_t p = first + threadIdx.x; p < last; p += TPB_TREE) {

@@ -57,7 +57,7 @@ int Launch<C>::affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const
         AffLevelIn<C> in{l == 0 ? bases : nodes[(l - 1) & 1], l == 0 ? entries : nullptr};
         const uint32_t NT = affine_threads(out_max[l]);
         k_affine_den<C><<<NT / AFF_TPB, AFF_TPB, 0, st>>>(in, off[l], off[l + 1], G, NT, pre, tot);
-        k_batch_inv<typename C::Elem><<<cdiv(NT, AFF_TPB * INV_K), AFF_TPB, 0, st>>>(tot, NT, NT, tot + (size_t)NT * El<typename C::Elem>::WORDS);
+        k_batch_inv<typename C::Elem><<<cdiv(NT, AFF_TPB * INV_K), AFF_TPB, 0, st>>>(tot, NT, NT, tot + (size_t)NT * El<typename C::Elem>::WORDS, off[l + 1] + G);
         k_affine_add<C><<<NT / AFF_TPB, AFF_TPB, 0, st>>>(in, off[l], off[l + 1], G, NT, pre, tot, nodes[l & 1]);
         launches += 4 + (scan_num_tiles(G + 1) > 1 ? 3 : 1);
     }

@@ -621,12 +621,15 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
                 e.tail.ensure((size_t)chunks * sizeof(X));
                 e.tail_bucket.ensure((size_t)chunks + 1);
                 off_k = off[levels];
+                shp.chunks = P.chunk > 0 ? 0u : chunks;  // the chunk length follows the entries actually on the device (eff_chunk_len) unless it is forced
                 K::accumulate(e.st, shp, chunks, nodes[(levels - 1) & 1], off_k, nullptr, piece_dst, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
                 levels_ran = true;
             }
         }
-        if (!levels_ran)
+        if (!levels_ran) {
+            shp.chunks = P.chunk > 0 ? 0u : chunks;
             K::accumulate(e.st, shp, chunks, bases_k, e.offsets.p, e.entries.p, piece_dst, (X *)e.head.p, (X *)e.tail.p, e.tail_bucket.p);
+        }
         CK(cudaEventRecord(pe[PE_ACC], e.st));
         {
             const size_t rec = K::fixup_records_max(chunks);

@@ -29,7 +29,7 @@ struct MsmShape {
     uint32_t W;  // windows = ceil(255 / c)  (scalars < 2^254, one spare bit for the signed carry)
     uint32_t B;  // buckets per window = 2^(c-1)
     uint32_t G;  // W * B
-    uint32_t L;  // entries per accumulate thread
+    uint32_t L;  // entries per accumulate thread (at most: see eff_chunk_len)
     uint32_t K;  // reduce fan-in
     // Window-collapsed mode (bases registered with kgr_bases_precompute): the table holds 2^(c*w) * P_i for
     // every window w at index w * pstride + i, so all windows share ONE set of B buckets (gstride = 0,
@@ -37,6 +37,9 @@ struct MsmShape {
     uint32_t gstride;  // global bucket id = w * gstride + bucket
     uint32_t pstride;  // entry payload  = w * pstride + poff + i
     uint32_t poff;
+    // Threads of the accumulate grid the host launched for its BOUND on the entries (n * W, or the node bound after the batched-affine levels).
+    // 0: every chunk is exactly L entries.  Otherwise the chunk length follows the number of entries actually on the device (eff_chunk_len).
+    uint32_t chunks = 0;
 };
 
 KGR_HD uint32_t window_raw(const uint32_t s[8], uint32_t bit, uint32_t c) {
@@ -255,6 +258,15 @@ template <class C> KGR_HD void store_xyzz(XyzzPt<C> *dst, const XyzzPt<C> &p) {
     el_store(&dst->zzz, p.zzz);
 }
 
+// Chunk length actually used.  With fewer entries on the device than the host's bound (zero digits, and above all skewed scalars: Nova witnesses
+// are mostly 0 / 1) the same grid takes shorter chunks, down to 4: the chain of L dependent additions per thread is the latency of the
+// accumulate kernel (2^20 points, all scalars 0 / 1: 131 K nodes left for 70 K threads that would otherwise run 2 K chunks of 64).
+KGR_HD uint32_t eff_chunk_len(const MsmShape &sh, uint32_t M) {
+    if (!sh.chunks) return sh.L;
+    uint32_t L = (uint32_t)(((uint64_t)M + sh.chunks - 1) / sh.chunks);
+    return L < 4 ? 4 : (L > sh.L ? sh.L : L);
+}
+
 // first g with offsets[g+1] > pos  (offsets is non-decreasing, offsets[G] = M > pos)
 KGR_HD uint32_t bucket_of_position(const uint32_t *offsets, uint32_t G, uint32_t pos) {
     uint32_t lo = 0, hi = G;  // answer in [lo, hi)
@@ -285,10 +297,11 @@ template <class C>
 KGR_HD void body_accumulate(uint32_t t, const MsmShape &sh, const AffinePt<C> *bases, const uint32_t *offsets, const uint32_t *entries,
                             XyzzPt<C> *bucket_acc, XyzzPt<C> *head, XyzzPt<C> *tail, uint32_t *tail_bucket) {
     uint32_t M = offsets[sh.G];
-    uint64_t s64 = (uint64_t)t * sh.L;
+    const uint32_t L = eff_chunk_len(sh, M);
+    uint64_t s64 = (uint64_t)t * L;
     if (s64 >= M) return;
     uint32_t s = (uint32_t)s64;
-    uint32_t e = (M - s > sh.L) ? s + sh.L : M;
+    uint32_t e = (M - s > L) ? s + L : M;
     uint32_t g = bucket_of_position(offsets, sh.G, s);
     uint32_t g_end = offsets[g + 1];
     XyzzPt<C> acc = xyzz_identity<C>();
@@ -375,10 +388,11 @@ template <class C>
 KGR_HD void body_fixup(uint32_t t, const MsmShape &sh, const uint32_t *offsets, XyzzPt<C> *bucket_acc, const XyzzPt<C> *head,
                        const XyzzPt<C> *tail, const uint32_t *tail_bucket, uint32_t *worklist, uint32_t *worklist_len) {
     uint32_t M = offsets[sh.G];
-    if ((uint64_t)t * sh.L >= M) return;
+    const uint32_t L = eff_chunk_len(sh, M);
+    if ((uint64_t)t * L >= M) return;
     uint32_t g = tail_bucket[t];
     if (g == NO_DIGIT) return;
-    uint32_t t1 = (offsets[g + 1] - 1) / sh.L;
+    uint32_t t1 = (offsets[g + 1] - 1) / L;
     if (t1 - t > FIXUP_INLINE_MAX && worklist) {
         worklist[atomic_add_u32(worklist_len, 1u)] = g;
         return;
@@ -405,7 +419,8 @@ template <class C>
 KGR_HD XyzzPt<C> fixup_long_partial(uint32_t g, uint32_t lane, uint32_t lanes, const MsmShape &sh, const uint32_t *offsets, const XyzzPt<C> *head,
                                     const XyzzPt<C> *tail) {
     uint32_t lo = offsets[g], hi = offsets[g + 1];
-    uint32_t t0 = lo / sh.L, t1 = (hi - 1) / sh.L;
+    const uint32_t L = eff_chunk_len(sh, offsets[sh.G]);
+    uint32_t t0 = lo / L, t1 = (hi - 1) / L;
     XyzzPt<C> acc = xyzz_identity<C>();
     for (uint32_t t = t0 + lane; t <= t1; t += lanes) xyzz_add(acc, t == t0 ? tail[t0] : head[t]);
     return acc;
