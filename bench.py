@@ -46,6 +46,31 @@ METRICS = {"bn254_g1": "bn254_g1_msm_throughput", "grumpkin": "grumpkin_msm_thro
 IMAD_PEAK_T = 148 * 64 * 1.965e9 / 1e12  # nominal; kgr_microbench measured 18.4-18.5 T mad.lo.u32/s on this pool (profiles/r01_microbench.md)
 
 
+def kernel_sources_sha():
+    """sha256 over the CUDA kernel sources (not the host engine): ties an ncu capture in profiles/ncu_traffic.json to the kernels it measured."""
+    import hashlib
+    h = hashlib.sha256()
+    d = os.path.join(ROOT, "kogarashi_b200", "csrc")
+    for name in sorted(os.listdir(d)):
+        if name.endswith(".cuh") or (name.startswith("kernels_") and name.endswith(".cu")):
+            h.update(name.encode())
+            h.update(open(os.path.join(d, name), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(n, curve_name):
+    """DRAM bytes (read + write) of the dominant phase per launch from the committed `ncu --set full` capture — only for the workload it was
+    taken on (2^20-point BN254 G1 / Grumpkin MSM: same kernels, same sizes) and only while the kernel sources still hash to the captured ones;
+    otherwise None (a stale constant is worse than no number)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        if n == (1 << 20) and curve_name in ("bn254_g1", "grumpkin") and t.get("kernel_sources_sha") == kernel_sources_sha():
+            return t["accumulate_phase_dram_bytes"], t["capture"]
+    except Exception:
+        pass
+    return None, None
+
+
 def ref_window_bits(n):  # groth16/src/msm.rs:7-14
     if n < 4:
         return 1
@@ -208,11 +233,13 @@ def measure_single(k, torch, curve_name, logn, steps, warmup, local_rank, flush,
     sort_bytes = n * 32 + n * shape["W"] * 4  # scalars read once + one 4-byte entry written per (scalar, window)
     rec["roofline"] = {
         "bound": "imad", "achieved": alg / (ms_per_step * 1e-3) / 1e12, "peak": IMAD_PEAK_T, "unit": "T IMAD/s", "frac": alg / (ms_per_step * 1e-3) / 1e12 / IMAD_PEAK_T,
-        "traffic": None, "kernel": "whole pipeline (all kernels of one MSM); dominant kernel below", "algorithmic_imads_per_launch": alg,
+        "traffic": measured_traffic(n, curve_name)[0], "traffic_source": measured_traffic(n, curve_name)[1],
+        "kernel": "whole pipeline (all kernels of one MSM); dominant kernel below; traffic = DRAM bytes of the dominant phase per launch (ncu), null when the kernels changed since the capture",
+        "algorithmic_imads_per_launch": alg,
         "peak_source": "148 SM x 64 IMAD/clk x 1.965 GHz; kgr_microbench measured 18.4-18.5 T mad.lo.u32/s on this pool (MEASURED_PEAKS.json has no integer figure)",
         "executed": {"imads_per_launch": exec_imads, "frac": exec_imads / (ms_per_step * 1e-3) / 1e12 / IMAD_PEAK_T,
                      "note": "additions this implementation issues (signed digits, its own window size, XYZZ formulas) x products per addition x 264"},
-        "dominant_kernel": {"name": "k_accumulate", "ms": phases.get("accumulate"), "algorithmic_imads": acc_alg,
+        "dominant_kernel": {"name": "accumulate phase: batched-affine levels (k_affine_den / k_batch_inv / k_affine_add) + k_accumulate", "ms": phases.get("accumulate"), "algorithmic_imads": acc_alg,
                             "frac": acc_alg / (phases["accumulate"] * 1e-3) / 1e12 / IMAD_PEAK_T if phases.get("accumulate") else None},
         "sort": {"kernels": "k_sort_digits + k_sort_scan + k_sort_partition + k_sort_buckets (or k_count + scan + k_fill below 2^21 entries)", "bound": "hbm", "ms": sort_ms,
                  "algorithmic_bytes": sort_bytes, "achieved_gbs": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None},
