@@ -161,6 +161,8 @@ struct Engine {
     bool wait_pts = false;
     cudaEvent_t ev[EV_N] = {};
     cudaEvent_t ev_piece_sc[16] = {}, ev_piece_pts[16] = {};  // piece k's scalars / points are on the device (recorded on st_copy)
+    cudaEvent_t ev_up0 = nullptr, ev_up1 = nullptr;            // around the uploads of a host-buffer call (timed: feeds h2d_gbs)
+    double h2d_gbs = 42.0;       // host -> device rate the last host-buffer calls of this engine saw (moving average; pinned H2D on this pool: 42 - 55 GB/s)
     cudaEvent_t pev[16][6] = {};      // per-piece phase marks of a streamed call (enqueue_msm)
     size_t n_pev = 0;
     uint32_t n_pieces = 1;            // pieces of the last MSM enqueued on this engine
@@ -233,6 +235,8 @@ struct Engine {
             for (auto &pe : pev[k]) if (pe) cudaEventDestroy(pe);
         n_pev = 0;
         for (auto &x : ev_piece_sc) if (x) { cudaEventDestroy(x); x = nullptr; }
+        if (ev_up0) { cudaEventDestroy(ev_up0); ev_up0 = nullptr; }
+        if (ev_up1) { cudaEventDestroy(ev_up1); ev_up1 = nullptr; }
         for (auto &x : ev_piece_pts) if (x) { cudaEventDestroy(x); x = nullptr; }
         for (auto &e : user_ev) if (e) cudaEventDestroy(e);
         for (auto &e : aux_ev) if (e) cudaEventDestroy(e);
@@ -930,7 +934,15 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 size_t k_auto = hp ? (lg < 20 ? 1 : lg < 22 ? 2 : lg == 22 ? 3 : lg == 23 ? 4 : 5) : (lg < 22 ? 1 : lg < 24 ? 2 : 3);
                 size_t k = P.oneshot_split > 0 ? (size_t)P.oneshot_split : k_auto;
                 k = std::min<size_t>(std::min<size_t>(k, MAX_PIECES), std::max<size_t>(jb.count, 1));
-                const double growth = (P.oneshot_growth > 0 ? (double)P.oneshot_growth : !hp ? 300.0 : k <= 2 ? 170.0 : k == 3 ? 150.0 : 130.0) / 100.0;
+                // growth = 1.3 x (pipeline time of the call) / (upload time of the call), from what this engine measured on its last calls: with a fast
+                // link the pipeline is the bottleneck and the pieces grow (the first upload overlaps nothing), with a slow or contended link (eight
+                // processes uploading at once) the uploads are, and the pieces shrink (after the last byte only the last piece's work remains).  With the
+                // default rate (42 GB/s): 2^20 points + scalars 1.7, 2^24 1.3, scalars only 3 — the values the sweeps of profiles/r02_e2e.md found.
+                const double up_bytes = (double)jb.count * (32.0 + (hp ? (double)sizeof(AffinePt<C>) : 0.0));
+                // device time per pair: 3.1 ns at 2^20, 2.6 at 2^22, 2.3 from 2^24 on (section 4 of DESIGN.md); Fq2 coordinates cost 3.5 times that
+                const double ns_per_pair = (jb.count >= (1u << 23) ? 2.35 : jb.count >= (1u << 21) ? 2.6 : 3.1) * (C::ID == Bn254G2::ID ? 3.5 : 1.0);
+                const double up_ms = up_bytes / (e.h2d_gbs * 1e6), dev_ms = ns_per_pair * (double)jb.count * 1e-6;
+                const double growth = P.oneshot_growth > 0 ? (double)P.oneshot_growth / 100.0 : std::min(3.0, std::max(0.6, 1.3 * dev_ms / up_ms));
                 std::vector<size_t> cut(k + 1, 0);
                 {
                     double tot_w = 0, w = 1, acc_w = 0;
@@ -965,6 +977,11 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                     try {
                         CK(cudaSetDevice(e.dev));
                         CK(cudaStreamWaitEvent(e.st_copy, e.ev[EV_START], 0));
+                        if (!e.ev_up0) {
+                            CK(cudaEventCreate(&e.ev_up0));
+                            CK(cudaEventCreate(&e.ev_up1));
+                        }
+                        CK(cudaEventRecord(e.ev_up0, e.st_copy));
                         for (size_t i = 0; i < pieces.size(); i++) {
                             const StreamPiece &pc = pieces[i];
                             upload_from_host(e, e.scalars.p + 8 * pc.first, scalars + 4 * (jb.sc_first + pc.first), pc.count * 32, e.st_copy);
@@ -979,6 +996,7 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                                 }
                                 CK(cudaEventRecord(pc.ev_pts, e.st_copy));
                             }
+                            if (i + 1 == pieces.size()) CK(cudaEventRecord(e.ev_up1, e.st_copy));
                             recorded.store(i + 1, std::memory_order_release);
                         }
                     } catch (CudaError &ce) {
@@ -1005,6 +1023,17 @@ static void run_msm(std::vector<Shard> &shards, size_t off, const uint64_t *scal
                 }
                 if (uploader.joinable()) uploader.join();
                 if (up_err.e != cudaSuccess) throw up_err;
+                CK(cudaStreamSynchronize(e.st));
+                collect_timing(e);
+                // what this call saw, for the piece sizes of the next one (calls large enough for the figures to mean something)
+                float up_meas = 0;
+                if (jb.count >= (1u << 18) && cudaEventSynchronize(e.ev_up1) == cudaSuccess && cudaEventElapsedTime(&up_meas, e.ev_up0, e.ev_up1) == cudaSuccess &&
+                    up_meas > 0.05f) {
+                    const double rate = up_bytes / (up_meas * 1e6);
+                    e.h2d_gbs = 0.5 * e.h2d_gbs + 0.5 * std::min(80.0, std::max(2.0, rate));
+                }
+                cudaGetLastError();
+                return;
             }
             CK(cudaStreamSynchronize(e.st));
             collect_timing(e);
