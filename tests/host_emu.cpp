@@ -136,6 +136,9 @@ template <class C, class OC> static int run(uint32_t n, uint32_t c, uint32_t L, 
     }
     for (uint32_t g = 0; g <= sh.G; g++) if (counts[g] != 0) { printf("FAIL counts not consumed at %u\n", g); return 1; }
     uint32_t chunks = ((uint64_t)n_k * sh.W + L - 1) / L + 1;
+    // seed bit 6: the chunk length follows the entries actually present (eff_chunk_len): the grid is sized for the bound n * W, zero digits and
+    // the batched-affine levels leave fewer entries, and accumulate / fix-up / hot-bucket sums must agree on the shorter chunks
+    if ((seed >> 6) & 1) sh.chunks = chunks;
     // poison so that a missing write is noticed
     memset(bucket_acc.data(), 0xAB, bucket_acc.size() * sizeof(XyzzPt<C>));
     memset(head.data(), 0xCD, head.size() * sizeof(XyzzPt<C>));

@@ -25,7 +25,8 @@ def host_emu():
 
 
 # curve n c L K mode seed   (mode: 0 uniform, 1 skewed zeros/ones/r-1, 2 duplicates + opposites + identity bases, 3 canonical scalars)
-# seed bits select variants: bit 0 window-major fill, bits 1-2 batched-affine tree levels in front of the XYZZ accumulation, bit 4 fold reduce, bit 5 two streamed pieces
+# seed bits select variants: bit 0 window-major fill, bits 1-2 batched-affine tree levels in front of the XYZZ accumulation, bit 4 fold reduce, bit 5 two streamed pieces,
+# bit 6 chunk length from the entries actually present
 EMU_CASES = [
     (0, 1, 4, 16, 16, 0, 1), (0, 2, 1, 16, 2, 0, 2), (0, 3, 3, 16, 4, 0, 3), (0, 37, 5, 8, 4, 0, 4), (0, 300, 8, 16, 16, 0, 5),
     (0, 300, 8, 16, 16, 1, 6), (0, 300, 7, 5, 8, 2, 7), (1, 257, 9, 32, 16, 0, 8), (1, 200, 6, 16, 2, 2, 9), (0, 129, 1, 16, 16, 0, 10),
@@ -44,6 +45,10 @@ EMU_CASES = [
     # window tables, hot buckets (several of the curve-2 cases above have the bit set as well)
     (0, 300, 8, 16, 16, 0, 37), (1, 257, 9, 32, 16, 1, 54), (0, 3, 3, 16, 4, 0, 35), (0, 600, 10, 2, 16, 1, 50, 8), (0, 2, 5, 16, 16, 2, 32),
     (1, 333, 12, 1, 16, 2, 46), (0, 120, 11, 32, 16, 12, 53, 1), (0, 700, 6, 3, 4, 1, 39, 4096),
+    # seed bit 6: chunk length derived from the entries actually present (eff_chunk_len): skewed scalars, affine levels (far fewer nodes than the
+    # bound), streamed pieces, window tables, G2
+    (0, 300, 8, 64, 16, 1, 64), (0, 700, 10, 256, 4, 1, 70 + 16), (1, 257, 9, 32, 16, 1, 64 + 54), (0, 500, 11, 64, 16, 3, 64 + 18), (2, 150, 7, 16, 4, 1, 64 + 49),
+    (0, 200, 7, 16, 16, 11, 64 + 51, 4096), (1, 333, 6, 24, 16, 2, 64 + 6), (0, 600, 5, 100, 16, 1, 64 + 4),
 ]
 
 
