@@ -12,6 +12,7 @@ whatever the sharding.
 N = 1   workload = BASELINE configs[1]: one 2^20-point BN254 G1 MSM.
         `value`        bases and scalars resident in HBM, device time from the engine's CUDA events, L2 flushed between steps
         `e2e`          kgr_msm_oneshot = msm_curve_addition on host slices: points AND scalars uploaded from pinned memory in every call
+        `e2e_pageable` the same call with both vectors in ordinary (pageable) memory, as a Rust Vec or a numpy array is; `e2e_registered`: scalars only
         `roofline`     integer-multiply roofline, whole pipeline + the dominant kernel; `cpu_baseline` = oracle on the host cores
         `north_star`   2^24 points (the north-star size): device time, roofline, e2e, FULL comparison with the restated reference MSM
         `grumpkin_2p20`, `groth16_2p16`   BASELINE configs[2] and [3];  `strong_scaling_base`   2^26 / 2^24 points on this one GPU
@@ -274,6 +275,17 @@ def measure_single(k, torch, curve_name, logn, steps, warmup, local_rank, flush,
                       "ms_per_step": e2e_ms, "steps": e2e_steps, "call": "kgr_msm_oneshot (points + scalars uploaded from pinned host memory every call)"}
         rec["e2e_registered"] = {"value": n / reg_ms / 1e3, "unit": UNIT, "h2d_bytes_per_step": 32 * n, "d2h_bytes_per_step": shape["W"] * 2 * pt_bytes,
                                  "ms_per_step": reg_ms, "call": "kgr_msm (bases registered once, scalars uploaded every call)"}
+        if n <= (1 << 22):  # the same call from ORDINARY (pageable) memory — what a Rust Vec or a numpy array is: staged through pinned slots by host threads
+            sc_page = np.ascontiguousarray(sc)
+            for _ in range(2):
+                k.msm_oneshot_ptr(curve, pts_host.ctypes.data, n, sc_page.ctypes.data, n)
+            t0 = time.perf_counter()
+            for _ in range(e2e_steps):
+                out_pg = k.msm_oneshot_ptr(curve, pts_host.ctypes.data, n, sc_page.ctypes.data, n)
+            pg_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+            assert (k.to_affine(curve, out_pg) == aff).all()
+            rec["e2e_pageable"] = {"value": n / pg_ms / 1e3, "unit": UNIT, "ms_per_step": pg_ms, "h2d_bytes_per_step": (pt_bytes + 32) * n,
+                                   "call": "kgr_msm_oneshot with points and scalars in pageable host memory (no cudaHostAlloc / kgr_host_alloc on the caller's side)"}
     else:
         pts_host = None
     # ---- optional mode for reused vectors (CRS / Pedersen key): window table built once at registration ---------------------------------
@@ -555,7 +567,7 @@ def main():
         line = dict(common)
         line.update({"value": rec["value"], "ms_per_step": ms_per_step, "scaling": "weak", "l2": "flushed between steps (512 MiB write)",
                      "timing": "sum of per-step CUDA-event durations on the engine stream; wall_ms_per_step includes the flush and host gaps", "clocks": clocks})
-        for key in ("wall_ms_per_step", "phases_ms", "shape", "gpu_launches", "e2e", "e2e_registered", "roofline", "checksum_ok", "cpu_baseline", "precomputed_bases"):
+        for key in ("wall_ms_per_step", "phases_ms", "shape", "gpu_launches", "e2e", "e2e_registered", "e2e_pageable", "roofline", "checksum_ok", "cpu_baseline", "precomputed_bases"):
             if key in rec:
                 line[key] = rec[key]
         if not args.quick and args.curve == "bn254_g1":
