@@ -27,6 +27,16 @@ for name in ("g1_uniform_1024", "gr_skewed_128", "g1_dup_neg_96"):
     ok &= bool((got[:8] == z[name + "_aff"][:8]).all() or (got[8] and z[name + "_aff"][8]))
     for pname, v in (("sort_mode", -1), ("affine_levels", -1), ("oneshot_split", 0)):
         k.set_param(pname, v)
+# a hot bucket cut into thousands of pieces (all scalars equal, 2-entry chunks): k_fixup_long sums it on several CTAs (slice sums + arrival
+# counter), then with the chunk length derived from the entries on the device (chunk = 0)
+pts_h = A.random_points(0, 4096, seed=bytes(range(7, 23)))
+sc_h = np.repeat(A.random_field(A.FIELD_FR, 1, seed=bytes(range(9, 25))), 4096, axis=0)
+exp_h = A.to_affine(0, A.msm(0, pts_h, sc_h))
+for chunk in (2, 0):
+    k.set_param("chunk", chunk)
+    got = k.to_affine(0, k.msm_curve_addition(pts_h, sc_h, curve=0))
+    ok &= bool((got == exp_h).all())
+k.set_param("chunk", 0)
 z2 = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "g2_vectors.npz"))
 for name in ("g2_uniform_128", "g2_dup_neg_48", "g2_identity_bases_24", "g2_skewed_64", "g2_uniform_0"):
     for chunk in (0, 2):
