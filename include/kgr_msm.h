@@ -194,6 +194,7 @@ int kgr_groth16_msms(unsigned log_n, const uint64_t *a, const uint64_t *b, const
  * sums come back in one D2H copy and the host applies the doublings), "sort_mode" (-1 auto, 0 counting sort with a per-scalar fill,
  * 1 counting sort with a window-major fill from stored digits, 2 two block-local radix partitions: the default from 2^21 entries on), "reduce_mode" (1 fold reduce, 0 running sums), "affine_levels" (levels of pairwise batched-affine
  * sums inside every bucket before the XYZZ accumulation, affine_kernels.cuh: -1 (default) automatic from the entry count, 0 none, 1..5; 8-word curves only),
+ * "dense_x" (a dense copy of the x coordinates for the level-0 denominators of the batched-affine levels: -1 (default) automatic, 0 off, 1 on),
  * "oneshot_split" (pieces a large single-device kgr_msm_oneshot call is cut into so that uploads
  * overlap the pipeline; 0 (default) = automatic: 2 pieces from 2^20 pairs to 5 from 2^24 when points and scalars are uploaded, 2 - 3 from 2^22 for scalars only; 1 = off), "oneshot_growth" (size of piece i + 1
  * in percent of piece i: the first upload overlaps nothing, so it is the smallest; 0 (default) = automatic, 100 = equal pieces), "lane_threads" (kgr_groth16_msms: 1 (default) one

@@ -34,6 +34,9 @@ constexpr int INV_K = 16;     // values per thread of k_batch_inv (one inversion
 template <class C> struct AffLevelIn {
     const AffinePt<C> *bases;
     const uint32_t *entries;  // nullptr: nodes are addressed directly
+    // level 0, optional: the x coordinates of the bases alone, one 32-byte element per point (k_extract_x).  k_affine_den needs nothing else, and
+    // a gather from the dense array moves half the bytes of a gather of the x half of a 64-byte point (2^21 - 2^23 points: accumulate phase - 2 %)
+    const typename C::Elem *xs = nullptr;
     __device__ __forceinline__ const AffinePt<C> *addr(uint32_t pos, bool &neg) const {
         if (entries) {
             uint32_t ent = entries[pos];
@@ -62,6 +65,15 @@ template <class E> __device__ __forceinline__ E sm_get_el(const uint32_t *sm, in
 #pragma unroll
     for (int k = 0; k < El<E>::WORDS; k++) El<E>::word(v, k) = sm[k * stride + slot];
     return v;
+}
+
+// xs[i] = pts[i].x
+template <class C> __global__ void __launch_bounds__(256) k_extract_x(const AffinePt<C> *pts, uint32_t n, typename C::Elem *xs) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    typename C::Elem x;
+    el_load(x, &pts[i].x);
+    el_store(&xs[i], x);
 }
 
 // cnt[g] = ceil(len_l(g) / 2) for g < G, cnt[G] = 0 (so that the exclusive scan over G + 1 elements ends with the total)
@@ -123,7 +135,14 @@ __global__ void __launch_bounds__(AFF_TPB, 4) k_affine_den(AffLevelIn<C> in, con
             if (p0 + 1 < wk.in_hi) {
                 bool na, nb;
                 const AffinePt<C> *pa = in.addr(p0, na), *pb = in.addr(p0 + 1, nb);
-                E xa = load_x(pa), xb = load_x(pb);   // the chord denominator needs the x coordinates only
+                E xa, xb;   // the chord denominator needs the x coordinates only
+                if (in.xs) {
+                    el_load(xa, in.xs + (pa - in.bases));
+                    el_load(xb, in.xs + (pb - in.bases));
+                } else {
+                    xa = load_x(pa);
+                    xb = load_x(pb);
+                }
                 den = fp_sub(xb, xa);
                 if (fp_is_zero(den) || fp_is_zero(xa) || fp_is_zero(xb)) {  // equal x, or x = 0 (maybe the identity encoding (0, 0))
                     AffinePt<C> a = in.load(p0), b = in.load(p0 + 1);

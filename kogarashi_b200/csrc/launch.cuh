@@ -29,7 +29,7 @@ template <class C> struct Launch {
     // nodes[i & 1]; cnt: G + 1 words of scratch.  Returns the number of launches.  out_max[i]: host-side bound of the nodes of level i + 1.
     // pre: 8 words per node of the largest level, tot: 8 words per thread (affine_scratch_words gives both sizes for out_max[0])
     static int affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const A *bases, const uint32_t *entries, uint32_t *const off[], A *const nodes[2],
-                             const uint32_t out_max[], uint32_t *cnt, uint32_t *tile_sums, uint32_t *pre, uint32_t *tot);
+                             const uint32_t out_max[], uint32_t *cnt, uint32_t *tile_sums, uint32_t *pre, uint32_t *tot, uint32_t n_bases, void *xs);
     static void affine_scratch_words(uint32_t out_max0, size_t &pre_words, size_t &tot_words);
     // worklist: 4 words per record, fixup_records_max(chunks) records; partial: one XYZZ point per record; counter: one word per record, zero on
     // entry and left zero

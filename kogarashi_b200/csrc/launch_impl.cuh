@@ -49,12 +49,16 @@ template <class C> void Launch<C>::affine_scratch_words(uint32_t out_max0, size_
 }
 template <class C>
 int Launch<C>::affine_levels(cudaStream_t st, uint32_t levels, uint32_t G, const A *bases, const uint32_t *entries, uint32_t *const off[], A *const nodes[2],
-                             const uint32_t out_max[], uint32_t *cnt, uint32_t *tile_sums, uint32_t *pre, uint32_t *tot) {
+                             const uint32_t out_max[], uint32_t *cnt, uint32_t *tile_sums, uint32_t *pre, uint32_t *tot, uint32_t n_bases, void *xs) {
     int launches = 0;
+    if (xs) {  // dense copy of the x coordinates for the level-0 denominators (affine_kernels.cuh: AffLevelIn::xs)
+        k_extract_x<C><<<cdiv(n_bases, 256), 256, 0, st>>>(bases, n_bases, (typename C::Elem *)xs);
+        launches++;
+    }
     for (uint32_t l = 0; l < levels; l++) {
         k_affine_counts<<<cdiv((size_t)G + 1, 256), 256, 0, st>>>(off[l], G, cnt);
         exclusive_scan_u32(cnt, off[l + 1], G + 1, tile_sums, st);
-        AffLevelIn<C> in{l == 0 ? bases : nodes[(l - 1) & 1], l == 0 ? entries : nullptr};
+        AffLevelIn<C> in{l == 0 ? bases : nodes[(l - 1) & 1], l == 0 ? entries : nullptr, l == 0 ? (const typename C::Elem *)xs : nullptr};
         const uint32_t NT = affine_threads(out_max[l]);
         k_affine_den<C><<<NT / AFF_TPB, AFF_TPB, 0, st>>>(in, off[l], off[l + 1], G, NT, pre, tot);
         k_batch_inv<typename C::Elem><<<cdiv(NT, AFF_TPB * INV_K), AFF_TPB, 0, st>>>(tot, NT, NT, tot + (size_t)NT * El<typename C::Elem>::WORDS, off[l + 1] + G);

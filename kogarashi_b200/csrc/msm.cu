@@ -57,7 +57,7 @@ struct CudaError {
 
 // ---- engine -----------------------------------------------------------------------------------
 struct Params {
-    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_levels = -1, oneshot_split = 0, oneshot_growth = 0, lane_threads = 1;
+    long window_bits = 0, chunk = 0, reduce_fanin = 16, final_on_device = 0, running_sum_stop = 4096, sort_mode = -1, reduce_mode = 1, affine_levels = -1, oneshot_split = 0, oneshot_growth = 0, lane_threads = 1, dense_x = -1;
 };
 // Tuning state is per calling thread (kgr_set_param changes the calling thread's copy only): an entry point snapshots it once and hands the
 // snapshot to every engine it drives (Engine::params), so a kgr_set_param on one thread never changes an MSM in flight on another, and the
@@ -170,6 +170,7 @@ struct Engine {
     DevBuf<uint32_t> coarse_counts, coarse_off, coarse_cursor, part_pay;  // radix-partition sort (kernels_sort.cu)
     DevBuf<uint32_t> lvl_off[5], lvl_cnt, lvl_pre, lvl_tot;                                // batched-affine levels (affine_kernels.cuh): offsets per level
     DevBuf<uint8_t> lvl_nodes[2];                                          // ... and their node arrays (ping-pong)
+    DevBuf<uint8_t> lvl_x;                                                 // dense copy of the x coordinates of the bases (level-0 denominators)
     DevBuf<uint8_t> part_fine;
     DevBuf<uint8_t> piece_acc;  // bucket sums of one piece of a streamed call (enqueue_msm)
     DevBuf<uint8_t> fix_partial;  // slice sums of the hot buckets (k_fixup_long)
@@ -220,7 +221,7 @@ struct Engine {
         counts.release(); offsets.release(); tile_sums.release(); entries.release(); scalars.release(); worklist.release(); tail_bucket.release(); digits.release(); fix_partial.release(); fix_counter.release();
         coarse_counts.release(); coarse_off.release(); coarse_cursor.release(); part_pay.release(); part_fine.release();
         for (auto &b : lvl_off) b.release();
-        lvl_cnt.release(); lvl_pre.release(); lvl_tot.release(); lvl_nodes[0].release(); lvl_nodes[1].release();
+        lvl_cnt.release(); lvl_pre.release(); lvl_tot.release(); lvl_nodes[0].release(); lvl_nodes[1].release(); lvl_x.release();
         piece_acc.release();
         bucket_acc.release(); head.release(); tail.release(); result.release(); fold_f.release(); fold_partial.release(); fold_v.release();
         for (auto &t : fixed_table) t.release();
@@ -616,7 +617,16 @@ static void enqueue_msm(Engine &e, const AffinePt<C> *d_bases, const uint32_t *d
                 K::affine_scratch_words(out_max[0], pre_words, tot_words);
                 e.lvl_pre.ensure(pre_words);
                 e.lvl_tot.ensure(tot_words);
-                e.launches += K::affine_levels(e.st, levels, sh.G, bases_k, e.entries.p, off, nodes, out_max, e.lvl_cnt.p, e.tile_sums.p, e.lvl_pre.p, e.lvl_tot.p);
+                // dense x copy for the level-0 denominators ("dense_x": -1 auto, 0 off, 1 on).  Measured (accumulate phase, ms): 2^20 2.70 -> 2.69,
+                // 2^21 4.94 -> 4.80, 2^22 9.23 -> 8.98, 2^23 18.12 -> 17.83, 2^24 35.62 -> 35.46, 2^26 no change: a gathered 32-byte x out of a
+                // 64-byte point costs a wider DRAM fetch than one out of a dense array; below 2^21 points the copy costs what it saves
+                void *xs = nullptr;
+                const bool want_x = !table_c && (P.dense_x > 0 || (P.dense_x < 0 && n_k > (1u << 20) && n_k <= (1u << 24)));
+                if (want_x) {
+                    e.lvl_x.ensure((size_t)n_k * sizeof(typename C::Elem));
+                    xs = e.lvl_x.p;
+                }
+                e.launches += K::affine_levels(e.st, levels, sh.G, bases_k, e.entries.p, off, nodes, out_max, e.lvl_cnt.p, e.tile_sums.p, e.lvl_pre.p, e.lvl_tot.p, n_k, xs);
                 // the XYZZ kernel sums what is left: chunk length re-chosen for the shorter list
                 MsmShape sh2 = make_shape(P, n, e.acc_blocks_per_sm[C::ID], e.sm_count, table_c, table_stride, poff_k, out_max[levels - 1]);
                 shp.L = sh2.L;
@@ -1422,6 +1432,7 @@ int kgr_set_param(const char *name, long value) {
     else if (s == "oneshot_split") t_params.oneshot_split = std::min<long>(std::max<long>(value, 0), (long)MAX_LANES);
     else if (s == "oneshot_growth") t_params.oneshot_growth = std::min<long>(std::max<long>(value, 0), 1000);
     else if (s == "affine_levels") t_params.affine_levels = std::min<long>(std::max<long>(value, -1), 5);
+    else if (s == "dense_x") t_params.dense_x = std::min<long>(std::max<long>(value, -1), 1);
     else return fail(KGR_E_ARG, "unknown parameter");
     return KGR_OK;
 }

@@ -523,6 +523,7 @@ def test_batched_affine_levels_special_cases(k, golden, levels):
     """affine_levels = r (affine_kernels.cuh): pairs inside a bucket that are equal (tangent), opposite (identity), identities themselves, odd
     bucket lengths, empty buckets, a single bucket with everything in it — every golden, small windows so that buckets are long."""
     k.set_param("affine_levels", levels)
+    k.set_param("dense_x", levels & 1)   # odd levels: the level-0 denominators read the dense copy of the x coordinates (automatic only above 2^20 points)
     try:
         for c in (2, 5, 0):
             k.set_param("window_bits", c)
@@ -545,6 +546,7 @@ def test_batched_affine_levels_special_cases(k, golden, levels):
     finally:
         k.set_param("affine_levels", -1)
         k.set_param("window_bits", 0)
+        k.set_param("dense_x", -1)
 
 
 @pytest.mark.parametrize("curve,logn", [(A.BN254_G1, 16), (A.GRUMPKIN, 15)])
@@ -563,10 +565,16 @@ def test_batched_affine_levels_vs_oracle(k, curve, logn):
         for levels, c in ((1, 0), (2, 8), (3, 10), (4, 6)):
             k.set_param("affine_levels", levels)
             k.set_param("window_bits", c)
+            k.set_param("dense_x", levels & 1)
             assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp), (levels, c)
+            k.set_param("oneshot_split", 2)   # two streamed pieces: the copy is made per piece
+            assert same_affine(k.to_affine(curve, k.msm_curve_addition(pts, sc, curve=curve)), exp), (levels, c, "pieces")
+            k.set_param("oneshot_split", 0)
     finally:
         k.set_param("affine_levels", -1)
         k.set_param("window_bits", 0)
+        k.set_param("dense_x", -1)
+        k.set_param("oneshot_split", 0)
 
 
 def test_handles_die_with_their_kgr_init_and_pinned_arena(k):
