@@ -15,7 +15,7 @@ N = 1   workload = BASELINE configs[1]: one 2^20-point BN254 G1 MSM.
         `e2e_pageable` the same call with both vectors in ordinary (pageable) memory, as a Rust Vec or a numpy array is; `e2e_registered`: scalars only
         `roofline`     integer-multiply roofline, whole pipeline + the dominant kernel; `cpu_baseline` = oracle on the host cores
         `north_star`   2^24 points (the north-star size): device time, roofline, e2e, FULL comparison with the restated reference MSM
-        `grumpkin_2p20`, `groth16_2p16`   BASELINE configs[2] and [3];  `strong_scaling_base`   2^26 / 2^24 points on this one GPU
+        `grumpkin_2p20`, `groth16_2p16`   BASELINE configs[2] and [3]; `g2_2p18` the G2 query's MSM (row N3);  `strong_scaling_base`   2^26 / 2^24 points on this one GPU
 N > 1   workload = BASELINE configs[4], STRONG scaling: ONE 2^26-point MSM sharded evenly over the N ranks (contiguous shards, no data-path
         collective); a step = every rank's MSM + all_gather of one 96-byte point per rank + the host sum on rank 0, timed by wall clock between
         barriers.  `value`: scalars resident in HBM; `e2e`: scalars uploaded from pinned host memory every step (bases registered).
@@ -578,6 +578,12 @@ def main():
             gr, _, _ = measure_single(k, torch, "grumpkin", 20, 5, 3, local_rank, flush, want_e2e=True, full_cpu=True)
             gr["note"] = "BASELINE configs[2]: Grumpkin MSM, 2^20 points (Nova secondary-curve commitment shape)"
             line["grumpkin_2p20"] = gr
+            try:  # the G2 query of the prover (prover.rs:64-65), same pipeline over Fq2 coordinates
+                g2, _, _ = measure_single(k, torch, "bn254_g2", 18, 5, 3, local_rank, flush, want_e2e=True, full_cpu=True)
+                g2["note"] = "row N3: BN254 G2 MSM, 2^18 points (Fq2 coordinates, 128-byte points); cpu_baseline = the restated reference algorithm over Fq2, all pairs"
+                line["g2_2p18"] = g2
+            except Exception as ex:
+                line["g2_2p18"] = {"error": repr(ex)}
             try:
                 g16, first = groth16_record(args)
                 line["groth16_2p16"] = {"metric": "groth16_prove_latency", "unit": "ms", "value": g16["gpu_wall_ms"]["normal"], "idle_host_ms": first["gpu_wall_ms"]["normal"],
