@@ -15,7 +15,7 @@ N = 1   workload = BASELINE configs[1]: one 2^20-point BN254 G1 MSM.
         `e2e_pageable` the same call with both vectors in ordinary (pageable) memory, as a Rust Vec or a numpy array is; `e2e_registered`: scalars only
         `roofline`     integer-multiply roofline, whole pipeline + the dominant kernel; `cpu_baseline` = oracle on the host cores
         `north_star`   2^24 points (the north-star size): device time, roofline, e2e, FULL comparison with the restated reference MSM
-        `grumpkin_2p20`, `groth16_2p16`   BASELINE configs[2] and [3]; `g2_2p18` the G2 query's MSM (row N3);  `strong_scaling_base`   2^26 / 2^24 points on this one GPU
+        `grumpkin_2p20`, `groth16_2p16`   BASELINE configs[2] and [3]; `g2_2p18` the G2 query's MSM (row N3); `ntt_2p20` the Fr transform (row N2);  `strong_scaling_base`   2^26 / 2^24 points on this one GPU
 N > 1   workload = BASELINE configs[4], STRONG scaling: ONE 2^26-point MSM sharded evenly over the N ranks (contiguous shards, no data-path
         collective); a step = every rank's MSM + all_gather of one 96-byte point per rank + the host sum on rank 0, timed by wall clock between
         barriers.  `value`: scalars resident in HBM; `e2e`: scalars uploaded from pinned host memory every step (bases registered).
@@ -584,6 +584,32 @@ def main():
                 line["g2_2p18"] = g2
             except Exception as ex:
                 line["g2_2p18"] = {"error": repr(ex)}
+            try:  # the radix-2 transform of groth16/src/fft.rs on bn254 Fr, 2^20 elements, bit-exact with the restated reference dft
+                from oracle import oracle as A
+                nn = 1 << 20
+                xv = A.random_field(A.FIELD_FR, nn, seed=bytes(range(16)))
+                f = k.Fft(20)
+                dv = torch.from_numpy(xv.view(np.int64)).cuda()
+                torch.cuda.synchronize()
+                f.transform_device("dft", dv.data_ptr())
+                ntt_ms = []
+                for _ in range(10):
+                    f.transform_device("dft", dv.data_ptr())
+                    ntt_ms.append(k.last_timing(0)[0]["total"])
+                t0 = time.perf_counter()
+                exp_v, _ = A.fft(20, "dft", xv)
+                cpu_s = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                got_v = f.dft(xv)
+                e2e_s = time.perf_counter() - t0
+                bf = nn // 2 * 20
+                line["ntt_2p20"] = {"metric": "fr_ntt_time", "unit": "ms", "value": min(ntt_ms), "melem_per_s": nn / min(ntt_ms) / 1e3, "bit_exact_with_oracle": bool((got_v == exp_v).all()),
+                                    "e2e_host_buffers_ms": e2e_s * 1e3, "cpu_baseline": {"value": cpu_s * 1e3, "unit": "ms", "kind": "port", "cores": "recursion halves forked like rayon::join"},
+                                    "roofline": {"bound": "imad", "algorithmic_imads": bf * 264, "frac": bf * 264 / (min(ntt_ms) * 1e-3) / 1e12 / IMAD_PEAK_T,
+                                                 "note": "one 254-bit Montgomery product (264 IMAD) per butterfly, n/2 * log2(n) butterflies"},
+                                    "note": "row N2: dft of 2^20 Fr elements resident in HBM (device time, best of 10)"}
+            except Exception as ex:
+                line["ntt_2p20"] = {"error": repr(ex)}
             try:
                 g16, first = groth16_record(args)
                 line["groth16_2p16"] = {"metric": "groth16_prove_latency", "unit": "ms", "value": g16["gpu_wall_ms"]["normal"], "idle_host_ms": first["gpu_wall_ms"]["normal"],
