@@ -15,7 +15,7 @@ N = 1   workload = BASELINE configs[1]: one 2^20-point BN254 G1 MSM.
         `e2e_pageable` the same call with both vectors in ordinary (pageable) memory, as a Rust Vec or a numpy array is; `e2e_registered`: scalars only
         `roofline`     integer-multiply roofline, whole pipeline + the dominant kernel; `cpu_baseline` = oracle on the host cores
         `north_star`   2^24 points (the north-star size): device time, roofline, e2e, FULL comparison with the restated reference MSM
-        `grumpkin_2p20`, `groth16_2p16`   BASELINE configs[2] and [3]; `g2_2p18` the G2 query's MSM (row N3); `ntt_2p20` the Fr transform (row N2);  `strong_scaling_base`   2^26 / 2^24 points on this one GPU
+        `grumpkin_2p20`, `groth16_2p16`   BASELINE configs[2] and [3]; `g2_2p18` the G2 query's MSM (row N3); `ntt_2p20` the Fr transform (row N2); `nova_ivc_step_32k` Nova's folding vector work (row N4, tools/bench_ivc_step.py in a child process);  `strong_scaling_base`   2^26 / 2^24 points on this one GPU
 N > 1   workload = BASELINE configs[4], STRONG scaling: ONE 2^26-point MSM sharded evenly over the N ranks (contiguous shards, no data-path
         collective); a step = every rank's MSM + all_gather of one 96-byte point per rank + the host sum on rank 0, timed by wall clock between
         barriers.  `value`: scalars resident in HBM; `e2e`: scalars uploaded from pinned host memory every step (bases registered).
@@ -621,6 +621,14 @@ def main():
                                         "note": "BASELINE configs[3] scaled: create_proof after witness generation, chained x^3 + x + 5 circuit, wall clock, best of 5"}
             except Exception as ex:  # the secondary figure must not take the headline down with it
                 line["groth16_2p16"] = {"error": repr(ex)}
+            try:  # one Nova IVC step's vector work on one curve (commit(W), cross term, commit(T), two folds), state resident on the GPU
+                import subprocess
+                env = dict(os.environ, CUDA_VISIBLE_DEVICES=os.environ.get("CUDA_VISIBLE_DEVICES", str(local_rank)))
+                outp = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "bench_ivc_step.py"), "15", "1"], capture_output=True, text=True, timeout=300, env=env)
+                recs = [json.loads(l) for l in outp.stdout.splitlines() if l.startswith("{")]
+                line["nova_ivc_step_32k"] = recs[-1] if recs else {"error": (outp.stderr or "no output")[-300:]}
+            except Exception as ex:
+                line["nova_ivc_step_32k"] = {"error": repr(ex)}
             k.init([local_rank])
             base = {}
             for lg in sorted({24, args.strong_logn}):
