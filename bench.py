@@ -66,10 +66,11 @@ def measured_traffic(n, curve_name):
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         if n == (1 << 20) and curve_name in ("bn254_g1", "grumpkin") and t.get("kernel_sources_sha") == kernel_sources_sha():
-            return t["accumulate_phase_dram_bytes"], t["capture"]
+            sort_bytes = sum(v["bytes"] for kname, v in t["per_kernel_dram_bytes"].items() if kname.startswith("k_sort_"))
+            return t["accumulate_phase_dram_bytes"], t["capture"], sort_bytes
     except Exception:
         pass
-    return None, None
+    return None, None, None
 
 
 def ref_window_bits(n):  # groth16/src/msm.rs:7-14
@@ -245,11 +246,17 @@ def measure_single(k, torch, curve_name, logn, steps, warmup, local_rank, flush,
         "sort": {"kernels": "k_sort_digits + k_sort_scan + k_sort_partition + k_sort_buckets (or k_count + scan + k_fill below 2^21 entries)", "bound": "hbm", "ms": sort_ms,
                  "algorithmic_bytes": sort_bytes, "achieved_gbs": sort_bytes / (sort_ms * 1e-3) / 1e9 if sort_ms else None},
         "hbm": {"achieved_gbs": (pt_bytes + 32) * n / (ms_per_step * 1e-3) / 1e9, "note": f"{pt_bytes + 32} B/point algorithmic traffic; the path is multiply-bound, not HBM-bound"}}
+    sort_traffic = measured_traffic(n, curve_name)[2]
+    if sort_traffic and sort_ms:  # what the two partition passes really move (ncu): digit words, payloads and fine bytes are written and read again
+        rec["roofline"]["sort"]["traffic"] = sort_traffic
+        rec["roofline"]["sort"]["traffic_gbs"] = sort_traffic / (sort_ms * 1e-3) / 1e9
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         rec["roofline"]["hbm"]["peak_gbs"] = peaks.get("hbm_gbs")
         if sort_ms and peaks.get("hbm_gbs"):
             rec["roofline"]["sort"]["frac"] = rec["roofline"]["sort"]["achieved_gbs"] / peaks["hbm_gbs"]
+            if sort_traffic:
+                rec["roofline"]["sort"]["frac_of_traffic"] = rec["roofline"]["sort"]["traffic_gbs"] / peaks["hbm_gbs"]
     except Exception:
         pass
     # ---- e2e: host buffers through the reference-facing calls ----------------------------------------------------------------------------
